@@ -1,0 +1,504 @@
+// pg_capi.cu — host side of the C ABI declared in include/pgbart.h.
+//
+// Owns all device memory of one sampler (the reference's PySampler owns copies of X, y, the
+// forest and predictions: lib.rs:106-111,122-123) and one CUDA stream per handle
+// (`#[pyclass(unsendable)]`, lib.rs:106: one sampler per host thread).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+#include "../../include/pgbart.h"
+#include "pg_sweep.h"
+#include "pg_types.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct Sampler {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    PgState st{};
+    std::vector<void*> allocs;
+    std::string err;
+    bool dead = false;
+    bool stepwise = false;
+    size_t smem = 0;
+    double launches = 0;
+    bool timing_pending = false;
+    unsigned long long pool_factor = 2;
+    // owned optional buffers
+    double *tape_slot = nullptr, *tape_round = nullptr, *tape_upd = nullptr;
+    double *tr_slot = nullptr, *tr_round = nullptr, *tr_upd = nullptr;
+    long long tr_u_cap = 0;
+    int tr_r_cap = 0;
+    PgCtrl host_ctrl{};
+};
+
+const char* pg_error_text(int code) {
+    switch (code) {
+        case PG_ERR_DEPTH: return "Tree mutation would exceed maximum capacity (the reference panics here, tree.rs:98-102)";
+        case PG_ERR_POOL: return "segment pool exhausted (raise option pool_factor)";
+        case PG_ERR_TAPE: return "RNG tape exhausted or a taped split draw is not below the node maximum";
+        case PG_ERR_WATCHDOG: return "grid barrier watchdog fired";
+        case PG_ERR_WEIGHTS: return "final particle weights are not finite (the reference panics in WeightedIndex::new)";
+        case PG_ERR_INTERNAL: return "internal consistency check failed";
+        default: return "unknown device error";
+    }
+}
+
+bool ck(Sampler* s, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    s->err = std::string(what) + ": " + cudaGetErrorString(e);
+    if (e != cudaErrorInvalidValue && e != cudaErrorMemoryAllocation) s->dead = true;
+    return false;
+}
+
+template <typename T>
+bool dalloc(Sampler* s, T** out, size_t count, bool zero = true) {
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    if (!ck(s, cudaMalloc(&p, bytes), "cudaMalloc")) return false;
+    s->allocs.push_back(p);
+    if (zero && !ck(s, cudaMemsetAsync(p, 0, bytes, s->stream), "cudaMemset")) return false;
+    *out = (T*)p;
+    return true;
+}
+
+// ndarray's mean(): sum()/n with the 8-way unrolled fold of numeric_util (kernel.rs:40, smc.rs:40).
+double unrolled_mean(const double* xs, size_t n) {
+    if (n == 0) return 0.0;
+    double p[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc = 0.0;
+    size_t len = n;
+    while (len >= 8) {
+        for (int j = 0; j < 8; ++j) p[j] += xs[j];
+        xs += 8; len -= 8;
+    }
+    acc += p[0] + p[4];
+    acc += p[1] + p[5];
+    acc += p[2] + p[6];
+    acc += p[3] + p[7];
+    for (size_t i = 0; i < len && i < 7; ++i) acc += xs[i];
+    return acc / (double)n;
+}
+
+void free_all(Sampler* s) {
+    for (void* p : s->allocs) cudaFree(p);
+    s->allocs.clear();
+    for (double* p : {s->tape_slot, s->tape_round, s->tape_upd, s->tr_slot, s->tr_round, s->tr_upd})
+        if (p) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+}
+
+bool fetch_ctrl(Sampler* s) {
+    if (!ck(s, cudaMemcpyAsync(&s->host_ctrl, s->st.ctrl, sizeof(PgCtrl), cudaMemcpyDeviceToHost, s->stream), "read ctrl")) return false;
+    return ck(s, cudaStreamSynchronize(s->stream), "synchronize");
+}
+
+int finish_step(Sampler* s) {
+    if (!fetch_ctrl(s)) return 2;
+    if (s->host_ctrl.error != PG_OK) {
+        s->err = pg_error_text(s->host_ctrl.error);
+        // the sampler state is no longer meaningful after a device-side failure
+        s->dead = true;
+        return 3;
+    }
+    return 0;
+}
+
+int enqueue_step(Sampler* s, int tune) {
+    if (s->dead) { if (s->err.empty()) s->err = "sampler is unusable after an earlier failure"; return 2; }
+    if (!ck(s, cudaSetDevice(s->device), "cudaSetDevice")) return 2;
+    if (!ck(s, pg_launch_prepare(s->st, tune, s->stream), "launch prepare")) return 2;
+    s->launches += 1;
+    if (!ck(s, cudaEventRecord(s->ev0, s->stream), "event")) return 2;
+    if (!s->stepwise) {
+        if (!ck(s, pg_launch_persistent(s->st, s->smem, s->stream), "cooperative launch")) return 2;
+        s->launches += 1;
+    } else {
+        // serial(BEGIN) -> [pass -> serial]* until DONE, reading the phase back between launches
+        if (!ck(s, pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
+        s->launches += 1;
+        for (long long guard = 0; guard < (1ll << 40); ++guard) {
+            int phase = PH_DONE;
+            if (!ck(s, cudaMemcpyAsync(&phase, &s->st.ctrl->phase, sizeof(int), cudaMemcpyDeviceToHost, s->stream), "read phase")) return 2;
+            if (!ck(s, cudaStreamSynchronize(s->stream), "synchronize")) return 2;
+            if (phase == PH_DONE) break;
+            if (!ck(s, pg_launch_phase(s->st, s->smem, s->stream), "launch pass")) return 2;
+            if (!ck(s, pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
+            s->launches += 2;
+        }
+    }
+    if (!ck(s, cudaEventRecord(s->ev1, s->stream), "event")) return 2;
+    s->timing_pending = true;
+    return 0;
+}
+
+}  // namespace
+
+struct pgbart_sampler { Sampler s; };
+
+extern "C" {
+
+const char* pgbart_last_error(pgbart_handle h) { return h ? h->s.err.c_str() : g_create_error.c_str(); }
+
+int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t p, const double* y,
+                  const pgbart_settings* cfg, int device, pgbart_handle* out) {
+    g_create_error.clear();
+    if (!out) { g_create_error = "out handle is null"; return 1; }
+    *out = nullptr;
+    auto fail = [&](const std::string& m) { g_create_error = m; return 1; };
+    if (!x || !y || !cfg) return fail("null input");
+    if (n < 1 || p < 1) return fail("x must have at least one row and one column");
+    if (n >= 0xFFFFFFF0ull) return fail("n must fit in 32 bits (sample indices are u32 as in the reference)");
+    if (cfg->n_trees < 1) return fail("n_trees must be >= 1");
+    if (cfg->n_particles < 2) return fail("n_particles must be >= 2 (one reference stump + at least one growing particle)");
+    if (cfg->n_particles > 4096) return fail("n_particles > 4096 is not supported");
+    if (cfg->max_depth > 12) return fail("max_depth > 12 is not supported (node tables are heap-indexed)");
+    if (cfg->n_split_prior != 0 && cfg->n_split_prior != p) return fail("split_prior must be empty or have one weight per column");
+    for (uint64_t i = 0; i < cfg->n_split_rules; ++i) {   // lib.rs:129-132
+        const char* r = cfg->split_rules ? cfg->split_rules[i] : nullptr;
+        if (!r) return fail("null split rule");
+        if (std::strcmp(r, "ContinuousSplit") == 0) continue;
+        if (std::strcmp(r, "OneHotSplit") == 0)
+            return fail("OneHotSplit is not available on the device path (SURVEY.md: out of scope; no CPU fallback)");
+        return fail(std::string("Unknown split rule: '") + r + "'. Supported: 'ContinuousSplit', 'OneHotSplit'.");
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("invalid CUDA device ordinal");
+
+    auto* h = new pgbart_sampler();
+    Sampler* s = &h->s;
+    auto bail = [&]() { g_create_error = s->err; free_all(s); delete h; return 2; };
+    s->device = device;
+    if (!ck(s, cudaSetDevice(device), "cudaSetDevice")) return bail();
+    if (!ck(s, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "stream")) return bail();
+    if (!ck(s, cudaEventCreate(&s->ev0), "event") || !ck(s, cudaEventCreate(&s->ev1), "event")) return bail();
+
+    PgState& st = s->st;
+    st.n = (long long)n;
+    st.ld = (long long)((n + 31) / 32 * 32);
+    st.p = (int)p; st.m = (int)cfg->n_trees; st.P = (int)cfg->n_particles; st.S = st.P - 1;
+    st.max_depth = (int)cfg->max_depth;
+    st.maxn = (1 << (st.max_depth + 1)) - 1;
+    st.leaf_sigma = cfg->sigma;
+    st.m_f = (double)st.m;
+    st.batch_tune = cfg->batch_tune; st.batch_post = cfg->batch_post;
+    st.family = PG_GAUSSIAN; st.lik_sigma = 1.0;
+    st.y_mean = unrolled_mean(y, n);
+    st.init_leaf = st.y_mean / (double)st.m;
+
+    char ebuf[256];
+    int grid = 0;
+    if (pg_query_grid(device, st.S, &grid, &s->smem, ebuf, sizeof ebuf)) { s->err = ebuf; return bail(); }
+    st.grid = grid;
+    st.n_gwarps = grid * PG_WARPS;
+
+    // ---- X -> column-major fp32 with per-column min/max; y -> fp32
+    {
+        std::vector<float> colbuf((size_t)st.ld);
+        std::vector<float> cmin(p), cmax(p);
+        float* dX = nullptr;
+        if (!dalloc(s, &dX, (size_t)st.ld * p, false)) return bail();
+        for (uint64_t j = 0; j < p; ++j) {
+            float mn = std::numeric_limits<float>::infinity(), mx = -mn;
+            for (uint64_t i = 0; i < n; ++i) {
+                const size_t src = x_order == PGBART_ORDER_F ? (size_t)j * n + i : (size_t)i * p + j;
+                const float v = x_dtype == PGBART_X_F32 ? ((const float*)x)[src] : (float)((const double*)x)[src];
+                colbuf[i] = v;
+                mn = std::fmin(mn, v); mx = std::fmax(mx, v);
+            }
+            for (uint64_t i = n; i < (uint64_t)st.ld; ++i) colbuf[i] = 0.0f;
+            cmin[j] = mn; cmax[j] = mx;
+            if (!ck(s, cudaMemcpy(dX + (size_t)j * st.ld, colbuf.data(), (size_t)st.ld * 4, cudaMemcpyHostToDevice), "upload X")) return bail();
+        }
+        st.X = dX;
+        float *dmin = nullptr, *dmax = nullptr, *dy = nullptr;
+        if (!dalloc(s, &dmin, p, false) || !dalloc(s, &dmax, p, false) || !dalloc(s, &dy, (size_t)st.ld, false)) return bail();
+        if (!ck(s, cudaMemcpy(dmin, cmin.data(), p * 4, cudaMemcpyHostToDevice), "upload") ||
+            !ck(s, cudaMemcpy(dmax, cmax.data(), p * 4, cudaMemcpyHostToDevice), "upload")) return bail();
+        for (uint64_t i = 0; i < n; ++i) colbuf[i] = (float)y[i];
+        if (!ck(s, cudaMemcpy(dy, colbuf.data(), (size_t)st.ld * 4, cudaMemcpyHostToDevice), "upload y")) return bail();
+        st.col_min = dmin; st.col_max = dmax; st.y = dy;
+    }
+    // ---- prior and depth thresholds
+    if (cfg->n_split_prior) {
+        double* d = nullptr;
+        if (!dalloc(s, &d, p, false)) return bail();
+        if (!ck(s, cudaMemcpy(d, cfg->split_prior, p * 8, cudaMemcpyHostToDevice), "upload prior")) return bail();
+        st.prior = d;
+        double tot = 0.0;
+        for (uint64_t j = 0; j < p; ++j) tot += cfg->split_prior[j];   // smc.rs:243 (sequential sum)
+        st.prior_total = tot;
+    }
+    {
+        std::vector<double> thr((size_t)st.max_depth + 2);
+        for (size_t d = 0; d < thr.size(); ++d) thr[d] = 1.0 - (cfg->alpha * std::pow(1.0 + (double)d, -cfg->beta));  // smc.rs:143
+        double* dt = nullptr;
+        if (!dalloc(s, &dt, thr.size(), false)) return bail();
+        if (!ck(s, cudaMemcpy(dt, thr.data(), thr.size() * 8, cudaMemcpyHostToDevice), "upload thr")) return bail();
+        st.thr_depth = dt;
+    }
+    // ---- state arrays
+    const size_t S = (size_t)st.S, MN = (size_t)st.maxn, M = (size_t)st.m, G = (size_t)st.grid, W = (size_t)st.n_gwarps;
+    bool ok = dalloc(s, &st.A, (size_t)st.ld)
+        && dalloc(s, &st.f_split_var, M * MN) && dalloc(s, &st.f_thr32, M * MN) && dalloc(s, &st.f_split_val, M * MN)
+        && dalloc(s, &st.f_leaf_val, M * MN) && dalloc(s, &st.f_size, M)
+        && dalloc(s, &st.pt_split_var, 2 * S * MN) && dalloc(s, &st.pt_thr32, 2 * S * MN) && dalloc(s, &st.pt_split_val, 2 * S * MN)
+        && dalloc(s, &st.pt_leaf_val, 2 * S * MN) && dalloc(s, &st.pt_seg_off, 2 * S * MN) && dalloc(s, &st.pt_cnt, 2 * S * MN)
+        && dalloc(s, &st.pt_So, 2 * S * MN) && dalloc(s, &st.pt_Sr, 2 * S * MN) && dalloc(s, &st.pt_g, 2 * S * MN)
+        && dalloc(s, &st.pt_queue, 2 * S * MN) && dalloc(s, &st.pt_size, 2 * S) && dalloc(s, &st.pt_qhead, 2 * S)
+        && dalloc(s, &st.pt_qtail, 2 * S) && dalloc(s, &st.pt_G, 2 * S)
+        && dalloc(s, &st.w, S) && dalloc(s, &st.mutated, S) && dalloc(s, &st.anc, S) && dalloc(s, &st.slot_job, S)
+        && dalloc(s, &st.pend_node, S) && dalloc(s, &st.pend_var, S) && dalloc(s, &st.Wfinal, 2 * (S + 1))
+        && dalloc(s, &st.job_slot, S) && dalloc(s, &st.job_node, S) && dalloc(s, &st.job_var, S) && dalloc(s, &st.job_thr32, S)
+        && dalloc(s, &st.job_split, S) && dalloc(s, &st.job_seg_off, S) && dalloc(s, &st.job_len, S) && dalloc(s, &st.job_lo, S)
+        && dalloc(s, &st.job_hi, S) && dalloc(s, &st.job_vL, S) && dalloc(s, &st.job_vR, S) && dalloc(s, &st.job_order, S)
+        && dalloc(s, &st.grp_first, S + 1) && dalloc(s, &st.red_So, S) && dalloc(s, &st.red_Sr, S) && dalloc(s, &st.red_llL, S)
+        && dalloc(s, &st.red_llR, S) && dalloc(s, &st.red_cnt, S)
+        && dalloc(s, &st.pj_anc, S) && dalloc(s, &st.pj_job, S) && dalloc(s, &st.pj_var, S) && dalloc(s, &st.pj_thr32, S)
+        && dalloc(s, &st.pj_src_off, S) && dalloc(s, &st.pj_len, S) && dalloc(s, &st.pj_dst_off, S) && dalloc(s, &st.pj_cntL, S)
+        && dalloc(s, &st.pj_warp_left, S * W) && dalloc(s, &st.pj_of_anc, S) && dalloc(s, &st.scan_tmp, PG_THREADS + 1)
+        && dalloc(s, &st.part_sum, G * S * 2) && dalloc(s, &st.part_cnt, W * S) && dalloc(s, &st.part_ccnt, G * S)
+        && dalloc(s, &st.part_tot, G * 4) && dalloc(s, &st.part_mm, G * S * 2) && dalloc(s, &st.part_ll, G * S * 2)
+        && dalloc(s, &st.info_depths, M) && dalloc(s, &st.ctrl, 1);
+    if (!ok) return bail();
+    {
+        // every surviving lineage appends at most n entries per tree level; 2S*n covers the reference's
+        // behaviour (one split per tree, Q1), (max_depth+2)*n covers one lineage growing to full depth
+        unsigned long long cap = std::max<unsigned long long>(s->pool_factor * (unsigned long long)S, (unsigned long long)st.max_depth + 2) * n;
+        if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;   // u32 offsets
+        if (cap < n) cap = n;
+        st.pool_cap = cap;
+        if (!dalloc(s, &st.pool, (size_t)cap, false)) return bail();
+    }
+    st.rng_mode = PG_RNG_PHILOX;
+    st.philox_key0 = (unsigned)cfg->seed;
+    st.philox_key1 = (unsigned)(cfg->seed >> 32);
+
+    PgCtrl c0{};
+    c0.phase = PH_DONE; c0.tune = 1; c0.t_add = -1; c0.t_sub = -1;
+    if (!ck(s, cudaMemcpyAsync(st.ctrl, &c0, sizeof c0, cudaMemcpyHostToDevice, s->stream), "init ctrl")) return bail();
+    if (!ck(s, pg_launch_fill(st.A, st.n, st.y_mean, s->stream), "fill predictions")) return bail();   // kernel.rs:48
+    if (!ck(s, pg_launch_init_forest(st, s->stream), "init forest")) return bail();
+    s->launches += 2;
+    if (!ck(s, cudaStreamSynchronize(s->stream), "synchronize")) return bail();
+    *out = h;
+    return 0;
+}
+
+int pgbart_destroy(pgbart_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->s.device);
+    cudaStreamSynchronize(h->s.stream);
+    free_all(&h->s);
+    delete h;
+    return 0;
+}
+
+int pgbart_set_likelihood(pgbart_handle h, int family, const double* params, int nparams) {
+    Sampler* s = &h->s;
+    if (family != PGBART_GAUSSIAN && family != PGBART_BERNOULLI_LOGIT && family != PGBART_GAUSSIAN_KERNEL) {
+        s->err = "unknown likelihood family (device path supports Gaussian and Bernoulli-logit; no CPU fallback)";
+        return 1;
+    }
+    if (family == PGBART_GAUSSIAN) {
+        if (nparams < 1 || !params || !(params[0] > 0.0)) { s->err = "Gaussian likelihood needs sigma > 0"; return 1; }
+        s->st.lik_sigma = params[0];
+    }
+    s->st.family = family;
+    return 0;
+}
+
+int pgbart_step_device(pgbart_handle h, int tune) { return enqueue_step(&h->s, tune); }
+
+int pgbart_sync(pgbart_handle h) { return finish_step(&h->s); }
+
+int pgbart_step(pgbart_handle h, int tune, double* out_pred) {
+    Sampler* s = &h->s;
+    int rc = enqueue_step(s, tune);
+    if (rc) return rc;
+    if (out_pred && !ck(s, cudaMemcpyAsync(out_pred, s->st.A, (size_t)s->st.n * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions")) return 2;
+    return finish_step(s);
+}
+
+const double* pgbart_predictions_device(pgbart_handle h) { return h->s.st.A; }
+
+int pgbart_get_predictions(pgbart_handle h, double* out_pred) {
+    Sampler* s = &h->s;
+    if (!ck(s, cudaMemcpyAsync(out_pred, s->st.A, (size_t)s->st.n * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions")) return 2;
+    return ck(s, cudaStreamSynchronize(s->stream), "synchronize") ? 0 : 2;
+}
+
+int pgbart_get_info(pgbart_handle h, double* ll, int64_t* acc, uint8_t* depths, int* n_depths) {
+    Sampler* s = &h->s;
+    if (!fetch_ctrl(s)) return 2;
+    *ll = s->host_ctrl.info_loglik;
+    *acc = s->host_ctrl.info_acc;
+    const int cap = *n_depths;
+    *n_depths = s->host_ctrl.info_n;
+    const int k = std::min(cap, s->host_ctrl.info_n);
+    if (k > 0 && !ck(s, cudaMemcpy(depths, s->st.info_depths, (size_t)k, cudaMemcpyDeviceToHost), "copy depths")) return 2;
+    return 0;
+}
+
+int pgbart_tree_size(pgbart_handle h, uint64_t t, int* size) {
+    Sampler* s = &h->s;
+    if (t >= (uint64_t)s->st.m) { s->err = "tree index out of range"; return 1; }
+    if (!ck(s, cudaStreamSynchronize(s->stream), "synchronize")) return 2;
+    return ck(s, cudaMemcpy(size, s->st.f_size + t, 4, cudaMemcpyDeviceToHost), "copy") ? 0 : 2;
+}
+
+int pgbart_get_tree(pgbart_handle h, uint64_t t, int32_t* split_var, double* split_val, double* leaf_val) {
+    Sampler* s = &h->s;
+    int size = 0;
+    int rc = pgbart_tree_size(h, t, &size);
+    if (rc) return rc;
+    const size_t fb = (size_t)t * s->st.maxn;
+    if (!ck(s, cudaMemcpy(split_var, s->st.f_split_var + fb, (size_t)size * 4, cudaMemcpyDeviceToHost), "copy") ||
+        !ck(s, cudaMemcpy(split_val, s->st.f_split_val + fb, (size_t)size * 8, cudaMemcpyDeviceToHost), "copy") ||
+        !ck(s, cudaMemcpy(leaf_val, s->st.f_leaf_val + fb, (size_t)size * 8, cudaMemcpyDeviceToHost), "copy")) return 2;
+    return 0;
+}
+
+int pgbart_get_leaf_indices(pgbart_handle h, uint64_t t, uint32_t* out) {
+    Sampler* s = &h->s;
+    if (t >= (uint64_t)s->st.m) { s->err = "tree index out of range"; return 1; }
+    unsigned* d = nullptr;
+    if (!ck(s, cudaMalloc(&d, (size_t)s->st.n * 4), "cudaMalloc")) return 2;
+    bool ok = ck(s, pg_launch_leaf_indices(s->st, (int)t, d, s->stream), "launch")
+           && ck(s, cudaMemcpyAsync(out, d, (size_t)s->st.n * 4, cudaMemcpyDeviceToHost, s->stream), "copy")
+           && ck(s, cudaStreamSynchronize(s->stream), "synchronize");
+    s->launches += 1;
+    cudaFree(d);
+    return ok ? 0 : 2;
+}
+
+int pgbart_get_state(pgbart_handle h, uint64_t* next_tree_idx, int* tune, uint64_t* n_updates) {
+    Sampler* s = &h->s;
+    if (!fetch_ctrl(s)) return 2;
+    if (next_tree_idx) *next_tree_idx = (uint64_t)s->host_ctrl.next_tree_idx;
+    if (tune) *tune = s->host_ctrl.tune;
+    if (n_updates) *n_updates = s->host_ctrl.n_updates;
+    return 0;
+}
+
+int pgbart_set_rng_philox(pgbart_handle h, uint64_t seed) {
+    Sampler* s = &h->s;
+    s->st.rng_mode = PG_RNG_PHILOX;
+    s->st.philox_key0 = (unsigned)seed;
+    s->st.philox_key1 = (unsigned)(seed >> 32);
+    return 0;
+}
+
+int pgbart_set_rng_tape(pgbart_handle h, const double* slot, const double* round, const double* upd,
+                        int64_t n_upd, int r_cap) {
+    Sampler* s = &h->s;
+    if (n_upd < 1 || r_cap < 1 || !slot || !round || !upd) { s->err = "bad tape"; return 1; }
+    if (!fetch_ctrl(s)) return 2;
+    for (double** p : {&s->tape_slot, &s->tape_round, &s->tape_upd}) if (*p) { cudaFree(*p); *p = nullptr; }
+    const size_t ns = (size_t)n_upd * r_cap * s->st.S * 5, nr = (size_t)n_upd * r_cap, nu = (size_t)n_upd;
+    if (!ck(s, cudaMalloc(&s->tape_slot, ns * 8), "cudaMalloc") || !ck(s, cudaMalloc(&s->tape_round, nr * 8), "cudaMalloc") ||
+        !ck(s, cudaMalloc(&s->tape_upd, nu * 8), "cudaMalloc")) return 2;
+    if (!ck(s, cudaMemcpy(s->tape_slot, slot, ns * 8, cudaMemcpyHostToDevice), "upload tape") ||
+        !ck(s, cudaMemcpy(s->tape_round, round, nr * 8, cudaMemcpyHostToDevice), "upload tape") ||
+        !ck(s, cudaMemcpy(s->tape_upd, upd, nu * 8, cudaMemcpyHostToDevice), "upload tape")) return 2;
+    s->st.rng_mode = PG_RNG_TAPE;
+    s->st.tape_slot = s->tape_slot; s->st.tape_round = s->tape_round; s->st.tape_upd = s->tape_upd;
+    s->st.tape_n_upd = n_upd; s->st.tape_r_cap = r_cap;
+    s->st.tape_base_upd = s->host_ctrl.upd;
+    return 0;
+}
+
+int pgbart_trace_enable(pgbart_handle h, int64_t u_cap, int r_cap) {
+    Sampler* s = &h->s;
+    for (double** p : {&s->tr_slot, &s->tr_round, &s->tr_upd}) if (*p) { cudaFree(*p); *p = nullptr; }
+    s->st.tr_slot = s->st.tr_round = s->st.tr_upd = nullptr;
+    if (u_cap <= 0) return 0;
+    const size_t S = s->st.S, P = s->st.P;
+    const size_t ns = (size_t)u_cap * r_cap * S * PG_TS_FIELDS, nr = (size_t)u_cap * r_cap * (2 + 2 * S), nu = (size_t)u_cap * (4 + 2 * P);
+    if (!ck(s, cudaMalloc(&s->tr_slot, ns * 8), "cudaMalloc") || !ck(s, cudaMalloc(&s->tr_round, nr * 8), "cudaMalloc") ||
+        !ck(s, cudaMalloc(&s->tr_upd, nu * 8), "cudaMalloc")) return 2;
+    // NaN-fill the slot records (all-ones bytes are a NaN) and zero the rest, like the oracle's buffers
+    if (!ck(s, cudaMemset(s->tr_slot, 0xFF, ns * 8), "memset") || !ck(s, cudaMemset(s->tr_round, 0, nr * 8), "memset") ||
+        !ck(s, cudaMemset(s->tr_upd, 0, nu * 8), "memset")) return 2;
+    s->st.tr_slot = s->tr_slot; s->st.tr_round = s->tr_round; s->st.tr_upd = s->tr_upd;
+    s->st.tr_u_cap = u_cap; s->st.tr_r_cap = r_cap;
+    s->tr_u_cap = u_cap; s->tr_r_cap = r_cap;
+    // restart the trace counter
+    if (!fetch_ctrl(s)) return 2;
+    s->host_ctrl.trace_n = 0; s->host_ctrl.trace_overflow = 0;
+    if (!ck(s, cudaMemcpy(&s->st.ctrl->trace_n, &s->host_ctrl.trace_n, 8, cudaMemcpyHostToDevice), "reset") ||
+        !ck(s, cudaMemcpy(&s->st.ctrl->trace_overflow, &s->host_ctrl.trace_overflow, 4, cudaMemcpyHostToDevice), "reset")) return 2;
+    return 0;
+}
+
+int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd, int64_t* n_upd, int* overflow) {
+    Sampler* s = &h->s;
+    if (!s->tr_slot) { s->err = "trace not enabled"; return 1; }
+    if (!fetch_ctrl(s)) return 2;
+    const size_t S = s->st.S, P = s->st.P;
+    const size_t ns = (size_t)s->tr_u_cap * s->tr_r_cap * S * PG_TS_FIELDS, nr = (size_t)s->tr_u_cap * s->tr_r_cap * (2 + 2 * S),
+                 nu = (size_t)s->tr_u_cap * (4 + 2 * P);
+    if (!ck(s, cudaMemcpy(slot, s->tr_slot, ns * 8, cudaMemcpyDeviceToHost), "copy trace") ||
+        !ck(s, cudaMemcpy(round, s->tr_round, nr * 8, cudaMemcpyDeviceToHost), "copy trace") ||
+        !ck(s, cudaMemcpy(upd, s->tr_upd, nu * 8, cudaMemcpyDeviceToHost), "copy trace")) return 2;
+    *n_upd = (int64_t)s->host_ctrl.trace_n;
+    *overflow = s->host_ctrl.trace_overflow;
+    return 0;
+}
+
+int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
+    Sampler* s = &h->s;
+    if (!key || !value) { s->err = "null option"; return 1; }
+    if (std::strcmp(key, "driver") == 0) {
+        if (std::strcmp(value, "persistent") == 0) { s->stepwise = false; return 0; }
+        if (std::strcmp(value, "stepwise") == 0) { s->stepwise = true; return 0; }
+        s->err = "driver must be 'persistent' or 'stepwise'";
+        return 1;
+    }
+    if (std::strcmp(key, "pool_factor") == 0) {
+        const long long f = std::atoll(value);
+        if (f < 1) { s->err = "pool_factor must be >= 1"; return 1; }
+        unsigned long long cap = (unsigned long long)f * (unsigned long long)s->st.S * (unsigned long long)s->st.n;
+        if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+        unsigned* np = nullptr;
+        if (!ck(s, cudaStreamSynchronize(s->stream), "synchronize")) return 2;
+        if (!ck(s, cudaMalloc(&np, (size_t)cap * 4), "cudaMalloc pool")) return 2;
+        auto it = std::find(s->allocs.begin(), s->allocs.end(), (void*)s->st.pool);
+        if (it != s->allocs.end()) { cudaFree(*it); *it = np; } else s->allocs.push_back(np);
+        s->st.pool = np; s->st.pool_cap = cap; s->pool_factor = (unsigned long long)f;
+        return 0;
+    }
+    s->err = std::string("unknown option '") + key + "'";
+    return 1;
+}
+
+int pgbart_get_counters(pgbart_handle h, double* out8) {
+    Sampler* s = &h->s;
+    if (!fetch_ctrl(s)) return 2;
+    float ms = 0.0f;
+    if (s->timing_pending) cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+    out8[0] = (double)s->host_ctrl.bytes_model;
+    out8[1] = (double)s->host_ctrl.bytes_contract;
+    out8[2] = (double)s->host_ctrl.n_phases;
+    out8[3] = (double)s->host_ctrl.n_updates;
+    out8[4] = s->launches;
+    out8[5] = (double)ms * 1000.0;
+    out8[6] = (double)s->st.grid;
+    out8[7] = (double)s->smem;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,505 @@
+// pg_passes.cuh — the streaming (grid-wide) halves of the sweep, sm_100a.
+//
+// Every pass partitions a segment of observation indices into one contiguous
+// range per GLOBAL WARP (pg_warp_range): the same ranges are used by the
+// statistics pass and, later, by the partition pass, so the per-warp LEFT
+// counts of the former are the scatter offsets of the latter.
+//
+//   pg_pass_root    PH_ROOT / PH_FINAL. One pass over all n rows:
+//                     A += tree_add(x)          kernel.rs:99-102  (commit previous tree)
+//                     A -= tree_sub(x)          kernel.rs:84-87   (open this tree: A = "residuals")
+//                     totals  sum A, sum (y-A), sum (y-A)^2       (stump weight, smc.rs:105-110)
+//                     per job (slot): LEFT count, sum A, sum (y-A) for x[var] < split
+//                                               smc.rs:201-217 fused over all slots of round 1
+//                   A, y are read once per row and reused from registers by every slot; only the
+//                   slots' split columns are streamed per slot.
+//   pg_pass_minmax  PH_MINMAX. splitting.rs:43-49 over a node's index segment.
+//   pg_pass_stats   PH_STATS.  smc.rs:201-217 over a node's index segment (gather).
+//   pg_pass_bern    PH_BERN.   Bernoulli-logit child log-likelihoods (weight.rs via smc.rs:89-95).
+//   pg_pass_part    PH_PART.   particle.rs:117-138 as a STABLE partition (warp ballot + prefix
+//                   compaction) appended to the segment pool; only for surviving particles.
+#pragma once
+#include <cuda_runtime.h>
+#include "pg_types.h"
+#include "pg_serial.h"
+
+#define PG_TREE_SM 63      // tree nodes staged in shared memory (depth <= 5); larger trees read global
+#define PG_FULL 0xFFFFFFFFu
+
+struct PgTreeSm {
+    int size;
+    int from_global;       // tree too large for shared memory
+    int split_var[PG_TREE_SM];
+    float thr32[PG_TREE_SM];
+    double leaf_val[PG_TREE_SM];
+};
+
+struct PgSmem {
+    PgTreeSm tadd, tsub;
+    double tot[PG_WARPS][4];
+    int is_last;
+    // followed by dynamic arrays, see pg_smem_* accessors
+};
+
+// dynamic shared memory layout after PgSmem (all sized by S):
+//   int   jvar[S]; float jthr[S]; int jorder[S]; int grp[S+1]; double jvL[S]; double jvR[S];
+//   double accA[PG_WARPS][S]; double accB[PG_WARPS][S]; unsigned accC[PG_WARPS][S];
+//   unsigned mmin[S]; unsigned mmax[S];
+__host__ __device__ inline size_t pg_smem_bytes(int S) {
+    size_t b = sizeof(PgSmem);
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)S * (4 + 4 + 4) + (size_t)(S + 1) * 4;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)S * 16;                       // jvL, jvR
+    b += (size_t)PG_WARPS * S * (8 + 8 + 4);   // accA, accB, accC
+    b += (size_t)S * 8;                        // mmin, mmax
+    return b + 64;
+}
+
+struct PgSmemView {
+    PgSmem* base;
+    int* jvar; float* jthr; int* jorder; int* grp; double* jvL; double* jvR;
+    double* accA; double* accB; unsigned* accC; unsigned* mmin; unsigned* mmax;
+};
+
+__device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
+    PgSmemView v;
+    v.base = reinterpret_cast<PgSmem*>(raw);
+    size_t off = (sizeof(PgSmem) + 15) & ~(size_t)15;
+    v.jvL = reinterpret_cast<double*>(raw + off); off += (size_t)S * 8;
+    v.jvR = reinterpret_cast<double*>(raw + off); off += (size_t)S * 8;
+    v.accA = reinterpret_cast<double*>(raw + off); off += (size_t)PG_WARPS * S * 8;
+    v.accB = reinterpret_cast<double*>(raw + off); off += (size_t)PG_WARPS * S * 8;
+    v.accC = reinterpret_cast<unsigned*>(raw + off); off += (size_t)PG_WARPS * S * 4;
+    v.mmin = reinterpret_cast<unsigned*>(raw + off); off += (size_t)S * 4;
+    v.mmax = reinterpret_cast<unsigned*>(raw + off); off += (size_t)S * 4;
+    v.jvar = reinterpret_cast<int*>(raw + off); off += (size_t)S * 4;
+    v.jthr = reinterpret_cast<float*>(raw + off); off += (size_t)S * 4;
+    v.jorder = reinterpret_cast<int*>(raw + off); off += (size_t)S * 4;
+    v.grp = reinterpret_cast<int*>(raw + off);
+    return v;
+}
+
+// ---- loads ------------------------------------------------------------------
+// X and y never change: read-only path.  A and the pool are rewritten between passes by other
+// SMs: read through L2 (ld.global.cg) so a stale L1 line can never be observed.
+__device__ __forceinline__ float4 pg_ld_x4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ double2 pg_ld_a2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+
+// ---- warp-transposed reduction of 4 jobs' partial sums ----------------------
+// Each lane holds 4 values (one per job).  After the call every lane holds the warp total of job
+// ((lane & 1) << 1) | ((lane >> 1) & 1): 6 shuffles instead of 20.  Fixed pattern => deterministic.
+template <typename T>
+__device__ __forceinline__ T pg_xreduce4(T v0, T v1, T v2, T v3, int lane) {
+    const bool b0 = lane & 1, b1 = lane & 2;
+    T s0 = b0 ? v0 : v2, k0 = b0 ? v2 : v0;
+    T s1 = b0 ? v1 : v3, k1 = b0 ? v3 : v1;
+    T u0 = k0 + __shfl_xor_sync(PG_FULL, s0, 1);
+    T u1 = k1 + __shfl_xor_sync(PG_FULL, s1, 1);
+    T s = b1 ? u0 : u1, k = b1 ? u1 : u0;
+    T t = k + __shfl_xor_sync(PG_FULL, s, 2);
+    t = t + __shfl_xor_sync(PG_FULL, t, 4);
+    t = t + __shfl_xor_sync(PG_FULL, t, 8);
+    t = t + __shfl_xor_sync(PG_FULL, t, 16);
+    return t;
+}
+__device__ __forceinline__ int pg_xreduce4_job(int lane) { return ((lane & 1) << 1) | ((lane >> 1) & 1); }
+
+__device__ __forceinline__ double pg_warp_sum(double v) {
+    v += __shfl_xor_sync(PG_FULL, v, 16);
+    v += __shfl_xor_sync(PG_FULL, v, 8);
+    v += __shfl_xor_sync(PG_FULL, v, 4);
+    v += __shfl_xor_sync(PG_FULL, v, 2);
+    v += __shfl_xor_sync(PG_FULL, v, 1);
+    return v;
+}
+
+// ---- tree staging / evaluation (tree.rs:169-192 traversal on training rows) ------------------
+__device__ __forceinline__ void pg_stage_tree(const PgState& st, int t, PgTreeSm& sm) {
+    if (t < 0) { if (threadIdx.x == 0) { sm.size = 0; sm.from_global = 0; } return; }
+    const int sz = __ldcg(&st.f_size[t]);
+    if (threadIdx.x == 0) { sm.size = sz; sm.from_global = sz > PG_TREE_SM; }
+    if (sz <= PG_TREE_SM)
+        for (int i = threadIdx.x; i < sz; i += blockDim.x) {
+            sm.split_var[i] = __ldcg(&st.f_split_var[(size_t)t * st.maxn + i]);
+            sm.thr32[i] = __ldcg(&st.f_thr32[(size_t)t * st.maxn + i]);
+            sm.leaf_val[i] = __ldcg(&st.f_leaf_val[(size_t)t * st.maxn + i]);
+        }
+}
+
+__device__ __forceinline__ double pg_tree_eval(const PgState& st, int t, const PgTreeSm& sm, long long row) {
+    int node = 0;
+    if (!sm.from_global) {
+        int sv;
+        while ((sv = sm.split_var[node]) >= 0) {
+            const float x = __ldg(&st.X[(size_t)sv * st.ld + row]);
+            node = 2 * node + 1 + (x < sm.thr32[node] ? 0 : 1);
+        }
+        return sm.leaf_val[node];
+    }
+    const size_t fb = (size_t)t * st.maxn;
+    int sv;
+    while ((sv = __ldcg(&st.f_split_var[fb + node])) >= 0) {
+        const float x = __ldg(&st.X[(size_t)sv * st.ld + row]);
+        node = 2 * node + 1 + (x < __ldcg(&st.f_thr32[fb + node]) ? 0 : 1);
+    }
+    return __ldcg(&st.f_leaf_val[fb + node]);
+}
+
+// Stage the job list of the current pass into shared memory.
+__device__ __forceinline__ void pg_stage_jobs(const PgState& st, const PgSmemView& sm, int J, int G, bool with_values) {
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        sm.jvar[j] = __ldcg(&st.job_var[j]);
+        sm.jthr[j] = __ldcg(&st.job_thr32[j]);
+        sm.jorder[j] = __ldcg(&st.job_order[j]);
+        if (with_values) { sm.jvL[j] = __ldcg(&st.job_vL[j]); sm.jvR[j] = __ldcg(&st.job_vR[j]); }
+    }
+    for (int g = threadIdx.x; g <= G; g += blockDim.x) sm.grp[g] = __ldcg(&st.grp_first[g]);
+}
+
+__device__ __forceinline__ void pg_zero_acc(const PgSmemView& sm, int S) {
+    for (int i = threadIdx.x; i < PG_WARPS * S; i += blockDim.x) { sm.accA[i] = 0.0; sm.accB[i] = 0.0; sm.accC[i] = 0u; }
+}
+
+// Write the block's per-job results: fixed warp order => deterministic.
+__device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgSmemView& sm, int J, bool counts, bool as_ll) {
+    const int S = st.S;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        double a = 0.0, b = 0.0;
+        unsigned cc = 0u;
+        for (int w = 0; w < PG_WARPS; ++w) { a += sm.accA[w * S + j]; b += sm.accB[w * S + j]; cc += sm.accC[w * S + j]; }
+        double* dst = as_ll ? st.part_ll : st.part_sum;
+        dst[((size_t)blockIdx.x * S + j) * 2 + 0] = a;
+        dst[((size_t)blockIdx.x * S + j) * 2 + 1] = b;
+        if (counts) {
+            st.part_ccnt[(size_t)blockIdx.x * S + j] = cc;
+            for (int w = 0; w < PG_WARPS; ++w)
+                st.part_cnt[((size_t)blockIdx.x * PG_WARPS + w) * S + j] = sm.accC[w * S + j];
+        }
+    }
+}
+
+// =============================================================================
+// PH_ROOT / PH_FINAL
+// =============================================================================
+// Rows per lane per iteration: 8 (two float4 groups) => 256 rows per warp-iteration.
+template <bool BERN>
+__device__ void pg_pass_root(const PgState& st, const PgSmemView& sm) {
+    PgCtrl* c = st.ctrl;
+    const int J = __ldcg(&c->n_jobs) * (__ldcg(&c->phase) == PH_ROOT ? 1 : 0);
+    const int t_add = __ldcg(&c->t_add), t_sub = __ldcg(&c->phase) == PH_ROOT ? __ldcg(&c->t_sub) : -1;
+    const int S = st.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * PG_WARPS + warp;
+
+    pg_stage_tree(st, t_add, sm.base->tadd);
+    pg_stage_tree(st, t_sub, sm.base->tsub);
+    pg_stage_jobs(st, sm, J, 0, false);
+    pg_zero_acc(sm, S);
+    __syncthreads();
+    const bool add_nontrivial = t_add >= 0 && sm.base->tadd.size > 1;
+    const bool sub_nontrivial = t_sub >= 0 && sm.base->tsub.size > 1;
+    const double add_c = (t_add >= 0 && !add_nontrivial) ? sm.base->tadd.leaf_val[0] : 0.0;
+    const double sub_c = (t_sub >= 0 && !sub_nontrivial) ? sm.base->tsub.leaf_val[0] : 0.0;
+
+    unsigned long long beg, end;
+    pg_warp_range((unsigned long long)st.n, gw, st.n_gwarps, 4, &beg, &end);
+    const long long n = st.n;
+    const size_t ld = (size_t)st.ld;
+    double tot_o = 0.0, tot_r = 0.0, tot_rr = 0.0, tot_ll = 0.0;
+
+    for (unsigned long long base = beg; base < end; base += 256) {
+        const long long r0 = (long long)base + 4 * lane, r1 = r0 + 128;
+        const bool g0 = r0 < (long long)end, g1 = r1 < (long long)end;   // group start inside the warp's range
+        double o[8];
+        float yv[8];
+        {
+            double2 a;
+            float4 yy;
+            if (g0) {
+                a = pg_ld_a2(st.A + r0); o[0] = a.x; o[1] = a.y;
+                a = pg_ld_a2(st.A + r0 + 2); o[2] = a.x; o[3] = a.y;
+                yy = pg_ld_x4(st.y + r0); yv[0] = yy.x; yv[1] = yy.y; yv[2] = yy.z; yv[3] = yy.w;
+            } else { o[0] = o[1] = o[2] = o[3] = 0.0; yv[0] = yv[1] = yv[2] = yv[3] = 0.0f; }
+            if (g1) {
+                a = pg_ld_a2(st.A + r1); o[4] = a.x; o[5] = a.y;
+                a = pg_ld_a2(st.A + r1 + 2); o[6] = a.x; o[7] = a.y;
+                yy = pg_ld_x4(st.y + r1); yv[4] = yy.x; yv[5] = yy.y; yv[6] = yy.z; yv[7] = yy.w;
+            } else { o[4] = o[5] = o[6] = o[7] = 0.0; yv[4] = yv[5] = yv[6] = yv[7] = 0.0f; }
+        }
+        bool valid[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) valid[q] = ((q < 4 ? r0 : r1 - 4) + q) < n && (q < 4 ? g0 : g1);
+        // kernel.rs:99-102 then :84-87, each a separately rounded f64 operation
+        if (t_add >= 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double v = add_nontrivial ? (valid[q] ? pg_tree_eval(st, t_add, sm.base->tadd, (q < 4 ? r0 : r1 - 4) + q) : 0.0) : add_c;
+                o[q] = o[q] + v;
+            }
+        }
+        if (t_sub >= 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double v = sub_nontrivial ? (valid[q] ? pg_tree_eval(st, t_sub, sm.base->tsub, (q < 4 ? r0 : r1 - 4) + q) : 0.0) : sub_c;
+                o[q] = o[q] - v;
+            }
+        }
+        if (g0) {
+            __stcg(reinterpret_cast<double2*>(st.A + r0), make_double2(o[0], o[1]));
+            __stcg(reinterpret_cast<double2*>(st.A + r0 + 2), make_double2(o[2], o[3]));
+        }
+        if (g1) {
+            __stcg(reinterpret_cast<double2*>(st.A + r1), make_double2(o[4], o[5]));
+            __stcg(reinterpret_cast<double2*>(st.A + r1 + 2), make_double2(o[6], o[7]));
+        }
+        if (J == 0 && t_sub < 0) continue;   // PH_FINAL: commit only
+        double r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (!valid[q]) { o[q] = 0.0; r[q] = 0.0; }
+            else r[q] = (double)yv[q] - o[q];
+            tot_o += o[q];
+            tot_r += r[q];
+            tot_rr += r[q] * r[q];
+            if (BERN && valid[q]) {
+                const double mu = o[q] + st.init_leaf;
+                tot_ll += (double)yv[q] * mu - pg_softplus(mu);
+            }
+        }
+        // smc.rs:201-217 for every slot of round 1, four slots at a time
+        for (int jb = 0; jb < J; jb += 4) {
+            double so[4], sr[4];
+            int cn[4];
+            float4 xa[4], xb[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool live = jb + q < J;
+                const float* col = st.X + (size_t)(live ? sm.jvar[jb + q] : 0) * ld;
+                xa[q] = (live && g0) ? pg_ld_x4(col + r0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xb[q] = (live && g1) ? pg_ld_x4(col + r1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool live = jb + q < J;
+                const float thr = live ? sm.jthr[jb + q] : 0.0f;
+                const float xs[8] = {xa[q].x, xa[q].y, xa[q].z, xa[q].w, xb[q].x, xb[q].y, xb[q].z, xb[q].w};
+                double a = 0.0, b = 0.0;
+                int cc = 0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const bool left = live && valid[e] && (xs[e] < thr);
+                    a += left ? o[e] : 0.0;
+                    b += left ? r[e] : 0.0;
+                    cc += left ? 1 : 0;
+                }
+                so[q] = a; sr[q] = b; cn[q] = cc;
+            }
+            const double ta = pg_xreduce4(so[0], so[1], so[2], so[3], lane);
+            const double tb = pg_xreduce4(sr[0], sr[1], sr[2], sr[3], lane);
+            const int tc = pg_xreduce4(cn[0], cn[1], cn[2], cn[3], lane);
+            const int jj = jb + pg_xreduce4_job(lane);
+            if (lane < 4 && jj < J) {
+                sm.accA[warp * S + jj] += ta;
+                sm.accB[warp * S + jj] += tb;
+                sm.accC[warp * S + jj] += (unsigned)tc;
+            }
+        }
+    }
+    // block totals
+    tot_o = pg_warp_sum(tot_o); tot_r = pg_warp_sum(tot_r); tot_rr = pg_warp_sum(tot_rr); tot_ll = pg_warp_sum(tot_ll);
+    if (lane == 0) { sm.base->tot[warp][0] = tot_o; sm.base->tot[warp][1] = tot_r; sm.base->tot[warp][2] = tot_rr; sm.base->tot[warp][3] = tot_ll; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+        for (int w = 0; w < PG_WARPS; ++w) v += sm.base->tot[w][threadIdx.x];
+        st.part_tot[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+    }
+    pg_flush_acc(st, sm, J, true, false);
+}
+
+// =============================================================================
+// PH_MINMAX — splitting.rs:43-49 over index segments
+// =============================================================================
+__device__ void pg_pass_minmax(const PgState& st, const PgSmemView& sm) {
+    PgCtrl* c = st.ctrl;
+    const int J = __ldcg(&c->n_jobs);
+    const int S = st.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * PG_WARPS + warp;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) { sm.mmin[j] = 0xFFFFFFFFu; sm.mmax[j] = 0u; sm.jvar[j] = __ldcg(&st.job_var[j]); }
+    __syncthreads();
+    const size_t ld = (size_t)st.ld;
+    for (int j = 0; j < J; ++j) {
+        const unsigned off = __ldcg(&st.job_seg_off[j]);
+        const unsigned long long L = __ldcg(&st.job_len[j]);
+        const float* col = st.X + (size_t)sm.jvar[j] * ld;
+        unsigned long long beg, end;
+        pg_warp_range(L, gw, st.n_gwarps, 1, &beg, &end);
+        float mn = INFINITY, mx = -INFINITY;
+        bool any = false;
+        for (unsigned long long e = beg + lane; e < end; e += 32) {
+            const unsigned idx = __ldcg(&st.pool[(size_t)off + e]);
+            const float x = __ldg(&col[idx]);
+            mn = fminf(mn, x); mx = fmaxf(mx, x);   // f64::min/max ignore NaN like fminf/fmaxf
+            any = true;
+        }
+        unsigned kmn = any ? pg_f2key(mn) : 0xFFFFFFFFu, kmx = any ? pg_f2key(mx) : 0u;
+        kmn = __reduce_min_sync(PG_FULL, kmn);
+        kmx = __reduce_max_sync(PG_FULL, kmx);
+        if (lane == 0) { atomicMin(&sm.mmin[j], kmn); atomicMax(&sm.mmax[j], kmx); }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        st.part_mm[((size_t)blockIdx.x * S + j) * 2 + 0] = sm.mmin[j];
+        st.part_mm[((size_t)blockIdx.x * S + j) * 2 + 1] = sm.mmax[j];
+    }
+}
+
+// =============================================================================
+// PH_STATS / PH_BERN — over index segments (gather); jobs sharing a segment share idx/A/y loads
+// =============================================================================
+// MODE 0: statistics (LEFT count, sum A, sum y-A).  MODE 1: Bernoulli child log-likelihoods
+// (A = left-child sum, B = right-child sum); identity segments allowed.
+template <int MODE>
+__device__ void pg_pass_seg(const PgState& st, const PgSmemView& sm) {
+    PgCtrl* c = st.ctrl;
+    const int J = __ldcg(&c->n_jobs), G = __ldcg(&c->n_groups);
+    const int S = st.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * PG_WARPS + warp;
+    pg_stage_jobs(st, sm, J, G, MODE == 1);
+    pg_zero_acc(sm, S);
+    __syncthreads();
+    const size_t ld = (size_t)st.ld;
+    constexpr int R = 4;   // entries per lane per iteration
+    for (int g = 0; g < G; ++g) {
+        const int jb0 = sm.grp[g], jb1 = sm.grp[g + 1];
+        const int j0 = sm.jorder[jb0];
+        const unsigned off = __ldcg(&st.job_seg_off[j0]);
+        const bool ident = off == PG_SEG_IDENTITY;
+        const unsigned long long L = __ldcg(&st.job_len[j0]);
+        unsigned long long beg, end;
+        pg_warp_range(L, gw, st.n_gwarps, ident ? 4 : 1, &beg, &end);
+        for (unsigned long long base = beg; base < end; base += 32 * R) {
+            unsigned idx[R];
+            double o[R], r[R];
+            float yv[R];
+            bool valid[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const unsigned long long e = base + lane + 32ull * k;
+                valid[k] = e < end;
+                idx[k] = valid[k] ? (ident ? (unsigned)e : __ldcg(&st.pool[(size_t)off + e])) : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                o[k] = valid[k] ? __ldcg(&st.A[idx[k]]) : 0.0;
+                yv[k] = valid[k] ? __ldg(&st.y[idx[k]]) : 0.0f;
+                r[k] = valid[k] ? (double)yv[k] - o[k] : 0.0;
+            }
+            for (int jb = jb0; jb < jb1; jb += 4) {
+                double va[4], vb[4];
+                int cn[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool live = jb + q < jb1;
+                    const int j = live ? sm.jorder[jb + q] : j0;
+                    const float* col = st.X + (size_t)sm.jvar[j] * ld;
+                    const float thr = sm.jthr[j];
+                    double a = 0.0, b = 0.0;
+                    int cc = 0;
+#pragma unroll
+                    for (int k = 0; k < R; ++k) {
+                        const bool ok = live && valid[k];
+                        const float x = ok ? __ldg(&col[idx[k]]) : 0.0f;
+                        const bool left = ok && (x < thr);
+                        if (MODE == 0) {
+                            a += left ? o[k] : 0.0;
+                            b += left ? r[k] : 0.0;
+                            cc += left ? 1 : 0;
+                        } else if (ok) {
+                            const double mu = o[k] + (left ? sm.jvL[j] : sm.jvR[j]);
+                            const double f = (double)yv[k] * mu - pg_softplus(mu);
+                            if (left) a += f; else b += f;
+                        }
+                    }
+                    va[q] = a; vb[q] = b; cn[q] = cc;
+                }
+                const double ta = pg_xreduce4(va[0], va[1], va[2], va[3], lane);
+                const double tb = pg_xreduce4(vb[0], vb[1], vb[2], vb[3], lane);
+                const int tc = MODE == 0 ? pg_xreduce4(cn[0], cn[1], cn[2], cn[3], lane) : 0;
+                const int q = pg_xreduce4_job(lane);
+                if (lane < 4 && jb + q < jb1) {
+                    const int j = sm.jorder[jb + q];
+                    sm.accA[warp * S + j] += ta;
+                    sm.accB[warp * S + j] += tb;
+                    sm.accC[warp * S + j] += (unsigned)tc;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    pg_flush_acc(st, sm, J, MODE == 0, MODE == 1);
+}
+
+// =============================================================================
+// PH_PART — stable partition of a segment by x[var] < split into the pool
+// =============================================================================
+__device__ void pg_pass_part(const PgState& st, const PgSmemView& sm) {
+    PgCtrl* c = st.ctrl;
+    const int K = __ldcg(&c->n_pjobs);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * PG_WARPS + warp;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const size_t ld = (size_t)st.ld;
+    for (int k = 0; k < K; ++k) {
+        const unsigned src = __ldcg(&st.pj_src_off[k]);
+        const bool ident = src == PG_SEG_IDENTITY;
+        const unsigned long long L = __ldcg(&st.pj_len[k]);
+        const float* col = st.X + (size_t)__ldcg(&st.pj_var[k]) * ld;
+        const float thr = __ldcg(&st.pj_thr32[k]);
+        unsigned long long beg, end;
+        pg_warp_range(L, gw, st.n_gwarps, ident ? 4 : 1, &beg, &end);
+        unsigned left_run = __ldcg(&st.pj_warp_left[(size_t)k * st.n_gwarps + gw]);
+        unsigned right_run = (unsigned)beg - left_run;
+        const unsigned left0 = left_run;
+        unsigned* dstL = st.pool + (size_t)__ldcg(&st.pj_dst_off[k]);
+        unsigned* dstR = dstL + __ldcg(&st.pj_cntL[k]);
+        for (unsigned long long base = beg; base < end; base += 32) {
+            const unsigned long long e = base + lane;
+            const bool valid = e < end;
+            const unsigned idx = valid ? (ident ? (unsigned)e : __ldcg(&st.pool[(size_t)src + e])) : 0u;
+            const float x = valid ? __ldg(&col[idx]) : 0.0f;
+            const bool left = valid && (x < thr);
+            const unsigned bl = __ballot_sync(PG_FULL, left);
+            const unsigned bv = __ballot_sync(PG_FULL, valid);
+            const unsigned br = bv & ~bl;
+            if (valid) {
+                if (left) __stcg(&dstL[left_run + __popc(bl & lt_mask)], idx);
+                else __stcg(&dstR[right_run + __popc(br & lt_mask)], idx);
+            }
+            left_run += __popc(bl);
+            right_run += __popc(br);
+        }
+        // the statistics pass counted the same predicate over the same range
+        const int j = __ldcg(&st.pj_job[k]);
+        if (lane == 0 && (left_run - left0) != __ldcg(&st.part_cnt[(size_t)gw * st.S + j])) c->error = PG_ERR_INTERNAL;
+    }
+    (void)sm; (void)warp;
+}
+
+// Dispatch one grid pass.
+__device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView& sm, int phase) {
+    switch (phase) {
+        case PH_ROOT:
+        case PH_FINAL:
+            if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true>(st, sm); else pg_pass_root<false>(st, sm);
+            break;
+        case PH_MINMAX: pg_pass_minmax(st, sm); break;
+        case PH_STATS: pg_pass_seg<0>(st, sm); break;
+        case PH_BERN: pg_pass_seg<1>(st, sm); break;
+        case PH_PART: pg_pass_part(st, sm); break;
+        default: break;
+    }
+}

@@ -1,0 +1,212 @@
+// pg_types.h — plain data layout of the device-resident PGBART sampler.
+//
+// Everything the sweep touches lives in HBM behind the pointers of PgState:
+//   X      column-major fp32 [p][ld]   (reference: data.rs OwnedData.x, f64 F-order)
+//   y      fp32 [ld]                   (data.rs OwnedData.y)
+//   A      fp64 [ld]  running array: holds `predictions` between steps and
+//                     `residuals` (= sum of all OTHER trees, kernel.rs:84-87)
+//                     while a tree is being updated
+//   forest heap-indexed SoA tree arrays [m][maxn]   (tree.rs:9-23, state.rs:8)
+//   slots  per-particle tree + BFS queue + per-node segment/statistics tables
+//          [2][S][maxn] (double-buffered for resampling)   (particle.rs:48-52)
+//   pool   u32 segment pool: per-leaf observation-index lists, appended by the
+//          stable partition (particle.rs:13-23 LeafSamplesFlat)
+// The header is shared by the CUDA build and by the host-side simulation used
+// in tests (tests/cpu_sim), so it contains no CUDA-only constructs.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PG_HD __host__ __device__ __forceinline__
+#define PG_HDN __host__ __device__
+#else
+#define PG_HD inline
+#define PG_HDN
+#endif
+
+enum PgPhase : int {
+    PH_BEGIN = 0,   // start of a step: serial section prepares the first tree update
+    PH_ROOT = 1,    // fused pass: A += tree_add(x); A -= tree_sub(x); root totals; round-1 child statistics
+    PH_MINMAX = 2,  // per-job min/max of the split column over a node's index segment
+    PH_STATS = 3,   // per-job child statistics over a node's index segment
+    PH_BERN = 4,    // Bernoulli-logit: per-job child log-likelihood pass
+    PH_PART = 5,    // stable partition of surviving particles' freshly split nodes into the pool
+    PH_FINAL = 6,   // last pass of a step: A += tree_add(x) (A becomes `predictions` again)
+    PH_DONE = 7
+};
+
+enum PgFamily : int { PG_GAUSSIAN = 0, PG_BERNOULLI_LOGIT = 1, PG_GAUSSIAN_KERNEL = 2 };
+enum PgRngMode : int { PG_RNG_TAPE = 0, PG_RNG_PHILOX = 1 };
+
+enum PgDraw : int { PG_D_GROW = 0, PG_D_VAR = 1, PG_D_SPLIT = 2, PG_D_ZLEFT = 3, PG_D_ZRIGHT = 4,
+                    PG_D_RESAMPLE = 5, PG_D_SELECT = 6 };
+
+enum PgError : int {
+    PG_OK = 0,
+    PG_ERR_DEPTH = 1,      // split past max_depth: the reference panics here (tree.rs:98-102)
+    PG_ERR_POOL = 2,       // segment pool exhausted
+    PG_ERR_TAPE = 3,       // RNG tape exhausted / split draw not below max
+    PG_ERR_WATCHDOG = 4,   // grid barrier timed out
+    PG_ERR_WEIGHTS = 5,    // non-finite weights (reference: WeightedIndex::new(..).unwrap() panics)
+    PG_ERR_INTERNAL = 6
+};
+
+#define PG_SEG_IDENTITY 0xFFFFFFFFu  // node's samples are 0..n (root): no index list is read
+#define PG_SEG_NONE 0xFFFFFFFEu      // children not materialised yet
+#define PG_TS_FIELDS 12
+#define PG_THREADS 256
+#define PG_WARPS (PG_THREADS / 32)
+
+struct PgCtrl {
+    // ---- state machine (written by the serial section, read by all CTAs after the barrier)
+    int phase;
+    int k;            // tree update index within this step's batch
+    int batch;
+    int t_cur;        // tree being updated
+    int t_add;        // tree whose (new) values the next ROOT/FINAL pass adds to A, -1 = none
+    int t_sub;        // tree whose (old) values the next ROOT pass subtracts, -1 = none
+    int round;
+    int n_jobs;
+    int n_groups;
+    int n_pjobs;
+    int cur;          // which half of the slot tables is live
+    int error;
+    int snext;        // next serial sub-step (PgSerialNext), SN_NONE = run the grid pass `phase`
+    int max_size;     // largest slot tree size (bounds the resampling copy)
+    unsigned long long upd;       // tree-update counter since creation (RNG coordinate)
+    unsigned long long pool_top;
+    int next_tree_idx;
+    int tune;
+    // ---- per-update scalars
+    double T_o, T_r, T_rr, T_ll0;  // root totals over all rows: sum others, sum (y-others), sum (y-others)^2, stump ll (Bernoulli)
+    double C0;                      // particle-independent part of the log-likelihood
+    double g_stump;
+    int acc_update;                 // accepted grows in this update
+    int any_queue;
+    // ---- BartInfo (state.rs:16-20) of the current step
+    double info_loglik;
+    long long info_acc;
+    int info_n;
+    // ---- roofline counters (bytes the passes must move)
+    unsigned long long bytes_model;     // this implementation's compulsory bytes
+    unsigned long long bytes_contract;  // SURVEY.md §8(d) formula
+    unsigned long long n_phases;        // grid passes executed
+    unsigned long long n_updates;       // tree updates executed
+    unsigned long long trace_n;         // tree updates recorded in the trace
+    int trace_overflow;
+    int pad0;
+    // ---- grid barrier
+    unsigned int bar_count;
+    unsigned int bar_pad[31];
+    unsigned int bar_gen;
+    unsigned int bar_pad2[31];
+};
+
+struct PgState {
+    // dimensions
+    long long n, ld;
+    int p, m, P, S, max_depth, maxn;
+    int grid, n_gwarps;          // CTAs in the sweep grid, global warps (= grid * PG_WARPS)
+    // data
+    const float* X;
+    const float* y;
+    double* A;
+    const float* col_min;
+    const float* col_max;
+    const double* prior;         // split prior used as raw weights (Q3); null = uniform integer draw
+    double prior_total;
+    const double* thr_depth;     // [max_depth+2] 1 - alpha (1+d)^-beta (host pow, smc.rs:143)
+    double leaf_sigma, m_f, init_leaf, y_mean;
+    double batch_tune, batch_post;
+    // likelihood (weight.rs)
+    int family;
+    double lik_sigma;
+    // forest
+    int* f_split_var; float* f_thr32; double* f_split_val; double* f_leaf_val; int* f_size;
+    // particle slot tables, [2][S][maxn] / [2][S]
+    int* pt_split_var; float* pt_thr32; double* pt_split_val; double* pt_leaf_val;
+    unsigned int* pt_seg_off; unsigned int* pt_cnt;
+    double* pt_So; double* pt_Sr; double* pt_g;
+    int* pt_queue; int* pt_size; int* pt_qhead; int* pt_qtail; double* pt_G;
+    double* w; int* mutated; int* anc; int* slot_job;   // [S]
+    int* pend_node; int* pend_var;                       // [S] proposal being evaluated
+    double* Wfinal;                                      // [2P] log / normalised final weights
+    // jobs of the current grid pass, [S]
+    int* job_slot; int* job_node; int* job_var; float* job_thr32; double* job_split;
+    unsigned int* job_seg_off; unsigned int* job_len; float* job_lo; float* job_hi;
+    double* job_vL; double* job_vR;
+    int* job_order;              // [S] permutation of jobs: jobs sharing one index segment are adjacent
+    int* grp_first;              // [S+1] group boundaries in job_order
+    double* red_So; double* red_Sr; double* red_llL; double* red_llR;   // [S] reduced per-job sums (LEFT child; Bernoulli: both)
+    unsigned long long* red_cnt;                      // [S] reduced LEFT-child counts per job
+    // partition jobs, [S]
+    int* pj_anc; int* pj_job; int* pj_var; float* pj_thr32;
+    unsigned int* pj_src_off; unsigned int* pj_len; unsigned int* pj_dst_off; unsigned int* pj_cntL;
+    unsigned int* pj_warp_left;  // [S][n_gwarps] exclusive prefix of left counts per global warp
+    int* pj_of_anc;              // [S] partition job of an ancestor slot, -1 = none
+    unsigned int* scan_tmp;      // [PG_THREADS + 1]
+    // per-pass partial results
+    double* part_sum;            // [grid][S][2]  (sum others, sum y-others) of the LEFT child
+    unsigned int* part_cnt;      // [n_gwarps][S] left count per global warp (prefix for the partition)
+    unsigned int* part_ccnt;     // [grid][S]     left count per block
+    double* part_tot;            // [grid][4]
+    unsigned int* part_mm;       // [grid][S][2]  ordered-uint keys of min / max
+    double* part_ll;             // [grid][S][2]  Bernoulli: log-likelihood of the left / right child
+    // segment pool
+    unsigned int* pool; unsigned long long pool_cap;
+    // rng
+    int rng_mode; unsigned int philox_key0, philox_key1;
+    const double* tape_slot; const double* tape_round; const double* tape_upd;
+    long long tape_n_upd; int tape_r_cap; unsigned long long tape_base_upd;
+    // trace (tests): same layout as the oracle's
+    double* tr_slot; double* tr_round; double* tr_upd; long long tr_u_cap; int tr_r_cap;
+    unsigned char* info_depths;  // [m]
+    PgCtrl* ctrl;
+};
+
+// ---- small helpers ---------------------------------------------------------
+
+PG_HD int pg_depth_of(int node) {  // tree.rs:54-57
+    int d = 0;
+    unsigned v = (unsigned)node + 1u;
+    while (v > 1u) { v >>= 1; ++d; }
+    return d;
+}
+
+// Smallest float >= s, so that for float x:  (double)x < s  <=>  x < pg_thr32(s).
+PG_HD float pg_thr32(double s) {
+    float f = (float)s;  // round to nearest
+    if ((double)f < s) {
+        // next float up
+        union { float f; uint32_t u; } c; c.f = f;
+        if (f == 0.0f) c.u = 1u;                 // smallest positive subnormal
+        else if (f > 0.0f) c.u += 1u;
+        else c.u -= 1u;
+        f = c.f;
+    }
+    return f;
+}
+
+// Order-preserving map float -> uint32 (for integer min/max reductions).
+PG_HD uint32_t pg_f2key(float f) {
+    union { float f; uint32_t u; } c; c.f = f;
+    return (c.u & 0x80000000u) ? ~c.u : (c.u | 0x80000000u);
+}
+PG_HD float pg_key2f(uint32_t k) {
+    union { float f; uint32_t u; } c;
+    c.u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return c.f;
+}
+
+// Contiguous range of segment entries owned by one global warp.  Identity
+// segments use granule 4 (float4 loads), index segments granule 1.
+PG_HD void pg_warp_range(unsigned long long L, int gw, int n_gwarps, int granule,
+                         unsigned long long* beg, unsigned long long* end) {
+    unsigned long long units = (L + (unsigned long long)granule - 1) / (unsigned long long)granule;
+    unsigned long long per = (units + (unsigned long long)n_gwarps - 1) / (unsigned long long)n_gwarps;
+    unsigned long long b = (unsigned long long)gw * per * (unsigned long long)granule;
+    unsigned long long e = b + per * (unsigned long long)granule;
+    if (b > L) b = L;
+    if (e > L) e = L;
+    *beg = b; *end = e;
+}

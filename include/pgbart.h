@@ -1,0 +1,113 @@
+/* pgbart.h — C ABI of the B200-native Particle-Gibbs BART sweep (libpgbart_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of GStechschulte/bart-rs: the PGBART
+ * step.  Every entry point names the reference interface it replaces (paths relative to the
+ * reference tree).  Plain pointers and sizes only; every call returns 0 on success and a
+ * non-zero status otherwise, with text from pgbart_last_error().  There is no CPU fallback:
+ * pgbart_create fails when no CUDA device is usable.
+ *
+ * Reference surface being replaced (src/lib.rs):
+ *   PyBartSettings.__new__   lib.rs:54-104   -> pgbart_settings
+ *   PySampler.init           lib.rs:115-180  -> pgbart_create (+ pgbart_set_likelihood)
+ *   PySampler.step           lib.rs:182-202  -> pgbart_step
+ *   LogpFunc callback        lib.rs:33, weight.rs:10-30 -> pgbart_set_likelihood (device families)
+ * and, for Rust callers of the rlib (benches/particle_gibbs.rs:105-127,257-282):
+ *   BartKernel::init/step    kernel.rs:38-126 -> pgbart_create / pgbart_step_device
+ */
+#ifndef PGBART_H
+#define PGBART_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgbart_sampler* pgbart_handle;
+
+/* PyBartSettings (lib.rs:35-104), field for field.  response_rule / resampling_rule are accepted
+ * and ignored exactly as the reference ignores them (always Gaussian leaf rule, systematic
+ * resampling; lib.rs:47-48,166).  split_rules: only "ContinuousSplit" is executed on the device;
+ * an unknown name is an error as in lib.rs:129-132, "OneHotSplit" is rejected (out of scope). */
+typedef struct pgbart_settings {
+    uint64_t n_trees;
+    uint64_t n_particles;          /* includes the reference stump (smc.rs:42-52) */
+    uint32_t max_depth;            /* u8 in the reference */
+    double alpha, beta, sigma;     /* sigma = leaf standard deviation */
+    const double* split_prior;     /* used as RAW weights like the reference (smc.rs:242-254) */
+    uint64_t n_split_prior;        /* 0 = uniform integer draw (lib.rs:153-157) */
+    const char* const* split_rules;
+    uint64_t n_split_rules;
+    const char* response_rule;
+    const char* resampling_rule;
+    double batch_tune, batch_post; /* defaults 0.1 in the reference */
+    uint64_t seed;                 /* default 0 */
+} pgbart_settings;
+
+/* Likelihood families evaluated on the device in place of the host logp callback. */
+enum { PGBART_GAUSSIAN = 0,        /* params = {sigma}: sum -0.5((y-mu)/sigma)^2 - log sigma - 0.5 log 2pi */
+       PGBART_BERNOULLI_LOGIT = 1, /* no params:        sum y*mu - softplus(mu) */
+       PGBART_GAUSSIAN_KERNEL = 2  /* no params:        sum -0.5 (mu-y)^2  (benches/particle_gibbs.rs:22-32) */ };
+
+enum { PGBART_X_F64 = 0, PGBART_X_F32 = 1 };
+enum { PGBART_ORDER_C = 0, PGBART_ORDER_F = 1 };
+
+/* PySampler.init (lib.rs:115-180).  x: n-by-p host matrix (f64 or f32, C or Fortran order), y: f64[n].
+ * Copies both (as the reference does), stores X column-major fp32 and y fp32 in HBM, builds m stump
+ * trees and predictions = mean(y) (kernel.rs:38-58).  device = CUDA ordinal. */
+int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t p, const double* y,
+                  const pgbart_settings* settings, int device, pgbart_handle* out);
+int pgbart_destroy(pgbart_handle h);
+const char* pgbart_last_error(pgbart_handle h);   /* h may be NULL: error of the last failed create */
+
+/* Replaces the LogpFunc pointer (lib.rs:125-126): callable before every step, e.g. with the
+ * current sigma, like CompiledPyMCModel.update_shared_arrays (pgbart.py:190). */
+int pgbart_set_likelihood(pgbart_handle h, int family, const double* params, int nparams);
+
+/* PySampler.step (lib.rs:182-202): tune = 1/0, or -1 to keep the current flag (None).  Writes the
+ * new sum-of-trees, f64[n], to HOST memory out_pred (device->host copy inside the call). */
+int pgbart_step(pgbart_handle h, int tune, double* out_pred);
+/* Same step, result left in HBM; asynchronous until pgbart_sync. */
+int pgbart_step_device(pgbart_handle h, int tune);
+int pgbart_sync(pgbart_handle h);
+const double* pgbart_predictions_device(pgbart_handle h);
+int pgbart_get_predictions(pgbart_handle h, double* out_pred);
+
+/* BartInfo of the last step (state.rs:16-20; dropped at the PyO3 boundary, lib.rs:197). */
+int pgbart_get_info(pgbart_handle h, double* log_likelihood, int64_t* acceptance_count,
+                    uint8_t* tree_depths, int* n_depths /* in: capacity, out: count */);
+
+/* Forest export: TreeArrays (tree.rs:9-23).  split_var = -1 for leaves (u32::MAX sentinel). */
+int pgbart_tree_size(pgbart_handle h, uint64_t tree, int* size);
+int pgbart_get_tree(pgbart_handle h, uint64_t tree, int32_t* split_var, double* split_val, double* leaf_val);
+int pgbart_get_leaf_indices(pgbart_handle h, uint64_t tree, uint32_t* out /* n */);
+int pgbart_get_state(pgbart_handle h, uint64_t* next_tree_idx, int* tune, uint64_t* n_updates);
+
+/* Random source.  Default: Philox4x32-10 keyed by settings.seed.
+ * Tape (replay mode): typed draws by coordinates, host arrays copied to the device:
+ *   slot[n_upd][r_cap][n_particles-1][5] = u1,u2,u3,zL,zR ; round[n_upd][r_cap] = u6 ; upd[n_upd] = u7.
+ * The tape's first record corresponds to the sampler's next tree update. */
+int pgbart_set_rng_philox(pgbart_handle h, uint64_t seed);
+int pgbart_set_rng_tape(pgbart_handle h, const double* slot, const double* round, const double* upd,
+                        int64_t n_upd, int r_cap);
+
+/* Decision trace for parity tests (same layout as the oracle's):
+ *   slot[u_cap][r_cap][S][12]: status(0 idle,1 depth-prior reject,2 empty,3 min>=max,4 accepted), node, var,
+ *        split, vL, vR, cntL, cntR, log-weight, min, max, sum-others-left
+ *   round[u_cap][r_cap][2+2S]: used, n_mutated, normalised weights[S], ancestors[S]
+ *   upd[u_cap][4+2P]: rounds, selected, tree, accepted, log W[P], normalised W[P] */
+int pgbart_trace_enable(pgbart_handle h, int64_t u_cap, int r_cap);
+int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd, int64_t* n_upd, int* overflow);
+
+/* Options: "driver" = "persistent" (default) | "stepwise"; "pool_factor" = integer >= 1. */
+int pgbart_set_option(pgbart_handle h, const char* key, const char* value);
+
+/* Counters since creation: [0] compulsory bytes of this implementation's passes, [1] bytes by the
+ * SURVEY.md §8(d) contract formula, [2] grid passes, [3] tree updates, [4] kernel launches,
+ * [5] GPU time of the last step in microseconds (CUDA events on the sampler's stream),
+ * [6] grid blocks, [7] dynamic shared memory per block. */
+int pgbart_get_counters(pgbart_handle h, double* out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

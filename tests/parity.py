@@ -1,0 +1,135 @@
+"""Replay-mode parity harness shared by the host-simulation tests (CPU) and the GPU tests.
+
+Protocol (BASELINE.json north_star): the oracle runs with its sequential
+generator and records a typed RNG tape plus a decision trace; the implementation under test replays
+the tape.  Bit-exact: status/node/variable/split of every proposal, child counts, column min/max,
+ancestors, selected particle, round counts, tree structure, leaf_indices.  Within `rtol` (default
+1e-6 relative, the tolerance north_star states): log-weights, leaf values, predictions.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import pyoracle as po
+
+RTOL = 1e-6
+
+
+def assert_traces_match(ref, got, n_upd, S, P, rtol=RTOL):
+    """ref/got: (slot, round, upd) arrays in the layout of include/pgbart.h."""
+    rs, rr, ru = ref
+    gs, gr, gu = got
+    for u in range(n_upd):
+        assert int(ru[u, 0]) == int(gu[u, 0]), f"update {u}: rounds {ru[u, 0]} vs {gu[u, 0]}"
+        assert ru[u, 1] == gu[u, 1], f"update {u}: selected particle {ru[u, 1]} vs {gu[u, 1]}"
+        assert ru[u, 2] == gu[u, 2] and ru[u, 3] == gu[u, 3], f"update {u}: tree/acceptance"
+        np.testing.assert_allclose(gu[u, 4:4 + P], ru[u, 4:4 + P], rtol=rtol, atol=0, err_msg=f"update {u} log W")
+        np.testing.assert_allclose(gu[u, 4 + P:4 + 2 * P], ru[u, 4 + P:4 + 2 * P], rtol=1e-4, atol=1e-12,
+                                   err_msg=f"update {u} normalised W")
+        for r in range(int(ru[u, 0])):
+            a, b = rs[u, r], gs[u, r]
+            for f, name in ((0, "status"), (1, "node"), (2, "var"), (3, "split"), (6, "cntL"), (7, "cntR"),
+                            (9, "min"), (10, "max")):
+                np.testing.assert_array_equal(b[:, f], a[:, f], err_msg=f"update {u} round {r} {name}")
+            for f, name in ((4, "vL"), (5, "vR"), (8, "logw"), (11, "SoL")):
+                np.testing.assert_allclose(b[:, f], a[:, f], rtol=rtol, atol=1e-9, err_msg=f"update {u} round {r} {name}")
+            np.testing.assert_array_equal(gr[u, r, 2 + S:2 + 2 * S], rr[u, r, 2 + S:2 + 2 * S],
+                                          err_msg=f"update {u} round {r} ancestors")
+            np.testing.assert_allclose(gr[u, r, 2:2 + S], rr[u, r, 2:2 + S], rtol=1e-4, atol=1e-12,
+                                       err_msg=f"update {u} round {r} normalised weights")
+            assert gr[u, r, 1] == rr[u, r, 1]
+
+
+def assert_forest_matches(orc, dev, m, rtol=RTOL, check_leaf_indices=True):
+    for t in range(m):
+        osv, osp, olv = orc.tree(t)
+        dsv, dsp, dlv = dev.tree(t)
+        np.testing.assert_array_equal(dsv, osv, err_msg=f"tree {t} split_var")
+        np.testing.assert_array_equal(np.nan_to_num(dsp, nan=-7e300), np.nan_to_num(osp, nan=-7e300),
+                                      err_msg=f"tree {t} split_val")   # bit-exact incl. NaN placement
+        np.testing.assert_array_equal(np.isnan(dlv), np.isnan(olv), err_msg=f"tree {t} leaf NaN pattern")
+        np.testing.assert_allclose(np.nan_to_num(dlv), np.nan_to_num(olv), rtol=rtol, atol=1e-12, err_msg=f"tree {t} leaf_val")
+        if check_leaf_indices:
+            np.testing.assert_array_equal(dev.leaf_indices(t), orc.leaf_indices(t), err_msg=f"tree {t} leaf_indices")
+
+
+def replay_parity(make_dev, X, y, cfg, family, lik_sigma, tunes, r_cap=24, rtol=RTOL, expect_error=None):
+    """Run oracle (recording) and implementation (replaying) side by side.
+
+    make_dev(X, y, cfg) -> object with set_likelihood_code / set_rng_tape / trace_enable / trace_read / step /
+    tree / leaf_indices / info.  cfg: dict of PyBartSettings-like fields.  Returns the oracle trace.
+    """
+    m, P = cfg["n_trees"], cfg["n_particles"]
+    S = P - 1
+    U = len(tunes) * m
+    orc = po.OracleSampler(X.astype(np.float64), y, **cfg)
+    orc.set_likelihood(family, [lik_sigma])
+    orc.set_rng(po.RNG_SEQ, cfg.get("seed", 0))
+    tape = po.TapeBuffers(U, r_cap, P)
+    tr = po.TraceBuffers(U, r_cap, P)
+    orc.attach_tape(tape)
+    orc.attach_trace(tr)
+    opreds = []
+    oerr = None
+    try:
+        for tune in tunes:
+            opreds.append(orc.step(tune))
+    except RuntimeError as e:
+        oerr = str(e)
+    assert orc.overflowed() == 0, "oracle trace/tape overflow: raise r_cap"
+
+    dev = make_dev(X, y, cfg)
+    dev.set_likelihood_code(family, [lik_sigma])
+    dev.set_rng_tape(tape.slot, tape.round, tape.upd)
+    dev.trace_enable(U, r_cap)
+    derr = None
+    dpreds = []
+    try:
+        for tune in tunes:
+            dpreds.append(dev.step(tune))
+    except RuntimeError as e:
+        derr = str(e)
+    if expect_error is not None:
+        assert oerr is not None and expect_error in oerr, f"oracle error: {oerr}"
+        assert derr is not None and expect_error in derr, f"device error: {derr}"
+        return tr
+    assert oerr is None and derr is None, (oerr, derr)
+    ds, dr, du, n_upd, ovf = dev.trace_read()
+    assert not ovf
+    assert n_upd == orc.trace_count()
+    assert_traces_match((tr.slot, tr.round, tr.upd), (ds, dr, du), n_upd, S, P, rtol)
+    for a, b in zip(opreds, dpreds):
+        np.testing.assert_allclose(b, a, rtol=rtol, atol=0, err_msg="predictions")
+    assert_forest_matches(orc, dev, m, rtol)
+    oll, oacc, odep = orc.info()
+    dll, dacc, ddep = dev.info()
+    assert oacc == dacc
+    np.testing.assert_array_equal(ddep, odep)
+    np.testing.assert_allclose(dll, oll, rtol=1e-4, atol=1e-12)
+    return tr
+
+
+def philox_parity(make_dev, X, y, cfg, family, lik_sigma, tunes, r_cap=24, rtol=RTOL):
+    """Free-running Philox: oracle and implementation generate the same draws independently."""
+    m, P = cfg["n_trees"], cfg["n_particles"]
+    S = P - 1
+    U = len(tunes) * m
+    seed = cfg.get("seed", 0)
+    orc = po.OracleSampler(X.astype(np.float64), y, **cfg)
+    orc.set_likelihood(family, [lik_sigma])
+    orc.set_rng(po.RNG_PHILOX, seed)
+    tr = po.TraceBuffers(U, r_cap, P)
+    orc.attach_trace(tr)
+    dev = make_dev(X, y, cfg)
+    dev.set_likelihood_code(family, [lik_sigma])
+    dev.set_rng_philox(seed)
+    dev.trace_enable(U, r_cap)
+    for tune in tunes:
+        a = orc.step(tune)
+        b = dev.step(tune)
+        np.testing.assert_allclose(b, a, rtol=rtol, atol=0)
+    ds, dr, du, n_upd, ovf = dev.trace_read()
+    assert not ovf and orc.overflowed() == 0
+    assert_traces_match((tr.slot, tr.round, tr.upd), (ds, dr, du), n_upd, S, P, rtol)
+    assert_forest_matches(orc, dev, m, rtol)
+    return tr
