@@ -23,7 +23,7 @@ std::string g_create_error;
 struct Sampler {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     PgState st{};
     std::vector<void*> allocs;
     std::string err;
@@ -95,6 +95,8 @@ void free_all(Sampler* s) {
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->tm0) cudaEventDestroy(s->tm0);
+    if (s->tm1) cudaEventDestroy(s->tm1);
     if (s->stream) cudaStreamDestroy(s->stream);
 }
 
@@ -184,7 +186,8 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     s->device = device;
     if (!ck(s, cudaSetDevice(device), "cudaSetDevice")) return bail();
     if (!ck(s, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "stream")) return bail();
-    if (!ck(s, cudaEventCreate(&s->ev0), "event") || !ck(s, cudaEventCreate(&s->ev1), "event")) return bail();
+    if (!ck(s, cudaEventCreate(&s->ev0), "event") || !ck(s, cudaEventCreate(&s->ev1), "event") ||
+        !ck(s, cudaEventCreate(&s->tm0), "event") || !ck(s, cudaEventCreate(&s->tm1), "event")) return bail();
 
     PgState& st = s->st;
     st.n = (long long)n;
@@ -498,6 +501,21 @@ int pgbart_get_counters(pgbart_handle h, double* out8) {
     out8[5] = (double)ms * 1000.0;
     out8[6] = (double)s->st.grid;
     out8[7] = (double)s->smem;
+    return 0;
+}
+
+int pgbart_timer_start(pgbart_handle h) {
+    Sampler* s = &h->s;
+    return ck(s, cudaEventRecord(s->tm0, s->stream), "event record") ? 0 : 2;
+}
+
+int pgbart_timer_stop(pgbart_handle h, double* elapsed_ms) {
+    Sampler* s = &h->s;
+    if (!ck(s, cudaEventRecord(s->tm1, s->stream), "event record")) return 2;
+    if (!ck(s, cudaEventSynchronize(s->tm1), "event synchronize")) return 2;
+    float ms = 0.0f;
+    if (!ck(s, cudaEventElapsedTime(&ms, s->tm0, s->tm1), "event elapsed")) return 2;
+    *elapsed_ms = (double)ms;
     return 0;
 }
 

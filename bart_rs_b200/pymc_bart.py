@@ -228,6 +228,15 @@ class PySampler:
                 "grid_blocks", "smem_bytes"]
         return dict(zip(keys, out.tolist()))
 
+    def timer_start(self) -> None:
+        """CUDA-event stopwatch on the sampler's stream (the stream the kernels run on)."""
+        self._check(self._L.pgbart_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self._L.pgbart_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._L.pgbart_destroy(self._h)

@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — PG sweeps/sec of the B200-native PGBART sweep (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm (oracle port)
+
+A "step" is one full PG sweep: m = 200 consecutive tree updates = one PySampler.step() with
+batch = (1.0, 1.0) (reference kernel.rs:60-126, pgbart.py:65).  Workload at N = 1 is BASELINE config C3
+(synthetic Friedman n = 1M, p = 50, m = 200, 20 particles, Gaussian sigma = 1).  At N > 1 (torchrun, one rank per
+GPU) every rank runs an independent chain of the same workload with its own seed — the "chains" sharding of
+SURVEY.md §8(e): no data-path collective, weak scaling; value = sweeps of all ranks / max-over-ranks time.
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  roofline      dominant (and only) hot kernel pg_sweep_persistent: achieved = compulsory bytes of its passes
+                (device counters) / CUDA-event time on the sampler's stream; peak = MEASURED_PEAKS.json
+  cpu_baseline  the oracle (C++ restatement of the bart-rs CPU path, 1 core) timed here on a bounded sample
+  e2e           same metric through PySampler.step() with host buffers (likelihood push H2D, predictions D2H)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C1": dict(n=1_000, p=10, m=50, P=20, family="gaussian"),
+    "C2": dict(n=100_000, p=20, m=200, P=20, family="gaussian"),
+    "C3": dict(n=1_000_000, p=50, m=200, P=20, family="gaussian"),
+    "C5": dict(n=1_000_000, p=50, m=200, P=256, family="bernoulli_logit"),
+}
+
+
+def make_data(w, seed=0):
+    from tests import datagen
+    X, y = datagen.friedman(w["n"], w["p"], seed=seed, bernoulli=(w["family"] == "bernoulli_logit"))
+    prm = datagen.pgbart_params(y, w["m"], w["p"])
+    return X, y, prm
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_sample(X, y, prm, w, updates, seed=0, warm=2):
+    """Time `updates` tree updates of the CPU oracle on the workload (single core, like the reference)."""
+    from oracle import pyoracle as po
+    m = w["m"]
+    frac = max(updates, 1) / m
+    o = po.OracleSampler(X.astype(np.float64), y, n_trees=m, n_particles=w["P"], max_depth=prm["max_depth"],
+                         alpha=0.95, beta=2.0, sigma=prm["sigma"], split_prior=prm["split_prior"],
+                         batch_tune=min(warm / m, 1.0), batch_post=min(frac, 1.0), seed=seed)
+    o.set_likelihood(po.FAM_BERNOULLI_LOGIT if w["family"] == "bernoulli_logit" else po.FAM_GAUSSIAN, [1.0])
+    o.set_rng(po.RNG_PHILOX, seed)
+    o.step(True)                      # warm-up: page in, allocate
+    t0 = time.perf_counter()
+    o.step(False)
+    dt = time.perf_counter() - t0
+    done = min(max(int(np.floor(frac * m + 0.5)), 1), m)
+    o.close()
+    return done, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The Rust crate cannot be built in
+    this image (no cargo/rustc), so this is the C++ oracle port, single-threaded like the reference
+    (`#[pyclass(unsendable)]`, no threads in src/)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    X, y, prm = make_data(w)
+    per_step = max(1, int(args.ref_updates))
+    times, done_total = [], 0
+    for i in range(args.warmup + args.steps):
+        done, dt = oracle_sample(X, y, prm, w, per_step, seed=i, warm=1)
+        if i >= args.warmup:
+            times.append(dt)
+            done_total += done
+    total = float(np.sum(times))
+    sweeps_per_s = (done_total / w["m"]) / total
+    line = {
+        "impl": "reference", "metric": "PG sweeps/sec", "value": sweeps_per_s, "unit": "sweeps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: Friedman n={w['n']} p={w['p']} m={w['m']} P={w['P']} {w['family']}",
+                   "sample": f"each step = {per_step} tree updates of the sweep, scaled to m={w['m']}"},
+        "cpu_baseline": {"value": sweeps_per_s, "unit": "sweeps/s", "cores": 1, "kind": "port",
+                         "sample": f"{done_total} tree updates in {total:.2f} s, scaled to m={w['m']}"},
+        "e2e": {"value": sweeps_per_s, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; this repo has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
+
+    w = WORKLOADS[args.workload]
+    X, y, prm = make_data(w)
+    st = PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, prm["sigma"], list(prm["split_prior"]),
+                        ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=rank)
+    lik = DeviceLikelihood(w["family"], 1.0)
+    smp = PySampler.init(X, y, lik, st, device=local_rank)   # X is float32 C-order: converted to column-major on upload
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: inputs already in HBM, K sweeps, CUDA events on the sampler's stream
+    for _ in range(args.warmup):
+        smp.step_device(False)
+    smp.sync()
+    c0 = smp.counters()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    smp.timer_start()
+    for _ in range(args.steps):
+        smp.step_device(False)
+    ms = smp.timer_stop()
+    smp.sync()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    c1 = smp.counters()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps / (ms_max / 1000.0)
+
+    # ---- end to end: PySampler.step() with host buffers (likelihood parameters H2D, predictions D2H each step)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    smp.set_likelihood(lik)
+    smp.step(False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        smp.set_likelihood(lik)          # the reference refreshes shared likelihood inputs before every step (pgbart.py:190)
+        pred = smp.step(False)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(t2.item())
+    assert np.all(np.isfinite(pred))
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        k = args.steps
+        bytes_per_launch = (c1["bytes_model"] - c0["bytes_model"]) / k
+        contract_per_launch = (c1["bytes_contract"] - c0["bytes_contract"]) / k
+        achieved = bytes_per_launch / (ms / 1000.0 / k) / 1e9
+        contract_gbs = contract_per_launch / (ms / 1000.0 / k) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            done, dt = oracle_sample(X, y, prm, w, args.ref_updates)
+            cpu = {"value": (done / w["m"]) / dt, "unit": "sweeps/s", "cores": 1, "kind": "port",
+                   "sample": f"{done} tree updates of this workload in {dt:.2f} s on 1 host core, scaled to m={w['m']} "
+                             "(C++ restatement of the bart-rs CPU path; the Rust crate cannot be built in this image)"}
+        line = {
+            "metric": "PG sweeps/sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: Friedman n={w['n']} p={w['p']} m={w['m']} P={w['P']} {w['family']}, "
+                                   "batch=(1,1) so one step = one sweep",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent chains, one per GPU, no collective",
+                       "l2": "inputs larger than L2 (X 200 MB fp32 + A/y 12 MB vs 126 MB L2); no flush" if w["n"] * w["p"] * 4 > 126e6
+                             else "working set fits L2 (L2-resident by design of this config)",
+                       "storage": "X, y fp32; running sum-of-trees fp64; accumulation fp64"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "pg_sweep_persistent",
+                         "bytes_per_launch": bytes_per_launch,
+                         "contract_formula_gbs": contract_gbs, "contract_bytes_per_launch": contract_per_launch,
+                         "note": "achieved uses this implementation's compulsory bytes (A r/w, y, one read per distinct split "
+                                 "column per pass, index lists); contract_* uses SURVEY.md §8(d)'s per-slot formula, which "
+                                 "charges A/y once per slot — the fused root pass reads them once per tree"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8 * w["n"],
+                    "steps": e2e_steps},
+            "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
+            "grid_passes_per_step": (c1["grid_passes"] - c0["grid_passes"]) / k,
+            "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    smp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-updates", type=int, default=24, help="tree updates per timed CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -107,6 +107,11 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value);
  * [6] grid blocks, [7] dynamic shared memory per block. */
 int pgbart_get_counters(pgbart_handle h, double* out8);
 
+/* CUDA-event stopwatch on the sampler's own stream (the stream the sweep kernels are launched on):
+ * start records an event, stop records a second one, synchronises and returns the milliseconds between. */
+int pgbart_timer_start(pgbart_handle h);
+int pgbart_timer_stop(pgbart_handle h, double* elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,147 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI (libpgbart_b200.so via
+bart_rs_b200.PySampler), against the CPU oracle on the same seeded inputs and RNG tape.
+
+Bar (BASELINE.json north_star): split choices, index partitions (leaf_indices), ancestors and the
+selected particle bit-exact; log-weights, leaf values and predictions within 1e-6 relative.
+"""
+import numpy as np
+import pytest
+
+from tests import datagen, parity
+
+pytestmark = pytest.mark.gpu
+
+FAMILY_NAMES = {0: "gaussian", 1: "bernoulli_logit", 2: "gaussian_kernel"}
+
+
+class GpuAdapter:
+    """Adapts bart_rs_b200.PySampler to the harness in tests/parity.py."""
+
+    def __init__(self, X, y, cfg, driver):
+        from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
+        st = PyBartSettings(cfg["n_trees"], cfg["n_particles"], cfg["max_depth"], cfg["alpha"], cfg["beta"], cfg["sigma"],
+                            list(cfg["split_prior"]), ["ContinuousSplit"] * X.shape[1], "constant", "systematic",
+                            cfg["batch_tune"], cfg["batch_post"], cfg.get("seed", 0))
+        self.s = PySampler.init(np.asfortranarray(X.astype(np.float64)), y, DeviceLikelihood("gaussian", 1.0), st)
+        self.s.set_option("driver", driver)
+        self._DL = DeviceLikelihood
+
+    def set_likelihood_code(self, family, params=()):
+        self.s.set_likelihood(self._DL(FAMILY_NAMES[family], params[0] if len(params) else 1.0))
+
+    def __getattr__(self, name):
+        return getattr(self.s, name)
+
+
+def make_gpu(driver="persistent"):
+    def mk(X, y, cfg):
+        return GpuAdapter(X, y, cfg, driver)
+    return mk
+
+
+def cfg_for(y, m, P, p, *, max_depth=None, alpha=0.95, beta=2.0, prior=True, batch=(1.0, 1.0), seed=0):
+    prm = datagen.pgbart_params(y, m, p, alpha, beta)
+    return dict(n_trees=m, n_particles=P, max_depth=prm["max_depth"] if max_depth is None else max_depth, alpha=alpha,
+                beta=beta, sigma=prm["sigma"], split_prior=prm["split_prior"] if prior else [], batch_tune=batch[0],
+                batch_post=batch[1], seed=seed)
+
+
+CASES = [
+    # n, p, m, P, family, lik_sigma, kwargs, tunes
+    (1000, 10, 50, 20, 0, 1.0, dict(), [True, False]),                       # BASELINE config C1
+    (5000, 8, 10, 20, 0, 0.7, dict(batch=(0.5, 0.3)), [True, True, False, False]),
+    (777, 3, 5, 2, 0, 1.0, dict(beta=1.0, max_depth=10, prior=False), [True, True, True]),   # deep trees
+    (901, 4, 6, 3, 0, 1.0, dict(beta=0.5, max_depth=10), [True, True]),
+    (2000, 5, 6, 6, 1, 1.0, dict(), [True, False]),                          # Bernoulli-logit
+    (600, 3, 4, 2, 1, 1.0, dict(beta=1.0, max_depth=10), [True, True]),
+    (1500, 5, 7, 5, 2, 1.0, dict(), [True, True]),                           # bench mock likelihood
+    (400, 2, 3, 4, 0, 0.01, dict(), [True, True, True]),                     # positive log-likelihoods
+    (33, 2, 4, 6, 0, 1.0, dict(), [True]),                                   # ragged: fewer rows than warps
+    (1, 2, 3, 4, 0, 1.0, dict(), [True]),                                    # single row
+    (20000, 12, 8, 40, 0, 1.0, dict(), [True]),                              # more particles
+]
+
+
+@pytest.mark.parametrize("n,p,m,P,family,lik_sigma,kw,tunes", CASES)
+def test_gpu_replay_parity(n, p, m, P, family, lik_sigma, kw, tunes):
+    X, y = datagen.small(n, p, seed=n + m, bernoulli=(family == 1))
+    cfg = cfg_for(y, m, P, p, seed=n, **kw)
+    parity.replay_parity(make_gpu(), X, y, cfg, family, lik_sigma, tunes, r_cap=64)
+
+
+@pytest.mark.parametrize("case", [0, 2, 4])
+def test_gpu_stepwise_driver_matches(case):
+    n, p, m, P, family, lik_sigma, kw, tunes = CASES[case]
+    X, y = datagen.small(n, p, seed=n + m, bernoulli=(family == 1))
+    cfg = cfg_for(y, m, P, p, seed=n, **kw)
+    parity.replay_parity(make_gpu("stepwise"), X, y, cfg, family, lik_sigma, tunes, r_cap=64)
+
+
+def test_gpu_philox_parity():
+    X, y = datagen.friedman(3000, 5, seed=2)
+    cfg = cfg_for(y, 12, 10, 5, seed=5)
+    parity.philox_parity(make_gpu(), X, y, cfg, 0, 1.0, [True, False, False])
+
+
+def test_gpu_constant_column_and_ties():
+    rng = np.random.default_rng(3)
+    X = rng.random((1500, 4), dtype=np.float32)
+    X[:, 3] = 0.25
+    X[:, 2] = np.round(X[:, 2] * 3) / 3
+    y = (X[:, 0] * 3 + rng.standard_normal(1500) * 0.3).astype(np.float32).astype(np.float64)
+    cfg = cfg_for(y, 8, 6, 4, seed=1)
+    tr = parity.replay_parity(make_gpu(), X, y, cfg, 0, 1.0, [True, True, True], r_cap=64)
+    assert np.any(tr.slot[..., 0] == 3)
+
+
+def test_gpu_depth_overflow_is_an_error_like_the_reference_panic():
+    X, y = datagen.small(600, 2, seed=9)
+    cfg = cfg_for(y, 3, 2, 2, max_depth=1, alpha=0.999, beta=0.01, seed=4)
+    parity.replay_parity(make_gpu(), X, y, cfg, 0, 1.0, [True, True, True, True], r_cap=64,
+                         expect_error="exceed maximum capacity")
+
+
+def test_gpu_partition_kat():
+    """Reference src/particle.rs:170-201: x=[0..4], split 2.5 -> leaf_indices [1,1,1,2,2] — here through a
+    forced replay: one growing particle, u1 passes, var 0, u3 = 0.625 -> split = 0 + .625*4 = 2.5."""
+    from oracle import pyoracle as po
+    X = np.arange(5, dtype=np.float32).reshape(5, 1)
+    y = np.array([0.0, 0.1, 0.2, 3.0, 3.1])
+    cfg = dict(n_trees=1, n_particles=2, max_depth=3, alpha=0.95, beta=2.0, sigma=0.1, split_prior=[1.0],
+               batch_tune=1.0, batch_post=1.0, seed=0)
+    tape = po.TapeBuffers(1, 8, 2)
+    tape.slot[0, 0, 0] = [0.99, 0.0, 0.625, -1.0, 1.0]     # grow root on var 0 at 2.5
+    tape.slot[0, 1:, 0, 0] = 0.0                            # later rounds: depth prior rejects (thr > 0)
+    tape.round[:] = 0.5
+    tape.upd[:] = 0.999999                                  # select the last particle (the grown one)
+    dev = make_gpu()(X, y, cfg)
+    dev.set_likelihood_code(0, [1.0])
+    dev.set_rng_tape(tape.slot, tape.round, tape.upd)
+    dev.step(True)
+    sv, sp, lv = dev.tree(0)
+    assert list(sv) == [0, -1, -1] and sp[0] == 2.5
+    assert list(dev.leaf_indices(0)) == [1, 1, 1, 2, 2]
+
+
+def test_gpu_large_n_properties():
+    """n = 1M rows (BASELINE C3 row count, fewer columns): size-independent properties.
+    predictions == sum over trees of leaf_val[leaf_indices] recomputed on the host (linearity), run-to-run
+    bit reproducibility, and stepwise == persistent."""
+    n, p, m, P = 1_000_000, 8, 6, 20
+    X, y = datagen.friedman(n, p, seed=4)
+    cfg = cfg_for(y, m, P, p, seed=3)
+    outs = []
+    for driver in ("persistent", "persistent", "stepwise"):
+        dev = make_gpu(driver)(X, y, cfg)
+        dev.set_rng_philox(11)
+        for _ in range(3):
+            pred = dev.step(True)
+        total = np.zeros(n)
+        for t in range(m):
+            sv, sp, lv = dev.tree(t)
+            total += lv[dev.leaf_indices(t)]
+        np.testing.assert_allclose(pred, total, rtol=1e-9)
+        outs.append(pred)
+        dev.close()
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], outs[2])
