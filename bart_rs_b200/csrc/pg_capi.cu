@@ -29,6 +29,7 @@ struct Sampler {
     std::string err;
     bool dead = false;
     bool stepwise = false;
+    bool stepwise_fast = false;   // stepwise driver, but with the latency-organised serial section (P <= 32)
     size_t smem = 0;
     double launches = 0;
     bool timing_pending = false;
@@ -127,7 +128,8 @@ int enqueue_step(Sampler* s, int tune) {
         s->launches += 1;
     } else {
         // serial(BEGIN) -> [pass -> serial]* until DONE, reading the phase back between launches
-        if (!ck(s, pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
+        const bool fastser = s->stepwise_fast && s->st.P <= 32;
+        if (!ck(s, fastser ? pg_launch_serial_fast(s->st, s->smem, 1, s->stream) : pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
         s->launches += 1;
         for (long long guard = 0; guard < (1ll << 40); ++guard) {
             int phase = PH_DONE;
@@ -135,7 +137,7 @@ int enqueue_step(Sampler* s, int tune) {
             if (!ck(s, cudaStreamSynchronize(s->stream), "synchronize")) return 2;
             if (phase == PH_DONE) break;
             if (!ck(s, pg_launch_phase(s->st, s->smem, s->stream), "launch pass")) return 2;
-            if (!ck(s, pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
+            if (!ck(s, fastser ? pg_launch_serial_fast(s->st, s->smem, 0, s->stream) : pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
             s->launches += 2;
         }
     }
@@ -257,7 +259,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     const size_t S = (size_t)st.S, MN = (size_t)st.maxn, M = (size_t)st.m, G = (size_t)st.grid, W = (size_t)st.n_gwarps;
     bool ok = dalloc(s, &st.A, (size_t)st.ld)
         && dalloc(s, &st.f_split_var, M * MN) && dalloc(s, &st.f_thr32, M * MN) && dalloc(s, &st.f_split_val, M * MN)
-        && dalloc(s, &st.f_leaf_val, M * MN) && dalloc(s, &st.f_size, M)
+        && dalloc(s, &st.f_leaf_val, M * MN) && dalloc(s, &st.f_size, M) && dalloc(s, &st.f_internal, M)
         && dalloc(s, &st.pt_split_var, 2 * S * MN) && dalloc(s, &st.pt_thr32, 2 * S * MN) && dalloc(s, &st.pt_split_val, 2 * S * MN)
         && dalloc(s, &st.pt_leaf_val, 2 * S * MN) && dalloc(s, &st.pt_seg_off, 2 * S * MN) && dalloc(s, &st.pt_cnt, 2 * S * MN)
         && dalloc(s, &st.pt_So, 2 * S * MN) && dalloc(s, &st.pt_Sr, 2 * S * MN) && dalloc(s, &st.pt_g, 2 * S * MN)
@@ -466,8 +468,9 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
     Sampler* s = &h->s;
     if (!key || !value) { s->err = "null option"; return 1; }
     if (std::strcmp(key, "driver") == 0) {
-        if (std::strcmp(value, "persistent") == 0) { s->stepwise = false; return 0; }
-        if (std::strcmp(value, "stepwise") == 0) { s->stepwise = true; return 0; }
+        if (std::strcmp(value, "persistent") == 0) { s->stepwise = false; s->stepwise_fast = false; return 0; }
+        if (std::strcmp(value, "stepwise") == 0) { s->stepwise = true; s->stepwise_fast = false; return 0; }
+        if (std::strcmp(value, "stepwise_fast") == 0) { s->stepwise = true; s->stepwise_fast = true; return 0; }
         s->err = "driver must be 'persistent' or 'stepwise'";
         return 1;
     }
@@ -501,6 +504,14 @@ int pgbart_get_counters(pgbart_handle h, double* out8) {
     out8[5] = (double)ms * 1000.0;
     out8[6] = (double)s->st.grid;
     out8[7] = (double)s->smem;
+    return 0;
+}
+
+int pgbart_get_profile(pgbart_handle h, double* out32) {
+    Sampler* s = &h->s;
+    if (!fetch_ctrl(s)) return 2;
+    for (int i = 0; i < 32; ++i) out32[i] = (double)s->host_ctrl.prof[i];
+    for (int i = 0; i < 16; ++i) out32[32 + i] = (double)s->host_ctrl.prof2[i];
     return 0;
 }
 

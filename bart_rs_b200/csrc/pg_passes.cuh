@@ -34,12 +34,34 @@ struct PgTreeSm {
     double leaf_val[PG_TREE_SM];
 };
 
+struct PgFastSm {          // scratch of the latency-organised serial section (pg_serial_fast.cuh), P <= 32
+    PgCtrl lc;                                   // working copy of the control block
+    double hw[32], hG[64];                       // slot scalars: weights; [2][S] particle log-lik sums
+    int hmut[32], hanc[32], hsjob[32], hsize[64], hqh[64], hqt[64];
+    int jslot[32], jnode[32], jvar[32];          // job list of the pass that just ran
+    unsigned jseg[32], jlen[32];
+    float jthr[32];
+    double jsplit[32];
+    double rSo[32], rSr[32], rllL[32], rllR[32]; // reduced per-job partials
+    double tot[4];
+    unsigned rCnt[32], rMin[32], rMax[32];
+    double wsA[PG_WARPS][32], wsB[PG_WARPS][32], wsT[PG_WARPS][4];   // per-warp stage of the reduction
+    unsigned wsC[PG_WARPS][32], wsD[PG_WARPS][32];
+    int sn;
+    unsigned scan[PG_THREADS + 1];
+};
+
 struct PgSmem {
     PgTreeSm tadd, tsub;
     double tot[PG_WARPS][4];
+    PgFastSm fast;
+    double cthr[16];       // depth-prior thresholds (staged once per kernel)
+    int cstaged;           // split prior / column min-max are staged in the dynamic area
     int is_last;
     // followed by dynamic arrays, see pg_smem_* accessors
 };
+
+#define FW_MAXP 512   // split prior / column min-max staged in shared memory up to this many columns
 
 // dynamic shared memory layout after PgSmem (all sized by S):
 //   int   jvar[S]; float jthr[S]; int jorder[S]; int grp[S+1]; double jvL[S]; double jvR[S];
@@ -53,6 +75,8 @@ __host__ __device__ inline size_t pg_smem_bytes(int S) {
     b += (size_t)S * 16;                       // jvL, jvR
     b += (size_t)PG_WARPS * S * (8 + 8 + 4);   // accA, accB, accC
     b += (size_t)S * 8;                        // mmin, mmax
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)FW_MAXP * (8 + 4 + 4);        // cprior, cmin, cmax
     return b + 64;
 }
 
@@ -60,6 +84,7 @@ struct PgSmemView {
     PgSmem* base;
     int* jvar; float* jthr; int* jorder; int* grp; double* jvL; double* jvR;
     double* accA; double* accB; unsigned* accC; unsigned* mmin; unsigned* mmax;
+    double* cprior; float* cmin; float* cmax;
 };
 
 __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
@@ -76,7 +101,11 @@ __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
     v.jvar = reinterpret_cast<int*>(raw + off); off += (size_t)S * 4;
     v.jthr = reinterpret_cast<float*>(raw + off); off += (size_t)S * 4;
     v.jorder = reinterpret_cast<int*>(raw + off); off += (size_t)S * 4;
-    v.grp = reinterpret_cast<int*>(raw + off);
+    v.grp = reinterpret_cast<int*>(raw + off); off += (size_t)(S + 1) * 4;
+    off = (off + 15) & ~(size_t)15;
+    v.cprior = reinterpret_cast<double*>(raw + off); off += (size_t)FW_MAXP * 8;
+    v.cmin = reinterpret_cast<float*>(raw + off); off += (size_t)FW_MAXP * 4;
+    v.cmax = reinterpret_cast<float*>(raw + off);
     return v;
 }
 

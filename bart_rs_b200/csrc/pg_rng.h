@@ -44,10 +44,10 @@ PG_HD void pg_philox_pair(const PgState& st, int kind, unsigned long long upd, i
 }
 
 // Address of a tape entry, or null (and the error flag raised) when out of range.
-PG_HD const double* pg_tape_at(const PgState& st, int kind, unsigned long long upd, int round, int slot) {
-    if (upd < st.tape_base_upd) { st.ctrl->error = PG_ERR_TAPE; return 0; }
+PG_HD const double* pg_tape_at(const PgState& st, PgCtrl* c, int kind, unsigned long long upd, int round, int slot) {
+    if (upd < st.tape_base_upd) { c->error = PG_ERR_TAPE; return 0; }
     const unsigned long long u = upd - st.tape_base_upd;
-    if ((long long)u >= st.tape_n_upd || round >= st.tape_r_cap) { st.ctrl->error = PG_ERR_TAPE; return 0; }
+    if ((long long)u >= st.tape_n_upd || round >= st.tape_r_cap) { c->error = PG_ERR_TAPE; return 0; }
     if (kind <= PG_D_ZRIGHT)
         return st.tape_slot + (((u * (unsigned long long)st.tape_r_cap + (unsigned long long)round) * (unsigned long long)st.S
                                 + (unsigned long long)slot) * 5ull + (unsigned long long)kind);
@@ -55,9 +55,10 @@ PG_HD const double* pg_tape_at(const PgState& st, int kind, unsigned long long u
     return st.tape_upd + u;
 }
 
-PG_HD double pg_uniform(const PgState& st, int kind, unsigned long long upd, int round, int slot) {
+// `c` = the control block to flag errors in (the global one, or the serial section's working copy)
+PG_HD double pg_uniform(const PgState& st, PgCtrl* c, int kind, unsigned long long upd, int round, int slot) {
     if (st.rng_mode == PG_RNG_TAPE) {
-        const double* p = pg_tape_at(st, kind, upd, round, slot);
+        const double* p = pg_tape_at(st, c, kind, upd, round, slot);
         return p ? *p : 0.0;
     }
     double ua, ub;
@@ -65,9 +66,9 @@ PG_HD double pg_uniform(const PgState& st, int kind, unsigned long long upd, int
     return ua;
 }
 
-PG_HD double pg_normal(const PgState& st, int kind, unsigned long long upd, int round, int slot) {
+PG_HD double pg_normal(const PgState& st, PgCtrl* c, int kind, unsigned long long upd, int round, int slot) {
     if (st.rng_mode == PG_RNG_TAPE) {
-        const double* p = pg_tape_at(st, kind, upd, round, slot);
+        const double* p = pg_tape_at(st, c, kind, upd, round, slot);
         return p ? *p : 0.0;
     }
     double ua, ub;
@@ -78,10 +79,10 @@ PG_HD double pg_normal(const PgState& st, int kind, unsigned long long upd, int 
 // Split value: lo + u3 (hi - lo) with separately rounded multiply and add (the
 // reference's `value0_1 * scale + low` is never contracted), redrawn while the
 // result is not below hi (rand's UniformFloat::sample_single).
-PG_HD double pg_split_draw(const PgState& st, unsigned long long upd, int round, int slot, double lo, double hi) {
+PG_HD double pg_split_draw(const PgState& st, PgCtrl* c, unsigned long long upd, int round, int slot, double lo, double hi) {
     const double scale = hi - lo;
     if (st.rng_mode == PG_RNG_TAPE) {
-        const double* p = pg_tape_at(st, PG_D_SPLIT, upd, round, slot);
+        const double* p = pg_tape_at(st, c, PG_D_SPLIT, upd, round, slot);
         const double u = p ? *p : 0.0;
 #if defined(__CUDA_ARCH__)
         const double r = __dadd_rn(__dmul_rn(u, scale), lo);
@@ -89,7 +90,7 @@ PG_HD double pg_split_draw(const PgState& st, unsigned long long upd, int round,
         volatile double prod = u * scale;
         const double r = prod + lo;
 #endif
-        if (!(r < hi)) st.ctrl->error = PG_ERR_TAPE;
+        if (!(r < hi)) c->error = PG_ERR_TAPE;
         return r;
     }
     for (int attempt = 0; attempt < 64; ++attempt) {
@@ -105,3 +106,8 @@ PG_HD double pg_split_draw(const PgState& st, unsigned long long upd, int round,
     }
     return lo;
 }
+
+// convenience forms on the global control block
+PG_HD double pg_uniform(const PgState& st, int kind, unsigned long long upd, int round, int slot) { return pg_uniform(st, st.ctrl, kind, upd, round, slot); }
+PG_HD double pg_normal(const PgState& st, int kind, unsigned long long upd, int round, int slot) { return pg_normal(st, st.ctrl, kind, upd, round, slot); }
+PG_HD double pg_split_draw(const PgState& st, unsigned long long upd, int round, int slot, double lo, double hi) { return pg_split_draw(st, st.ctrl, upd, round, slot, lo, hi); }

@@ -45,12 +45,13 @@ PG_HD size_t pg_tix(const PgState& st, int buf, int s, int node) {
 }
 PG_HD int pg_six(const PgState& st, int buf, int s) { return buf * st.S + s; }
 
-PG_HD double* pg_trace_slot(const PgState& st, int round, int s) {
+PG_HD double* pg_trace_slot(const PgState& st, PgCtrl* c, int round, int s) {
     if (!st.tr_slot) return 0;
-    PgCtrl* c = st.ctrl;
     if ((long long)c->trace_n >= st.tr_u_cap || round >= st.tr_r_cap) { c->trace_overflow = 1; return 0; }
     return st.tr_slot + (((size_t)c->trace_n * (size_t)st.tr_r_cap + (size_t)round) * (size_t)st.S + (size_t)s) * PG_TS_FIELDS;
 }
+
+PG_HD double* pg_trace_slot(const PgState& st, int round, int s) { return pg_trace_slot(st, st.ctrl, round, s); }
 
 // Separately rounded a*b + c (the reference is Rust: no FMA contraction).
 PG_HD double pg_mul_add(double a, double b, double c) {
@@ -183,8 +184,7 @@ PG_HDN inline void pg_compact_jobs_single(const PgState& st) {
 
 // job_order: permutation with the jobs of one index segment adjacent (first-seen order);
 // grp_first: group boundaries in job_order.  J is small (<= S).
-PG_HDN inline void pg_group_jobs_single(const PgState& st) {
-    PgCtrl* c = st.ctrl;
+PG_HDN inline void pg_group_jobs_single(const PgState& st, PgCtrl* c) {
     const int J = c->n_jobs;
     int G = 0, filled = 0;
     bool one = true;   // common case (round 1, or all slots copies of one ancestor): a single segment
@@ -209,6 +209,8 @@ PG_HDN inline void pg_group_jobs_single(const PgState& st) {
     st.grp_first[G] = filled;
     c->n_groups = G;
 }
+
+PG_HDN inline void pg_group_jobs_single(const PgState& st) { pg_group_jobs_single(st, st.ctrl); }
 
 PG_HDN inline int pg_count_unique_vars(const PgState& st) {
     const int J = st.ctrl->n_jobs;
@@ -715,6 +717,8 @@ PG_HDN inline void pg_s_finalize(const PgState& st, const PgTeam& tm) {
             if (st.f_split_var[fb + i] < 0) { const int d = pg_depth_of(i); depth = d > depth ? d : depth; }
         if (c->info_n < st.m) st.info_depths[c->info_n] = (unsigned char)depth;
         c->info_n += 1;
+        st.f_internal[t] = pg_tree_internal_nodes(st, t);
+        c->t_add_internal = st.f_internal[t];
         if (st.tr_upd && (long long)c->trace_n < st.tr_u_cap) c->trace_n += 1;
         c->upd += 1;
         c->n_updates += 1;

@@ -10,72 +10,113 @@
 #include <cooperative_groups.h>
 #include <cstdio>
 #include "pg_passes.cuh"
+#include "pg_serial_fast.cuh"
 #include "pg_sweep.h"
 
 namespace cg = cooperative_groups;
 
-__device__ __forceinline__ unsigned pg_ld_acquire(const unsigned* p) {
+// Polling load: relaxed at gpu scope (served by L2, does not touch this SM's L1); the acquire is one
+// fence after the flag has flipped, so a spinning block does not keep invalidating the L1 that the
+// serial section running on the same SM depends on.
+__device__ __forceinline__ unsigned pg_ld_relaxed(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void pg_st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Grid barrier whose last arriver runs the serial section before releasing the others.
-// `gen` counts barriers passed by this block since kernel start (bar_count/bar_gen are zeroed by
-// pg_prepare_step before every launch).  A watchdog turns a lost block into an error, not a hang.
-__device__ void pg_barrier_serial(const PgState& st, PgSmem* sm, unsigned& gen) {
+__device__ __forceinline__ void pg_spin_until(const unsigned* p, unsigned target, PgCtrl* c) {
+    const long long t0 = clock64();
+    unsigned ns = 20;
+    while (pg_ld_relaxed(p) < target) {
+        __nanosleep(ns);
+        if (ns < 160) ns <<= 1;
+        if (clock64() - t0 > 40000000000ll) {   // ~20 s at 2 GHz: a lost block becomes an error, not a hang
+            c->error = PG_ERR_WATCHDOG;
+            __threadfence();
+            __trap();
+        }
+    }
+    __threadfence();   // acquire side of the fence/atomic/fence pattern
+}
+
+// Grid barrier with a serial section.  Block 0 is ALWAYS the serial block: its SM keeps the (large,
+// straight-line) control code in its instruction caches, which is what the section's latency is made of.
+// Other blocks arrive (release fence + counter) and wait for the generation flag; block 0 waits for the
+// counter, runs the serial section, publishes, and flips the flag.  `gen` counts barriers since launch
+// (bar_count / bar_gen are zeroed by pg_prepare_step).  phase / J describe the pass that just ended.
+template <bool FAST>
+__device__ void pg_barrier_serial(const PgState& st, const PgSmemView& smv, unsigned& gen, int phase, int J) {
     PgCtrl* c = st.ctrl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned ticket = atomicAdd(&c->bar_count, 1u);
-        sm->is_last = (ticket == (gen + 1u) * gridDim.x - 1u) ? 1 : 0;
-    }
-    __syncthreads();
-    if (sm->is_last) {
-        __threadfence();
-        PgTeam tm{(int)threadIdx.x, (int)blockDim.x};
-        pg_serial(st, tm);
+    if (blockIdx.x != 0) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&c->bar_count, 1u);
+            pg_spin_until(&c->bar_gen, gen + 1u, c);
+        }
+        __syncthreads();
+    } else {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            pg_spin_until(&c->bar_count, (gen + 1u) * (gridDim.x - 1u), c);
+        }
+        __syncthreads();
+        if (FAST) pg_serial_fast(st, smv, phase, J);   // latency-organised control logic (one lane per particle)
+        else {                                         // generic team version (P > 32)
+            PgTeam tm{(int)threadIdx.x, (int)blockDim.x};
+            const long long ts = clock64();
+            pg_serial(st, tm);
+            if (threadIdx.x == 0) c->prof[16 + (phase & 7)] += (unsigned long long)(clock64() - ts);
+        }
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) pg_st_release(&c->bar_gen, gen + 1u);
-    } else {
-        if (threadIdx.x == 0) {
-            const long long t0 = clock64();
-            unsigned ns = 32;
-            while (pg_ld_acquire(&c->bar_gen) < gen + 1u) {
-                __nanosleep(ns);
-                if (ns < 256) ns <<= 1;
-                if (clock64() - t0 > 40000000000ll) {   // ~20 s at 2 GHz
-                    c->error = PG_ERR_WATCHDOG;
-                    __threadfence();
-                    __trap();
-                }
-            }
-            __threadfence();
-        }
-        __syncthreads();
     }
     gen += 1u;
 }
 
-extern "C" __global__ void __launch_bounds__(PG_THREADS, 2) pg_sweep_persistent(const PgState st) {
+template <bool FAST>
+__device__ __forceinline__ void pg_sweep_body(const PgState& st) {
     extern __shared__ __align__(16) unsigned char pg_smem_raw[];
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
+    // sampler constants the serial section reads: staged once per launch
+    for (int i = threadIdx.x; i < st.max_depth + 2 && i < 16; i += blockDim.x) sm.base->cthr[i] = st.thr_depth[i];
+    if (threadIdx.x == 0) sm.base->cstaged = (st.p <= FW_MAXP && st.max_depth + 2 <= 16) ? 1 : 0;
+    if (st.p <= FW_MAXP)
+        for (int i = threadIdx.x; i < st.p; i += blockDim.x) {
+            sm.cprior[i] = st.prior ? st.prior[i] : 0.0;
+            sm.cmin[i] = st.col_min[i];
+            sm.cmax[i] = st.col_max[i];
+        }
+    __syncthreads();
     unsigned gen = 0;
-    pg_barrier_serial(st, sm.base, gen);   // serial section of PH_BEGIN prepares the first pass
+    pg_barrier_serial<FAST>(st, sm, gen, PH_BEGIN, 0);   // serial section of PH_BEGIN prepares the first pass
     for (;;) {
         const int phase = __ldcg(&st.ctrl->phase);
+        const int J = __ldcg(&st.ctrl->n_jobs);
         if (phase == PH_DONE) break;
+        const long long t0 = clock64();
         pg_run_pass(st, sm, phase);
-        pg_barrier_serial(st, sm.base, gen);
+        __syncthreads();
+        const long long t1 = clock64();
+        pg_barrier_serial<FAST>(st, sm, gen, phase, J);
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // stopwatch kept by a block that never runs the serial section
+            PgCtrl* c = st.ctrl;
+            c->prof[phase & 7] += (unsigned long long)(t1 - t0);
+            c->prof[8 + (phase & 7)] += (unsigned long long)(clock64() - t1);
+            c->prof[24 + (phase & 7)] += 1ull;
+        }
     }
 }
 
-extern "C" __global__ void __launch_bounds__(PG_THREADS, 2) pg_phase_kernel(const PgState st) {
+// P <= 32: latency-organised serial section; P > 32: generic team serial section.
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent(const PgState st) { pg_sweep_body<true>(st); }
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_generic(const PgState st) { pg_sweep_body<false>(st); }
+
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_phase_kernel(const PgState st) {
     extern __shared__ __align__(16) unsigned char pg_smem_raw[];
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     pg_run_pass(st, sm, __ldcg(&st.ctrl->phase));
@@ -84,6 +125,22 @@ extern "C" __global__ void __launch_bounds__(PG_THREADS, 2) pg_phase_kernel(cons
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_serial_kernel(const PgState st) {
     PgTeam tm{(int)threadIdx.x, (int)blockDim.x};
     pg_serial(st, tm);
+}
+
+// stepwise driver with the latency-organised serial section (isolates it for profiling)
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_serial_fast_kernel(const PgState st, int first) {
+    extern __shared__ __align__(16) unsigned char pg_smem_raw[];
+    const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
+    for (int i = threadIdx.x; i < st.max_depth + 2 && i < 16; i += blockDim.x) sm.base->cthr[i] = st.thr_depth[i];
+    if (threadIdx.x == 0) sm.base->cstaged = (st.p <= FW_MAXP && st.max_depth + 2 <= 16) ? 1 : 0;
+    if (st.p <= FW_MAXP)
+        for (int i = threadIdx.x; i < st.p; i += blockDim.x) {
+            sm.cprior[i] = st.prior ? st.prior[i] : 0.0;
+            sm.cmin[i] = st.col_min[i];
+            sm.cmax[i] = st.col_max[i];
+        }
+    __syncthreads();
+    pg_serial_fast(st, sm, first ? PH_BEGIN : __ldcg(&st.ctrl->phase), first ? 0 : __ldcg(&st.ctrl->n_jobs));
 }
 
 extern "C" __global__ void pg_prepare_step(const PgState st, int tune) {
@@ -135,13 +192,15 @@ int pg_query_grid(int device, int S, int* grid_out, size_t* smem_out, char* err,
     const size_t smem = pg_smem_bytes(S);
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(pg_sweep_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_sweep_persistent_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_serial_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { snprintf(err, errlen, "shared memory request %zu B: %s", smem, cudaGetErrorString(e)); return 1; }
     }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_sweep_persistent, PG_THREADS, smem);
     if (e != cudaSuccess || per_sm < 1) { snprintf(err, errlen, "occupancy query failed: %s", cudaGetErrorString(e)); return 1; }
-    if (per_sm > 2) per_sm = 2;
+    if (per_sm > 1) per_sm = 1;   // one 512-thread block per SM: 148 partials per pass for the serial reduce
     if (!prop.cooperativeLaunch) { snprintf(err, errlen, "device lacks cooperative launch"); return 1; }
     *grid_out = per_sm * prop.multiProcessorCount;
     *smem_out = smem;
@@ -155,7 +214,8 @@ cudaError_t pg_launch_prepare(const PgState& st, int tune, cudaStream_t s) {
 
 cudaError_t pg_launch_persistent(const PgState& st, size_t smem, cudaStream_t s) {
     void* args[] = {(void*)&st};
-    return cudaLaunchCooperativeKernel((void*)pg_sweep_persistent, dim3(st.grid), dim3(PG_THREADS), args, smem, s);
+    void* fn = st.P <= 32 ? (void*)pg_sweep_persistent : (void*)pg_sweep_persistent_generic;
+    return cudaLaunchCooperativeKernel(fn, dim3(st.grid), dim3(PG_THREADS), args, smem, s);
 }
 
 cudaError_t pg_launch_phase(const PgState& st, size_t smem, cudaStream_t s) {
@@ -165,6 +225,11 @@ cudaError_t pg_launch_phase(const PgState& st, size_t smem, cudaStream_t s) {
 
 cudaError_t pg_launch_serial(const PgState& st, cudaStream_t s) {
     pg_serial_kernel<<<1, PG_THREADS, 0, s>>>(st);
+    return cudaGetLastError();
+}
+
+cudaError_t pg_launch_serial_fast(const PgState& st, size_t smem, int first, cudaStream_t s) {
+    pg_serial_fast_kernel<<<1, PG_THREADS, smem, s>>>(st, first);
     return cudaGetLastError();
 }
 

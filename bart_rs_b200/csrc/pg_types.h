@@ -54,7 +54,7 @@ enum PgError : int {
 #define PG_SEG_IDENTITY 0xFFFFFFFFu  // node's samples are 0..n (root): no index list is read
 #define PG_SEG_NONE 0xFFFFFFFEu      // children not materialised yet
 #define PG_TS_FIELDS 12
-#define PG_THREADS 256
+#define PG_THREADS 512
 #define PG_WARPS (PG_THREADS / 32)
 
 struct PgCtrl {
@@ -73,6 +73,8 @@ struct PgCtrl {
     int error;
     int snext;        // next serial sub-step (PgSerialNext), SN_NONE = run the grid pass `phase`
     int max_size;     // largest slot tree size (bounds the resampling copy)
+    int t_add_internal;   // internal nodes of tree t_add (bytes accounting)
+    int pad1;
     unsigned long long upd;       // tree-update counter since creation (RNG coordinate)
     unsigned long long pool_top;
     int next_tree_idx;
@@ -95,6 +97,13 @@ struct PgCtrl {
     unsigned long long trace_n;         // tree updates recorded in the trace
     int trace_overflow;
     int pad0;
+    // ---- in-kernel stopwatch (SM cycles): [0..7] pass time by phase (block 0), [8..15] pass end -> barrier exit
+    // (block 0: wait for the slowest block + serial section), [16..23] serial section alone (last arriver),
+    // [24..31] number of passes by phase
+    unsigned long long prof[32];
+    // serial-section breakdown (cycles / calls): 0 reduce, 1 after_stats, 2 after_minmax, 3 finish_round, 4 prep_part,
+    // 5 finalize, 6 begin_update, 7 draw_round; [8..15] call counts
+    unsigned long long prof2[16];
     // ---- grid barrier
     unsigned int bar_count;
     unsigned int bar_pad[31];
@@ -123,6 +132,7 @@ struct PgState {
     double lik_sigma;
     // forest
     int* f_split_var; float* f_thr32; double* f_split_val; double* f_leaf_val; int* f_size;
+    int* f_internal;             // [m] number of internal nodes per forest tree
     // particle slot tables, [2][S][maxn] / [2][S]
     int* pt_split_var; float* pt_thr32; double* pt_split_val; double* pt_leaf_val;
     unsigned int* pt_seg_off; unsigned int* pt_cnt;

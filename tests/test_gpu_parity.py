@@ -143,5 +143,5 @@ def test_gpu_large_n_properties():
         np.testing.assert_allclose(pred, total, rtol=1e-9)
         outs.append(pred)
         dev.close()
-    np.testing.assert_array_equal(outs[0], outs[1])
-    np.testing.assert_array_equal(outs[0], outs[2])
+    np.testing.assert_array_equal(outs[0], outs[1])              # run-to-run bit reproducibility
+    np.testing.assert_allclose(outs[0], outs[2], rtol=1e-9)       # stepwise driver: generic serial code, other reduction order
