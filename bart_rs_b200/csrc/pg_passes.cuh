@@ -26,6 +26,10 @@
 #define PG_TREE_SM 63      // tree nodes staged in shared memory (depth <= 5); larger trees read global
 #define PG_FULL 0xFFFFFFFFu
 
+// Index of this block among the PASS blocks (st.grid of them).  In the persistent kernel block 0 is the serial
+// block and streams nothing (its SM keeps the control code in its instruction caches), so pass block = blockIdx - 1.
+#define PG_BID (sm.base->pass_bid)
+
 struct PgTreeSm {
     int size;
     int from_global;       // tree too large for shared memory
@@ -34,19 +38,35 @@ struct PgTreeSm {
     double leaf_val[PG_TREE_SM];
 };
 
-struct PgFastSm {          // scratch of the latency-organised serial section (pg_serial_fast.cuh), P <= 32
+#define FW_DR 4            // SMC rounds whose data-independent draws are precomputed per tree update
+
+struct PgFastSm {          // state of the latency-organised serial section (pg_serial_fast.cuh), P <= 32.
+    // Lives in block 0's shared memory for the whole kernel: loaded at launch, stored at exit.
     PgCtrl lc;                                   // working copy of the control block
     double hw[32], hG[64];                       // slot scalars: weights; [2][S] particle log-lik sums
     int hmut[32], hanc[32], hsjob[32], hsize[64], hqh[64], hqt[64];
-    int jslot[32], jnode[32], jvar[32];          // job list of the pass that just ran
+    int jslot[32], jnode[32], jvar[32];          // job list of the current round
     unsigned jseg[32], jlen[32];
     float jthr[32];
     double jsplit[32];
+    // round-0 proposals' results, kept in registers/shared memory until resampling decides who survives
+    double jr_vL[32], jr_vR[32], jr_gL[32], jr_gR[32], jr_SoL[32], jr_SrL[32];
+    unsigned jr_cL[32];
     double rSo[32], rSr[32], rllL[32], rllR[32]; // reduced per-job partials
     double tot[4];
     unsigned rCnt[32], rMin[32], rMax[32];
     double wsA[PG_WARPS][32], wsB[PG_WARPS][32], wsT[PG_WARPS][4];   // per-warp stage of the reduction
     unsigned wsC[PG_WARPS][32], wsD[PG_WARPS][32];
+    // draws precomputed by idle warps: [update parity][round][slot]
+    double d_u1[2][FW_DR][32], d_u3[2][FW_DR][32], d_zL[2][FW_DR][32], d_zR[2][FW_DR][32];
+    int d_var[2][FW_DR][32];
+    double d_u6[2][FW_DR], d_u7[2];
+    int d_ok[2][FW_DR + 1];                      // draw source in range for (round) / for u7
+    int d0_status[2][32];                        // complete round-0 proposal: 1 depth reject, 3 min>=max, 5 live, 6 tape error, 7 depth error
+    float d0_lo[2][32], d0_hi[2][32], d0_thr[2][32];
+    double d0_split[2][32];
+    unsigned long long d_upd[2];                 // which tree update each buffer holds
+    volatile unsigned long long d_flag[2][FW_DR + 1];   // per helper warp: token (= update + 1) when its part is written
     int sn;
     unsigned scan[PG_THREADS + 1];
 };
@@ -57,6 +77,7 @@ struct PgSmem {
     PgFastSm fast;
     double cthr[16];       // depth-prior thresholds (staged once per kernel)
     int cstaged;           // split prior / column min-max are staged in the dynamic area
+    int pass_bid;          // this block's index among the pass blocks (-1: serial-only block)
     int is_last;
     // followed by dynamic arrays, see pg_smem_* accessors
 };
@@ -198,12 +219,12 @@ __device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgSmemView
         unsigned cc = 0u;
         for (int w = 0; w < PG_WARPS; ++w) { a += sm.accA[w * S + j]; b += sm.accB[w * S + j]; cc += sm.accC[w * S + j]; }
         double* dst = as_ll ? st.part_ll : st.part_sum;
-        dst[((size_t)blockIdx.x * S + j) * 2 + 0] = a;
-        dst[((size_t)blockIdx.x * S + j) * 2 + 1] = b;
+        dst[((size_t)PG_BID * S + j) * 2 + 0] = a;
+        dst[((size_t)PG_BID * S + j) * 2 + 1] = b;
         if (counts) {
-            st.part_ccnt[(size_t)blockIdx.x * S + j] = cc;
+            st.part_ccnt[(size_t)PG_BID * S + j] = cc;
             for (int w = 0; w < PG_WARPS; ++w)
-                st.part_cnt[((size_t)blockIdx.x * PG_WARPS + w) * S + j] = sm.accC[w * S + j];
+                st.part_cnt[((size_t)PG_BID * PG_WARPS + w) * S + j] = sm.accC[w * S + j];
         }
     }
 }
@@ -219,7 +240,7 @@ __device__ void pg_pass_root(const PgState& st, const PgSmemView& sm) {
     const int t_add = __ldcg(&c->t_add), t_sub = __ldcg(&c->phase) == PH_ROOT ? __ldcg(&c->t_sub) : -1;
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * PG_WARPS + warp;
+    const int gw = PG_BID * PG_WARPS + warp;
 
     pg_stage_tree(st, t_add, sm.base->tadd);
     pg_stage_tree(st, t_sub, sm.base->tsub);
@@ -342,7 +363,7 @@ __device__ void pg_pass_root(const PgState& st, const PgSmemView& sm) {
     if (threadIdx.x < 4) {
         double v = 0.0;
         for (int w = 0; w < PG_WARPS; ++w) v += sm.base->tot[w][threadIdx.x];
-        st.part_tot[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+        st.part_tot[(size_t)PG_BID * 4 + threadIdx.x] = v;
     }
     pg_flush_acc(st, sm, J, true, false);
 }
@@ -355,7 +376,7 @@ __device__ void pg_pass_minmax(const PgState& st, const PgSmemView& sm) {
     const int J = __ldcg(&c->n_jobs);
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * PG_WARPS + warp;
+    const int gw = PG_BID * PG_WARPS + warp;
     for (int j = threadIdx.x; j < J; j += blockDim.x) { sm.mmin[j] = 0xFFFFFFFFu; sm.mmax[j] = 0u; sm.jvar[j] = __ldcg(&st.job_var[j]); }
     __syncthreads();
     const size_t ld = (size_t)st.ld;
@@ -380,8 +401,8 @@ __device__ void pg_pass_minmax(const PgState& st, const PgSmemView& sm) {
     }
     __syncthreads();
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
-        st.part_mm[((size_t)blockIdx.x * S + j) * 2 + 0] = sm.mmin[j];
-        st.part_mm[((size_t)blockIdx.x * S + j) * 2 + 1] = sm.mmax[j];
+        st.part_mm[((size_t)PG_BID * S + j) * 2 + 0] = sm.mmin[j];
+        st.part_mm[((size_t)PG_BID * S + j) * 2 + 1] = sm.mmax[j];
     }
 }
 
@@ -396,7 +417,7 @@ __device__ void pg_pass_seg(const PgState& st, const PgSmemView& sm) {
     const int J = __ldcg(&c->n_jobs), G = __ldcg(&c->n_groups);
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * PG_WARPS + warp;
+    const int gw = PG_BID * PG_WARPS + warp;
     pg_stage_jobs(st, sm, J, G, MODE == 1);
     pg_zero_acc(sm, S);
     __syncthreads();
@@ -479,7 +500,7 @@ __device__ void pg_pass_part(const PgState& st, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     const int K = __ldcg(&c->n_pjobs);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * PG_WARPS + warp;
+    const int gw = PG_BID * PG_WARPS + warp;
     const unsigned lt_mask = (1u << lane) - 1u;
     const size_t ld = (size_t)st.ld;
     for (int k = 0; k < K; ++k) {

@@ -1,27 +1,30 @@
-// pg_serial_fast.cuh — latency-organised serial section for the persistent kernel (P <= 32).
+// pg_serial_fast.cuh — latency-organised serial section of the persistent kernel (P <= 32).
 //
-// Same state machine and the same arithmetic as pg_serial.h (which stays the reference
-// implementation: host simulation, stepwise driver, P > 32).  What differs is WHERE the state lives
-// while the section runs, because every dependent global load here costs ~0.35 us (an L2 round trip
-// at 1.97 GHz) and nothing else is running on the GPU meanwhile:
-//   * PgCtrl, the per-slot scalars (w, mutated, anc, slot_job, size, queue head/tail, G), the job list
-//     of the pass that just ran, and the sampler constants (depth-prior table, split prior, column
-//     min/max) are staged in shared memory: one batch of loads at entry, one batch of stores at exit.
-//     The generic helpers of pg_serial.h run unchanged on a PgState copy whose pointers are redirected
-//     to those shared arrays.
-//   * per-block partials are reduced with lane = job, warp = block subset: every load of the
-//     reduction is in flight at once (one L2 round trip), then a fixed-order combine.
-//   * one lane per particle slot / per job; the order-sensitive loops of the reference
-//       normalize_weights_inplace  smc.rs:257-268  (sequential sum)
-//       systematic resampling      resampling.rs:24-44 (sequential cumulative walk)
-//       WeightedIndex              smc.rs:113-114
+// Same state machine and arithmetic as pg_serial.h (the generic implementation used by the host
+// simulation, the stepwise driver and P > 32).  ncu on the isolated section showed it is bound by
+// INSTRUCTION FETCH (~7 stall cycles per instruction on `no_instruction`: ~9k cold, straight-line
+// instructions executed once) and by dependent L2 round trips (~0.35 us each), so this version is
+// organised around executing few instructions and touching global memory rarely:
+//   * Block 0 is always the serial block and keeps PgCtrl, the per-slot scalars and the job list in
+//     its shared memory for the whole kernel (loaded at launch, stored at exit); after each section
+//     it publishes only the few words the grid passes read.
+//   * Everything that does not depend on the data — the Philox/tape draws of the next tree update
+//     (depth-prior uniforms, split variables, split fractions, leaf normals, resampling and
+//     selection uniforms) and, for round 0, the complete proposals (the root's column min/max are
+//     constants) — is computed by otherwise idle warps (1..FW_DR+1) while warp 0 runs the logic.
+//   * Round 0 is table-free: proposals' results stay in shared memory; per-slot node tables are only
+//     written for particles that survive resampling after growing (the reference's stale-weight rule,
+//     Q1, kills grown particles in 62 % of updates, which then end as a stump without touching a table).
+//   * One lane per particle slot / per job; the order-sensitive loops of the reference
+//       normalize_weights_inplace smc.rs:257-268, systematic resampling resampling.rs:24-44,
+//       WeightedIndex smc.rs:113-114
 //     keep the reference's summation order through warp-uniform loops over shuffle broadcasts.
+//   * Loops are kept rolled (#pragma unroll 1): code bytes, not instruction count, are the cost.
 #pragma once
 #include <cstddef>
 #include "pg_passes.cuh"
 
-// Where the section's hot state lives while it runs (shared memory) — passed by value, stays in registers.
-struct FwCx {
+struct FwCx {               // passed by value: stays in registers
     PgFastSm* f;
     PgCtrl* c;              // working copy of the control block (f->lc)
     const double* thr;      // depth-prior thresholds
@@ -31,22 +34,60 @@ struct FwCx {
 
 __device__ __forceinline__ double fw_sum_seq(double v, int n) {   // lanes 0..n-1 in order; uniform result
     double acc = 0.0;
+#pragma unroll 1
     for (int k = 0; k < n; ++k) acc += __shfl_sync(PG_FULL, v, k);
     return acc;
 }
 __device__ __forceinline__ double fw_max(double v) {
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(PG_FULL, v, o));
     return v;
 }
 __device__ __forceinline__ int fw_imax(int v) { return __reduce_max_sync(PG_FULL, v); }
 
-// Number of 8-byte words of PgCtrl that the serial section owns (everything before the barrier words).
+// 8-byte words of PgCtrl owned by the serial block (everything before the barrier words).
 __device__ __forceinline__ int fw_ctrl_words() { return (int)(offsetof(PgCtrl, bar_count) / 8); }
+
+// ---- kernel-lifetime state of block 0 ----------------------------------------------------------
+__device__ void fw_load_state(const PgState& st, PgFastSm* f) {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st.ctrl);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&f->lc);
+    for (int i = threadIdx.x; i < fw_ctrl_words(); i += blockDim.x) dst[i] = __ldcg(&src[i]);
+    const int S = st.S;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        f->hw[s] = __ldcg(&st.w[s]); f->hmut[s] = __ldcg(&st.mutated[s]);
+        f->hanc[s] = __ldcg(&st.anc[s]); f->hsjob[s] = __ldcg(&st.slot_job[s]);
+    }
+    for (int s = threadIdx.x; s < 2 * S; s += blockDim.x) {
+        f->hsize[s] = __ldcg(&st.pt_size[s]); f->hqh[s] = __ldcg(&st.pt_qhead[s]);
+        f->hqt[s] = __ldcg(&st.pt_qtail[s]); f->hG[s] = __ldcg(&st.pt_G[s]);
+    }
+    if (threadIdx.x < 2) f->d_upd[threadIdx.x] = ~0ull;
+    if (threadIdx.x < 2 * (FW_DR + 1)) f->d_flag[threadIdx.x / (FW_DR + 1)][threadIdx.x % (FW_DR + 1)] = 0ull;
+}
+
+__device__ void fw_store_state(const PgState& st, PgFastSm* f) {
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(st.ctrl);
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&f->lc);
+    for (int i = threadIdx.x; i < fw_ctrl_words(); i += blockDim.x) dst[i] = src[i];
+    const int S = st.S;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        st.w[s] = f->hw[s]; st.mutated[s] = f->hmut[s]; st.anc[s] = f->hanc[s]; st.slot_job[s] = f->hsjob[s];
+    }
+    for (int s = threadIdx.x; s < 2 * S; s += blockDim.x) {
+        st.pt_size[s] = f->hsize[s]; st.pt_qhead[s] = f->hqh[s]; st.pt_qtail[s] = f->hqt[s]; st.pt_G[s] = f->hG[s];
+    }
+}
+
+// what the grid passes read: the first 16 ints of PgCtrl (phase .. max_size)
+__device__ __forceinline__ void fw_publish(const PgState& st, PgFastSm* f, int lane) {
+    if (lane < 16) reinterpret_cast<int*>(st.ctrl)[lane] = reinterpret_cast<const int*>(&f->lc)[lane];
+}
 
 // ---- stage A: reduce the pass's per-block partials --------------------------------------------
 // lane = job, warp = subset of blocks {warp, warp + PG_WARPS, ...}; rows of the [block][job] partial
-// arrays are contiguous in job, so every load is coalesced and all of a warp's loads are in flight.
-#define FW_RB 12   // blocks per warp per batch
+// arrays are contiguous in job: coalesced, and all of a warp's loads are in flight at once.
+#define FW_RB 10   // blocks per warp per batch (grid 148 / 16 warps = 9.25)
 __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = st.grid, S = st.S;
@@ -57,6 +98,7 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J) {
         double a = 0.0, bsum = 0.0;
         unsigned cc = 0u;
         if (lane < J) {
+#pragma unroll 1
             for (int b0 = warp; b0 < G; b0 += PG_WARPS * FW_RB) {
                 double2 v[FW_RB];
                 unsigned k[FW_RB];
@@ -75,11 +117,13 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J) {
         f->wsA[warp][lane] = a; f->wsB[warp][lane] = bsum; f->wsC[warp][lane] = cc;
     } else if (phase == PH_MINMAX) {
         unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
-        if (lane < J)
+        if (lane < J) {
+#pragma unroll 1
             for (int b = warp; b < G; b += PG_WARPS) {
                 const uint2 v = __ldcg(reinterpret_cast<const uint2*>(st.part_mm + ((size_t)b * S + lane) * 2));
                 kmin = min(kmin, v.x); kmax = max(kmax, v.y);
             }
+        }
         f->wsC[warp][lane] = kmin;
         f->wsD[warp][lane] = kmax;
     }
@@ -90,6 +134,7 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J) {
             const double2 v = __ldcg(reinterpret_cast<const double2*>(st.part_tot + (size_t)b * 4 + 2));
             t0 += u.x; t1 += u.y; t2 += v.x; t3 += v.y;
         }
+#pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) {
             t0 += __shfl_xor_sync(PG_FULL, t0, o); t1 += __shfl_xor_sync(PG_FULL, t1, o);
             t2 += __shfl_xor_sync(PG_FULL, t2, o); t3 += __shfl_xor_sync(PG_FULL, t3, o);
@@ -101,24 +146,120 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J) {
         if (sums && lane < J) {
             double a = 0.0, b = 0.0;
             unsigned cc = 0u;
-#pragma unroll
+#pragma unroll 1
             for (int w = 0; w < PG_WARPS; ++w) { a += f->wsA[w][lane]; b += f->wsB[w][lane]; cc += f->wsC[w][lane]; }
             if (phase == PH_BERN) { f->rllL[lane] = a; f->rllR[lane] = b; }
             else { f->rSo[lane] = a; f->rSr[lane] = b; f->rCnt[lane] = cc; }
         }
         if (phase == PH_MINMAX && lane < J) {
             unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
-#pragma unroll
+#pragma unroll 1
             for (int w = 0; w < PG_WARPS; ++w) { kmin = min(kmin, f->wsC[w][lane]); kmax = max(kmax, f->wsD[w][lane]); }
             f->rMin[lane] = kmin; f->rMax[lane] = kmax;
         }
         if (phase == PH_ROOT && lane < 4) {
             double v = 0.0;
-#pragma unroll
+#pragma unroll 1
             for (int w = 0; w < PG_WARPS; ++w) v += f->wsT[w][lane];
             f->tot[lane] = v;
         }
+        __syncwarp();
     }
+}
+
+// smc.rs:242-254 (prior in shared memory when staged), same subtraction order as the reference
+__device__ __forceinline__ int fw_feature_from_probs(const PgState& st, const double* prior, double u) {
+    double target = u * st.prior_total;
+    const int p = st.p;
+#pragma unroll 1
+    for (int j = 0; j < p; ++j) { target -= prior[j]; if (target <= 0.0) return j; }
+    return p - 1;
+}
+
+// ---- helper warps: draws of one tree update (data-independent) --------------------------------------
+__device__ __forceinline__ bool fw_tape_ok(const PgState& st, unsigned long long upd, int round) {
+    if (st.rng_mode != PG_RNG_TAPE) return true;
+    if (upd < st.tape_base_upd) return false;
+    return (long long)(upd - st.tape_base_upd) < st.tape_n_upd && round < st.tape_r_cap;
+}
+
+// warp hw (1..FW_DR): round hw-1; warp FW_DR+1: resampling / selection uniforms.  `scr` is a scratch control
+// block: helpers must not raise errors for draws that may never be consumed.
+__device__ void fw_prefetch_draws(const PgState& st, const FwCx& x, unsigned long long upd, int hw, int lane, PgCtrl* scr) {
+    PgFastSm* f = x.f;
+    const int buf = (int)(upd & 1ull);
+    const int S = st.S;
+    if (hw <= FW_DR) {
+        const int r = hw - 1;
+        const bool ok = fw_tape_ok(st, upd, r);
+        if (lane < S && ok) {
+            const int s = lane;
+            const double u1 = pg_uniform(st, scr, PG_D_GROW, upd, r, s);
+            const double u2 = pg_uniform(st, scr, PG_D_VAR, upd, r, s);
+            int var;
+            if (x.prior) var = fw_feature_from_probs(st, x.prior, u2);
+            else { var = (int)(u2 * (double)st.p); if (var > st.p - 1) var = st.p - 1; }
+            double u3;
+            if (st.rng_mode == PG_RNG_TAPE) u3 = *pg_tape_at(st, scr, PG_D_SPLIT, upd, r, s);
+            else { double ub; pg_philox_pair(st, PG_D_SPLIT, upd, r, s, 0, &u3, &ub); }
+            f->d_u1[buf][r][s] = u1; f->d_var[buf][r][s] = var; f->d_u3[buf][r][s] = u3;
+            f->d_zL[buf][r][s] = pg_normal(st, scr, PG_D_ZLEFT, upd, r, s);
+            f->d_zR[buf][r][s] = pg_normal(st, scr, PG_D_ZRIGHT, upd, r, s);
+            if (r == 0) {   // complete root proposal: splitting.rs:39-56 with the column's constant min/max
+                int status = 5;
+                float lo = 0.f, hi = 0.f, thr = 0.f;
+                double split = 0.0;
+                if (x.thr[0] > u1) status = 1;
+                else {
+                    lo = x.cmin[var]; hi = x.cmax[var];
+                    if (lo >= hi) status = 3;
+                    else if (2 >= st.maxn) status = 7;
+                    else {
+                        scr->error = PG_OK;
+                        split = pg_split_draw(st, scr, upd, 0, s, (double)lo, (double)hi);
+                        if (scr->error != PG_OK) status = 6;
+                        thr = pg_thr32(split);
+                    }
+                }
+                f->d0_status[buf][s] = status; f->d0_lo[buf][s] = lo; f->d0_hi[buf][s] = hi;
+                f->d0_thr[buf][s] = thr; f->d0_split[buf][s] = split;
+            }
+        }
+        if (lane == 0) f->d_ok[buf][r] = ok ? 1 : 0;
+    } else {
+        if (lane < FW_DR) {
+            const bool ok = fw_tape_ok(st, upd, lane);
+            f->d_u6[buf][lane] = ok ? pg_uniform(st, scr, PG_D_RESAMPLE, upd, lane, 0) : 0.0;
+        } else if (lane == FW_DR) {
+            const bool ok = fw_tape_ok(st, upd, 0);
+            f->d_u7[buf] = ok ? pg_uniform(st, scr, PG_D_SELECT, upd, 0, 0) : 0.0;
+            f->d_ok[buf][FW_DR] = ok ? 1 : 0;
+            f->d_upd[buf] = upd;
+        }
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) f->d_flag[buf][hw - 1] = upd + 1ull;
+}
+
+__device__ __forceinline__ void fw_wait_draws(PgFastSm* f, unsigned long long upd) {
+    const int buf = (int)(upd & 1ull);
+#pragma unroll 1
+    for (int q = 0; q <= FW_DR; ++q)
+        while (f->d_flag[buf][q] != upd + 1ull) __nanosleep(20);
+    __threadfence_block();
+}
+
+// draws as seen by warp 0: precomputed when in range, else the generic (error-raising) path
+__device__ __forceinline__ double fw_u6(const PgState& st, const FwCx& x, unsigned long long upd, int r) {
+    const int buf = (int)(upd & 1ull);
+    if (r < FW_DR && x.f->d_ok[buf][r]) return x.f->d_u6[buf][r];
+    return pg_uniform(st, x.c, PG_D_RESAMPLE, upd, r, 0);
+}
+__device__ __forceinline__ double fw_u7(const PgState& st, const FwCx& x, unsigned long long upd) {
+    const int buf = (int)(upd & 1ull);
+    if (x.f->d_ok[buf][FW_DR]) return x.f->d_u7[buf];
+    return pg_uniform(st, x.c, PG_D_SELECT, upd, 0, 0);
 }
 
 // ---- per-lane job view ------------------------------------------------------------------------
@@ -135,23 +276,22 @@ struct FwJob {
 __device__ __forceinline__ int fw_write_jobs(const PgState& st, const FwCx& x, const FwJob& jb, int lane, bool write_all) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
-    (void)f;
     const unsigned live = __ballot_sync(PG_FULL, jb.live);
     const int J = __popc(live);
     const int pos = __popc(live & ((1u << lane) - 1u));
-    if (lane < st.S) x.f->hsjob[lane] = -1;
+    if (lane < st.S) f->hsjob[lane] = -1;
     __syncwarp();
     if (jb.live) {
         st.job_slot[pos] = jb.slot; st.job_node[pos] = jb.node; st.job_var[pos] = jb.var;
         st.job_seg_off[pos] = jb.seg_off; st.job_len[pos] = jb.len;
-        x.f->jslot[pos] = jb.slot; x.f->jnode[pos] = jb.node; x.f->jvar[pos] = jb.var;
-        x.f->jseg[pos] = jb.seg_off; x.f->jlen[pos] = jb.len;
+        f->jslot[pos] = jb.slot; f->jnode[pos] = jb.node; f->jvar[pos] = jb.var;
+        f->jseg[pos] = jb.seg_off; f->jlen[pos] = jb.len;
         if (write_all) {
             st.job_thr32[pos] = jb.thr; st.job_split[pos] = jb.split; st.job_lo[pos] = jb.lo; st.job_hi[pos] = jb.hi;
-            x.f->jthr[pos] = jb.thr; x.f->jsplit[pos] = jb.split;
+            f->jthr[pos] = jb.thr; f->jsplit[pos] = jb.split;
         }
         st.job_order[pos] = pos;
-        x.f->hsjob[jb.slot] = pos;
+        f->hsjob[jb.slot] = pos;
     }
     const int first = __ffs(live) - 1;
     const unsigned off0 = __shfl_sync(PG_FULL, jb.seg_off, first < 0 ? 0 : first);
@@ -164,9 +304,7 @@ __device__ __forceinline__ int fw_write_jobs(const PgState& st, const FwCx& x, c
     } else {
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) {          // rare (several distinct survivors): generic grouping on the global arrays
-            pg_group_jobs_single(st, c);
-        }
+        if (lane == 0) pg_group_jobs_single(st, c);   // rare (several distinct survivors): generic grouping
     }
     __syncwarp();
     return J;
@@ -179,33 +317,23 @@ __device__ __forceinline__ int fw_unique(int var, bool live, int lane) {
     return __popc(__ballot_sync(PG_FULL, leader));
 }
 
-// smc.rs:242-254 with the prior in shared memory; 8 subtractions per trip, same order as the reference
-__device__ __forceinline__ int fw_feature_from_probs(const PgState& st, const FwCx& x, double u) {
-    double target = u * st.prior_total;
-    const int p = st.p;
-    int j = 0;
-    for (; j + 8 <= p; j += 8) {
-        double q[8];
-#pragma unroll
-        for (int z = 0; z < 8; ++z) q[z] = x.prior[j + z];
-#pragma unroll
-        for (int z = 0; z < 8; ++z) { target -= q[z]; if (target <= 0.0) return j + z; }
-    }
-    for (; j < p; ++j) { target -= x.prior[j]; if (target <= 0.0) return j; }
-    return p - 1;
-}
-
-// splitting.rs:39-56 for one job lane (mirrors pg_decide_split)
+// splitting.rs:39-56 for one job lane of a non-root round (u3 precomputed when available)
 __device__ __forceinline__ void fw_decide(const PgState& st, const FwCx& x, FwJob& jb) {
     PgCtrl* c = x.c;
-    PgFastSm* f = x.f;
-    (void)f;
     if (!jb.live) return;
-    double* tr = pg_trace_slot(st, x.c, c->round, jb.slot);
+    const int r = c->round;
+    double* tr = pg_trace_slot(st, c, r, jb.slot);
     if (tr) { tr[9] = (double)jb.lo; tr[10] = (double)jb.hi; }
     if (jb.lo >= jb.hi) { if (tr) tr[0] = 3; jb.live = false; return; }
     if (2 * jb.node + 2 >= st.maxn) { c->error = PG_ERR_DEPTH; jb.live = false; return; }
-    jb.split = pg_split_draw(st, x.c, c->upd, c->round, jb.slot, (double)jb.lo, (double)jb.hi);
+    const int buf = (int)(c->upd & 1ull);
+    bool done = false;
+    if (r < FW_DR && x.f->d_ok[buf][r]) {
+        const double lo = (double)jb.lo, hi = (double)jb.hi;
+        const double v = __dadd_rn(__dmul_rn(x.f->d_u3[buf][r][jb.slot], hi - lo), lo);
+        if (v < hi) { jb.split = v; done = true; }
+    }
+    if (!done) jb.split = pg_split_draw(st, c, c->upd, r, jb.slot, (double)jb.lo, (double)jb.hi);
     jb.thr = pg_thr32(jb.split);
     if (tr) tr[3] = jb.split;
 }
@@ -214,8 +342,6 @@ __device__ __forceinline__ void fw_decide(const PgState& st, const FwCx& x, FwJo
 
 __device__ __forceinline__ int fw_begin_step(const PgState& st, const FwCx& x, int lane) {
     PgCtrl* c = x.c;
-    PgFastSm* f = x.f;
-    (void)f;
     if (lane == 0) {
         const double frac = c->tune ? st.batch_tune : st.batch_post;
         long long b = (long long)floor(frac * (double)st.m + 0.5);
@@ -223,96 +349,123 @@ __device__ __forceinline__ int fw_begin_step(const PgState& st, const FwCx& x, i
         if (b > st.m) b = st.m;
         c->batch = (int)b; c->k = 0; c->t_add = -1; c->t_add_internal = 0;
         c->info_loglik = 0.0; c->info_acc = 0; c->info_n = 0;
+        if (st.family == PG_GAUSSIAN) {
+            c->inv_s2 = 1.0 / (st.lik_sigma * st.lik_sigma);
+            c->Cconst = -(double)st.n * (log(st.lik_sigma) + 0.5 * log(6.283185307179586476925286766559));
+        } else { c->inv_s2 = 1.0; c->Cconst = 0.0; }
     }
     __syncwarp();
     return SN_BEGIN_UPDATE;
 }
 
+// smc.rs:42-53 + round 0 of smc.rs:61-86: fresh particles; the precomputed root proposals become the job list
 __device__ __forceinline__ int fw_begin_update(const PgState& st, const FwCx& x, int lane) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
-    (void)f;
-    const int cur = c->cur;
+    const int S = st.S;
     if (lane == 0) {
         const int t = (c->next_tree_idx + c->k) % st.m;
         c->t_cur = t; c->t_sub = t; c->round = 0; c->acc_update = 0; c->pool_top = 0;
     }
-    if (lane < st.S) {
+    __syncwarp();
+    const unsigned long long upd = c->upd;
+    const int buf = (int)(upd & 1ull);
+    fw_wait_draws(f, upd);
+    FwJob jb;
+    jb.live = false; jb.slot = lane; jb.node = 0; jb.var = 0; jb.seg_off = PG_SEG_IDENTITY; jb.len = (unsigned)st.n;
+    jb.lo = jb.hi = jb.thr = 0.f; jb.split = 0.0;
+    bool passed = false;
+    if (lane < S) {
         const int s = lane;
-        const size_t i0 = pg_tix(st, cur, s, 0);
-        st.pt_split_var[i0] = -1; st.pt_split_val[i0] = pg_nan(); st.pt_thr32[i0] = 0.0f; st.pt_leaf_val[i0] = st.init_leaf;
-        st.pt_seg_off[i0] = PG_SEG_IDENTITY; st.pt_cnt[i0] = (unsigned)st.n;
-        st.pt_So[i0] = 0.0; st.pt_Sr[i0] = 0.0; st.pt_g[i0] = 0.0; st.pt_queue[i0] = 0;
-        const int ss = pg_six(st, cur, s);
-        x.f->hsize[ss] = 1; x.f->hqh[ss] = 0; x.f->hqt[ss] = 1; x.f->hG[ss] = 0.0;
-        x.f->hw[s] = 0.0;
+        f->hw[s] = 0.0;       // smc.rs:53: once per update, never reset (Q1)
+        f->hmut[s] = 0;
+        if (!f->d_ok[buf][0]) c->error = PG_ERR_TAPE;
+        const int status = f->d0_status[buf][s];
+        jb.var = f->d_var[buf][0][s];
+        jb.lo = f->d0_lo[buf][s]; jb.hi = f->d0_hi[buf][s]; jb.thr = f->d0_thr[buf][s]; jb.split = f->d0_split[buf][s];
+        passed = status != 1;
+        jb.live = status == 5;
+        if (status == 6) c->error = PG_ERR_TAPE;
+        if (status == 7) c->error = PG_ERR_DEPTH;
+        double* tr = pg_trace_slot(st, c, 0, s);
+        if (tr) {
+#pragma unroll 1
+            for (int q = 0; q < PG_TS_FIELDS; ++q) tr[q] = pg_nan();
+            tr[0] = status == 5 ? 1.0 : (double)status; tr[1] = 0.0; tr[2] = passed ? (double)jb.var : -1.0;
+            if (passed) { tr[9] = (double)jb.lo; tr[10] = (double)jb.hi; }
+            if (status == 5) tr[3] = jb.split;
+        }
+    }
+    const int J0 = __popc(__ballot_sync(PG_FULL, passed));
+    const int J = fw_write_jobs(st, x, jb, lane, true);
+    const int uniq = fw_unique(jb.var, jb.live, lane);
+    if (lane == 0) {
+        const unsigned long long n = (unsigned long long)st.n;
+        const int cols = uniq + c->t_add_internal + st.f_internal[c->t_sub];
+        c->bytes_model += n * (8 + 8 + 4) + 4ull * n * (unsigned long long)cols;
+        c->bytes_contract += 20ull * n + 4ull * n * (unsigned long long)J0 + 16ull * n * (unsigned long long)J;
+        c->phase = PH_ROOT; c->n_phases += 1;
     }
     __syncwarp();
-    return SN_DRAW_ROUND;
+    return SN_NONE;
 }
 
-// fresh = the slot tables were just initialised by fw_begin_update in this same serial section
-__device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, int lane, bool fresh) {
+// rounds >= 1: pop the next expandable node of every slot, depth-prior test, split variable (smc.rs:61-86 front half)
+__device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, int lane) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
-    (void)f;
     const int cur = c->cur, r = c->round, S = st.S;
     const unsigned long long upd = c->upd;
+    const int buf = (int)(upd & 1ull);
+    const bool pre = r < FW_DR && f->d_ok[buf][r];
     FwJob jb;
     jb.live = false; jb.slot = lane; jb.node = -1; jb.var = 0; jb.seg_off = 0; jb.len = 0; jb.lo = jb.hi = jb.thr = 0.f; jb.split = 0.0;
     if (lane < S) {
         const int s = lane;
-        x.f->hmut[s] = 0;
-        double* tr = pg_trace_slot(st, x.c, r, s);
-        if (tr) { for (int q = 0; q < PG_TS_FIELDS; ++q) tr[q] = pg_nan(); tr[0] = 0; }
+        f->hmut[s] = 0;
+        double* tr = pg_trace_slot(st, c, r, s);
+        if (tr) {
+#pragma unroll 1
+            for (int q = 0; q < PG_TS_FIELDS; ++q) tr[q] = pg_nan();
+            tr[0] = 0;
+        }
         const int ss = pg_six(st, cur, s);
-        const int qh = x.f->hqh[ss], qt = x.f->hqt[ss];
+        const int qh = f->hqh[ss], qt = f->hqt[ss];
         if (qh < qt) {
-            const int node = fresh ? 0 : st.pt_queue[pg_tix(st, cur, s, qh)];
-            x.f->hqh[ss] = qh + 1;
+            const int node = st.pt_queue[pg_tix(st, cur, s, qh)];
+            f->hqh[ss] = qh + 1;
             if (tr) { tr[0] = 1; tr[1] = (double)node; tr[2] = -1; }
-            const double u1 = pg_uniform(st, x.c, PG_D_GROW, upd, r, s);
+            const double u1 = pre ? f->d_u1[buf][r][s] : pg_uniform(st, c, PG_D_GROW, upd, r, s);
             if (!(x.thr[pg_depth_of(node)] > u1)) {
                 const size_t iN = pg_tix(st, cur, s, node);
-                const unsigned cnt = fresh ? (unsigned)st.n : st.pt_cnt[iN];
+                const unsigned cnt = st.pt_cnt[iN];
                 if (cnt == 0u) { if (tr) tr[0] = 2; }
                 else {
-                    const double u2 = pg_uniform(st, x.c, PG_D_VAR, upd, r, s);
                     int var;
-                    if (x.prior) var = fw_feature_from_probs(st, x, u2);
-                    else { var = (int)(u2 * (double)st.p); if (var > st.p - 1) var = st.p - 1; }
+                    if (pre) var = f->d_var[buf][r][s];
+                    else {
+                        const double u2 = pg_uniform(st, c, PG_D_VAR, upd, r, s);
+                        if (x.prior) var = fw_feature_from_probs(st, x.prior, u2);
+                        else { var = (int)(u2 * (double)st.p); if (var > st.p - 1) var = st.p - 1; }
+                    }
                     if (tr) tr[2] = (double)var;
                     jb.live = true; jb.node = node; jb.var = var; jb.len = cnt;
-                    jb.seg_off = fresh ? PG_SEG_IDENTITY : st.pt_seg_off[iN];
+                    jb.seg_off = st.pt_seg_off[iN];
                 }
             }
         }
-    }
-    if (r == 0) {
-        if (jb.live) { jb.lo = x.cmin[jb.var]; jb.hi = x.cmax[jb.var]; }
-        const int J0 = __popc(__ballot_sync(PG_FULL, jb.live));
-        fw_decide(st, x, jb);
-        const int J = fw_write_jobs(st, x, jb, lane, true);
-        const int uniq = fw_unique(jb.var, jb.live, lane);
-        if (lane == 0) {
-            const unsigned long long n = (unsigned long long)st.n;
-            const int cols = uniq + c->t_add_internal + (c->t_sub >= 0 ? st.f_internal[c->t_sub] : 0);
-            c->bytes_model += n * (8 + 8 + 4) + 4ull * n * (unsigned long long)cols;
-            c->bytes_contract += 20ull * n + 4ull * n * (unsigned long long)J0 + 16ull * n * (unsigned long long)J;
-            c->phase = PH_ROOT; c->n_phases += 1;
-        }
-        __syncwarp();
-        return SN_NONE;
     }
     const int J = fw_write_jobs(st, x, jb, lane, false);
     if (J == 0) return SN_FINISH_ROUND;
     if (lane == 0) {
         unsigned long long bm = 0, bc = 0;
+#pragma unroll 1
         for (int g = 0; g < c->n_groups; ++g) {
             const unsigned long long L = st.job_len[st.job_order[st.grp_first[g]]];
             bm += 4ull * L + 4ull * L * (unsigned long long)(st.grp_first[g + 1] - st.grp_first[g]);
         }
-        for (int j = 0; j < J; ++j) bc += 8ull * x.f->jlen[j];
+#pragma unroll 1
+        for (int j = 0; j < J; ++j) bc += 8ull * f->jlen[j];
         c->bytes_model += bm; c->bytes_contract += bc;
         c->phase = PH_MINMAX; c->n_phases += 1;
     }
@@ -320,37 +473,28 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
     return SN_NONE;
 }
 
-__device__ __forceinline__ FwJob fw_load_job(const FwCx& x, int lane, int J) {
-    FwJob jb;
-    jb.live = lane < J;
-    jb.slot = jb.live ? x.f->jslot[lane] : 0;
-    jb.node = jb.live ? x.f->jnode[lane] : 0;
-    jb.var = jb.live ? x.f->jvar[lane] : 0;
-    jb.seg_off = jb.live ? x.f->jseg[lane] : 0u;
-    jb.len = jb.live ? x.f->jlen[lane] : 0u;
-    jb.thr = jb.live ? x.f->jthr[lane] : 0.f;
-    jb.split = jb.live ? x.f->jsplit[lane] : 0.0;
-    jb.lo = jb.hi = 0.f;
-    return jb;
-}
-
 __device__ __forceinline__ int fw_after_minmax(const PgState& st, const FwCx& x, int lane) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
-    (void)f;
     const int J0 = c->n_jobs;
-    FwJob jb = fw_load_job(x, lane, J0);
-    if (jb.live) { jb.lo = pg_key2f(f->rMin[lane]); jb.hi = pg_key2f(f->rMax[lane]); }
+    FwJob jb;
+    jb.live = lane < J0;
+    jb.slot = jb.live ? f->jslot[lane] : 0; jb.node = jb.live ? f->jnode[lane] : 0; jb.var = jb.live ? f->jvar[lane] : 0;
+    jb.seg_off = jb.live ? f->jseg[lane] : 0u; jb.len = jb.live ? f->jlen[lane] : 0u;
+    jb.thr = 0.f; jb.split = 0.0;
+    jb.lo = jb.live ? pg_key2f(f->rMin[lane]) : 0.f; jb.hi = jb.live ? pg_key2f(f->rMax[lane]) : 0.f;
     fw_decide(st, x, jb);
     const int J = fw_write_jobs(st, x, jb, lane, true);
     if (J == 0) return SN_FINISH_ROUND;
     if (lane == 0) {
         unsigned long long bm = 0, bc = 0;
+#pragma unroll 1
         for (int g = 0; g < c->n_groups; ++g) {
             const unsigned long long L = st.job_len[st.job_order[st.grp_first[g]]];
             bm += (4ull + 8ull + 4ull) * L + 4ull * L * (unsigned long long)(st.grp_first[g + 1] - st.grp_first[g]);
         }
-        for (int j = 0; j < J; ++j) bc += 20ull * x.f->jlen[j];
+#pragma unroll 1
+        for (int j = 0; j < J; ++j) bc += 20ull * f->jlen[j];
         c->bytes_model += bm; c->bytes_contract += bc;
         c->phase = PH_STATS; c->n_phases += 1;
     }
@@ -358,7 +502,7 @@ __device__ __forceinline__ int fw_after_minmax(const PgState& st, const FwCx& x,
     return SN_NONE;
 }
 
-// particle.rs:91-148 bookkeeping half + smc.rs:76-81 (mirrors pg_apply_mutation on the shared slot scalars)
+// particle.rs:91-148 bookkeeping half + smc.rs:76-81 for rounds >= 1 (mirrors pg_apply_mutation on the shared scalars)
 __device__ __forceinline__ void fw_apply(const PgState& st, const FwCx& x, int j, double vL, double vR, double gL, double gR,
                                          unsigned cL, unsigned cR, double SoL, double SoR, double SrL, double SrR) {
     PgCtrl* c = x.c;
@@ -370,7 +514,8 @@ __device__ __forceinline__ void fw_apply(const PgState& st, const FwCx& x, int j
     const size_t iN = pg_tix(st, cur, s, node), iL = pg_tix(st, cur, s, L), iR = pg_tix(st, cur, s, R);
     const int ss = pg_six(st, cur, s);
     const int old_size = f->hsize[ss];
-    const double g_node = node == 0 ? c->g_stump : st.pt_g[iN];   // the root's leaf term is the stump's
+    const double g_node = st.pt_g[iN];
+#pragma unroll 1
     for (int q = old_size; q < R + 1; ++q) {          // tree.rs:105-110 filler nodes
         const size_t iq = pg_tix(st, cur, s, q);
         st.pt_split_var[iq] = -1; st.pt_split_val[iq] = pg_nan(); st.pt_thr32[iq] = 0.0f; st.pt_leaf_val[iq] = 0.0;
@@ -400,148 +545,120 @@ __device__ __forceinline__ void fw_apply(const PgState& st, const FwCx& x, int j
     if (tr) { tr[0] = 4; tr[4] = vL; tr[5] = vR; tr[6] = (double)cL; tr[7] = (double)cR; tr[8] = w; tr[11] = SoL; }
 }
 
-// After PH_ROOT / PH_STATS (and, for Bernoulli, completes after PH_BERN).
+// Leaf values of one job (smc.rs:219-239) and, for the Gaussian families, the leaf terms of the log-likelihood.
+struct FwVals { double vL, vR, gL, gR, SoL, SoR, SrL, SrR; unsigned cL, cR; };
+__device__ __forceinline__ FwVals fw_values(const PgState& st, const FwCx& x, int j, unsigned nc, double nSo, double nSr) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    FwVals v;
+    const int s = f->jslot[j];
+    const int r = c->round;
+    const int buf = (int)(c->upd & 1ull);
+    const bool pre = r < FW_DR && f->d_ok[buf][r];
+    v.cL = f->rCnt[j]; v.cR = nc - v.cL;
+    v.SoL = f->rSo[j]; v.SoR = nSo - v.SoL;
+    v.SrL = f->rSr[j]; v.SrR = nSr - v.SrL;
+    const double zL = pre ? f->d_zL[buf][r][s] : pg_normal(st, c, PG_D_ZLEFT, c->upd, r, s);   // drawn for both children, left first
+    const double zR = pre ? f->d_zR[buf][r][s] : pg_normal(st, c, PG_D_ZRIGHT, c->upd, r, s);
+    v.vL = v.cL == 0u ? zL * st.leaf_sigma : pg_mul_add(zL, st.leaf_sigma, v.SoL / (double)v.cL / st.m_f);
+    v.vR = v.cR == 0u ? zR * st.leaf_sigma : pg_mul_add(zR, st.leaf_sigma, v.SoR / (double)v.cR / st.m_f);
+    v.gL = pg_gauss_g(v.vL, v.SrL, v.cL, c->inv_s2);
+    v.gR = pg_gauss_g(v.vR, v.SrR, v.cR, c->inv_s2);
+    return v;
+}
+
+__device__ __forceinline__ void fw_bern_bytes(const PgState& st, const FwCx& x, int J) {
+    PgCtrl* c = x.c;
+    unsigned long long bm = 0, bc = 0;
+#pragma unroll 1
+    for (int g = 0; g < c->n_groups; ++g) {
+        const int j0 = st.job_order[st.grp_first[g]];
+        const unsigned long long L = x.f->jlen[j0];
+        const unsigned long long fixed = x.f->jseg[j0] == PG_SEG_IDENTITY ? 12ull : 16ull;
+        bm += fixed * L + 4ull * L * (unsigned long long)(st.grp_first[g + 1] - st.grp_first[g]);
+    }
+#pragma unroll 1
+    for (int j = 0; j < J; ++j) bc += 12ull * x.f->jlen[j];
+    c->bytes_model += bm; c->bytes_contract += bc;
+    c->phase = PH_BERN; c->n_phases += 1;
+}
+
+// After PH_STATS, rounds >= 1 (and the Bernoulli completion after PH_BERN)
 __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, int lane, int phase) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
-    (void)f;
-    const int J = c->n_jobs, cur = c->cur, S = st.S;
+    const int J = c->n_jobs, cur = c->cur;
     const bool bern = st.family == PG_BERNOULLI_LOGIT;
-    const bool root = phase == PH_ROOT;
-    if (root) {
-        const double T_o = f->tot[0], T_r = f->tot[1], T_rr = f->tot[2], T_ll0 = f->tot[3];
-        const double nn = (double)st.n;
-        double C0, g_stump;
-        if (st.family == PG_GAUSSIAN) {
-            const double s2 = st.lik_sigma * st.lik_sigma;
-            C0 = -nn * (log(st.lik_sigma) + 0.5 * log(6.283185307179586476925286766559)) - 0.5 * T_rr / s2;
-            g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n, 1.0 / s2);
-        } else if (st.family == PG_GAUSSIAN_KERNEL) {
-            C0 = -0.5 * T_rr;
-            g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n, 1.0);
-        } else { C0 = 0.0; g_stump = T_ll0; }
-        if (lane == 0) { c->T_o = T_o; c->T_r = T_r; c->T_rr = T_rr; c->T_ll0 = T_ll0; c->C0 = C0; c->g_stump = g_stump; }
-        if (lane < S) {
-            const size_t i0 = pg_tix(st, cur, lane, 0);
-            st.pt_So[i0] = T_o; st.pt_Sr[i0] = T_r; st.pt_g[i0] = g_stump;
-            x.f->hG[pg_six(st, cur, lane)] = g_stump;
-        }
-        __syncwarp();
-    }
     if (phase == PH_BERN) {
         if (lane < J) {
-            const int s = x.f->jslot[lane];
-            const size_t iN = pg_tix(st, cur, s, x.f->jnode[lane]);
-            const unsigned nc = st.pt_cnt[iN];
-            const unsigned cL = (unsigned)st.red_cnt[lane], cR = nc - cL;
-            const double SoL = st.red_So[lane], SoR = st.pt_So[iN] - SoL;
-            const double SrL = st.red_Sr[lane], SrR = st.pt_Sr[iN] - SrL;
-            fw_apply(st, x, lane, st.job_vL[lane], st.job_vR[lane], f->rllL[lane], f->rllR[lane], cL, cR, SoL, SoR, SrL, SrR);
+            const size_t iN = pg_tix(st, cur, f->jslot[lane], f->jnode[lane]);
+            const unsigned cL = f->jr_cL[lane];
+            fw_apply(st, x, lane, f->jr_vL[lane], f->jr_vR[lane], f->rllL[lane], f->rllR[lane], cL, st.pt_cnt[iN] - cL,
+                     f->jr_SoL[lane], st.pt_So[iN] - f->jr_SoL[lane], f->jr_SrL[lane], st.pt_Sr[iN] - f->jr_SrL[lane]);
         }
         __syncwarp();
         return SN_FINISH_ROUND;
     }
-    const double inv_s2 = st.family == PG_GAUSSIAN ? 1.0 / (st.lik_sigma * st.lik_sigma) : 1.0;
     if (lane < J) {
-        const int s = x.f->jslot[lane];
-        const int node = x.f->jnode[lane];
-        const size_t iN = pg_tix(st, cur, s, node);
-        // node totals: the root's are the pass totals just reduced (no table read needed)
-        const unsigned nc = root ? (unsigned)st.n : st.pt_cnt[iN];
-        const double nSo = root ? f->tot[0] : st.pt_So[iN];
-        const double nSr = root ? f->tot[1] : st.pt_Sr[iN];
-        const unsigned cL = f->rCnt[lane], cR = nc - cL;
-        const double SoL = f->rSo[lane], SoR = nSo - SoL;
-        const double zL = pg_normal(st, x.c, PG_D_ZLEFT, c->upd, c->round, s);
-        const double zR = pg_normal(st, x.c, PG_D_ZRIGHT, c->upd, c->round, s);
-        const double vL = cL == 0u ? zL * st.leaf_sigma : pg_mul_add(zL, st.leaf_sigma, SoL / (double)cL / st.m_f);
-        const double vR = cR == 0u ? zR * st.leaf_sigma : pg_mul_add(zR, st.leaf_sigma, SoR / (double)cR / st.m_f);
-        const double SrL = f->rSr[lane], SrR = nSr - SrL;
-        st.red_cnt[lane] = cL;   // the partition (and the Bernoulli completion) may read these in a later section
+        const size_t iN = pg_tix(st, cur, f->jslot[lane], f->jnode[lane]);
+        const FwVals v = fw_values(st, x, lane, st.pt_cnt[iN], st.pt_So[iN], st.pt_Sr[iN]);
+        f->jr_cL[lane] = v.cL;     // the partition reads the left count later
         if (bern) {
-            st.job_vL[lane] = vL; st.job_vR[lane] = vR; st.red_So[lane] = SoL; st.red_Sr[lane] = SrL;
-        } else {
-            fw_apply(st, x, lane, vL, vR, pg_gauss_g(vL, SrL, cL, inv_s2), pg_gauss_g(vR, SrR, cR, inv_s2),
-                              cL, cR, SoL, SoR, SrL, SrR);
-        }
+            f->jr_vL[lane] = v.vL; f->jr_vR[lane] = v.vR; f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL;
+            st.job_vL[lane] = v.vL; st.job_vR[lane] = v.vR;
+        } else fw_apply(st, x, lane, v.vL, v.vR, v.gL, v.gR, v.cL, v.cR, v.SoL, v.SoR, v.SrL, v.SrR);
     }
     __syncwarp();
     if (bern && J > 0) {
-        if (lane == 0) {
-            unsigned long long bm = 0, bc = 0;
-            for (int g = 0; g < c->n_groups; ++g) {
-                const int j0 = st.job_order[st.grp_first[g]];
-                const unsigned long long L = x.f->jlen[j0];
-                const unsigned long long fixed = x.f->jseg[j0] == PG_SEG_IDENTITY ? 12ull : 16ull;
-                bm += fixed * L + 4ull * L * (unsigned long long)(st.grp_first[g + 1] - st.grp_first[g]);
-            }
-            for (int j = 0; j < J; ++j) bc += 12ull * x.f->jlen[j];
-            c->bytes_model += bm; c->bytes_contract += bc;
-            c->phase = PH_BERN; c->n_phases += 1;
-        }
+        if (lane == 0) fw_bern_bytes(st, x, J);
         __syncwarp();
         return SN_NONE;
     }
     return SN_FINISH_ROUND;
 }
 
-// smc.rs:96-102 + bookkeeping of the lazy partition
-__device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x, int lane, bool cnt_in_smem) {
+// smc.rs:257-268 + resampling.rs:24-44 on the shared slot scalars; returns this lane's ancestor
+__device__ __forceinline__ int fw_normalize_resample(const PgState& st, const FwCx& x, int lane, int* n_mut_out, int* mut_out) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
-    (void)f;
     const int S = st.S;
-    const int src = c->cur, dst = 1 - c->cur;
     const bool act = lane < S;
-    const int mut = act ? x.f->hmut[lane] : 0;
-    double w = act ? x.f->hw[lane] : -INFINITY;
+    const int mut = act ? f->hmut[lane] : 0;
+    const double w = act ? f->hw[lane] : -INFINITY;
     const int n_mut = __popc(__ballot_sync(PG_FULL, mut != 0));
-    // smc.rs:257-268
     const double mx = fw_max(w);
-    double e = act ? exp(w - mx) : 0.0;
+    const double e = act ? exp(w - mx) : 0.0;
     const double sum = fw_sum_seq(e, S);
     const double wn = e / sum;
-    if (act) x.f->hw[lane] = wn;
-    // resampling.rs:24-44
-    const double u6 = pg_uniform(st, x.c, PG_D_RESAMPLE, c->upd, c->round, 0);
+    if (act) f->hw[lane] = wn;          // kept for the next round: stale-weight rule (Q1)
+    const double u6 = fw_u6(st, x, c->upd, c->round);
     const double target = ((double)lane + u6) / (double)S;
     int cidx = 0;
     double cum = 0.0;
+#pragma unroll 1
     for (int k = 0; k < S; ++k) {          // cum == sum of the first k weights, in order, on every lane
         if (cum < target) cidx = k + 1;     // the reference's pointer passes k
         cum += __shfl_sync(PG_FULL, wn, k);
     }
     const int anc = act ? (cidx == 0 ? 0 : cidx - 1) : 0;
-    if (act) x.f->hanc[lane] = anc;
-    if (st.tr_round && lane == 0) {
-        if (!((long long)c->trace_n < st.tr_u_cap && c->round < st.tr_r_cap)) c->trace_overflow = 1;
+    if (act) f->hanc[lane] = anc;
+    if (st.tr_round) {
+        if ((long long)c->trace_n < st.tr_u_cap && c->round < st.tr_r_cap) {
+            double* tr = st.tr_round + ((size_t)c->trace_n * st.tr_r_cap + c->round) * (size_t)(2 + 2 * S);
+            if (lane == 0) { tr[0] = 1; tr[1] = (double)n_mut; }
+            if (act) { tr[2 + lane] = wn; tr[2 + S + lane] = (double)anc; }
+        } else if (lane == 0) c->trace_overflow = 1;
     }
-    if (st.tr_round && (long long)c->trace_n < st.tr_u_cap && c->round < st.tr_r_cap) {
-        double* tr = st.tr_round + ((size_t)c->trace_n * st.tr_r_cap + c->round) * (size_t)(2 + 2 * S);
-        if (lane == 0) { tr[0] = 1; tr[1] = (double)n_mut; }
-        if (act) { tr[2 + lane] = wn; tr[2 + S + lane] = (double)anc; }
-    }
-    // clone survivors: slot `lane` <- slot `anc`
-    const int fs = pg_six(st, src, anc), ts = pg_six(st, dst, lane);
-    const int sz = act ? x.f->hsize[fs] : 0;
-    const int qh = act ? x.f->hqh[fs] : 0, qt = act ? x.f->hqt[fs] : 0;
-    const double Gs = act ? x.f->hG[fs] : 0.0;
-    const int mxs = fw_imax(sz);
-    for (int node = 0; node < mxs; ++node) {
-        if (node < sz) {
-            const size_t a = pg_tix(st, src, anc, node), t = pg_tix(st, dst, lane, node);
-            st.pt_split_var[t] = st.pt_split_var[a]; st.pt_thr32[t] = st.pt_thr32[a];
-            st.pt_split_val[t] = st.pt_split_val[a]; st.pt_leaf_val[t] = st.pt_leaf_val[a];
-            st.pt_seg_off[t] = st.pt_seg_off[a]; st.pt_cnt[t] = st.pt_cnt[a];
-            st.pt_So[t] = st.pt_So[a]; st.pt_Sr[t] = st.pt_Sr[a]; st.pt_g[t] = st.pt_g[a];
-            st.pt_queue[t] = st.pt_queue[a];
-        }
-    }
-    __syncwarp();
-    if (act) { x.f->hsize[ts] = sz; x.f->hqh[ts] = qh; x.f->hqt[ts] = qt; x.f->hG[ts] = Gs; st.pj_of_anc[lane] = -1; }
-    // one stable partition per distinct surviving ancestor that grew this round
-    const int mut_a = __shfl_sync(PG_FULL, mut, anc);
-    const bool need = act && mut_a != 0;
+    *n_mut_out = n_mut;
+    *mut_out = mut;
+    return anc;
+}
+
+// Partition jobs for the distinct surviving ancestors that grew this round; returns K and this lane's child offsets.
+__device__ __forceinline__ int fw_plan_partitions(const PgState& st, const FwCx& x, int lane, int anc, bool need,
+                                                  unsigned* off_out, unsigned* cntL_out, int* node_out) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
     const unsigned needm = __ballot_sync(PG_FULL, need);
     const unsigned same = __match_any_sync(PG_FULL, need ? anc : -1 - lane);
     const bool leader = need && ((__ffs(same & needm) - 1) == lane);
@@ -550,16 +667,12 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
     const int k = __popc(leadm & ((1u << lane) - 1u));
     int j = 0, node = 0;
     unsigned len = 0u, cntL = 0u;
-    if (need) {
-        j = x.f->hsjob[anc];
-        node = x.f->jnode[j];
-        len = x.f->jlen[j];
-        cntL = cnt_in_smem ? f->rCnt[j] : (unsigned)st.red_cnt[j];
-    }
+    if (need) { j = f->hsjob[anc]; node = f->jnode[j]; len = f->jlen[j]; cntL = f->jr_cL[j]; }
     unsigned long long off = 0;
     {
         const unsigned long long mylen = leader ? (unsigned long long)len : 0ull;
         unsigned long long run = c->pool_top;
+#pragma unroll 1
         for (int q = 0; q < 32; ++q) {
             if (!((leadm >> q) & 1u)) continue;       // leadm is warp-uniform
             const unsigned long long v = __shfl_sync(PG_FULL, mylen, q);
@@ -571,24 +684,58 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
             c->pool_top = run;
         }
     }
+    if (lane < st.S) st.pj_of_anc[lane] = -1;
+    __syncwarp();
     if (leader) {
         st.pj_of_anc[anc] = k;
-        st.pj_anc[k] = anc; st.pj_job[k] = j; st.pj_var[k] = x.f->jvar[j]; st.pj_thr32[k] = x.f->jthr[j];
-        st.pj_src_off[k] = x.f->jseg[j]; st.pj_len[k] = len; st.pj_cntL[k] = cntL; st.pj_dst_off[k] = (unsigned)off;
+        st.pj_anc[k] = anc; st.pj_job[k] = j; st.pj_var[k] = f->jvar[j]; st.pj_thr32[k] = f->jthr[j];
+        st.pj_src_off[k] = f->jseg[j]; st.pj_len[k] = len; st.pj_cntL[k] = cntL; st.pj_dst_off[k] = (unsigned)off;
     }
     const int lead_lane = need ? (__ffs(same & needm) - 1) : 0;
-    const unsigned long long off_l = __shfl_sync(PG_FULL, off, lead_lane);
+    *off_out = (unsigned)__shfl_sync(PG_FULL, off, lead_lane);
+    *cntL_out = cntL;
+    *node_out = node;
+    return K;
+}
+
+// smc.rs:96-102 for rounds >= 1: clone survivors' tables, plan the lazy partitions
+__device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const int S = st.S;
+    const int src = c->cur, dst = 1 - c->cur;
+    const bool act = lane < S;
+    int n_mut, mut;
+    const int anc = fw_normalize_resample(st, x, lane, &n_mut, &mut);
+    const int fs = pg_six(st, src, anc), ts = pg_six(st, dst, lane);
+    const int sz = act ? f->hsize[fs] : 0;
+    const int qh = act ? f->hqh[fs] : 0, qt = act ? f->hqt[fs] : 0;
+    const double Gs = act ? f->hG[fs] : 0.0;
+    const int mxs = fw_imax(sz);
+#pragma unroll 1
+    for (int node = 0; node < mxs; ++node) {
+        if (node < sz) {
+            const size_t a = pg_tix(st, src, anc, node), t = pg_tix(st, dst, lane, node);
+            st.pt_split_var[t] = st.pt_split_var[a]; st.pt_thr32[t] = st.pt_thr32[a];
+            st.pt_split_val[t] = st.pt_split_val[a]; st.pt_leaf_val[t] = st.pt_leaf_val[a];
+            st.pt_seg_off[t] = st.pt_seg_off[a]; st.pt_cnt[t] = st.pt_cnt[a];
+            st.pt_So[t] = st.pt_So[a]; st.pt_Sr[t] = st.pt_Sr[a]; st.pt_g[t] = st.pt_g[a];
+            st.pt_queue[t] = st.pt_queue[a];
+        }
+    }
+    __syncwarp();
+    if (act) { f->hsize[ts] = sz; f->hqh[ts] = qh; f->hqt[ts] = qt; f->hG[ts] = Gs; }
+    const int mut_a = __shfl_sync(PG_FULL, mut, anc);
+    const bool need = act && mut_a != 0;
+    unsigned off, cntL;
+    int node;
+    const int K = fw_plan_partitions(st, x, lane, anc, need, &off, &cntL, &node);
     if (need) {
-        st.pt_seg_off[pg_tix(st, dst, lane, 2 * node + 1)] = (unsigned)off_l;
-        st.pt_seg_off[pg_tix(st, dst, lane, 2 * node + 2)] = (unsigned)off_l + cntL;
+        st.pt_seg_off[pg_tix(st, dst, lane, 2 * node + 1)] = off;
+        st.pt_seg_off[pg_tix(st, dst, lane, 2 * node + 2)] = off + cntL;
     }
     const int any_queue = __any_sync(PG_FULL, act && qh < qt);
-    if (lane == 0) {
-        c->acc_update += n_mut;
-        c->cur = dst;
-        c->n_pjobs = K;
-        c->any_queue = any_queue;
-    }
+    if (lane == 0) { c->acc_update += n_mut; c->cur = dst; c->n_pjobs = K; c->any_queue = any_queue; }
     __syncwarp();
     if (c->error != PG_OK) return SN_NONE;
     if (K > 0) return SN_PREP_PART;
@@ -601,10 +748,10 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
 __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
-    (void)f;
     const int K = c->n_pjobs, W = st.n_gwarps, S = st.S;
     const int tid = threadIdx.x, T = blockDim.x;
     const int chunk = (W + T - 1) / T;
+#pragma unroll 1
     for (int k = 0; k < K; ++k) {
         const int j = st.pj_job[k];
         const int b = tid * chunk;
@@ -619,12 +766,14 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
             __syncthreads();
             if (tid < 32) {
                 unsigned carry = 0;
+#pragma unroll 1
                 for (int base = 0; base < T; base += 32) {
                     const unsigned x0 = f->scan[base + tid];
-                    unsigned x = x0;
-                    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(PG_FULL, x, o); if (tid >= o) x += y; }
-                    f->scan[base + tid] = carry + x - x0;
-                    carry += __shfl_sync(PG_FULL, x, 31);
+                    unsigned xx = x0;
+#pragma unroll 1
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(PG_FULL, xx, o); if (tid >= o) xx += y; }
+                    f->scan[base + tid] = carry + xx - x0;
+                    carry += __shfl_sync(PG_FULL, xx, 31);
                 }
             }
             __syncthreads();
@@ -646,6 +795,7 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
     }
     if (tid == 0) {
         unsigned long long bm = 0;
+#pragma unroll 1
         for (int k = 0; k < K; ++k) {
             const unsigned long long L = st.pj_len[k];
             bm += (st.pj_src_off[k] == PG_SEG_IDENTITY ? 0ull : 4ull * L) + 4ull * L + 4ull * L;
@@ -655,66 +805,14 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
     }
 }
 
-// smc.rs:105-122 + kernel.rs:99-117
-__device__ __forceinline__ int fw_finalize(const PgState& st, const FwCx& x, int lane) {
+// end of a tree update: diagnostics, counters, next update or the step's final pass (kernel.rs:104-117)
+__device__ __forceinline__ int fw_end_update(const PgState& st, const FwCx& x, int lane, int depth, int internal, double Wn0) {
     PgCtrl* c = x.c;
-    PgFastSm* f = x.f;
-    (void)f;
-    const int P = st.P, cur = c->cur, t = c->t_cur;
-    const bool act = lane < P;
-    double Wl = -INFINITY;
-    if (act) Wl = c->C0 + (lane == 0 ? c->g_stump : x.f->hG[pg_six(st, cur, lane == 0 ? 0 : lane - 1)]);
-    const double mx = fw_max(Wl);
-    const double e = act ? exp(Wl - mx) : 0.0;
-    const double sum = fw_sum_seq(e, P);
-    const double Wn = e / sum;
-    const double total = fw_sum_seq(act ? Wn : 0.0, P);
-    const double u7 = pg_uniform(st, x.c, PG_D_SELECT, c->upd, 0, 0);
-    const double chosen = u7 * total;
-    int sel = 0;
-    {
-        double cum = 0.0;
-        bool open = true;
-        for (int i = 0; i + 1 < P; ++i) {
-            cum += __shfl_sync(PG_FULL, Wn, i);
-            if (open && cum <= chosen) sel = i + 1; else open = false;
-        }
-    }
-    if (lane == 0) {
-        if (!(total > 0.0) || !(total < INFINITY)) c->error = PG_ERR_WEIGHTS;
-        c->info_loglik += Wn;      // lane 0 holds the reference stump's normalised weight
-        c->info_acc += c->acc_update;
-    }
-    if (st.tr_upd) {
-        if ((long long)c->trace_n < st.tr_u_cap) {
-            double* tr = st.tr_upd + (size_t)c->trace_n * (size_t)(4 + 2 * P);
-            if (lane == 0) { tr[0] = (double)(c->round + 1); tr[1] = (double)sel; tr[2] = (double)t; tr[3] = (double)c->acc_update; }
-            if (act) { tr[4 + lane] = Wl; tr[4 + P + lane] = Wn; }
-        } else if (lane == 0) c->trace_overflow = 1;
-    }
-    const size_t fb = (size_t)t * st.maxn;
-    int depth = 0, internal = 0, sz = 1;
-    if (sel == 0) {
-        if (lane == 0) {
-            st.f_split_var[fb] = -1; st.f_split_val[fb] = pg_nan(); st.f_thr32[fb] = 0.0f; st.f_leaf_val[fb] = st.init_leaf;
-            st.f_size[t] = 1;
-        }
-    } else {
-        const int s = sel - 1;
-        sz = x.f->hsize[pg_six(st, cur, s)];
-        for (int node = lane; node < sz; node += 32) {
-            const size_t a = pg_tix(st, cur, s, node);
-            const int sv = st.pt_split_var[a];
-            st.f_split_var[fb + node] = sv; st.f_split_val[fb + node] = st.pt_split_val[a];
-            st.f_thr32[fb + node] = st.pt_thr32[a]; st.f_leaf_val[fb + node] = st.pt_leaf_val[a];
-            if (sv < 0) { const int d = pg_depth_of(node); depth = d > depth ? d : depth; } else internal += 1;
-        }
-        depth = fw_imax(depth);
-        internal = __reduce_add_sync(PG_FULL, internal);
-        if (lane == 0) st.f_size[t] = sz;
-    }
     int next = SN_NONE;
     if (lane == 0) {
+        const int t = c->t_cur;
+        c->info_loglik += Wn0;
+        c->info_acc += c->acc_update;
         st.f_internal[t] = internal;
         c->t_add_internal = internal;
         if (c->info_n < st.m) st.info_depths[c->info_n] = (unsigned char)depth;
@@ -726,53 +824,192 @@ __device__ __forceinline__ int fw_finalize(const PgState& st, const FwCx& x, int
             c->t_sub = -1;
             c->bytes_model += (unsigned long long)st.n * (16ull + 4ull * (unsigned long long)internal);
             c->phase = PH_FINAL; c->n_phases += 1;
-            next = SN_NONE;
         }
     }
     __syncwarp();
-    next = __shfl_sync(PG_FULL, next, 0);
-    return next;
+    return __shfl_sync(PG_FULL, next, 0);
+}
+
+// smc.rs:105-122 final selection among the reference stump and the S slots (lane i = particle i)
+__device__ __forceinline__ int fw_select(const PgState& st, const FwCx& x, int lane, double Wl, double* Wn0_out) {
+    PgCtrl* c = x.c;
+    const int P = st.P;
+    const bool act = lane < P;
+    const double mx = fw_max(act ? Wl : -INFINITY);
+    const double e = act ? exp(Wl - mx) : 0.0;
+    const double sum = fw_sum_seq(e, P);
+    const double Wn = e / sum;
+    const double total = fw_sum_seq(act ? Wn : 0.0, P);
+    const double chosen = fw_u7(st, x, c->upd) * total;
+    int sel = 0;
+    {
+        double cum = 0.0;
+        bool open = true;
+#pragma unroll 1
+        for (int i = 0; i + 1 < P; ++i) {
+            cum += __shfl_sync(PG_FULL, Wn, i);
+            if (open && cum <= chosen) sel = i + 1; else open = false;
+        }
+    }
+    if (lane == 0 && (!(total > 0.0) || !(total < INFINITY))) c->error = PG_ERR_WEIGHTS;
+    if (st.tr_upd) {
+        if ((long long)c->trace_n < st.tr_u_cap) {
+            double* tr = st.tr_upd + (size_t)c->trace_n * (size_t)(4 + 2 * P);
+            if (lane == 0) { tr[0] = (double)(c->round + 1); tr[1] = (double)sel; tr[2] = (double)c->t_cur; tr[3] = (double)c->acc_update; }
+            if (act) { tr[4 + lane] = Wl; tr[4 + P + lane] = Wn; }
+        } else if (lane == 0) c->trace_overflow = 1;
+    }
+    *Wn0_out = __shfl_sync(PG_FULL, Wn, 0);
+    return sel;
+}
+
+__device__ __forceinline__ void fw_write_stump(const PgState& st, int t) {
+    const size_t fb = (size_t)t * st.maxn;
+    st.f_split_var[fb] = -1; st.f_split_val[fb] = pg_nan(); st.f_thr32[fb] = 0.0f; st.f_leaf_val[fb] = st.init_leaf;
+    st.f_size[t] = 1;
+}
+
+// general finalize (rounds >= 1 happened): the selected particle's tree comes from the slot tables
+__device__ __forceinline__ int fw_finalize(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const int cur = c->cur, t = c->t_cur;
+    const double Wl = lane < st.P ? c->C0 + (lane == 0 ? c->g_stump : f->hG[pg_six(st, cur, lane - 1)]) : -INFINITY;
+    double Wn0;
+    const int sel = fw_select(st, x, lane, Wl, &Wn0);
+    const size_t fb = (size_t)t * st.maxn;
+    int depth = 0, internal = 0;
+    if (sel == 0) { if (lane == 0) fw_write_stump(st, t); }
+    else {
+        const int s = sel - 1;
+        const int sz = f->hsize[pg_six(st, cur, s)];
+#pragma unroll 1
+        for (int node = lane; node < sz; node += 32) {
+            const size_t a = pg_tix(st, cur, s, node);
+            const int sv = st.pt_split_var[a];
+            st.f_split_var[fb + node] = sv; st.f_split_val[fb + node] = st.pt_split_val[a];
+            st.f_thr32[fb + node] = st.pt_thr32[a]; st.f_leaf_val[fb + node] = st.pt_leaf_val[a];
+            if (sv < 0) { const int d = pg_depth_of(node); depth = d > depth ? d : depth; } else internal += 1;
+        }
+        depth = fw_imax(depth);
+        internal = __reduce_add_sync(PG_FULL, internal);
+        if (lane == 0) st.f_size[t] = sz;
+    }
+    return fw_end_update(st, x, lane, depth, internal, Wn0);
+}
+
+// ---- round 0, table-free ---------------------------------------------------------------------------
+// After PH_ROOT: totals, leaf values and weights of the root proposals (kept in shared memory).
+__device__ __forceinline__ int fw_r0_values(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const int J = c->n_jobs;
+    const bool bern = st.family == PG_BERNOULLI_LOGIT;
+    const double T_o = f->tot[0], T_r = f->tot[1], T_rr = f->tot[2], T_ll0 = f->tot[3];
+    double C0, g_stump;
+    if (bern) { C0 = 0.0; g_stump = T_ll0; }
+    else if (st.family == PG_GAUSSIAN) {
+        C0 = c->Cconst - 0.5 * T_rr / (st.lik_sigma * st.lik_sigma);   // same expression as the generic path
+        g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n, c->inv_s2);
+    } else { C0 = -0.5 * T_rr; g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n, 1.0); }
+    if (lane == 0) { c->T_o = T_o; c->T_r = T_r; c->T_rr = T_rr; c->T_ll0 = T_ll0; c->C0 = C0; c->g_stump = g_stump; }
+    __syncwarp();
+    if (lane < J) {
+        const FwVals v = fw_values(st, x, lane, (unsigned)st.n, T_o, T_r);
+        f->jr_vL[lane] = v.vL; f->jr_vR[lane] = v.vR; f->jr_gL[lane] = v.gL; f->jr_gR[lane] = v.gR;
+        f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL; f->jr_cL[lane] = v.cL;
+        if (bern) { st.job_vL[lane] = v.vL; st.job_vR[lane] = v.vR; }
+    }
+    __syncwarp();
+    if (bern && J > 0) {
+        if (lane == 0) fw_bern_bytes(st, x, J);
+        __syncwarp();
+        return SN_NONE;
+    }
+    return SN_FINISH_ROUND;
+}
+
+// Weights of the root proposals, stale-weight normalisation, resampling; then either the update ends as a
+// stump (no survivor grew) or the survivors' tables are materialised and the general path takes over.
+__device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, int lane, bool after_bern) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const int S = st.S, J = c->n_jobs, cur = c->cur;
+    const bool act = lane < S;
+    if (lane < J) {
+        if (after_bern) { f->jr_gL[lane] = f->rllL[lane]; f->jr_gR[lane] = f->rllR[lane]; }
+        const int s = f->jslot[lane];
+        const double G = (c->g_stump - c->g_stump) + (f->jr_gL[lane] + f->jr_gR[lane]);   // as pg_apply_mutation on a root
+        const double w = c->C0 + G;
+        f->hw[s] = w;
+        f->hmut[s] = 1;
+        double* tr = pg_trace_slot(st, c, 0, s);
+        if (tr) {
+            tr[0] = 4; tr[4] = f->jr_vL[lane]; tr[5] = f->jr_vR[lane]; tr[6] = (double)f->jr_cL[lane];
+            tr[7] = (double)((unsigned)st.n - f->jr_cL[lane]); tr[8] = w; tr[11] = f->jr_SoL[lane];
+        }
+    }
+    __syncwarp();
+    int n_mut, mut;
+    const int anc = fw_normalize_resample(st, x, lane, &n_mut, &mut);
+    const int mut_a = __shfl_sync(PG_FULL, mut, anc);
+    const bool need = act && mut_a != 0;
+    if (lane == 0) c->acc_update += n_mut;
+    __syncwarp();
+    if (!__any_sync(PG_FULL, need)) {
+        // every survivor is an untouched stump with an empty queue: the loop of smc.rs:61 ends here.  All P
+        // particles are stumps with the same log-likelihood (smc.rs:105-111).
+        double Wn0;
+        (void)fw_select(st, x, lane, c->C0 + c->g_stump, &Wn0);
+        if (lane == 0) fw_write_stump(st, c->t_cur);
+        return fw_end_update(st, x, lane, 0, 0, Wn0);
+    }
+    // ---- survivors that grew: write the slot tables of ALL slots (copies of their ancestors) into half `cur`
+    unsigned off, cntL;
+    int node;
+    const int K = fw_plan_partitions(st, x, lane, anc, need, &off, &cntL, &node);
+    if (act) {
+        const int ss = pg_six(st, cur, lane);
+        const size_t i0 = pg_tix(st, cur, lane, 0);
+        if (need) {
+            const int j = f->hsjob[anc];
+            const size_t i1 = i0 + 1, i2 = i0 + 2;
+            const unsigned cL = f->jr_cL[j], cR = (unsigned)st.n - cL;
+            st.pt_split_var[i0] = f->jvar[j]; st.pt_split_val[i0] = f->jsplit[j]; st.pt_thr32[i0] = f->jthr[j];
+            st.pt_leaf_val[i0] = pg_nan(); st.pt_seg_off[i0] = PG_SEG_IDENTITY; st.pt_cnt[i0] = (unsigned)st.n;
+            st.pt_So[i0] = c->T_o; st.pt_Sr[i0] = c->T_r; st.pt_g[i0] = c->g_stump;
+            st.pt_split_var[i1] = -1; st.pt_split_val[i1] = pg_nan(); st.pt_thr32[i1] = 0.0f; st.pt_leaf_val[i1] = f->jr_vL[j];
+            st.pt_split_var[i2] = -1; st.pt_split_val[i2] = pg_nan(); st.pt_thr32[i2] = 0.0f; st.pt_leaf_val[i2] = f->jr_vR[j];
+            st.pt_seg_off[i1] = off; st.pt_seg_off[i2] = off + cL;
+            st.pt_cnt[i1] = cL; st.pt_cnt[i2] = cR;
+            st.pt_So[i1] = f->jr_SoL[j]; st.pt_So[i2] = c->T_o - f->jr_SoL[j];
+            st.pt_Sr[i1] = f->jr_SrL[j]; st.pt_Sr[i2] = c->T_r - f->jr_SrL[j];
+            st.pt_g[i1] = f->jr_gL[j]; st.pt_g[i2] = f->jr_gR[j];
+            st.pt_queue[i0] = 1; st.pt_queue[i1] = 2;      // particle.rs:146-147: left then right
+            f->hsize[ss] = 3; f->hqh[ss] = 0; f->hqt[ss] = 2;
+            f->hG[ss] = (c->g_stump - c->g_stump) + (f->jr_gL[j] + f->jr_gR[j]);
+        } else {
+            st.pt_split_var[i0] = -1; st.pt_split_val[i0] = pg_nan(); st.pt_thr32[i0] = 0.0f; st.pt_leaf_val[i0] = st.init_leaf;
+            st.pt_seg_off[i0] = PG_SEG_IDENTITY; st.pt_cnt[i0] = (unsigned)st.n;
+            st.pt_So[i0] = c->T_o; st.pt_Sr[i0] = c->T_r; st.pt_g[i0] = c->g_stump;
+            f->hsize[ss] = 1; f->hqh[ss] = 1; f->hqt[ss] = 1;
+            f->hG[ss] = c->g_stump;
+        }
+    }
+    if (lane == 0) { c->n_pjobs = K; c->any_queue = 1; }
+    __syncwarp();
+    if (c->error != PG_OK) return SN_NONE;
+    return SN_PREP_PART;     // K >= 1 here; after PH_PART the general rounds continue
 }
 
 // ---- entry: the whole serial block (block 0) -------------------------------------------------------
 // phase / J: the pass that just completed (every block knows them: no load needed).
-__device__ void pg_serial_fast(const PgState& st, const PgSmemView& sm, int phase, int J) {
-    PgCtrl* gc = st.ctrl;
+// Returns the section's duration in SM cycles (thread 0).
+__device__ long long pg_serial_fast(const PgState& st, const PgSmemView& sm, int phase, int J) {
+    __shared__ PgCtrl fw_scratch[FW_DR + 1];   // helpers must not raise errors for draws that may never be consumed
     PgFastSm* f = &sm.base->fast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int S = st.S;
     const long long t_entry = clock64();
-
-    // ---- prologue: ONE batch of loads. Warp 1: PgCtrl; warp 2: slot scalars; warp 3: job list; then every warp
-    // takes its share of the partial reduction (fw_reduce) — all in the same L2 round trip.
-    if (warp == 1) {
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gc);
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&f->lc);
-        const int nw = fw_ctrl_words();
-        for (int i = lane; i < nw; i += 32) dst[i] = __ldcg(&src[i]);
-    } else if (warp == 2) {
-        if (lane < S) {   // both halves of the double-buffered scalars: no dependent load on ctrl->cur
-            const int s0 = lane, s1 = S + lane;
-            const double w = __ldcg(&st.w[lane]); const int mu = __ldcg(&st.mutated[lane]);
-            const int an = __ldcg(&st.anc[lane]); const int sj = __ldcg(&st.slot_job[lane]);
-            const int sz0 = __ldcg(&st.pt_size[s0]), qh0 = __ldcg(&st.pt_qhead[s0]), qt0 = __ldcg(&st.pt_qtail[s0]);
-            const int sz1 = __ldcg(&st.pt_size[s1]), qh1 = __ldcg(&st.pt_qhead[s1]), qt1 = __ldcg(&st.pt_qtail[s1]);
-            const double G0 = __ldcg(&st.pt_G[s0]), G1 = __ldcg(&st.pt_G[s1]);
-            f->hw[lane] = w; f->hmut[lane] = mu; f->hanc[lane] = an; f->hsjob[lane] = sj;
-            f->hsize[s0] = sz0; f->hqh[s0] = qh0; f->hqt[s0] = qt0; f->hG[s0] = G0;
-            f->hsize[s1] = sz1; f->hqh[s1] = qh1; f->hqt[s1] = qt1; f->hG[s1] = G1;
-        }
-    } else if (warp == 3) {
-        if (lane < J) {
-            const int a = __ldcg(&st.job_slot[lane]), b = __ldcg(&st.job_node[lane]), v = __ldcg(&st.job_var[lane]);
-            const unsigned so = __ldcg(&st.job_seg_off[lane]), ln = __ldcg(&st.job_len[lane]);
-            const float th = __ldcg(&st.job_thr32[lane]); const double sp = __ldcg(&st.job_split[lane]);
-            f->jslot[lane] = a; f->jnode[lane] = b; f->jvar[lane] = v; f->jseg[lane] = so; f->jlen[lane] = ln;
-            f->jthr[lane] = th; f->jsplit[lane] = sp;
-        }
-    }
-    fw_reduce(st, f, phase, J);   // contains a __syncthreads before its combine step
-    __syncthreads();
 
     FwCx x;
     x.f = f;
@@ -784,17 +1021,40 @@ __device__ void pg_serial_fast(const PgState& st, const PgSmemView& sm, int phas
     x.cmax = staged ? sm.cmax : st.col_max;
     PgCtrl* c = x.c;
 
+    const int gerr = threadIdx.x == 0 ? __ldcg(&st.ctrl->error) : PG_OK;   // a pass may have flagged an error
+    fw_reduce(st, f, phase, J);   // contains a __syncthreads before its combine step
+    if (threadIdx.x == 0 && gerr != PG_OK) c->error = gerr;
+    __syncthreads();
+    const unsigned long long upd0 = c->upd;   // the update in progress at entry
+    const bool need_cur = f->d_upd[(int)(upd0 & 1ull)] != upd0;                    // draws missing (right after launch)
+    const bool need_next = f->d_upd[(int)((upd0 + 1ull) & 1ull)] != upd0 + 1ull;   // next update's draws not prefetched yet
+    __syncthreads();                           // ... all read by every warp before anything is advanced
+
     long long tq = clock64();
 #define FW_TICK(slot) do { if (threadIdx.x == 0) { const long long now_ = clock64(); c->prof2[slot] += (unsigned long long)(now_ - tq); c->prof2[8 + slot] += 1ull; tq = now_; } } while (0)
     if (threadIdx.x == 0) { c->prof2[0] += (unsigned long long)(tq - t_entry); c->prof2[8] += 1ull; }
 
-    bool fresh = false;
-    bool cnt_in_smem = (phase == PH_ROOT || phase == PH_STATS);   // f->rCnt holds this round's left counts
+    // ---- helper warps: draws of the update in progress (only missing right after launch) and of the next one
+    if (warp >= 1 && warp <= FW_DR + 1) {
+        PgCtrl* scr = &fw_scratch[warp - 1];
+        if (need_cur) fw_prefetch_draws(st, x, upd0, warp, lane, scr);
+        if (need_next) fw_prefetch_draws(st, x, upd0 + 1ull, warp, lane, scr);
+    }
+
     if (warp == 0) {
         int sn = SN_NONE;
         switch (phase) {
             case PH_BEGIN: sn = fw_begin_step(st, x, lane); break;
-            case PH_ROOT: case PH_STATS: case PH_BERN: sn = fw_after_stats(st, x, lane, phase); FW_TICK(1); break;
+            case PH_ROOT:
+                sn = fw_r0_values(st, x, lane);
+                if (sn == SN_FINISH_ROUND) sn = fw_r0_finish(st, x, lane, false);
+                FW_TICK(1);
+                break;
+            case PH_STATS: sn = fw_after_stats(st, x, lane, phase); FW_TICK(1); break;
+            case PH_BERN:
+                if (c->round == 0) sn = fw_r0_finish(st, x, lane, true); else sn = fw_after_stats(st, x, lane, phase);
+                FW_TICK(1);
+                break;
             case PH_MINMAX: sn = fw_after_minmax(st, x, lane); FW_TICK(2); break;
             case PH_PART:
                 if (lane == 0) c->round += 1;
@@ -806,54 +1066,31 @@ __device__ void pg_serial_fast(const PgState& st, const PgSmemView& sm, int phas
                 break;
             default: break;
         }
+        // warp-only sub-steps chain without block barriers until a grid pass or a block-wide step is needed
+#pragma unroll 1
+        for (int guard = 0; guard < (1 << 20); ++guard) {
+            if (c->error != PG_OK) { sn = SN_NONE; break; }
+            if (sn == SN_NONE || sn == SN_PREP_PART) break;
+            if (sn == SN_BEGIN_UPDATE) { sn = fw_begin_update(st, x, lane); FW_TICK(6); }
+            else if (sn == SN_DRAW_ROUND) { sn = fw_draw_round(st, x, lane); FW_TICK(7); }
+            else if (sn == SN_FINISH_ROUND) { sn = fw_finish_round(st, x, lane); FW_TICK(3); }
+            else if (sn == SN_FINALIZE) { sn = fw_finalize(st, x, lane); FW_TICK(5); }
+            else { if (lane == 0) c->error = PG_ERR_INTERNAL; sn = SN_NONE; }
+        }
         if (lane == 0) f->sn = sn;
     }
-    for (int guard = 0; guard < (1 << 20); ++guard) {
+    __syncthreads();
+    if (f->sn == SN_PREP_PART) {
+        tq = clock64();
+        fb_prep_part(st, x);
+        FW_TICK(4);
         __syncthreads();
-        const int sn = f->sn;
-        __syncthreads();
-        if (sn == SN_NONE) break;
-        if (sn == SN_PREP_PART) {
-            tq = clock64();
-            fb_prep_part(st, x);
-            FW_TICK(4);
-            if (threadIdx.x == 0) f->sn = SN_NONE;
-            continue;
-        }
-        if (warp == 0) {
-            int nx = SN_NONE;
-            int cur_sn = sn;
-            tq = clock64();
-            for (;;) {   // warp-only sub-steps chain without block barriers
-                if (c->error != PG_OK) { nx = SN_NONE; break; }
-                if (cur_sn == SN_BEGIN_UPDATE) { nx = fw_begin_update(st, x, lane); fresh = true; FW_TICK(6); }
-                else if (cur_sn == SN_DRAW_ROUND) { nx = fw_draw_round(st, x, lane, fresh); fresh = false; FW_TICK(7); }
-                else if (cur_sn == SN_FINISH_ROUND) { nx = fw_finish_round(st, x, lane, cnt_in_smem); cnt_in_smem = false; FW_TICK(3); }
-                else if (cur_sn == SN_FINALIZE) { nx = fw_finalize(st, x, lane); FW_TICK(5); }
-                else { if (lane == 0) c->error = PG_ERR_INTERNAL; nx = SN_NONE; }
-                if (nx == SN_NONE || nx == SN_PREP_PART) break;
-                cur_sn = nx;
-            }
-            if (lane == 0) { if (c->error != PG_OK) c->phase = PH_DONE; f->sn = nx; }
-        }
+    }
+    if (warp == 0) {
+        if (lane == 0 && c->error != PG_OK) c->phase = PH_DONE;
+        __syncwarp();
+        fw_publish(st, f, lane);
     }
     __syncthreads();
-    // ---- epilogue: publish PgCtrl (warp 1) and the slot scalars (warp 2)
-    if (threadIdx.x == 0) c->prof[16 + (phase & 7)] += (unsigned long long)(clock64() - t_entry);
-    __syncthreads();
-    if (warp == 1) {
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(gc);
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&f->lc);
-        const int nw = fw_ctrl_words();
-        for (int i = lane; i < nw; i += 32) dst[i] = src[i];
-    } else if (warp == 2) {
-        const int cur = f->lc.cur;
-        if (lane < S) {
-            st.w[lane] = f->hw[lane]; st.mutated[lane] = f->hmut[lane]; st.anc[lane] = f->hanc[lane];
-            st.slot_job[lane] = f->hsjob[lane];
-            const int ss = cur * S + lane;
-            st.pt_size[ss] = f->hsize[ss]; st.pt_qhead[ss] = f->hqh[ss]; st.pt_qtail[ss] = f->hqt[ss]; st.pt_G[ss] = f->hG[ss];
-        }
-    }
-    __syncthreads();
+    return clock64() - t_entry;
 }

@@ -64,16 +64,20 @@ __device__ void pg_barrier_serial(const PgState& st, const PgSmemView& smv, unsi
             pg_spin_until(&c->bar_count, (gen + 1u) * (gridDim.x - 1u), c);
         }
         __syncthreads();
-        if (FAST) pg_serial_fast(st, smv, phase, J);   // latency-organised control logic (one lane per particle)
-        else {                                         // generic team version (P > 32)
+        long long dur;
+        if (FAST) dur = pg_serial_fast(st, smv, phase, J);   // latency-organised control logic (one lane per particle)
+        else {                                               // generic team version (P > 32)
             PgTeam tm{(int)threadIdx.x, (int)blockDim.x};
             const long long ts = clock64();
             pg_serial(st, tm);
-            if (threadIdx.x == 0) c->prof[16 + (phase & 7)] += (unsigned long long)(clock64() - ts);
+            dur = clock64() - ts;
         }
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) pg_st_release(&c->bar_gen, gen + 1u);
+        if (threadIdx.x == 0) {
+            pg_st_release(&c->bar_gen, gen + 1u);
+            c->prof[16 + (phase & 7)] += (unsigned long long)dur;   // after the release: off the critical path
+        }
     }
     gen += 1u;
 }
@@ -84,13 +88,14 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     // sampler constants the serial section reads: staged once per launch
     for (int i = threadIdx.x; i < st.max_depth + 2 && i < 16; i += blockDim.x) sm.base->cthr[i] = st.thr_depth[i];
-    if (threadIdx.x == 0) sm.base->cstaged = (st.p <= FW_MAXP && st.max_depth + 2 <= 16) ? 1 : 0;
+    if (threadIdx.x == 0) { sm.base->cstaged = (st.p <= FW_MAXP && st.max_depth + 2 <= 16) ? 1 : 0; sm.base->pass_bid = (int)blockIdx.x - 1; }
     if (st.p <= FW_MAXP)
         for (int i = threadIdx.x; i < st.p; i += blockDim.x) {
             sm.cprior[i] = st.prior ? st.prior[i] : 0.0;
             sm.cmin[i] = st.col_min[i];
             sm.cmax[i] = st.col_max[i];
         }
+    if (FAST && blockIdx.x == 0) fw_load_state(st, &sm.base->fast);   // the serial block keeps the control state in shared memory
     __syncthreads();
     unsigned gen = 0;
     pg_barrier_serial<FAST>(st, sm, gen, PH_BEGIN, 0);   // serial section of PH_BEGIN prepares the first pass
@@ -99,7 +104,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
         const int J = __ldcg(&st.ctrl->n_jobs);
         if (phase == PH_DONE) break;
         const long long t0 = clock64();
-        pg_run_pass(st, sm, phase);
+        if (blockIdx.x != 0) pg_run_pass(st, sm, phase);   // block 0 = serial block: streams nothing
         __syncthreads();
         const long long t1 = clock64();
         pg_barrier_serial<FAST>(st, sm, gen, phase, J);
@@ -110,6 +115,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
             c->prof[24 + (phase & 7)] += 1ull;
         }
     }
+    if (FAST && blockIdx.x == 0) { __syncthreads(); fw_store_state(st, &sm.base->fast); }
 }
 
 // P <= 32: latency-organised serial section; P > 32: generic team serial section.
@@ -119,6 +125,8 @@ extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_phase_kernel(const PgState st) {
     extern __shared__ __align__(16) unsigned char pg_smem_raw[];
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
+    if (threadIdx.x == 0) sm.base->pass_bid = (int)blockIdx.x;
+    __syncthreads();
     pg_run_pass(st, sm, __ldcg(&st.ctrl->phase));
 }
 
@@ -139,8 +147,11 @@ extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_serial_fast_kerne
             sm.cmin[i] = st.col_min[i];
             sm.cmax[i] = st.col_max[i];
         }
+    fw_load_state(st, &sm.base->fast);
     __syncthreads();
     pg_serial_fast(st, sm, first ? PH_BEGIN : __ldcg(&st.ctrl->phase), first ? 0 : __ldcg(&st.ctrl->n_jobs));
+    __syncthreads();
+    fw_store_state(st, &sm.base->fast);
 }
 
 extern "C" __global__ void pg_prepare_step(const PgState st, int tune) {
@@ -202,7 +213,8 @@ int pg_query_grid(int device, int S, int* grid_out, size_t* smem_out, char* err,
     if (e != cudaSuccess || per_sm < 1) { snprintf(err, errlen, "occupancy query failed: %s", cudaGetErrorString(e)); return 1; }
     if (per_sm > 1) per_sm = 1;   // one 512-thread block per SM: 148 partials per pass for the serial reduce
     if (!prop.cooperativeLaunch) { snprintf(err, errlen, "device lacks cooperative launch"); return 1; }
-    *grid_out = per_sm * prop.multiProcessorCount;
+    *grid_out = per_sm * prop.multiProcessorCount - 1;   // pass blocks; one more SM hosts the serial block
+    if (*grid_out < 1) { snprintf(err, errlen, "device has too few SMs"); return 1; }
     *smem_out = smem;
     return 0;
 }
@@ -215,7 +227,7 @@ cudaError_t pg_launch_prepare(const PgState& st, int tune, cudaStream_t s) {
 cudaError_t pg_launch_persistent(const PgState& st, size_t smem, cudaStream_t s) {
     void* args[] = {(void*)&st};
     void* fn = st.P <= 32 ? (void*)pg_sweep_persistent : (void*)pg_sweep_persistent_generic;
-    return cudaLaunchCooperativeKernel(fn, dim3(st.grid), dim3(PG_THREADS), args, smem, s);
+    return cudaLaunchCooperativeKernel(fn, dim3(st.grid + 1), dim3(PG_THREADS), args, smem, s);   // + the serial block
 }
 
 cudaError_t pg_launch_phase(const PgState& st, size_t smem, cudaStream_t s) {

@@ -82,6 +82,7 @@ struct PgCtrl {
     // ---- per-update scalars
     double T_o, T_r, T_rr, T_ll0;  // root totals over all rows: sum others, sum (y-others), sum (y-others)^2, stump ll (Bernoulli)
     double C0;                      // particle-independent part of the log-likelihood
+    double Cconst, inv_s2;          // per step: -n (log sigma + 0.5 log 2 pi) and 1/sigma^2 (Gaussian), else 0 and 1
     double g_stump;
     int acc_update;                 // accepted grows in this update
     int any_queue;
@@ -97,10 +98,6 @@ struct PgCtrl {
     unsigned long long trace_n;         // tree updates recorded in the trace
     int trace_overflow;
     int pad0;
-    // ---- in-kernel stopwatch (SM cycles): [0..7] pass time by phase (block 0), [8..15] pass end -> barrier exit
-    // (block 0: wait for the slowest block + serial section), [16..23] serial section alone (last arriver),
-    // [24..31] number of passes by phase
-    unsigned long long prof[32];
     // serial-section breakdown (cycles / calls): 0 reduce, 1 after_stats, 2 after_minmax, 3 finish_round, 4 prep_part,
     // 5 finalize, 6 begin_update, 7 draw_round; [8..15] call counts
     unsigned long long prof2[16];
@@ -109,6 +106,10 @@ struct PgCtrl {
     unsigned int bar_pad[31];
     unsigned int bar_gen;
     unsigned int bar_pad2[31];
+    // ---- in-kernel stopwatch (SM cycles), kept by the LAST block (outside the serial block's working copy):
+    // [0..7] pass time by phase, [8..15] pass end -> barrier exit (wait for the slowest block + serial section),
+    // [16..23] serial section alone (written by the serial block), [24..31] number of passes by phase
+    unsigned long long prof[32];
 };
 
 struct PgState {
