@@ -5,6 +5,7 @@ reference's compiled module (PyBartSettings / PySampler), `pgbart` mirrors the P
 parameter derivations and astep loop.  The compute lives in csrc/ (CUDA, sm_100a) behind the C ABI
 of include/pgbart.h; importing this package does not load the library until a sampler is created.
 """
+from .pgbart import PGBART, calculate_max_tree_depth  # noqa: F401
 from .pymc_bart import DeviceLikelihood, PyBartSettings, PySampler  # noqa: F401
 
-__all__ = ["DeviceLikelihood", "PyBartSettings", "PySampler"]
+__all__ = ["DeviceLikelihood", "PyBartSettings", "PySampler", "PGBART", "calculate_max_tree_depth"]

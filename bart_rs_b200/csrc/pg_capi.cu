@@ -178,8 +178,10 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
-        return fail(std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (e != cudaSuccess || ndev == 0) {   // runtime failure, not a bad argument: status 2
+        g_create_error = std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e);
+        return 2;
+    }
     if (device < 0 || device >= ndev) return fail("invalid CUDA device ordinal");
 
     auto* h = new pgbart_sampler();
