@@ -128,8 +128,7 @@ int enqueue_step(Sampler* s, int tune) {
         s->launches += 1;
     } else {
         // serial(BEGIN) -> [pass -> serial]* until DONE, reading the phase back between launches
-        const bool fastser = s->stepwise_fast && s->st.P <= 32;
-        if (!ck(s, fastser ? pg_launch_serial_fast(s->st, s->smem, 1, s->stream) : pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
+        if (!ck(s, pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
         s->launches += 1;
         for (long long guard = 0; guard < (1ll << 40); ++guard) {
             int phase = PH_DONE;
@@ -137,7 +136,7 @@ int enqueue_step(Sampler* s, int tune) {
             if (!ck(s, cudaStreamSynchronize(s->stream), "synchronize")) return 2;
             if (phase == PH_DONE) break;
             if (!ck(s, pg_launch_phase(s->st, s->smem, s->stream), "launch pass")) return 2;
-            if (!ck(s, fastser ? pg_launch_serial_fast(s->st, s->smem, 0, s->stream) : pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
+            if (!ck(s, pg_launch_serial(s->st, s->stream), "launch serial")) return 2;
             s->launches += 2;
         }
     }
@@ -259,7 +258,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     }
     // ---- state arrays
     const size_t S = (size_t)st.S, MN = (size_t)st.maxn, M = (size_t)st.m, G = (size_t)st.grid, W = (size_t)st.n_gwarps;
-    bool ok = dalloc(s, &st.A, (size_t)st.ld)
+    bool ok = dalloc(s, &st.A, (size_t)st.ld) && dalloc(s, &st.A2, (size_t)st.ld)
         && dalloc(s, &st.f_split_var, M * MN) && dalloc(s, &st.f_thr32, M * MN) && dalloc(s, &st.f_split_val, M * MN)
         && dalloc(s, &st.f_leaf_val, M * MN) && dalloc(s, &st.f_size, M) && dalloc(s, &st.f_internal, M)
         && dalloc(s, &st.pt_split_var, 2 * S * MN) && dalloc(s, &st.pt_thr32, 2 * S * MN) && dalloc(s, &st.pt_split_val, 2 * S * MN)
@@ -269,16 +268,16 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         && dalloc(s, &st.pt_qtail, 2 * S) && dalloc(s, &st.pt_G, 2 * S)
         && dalloc(s, &st.w, S) && dalloc(s, &st.mutated, S) && dalloc(s, &st.anc, S) && dalloc(s, &st.slot_job, S)
         && dalloc(s, &st.pend_node, S) && dalloc(s, &st.pend_var, S) && dalloc(s, &st.Wfinal, 2 * (S + 1))
-        && dalloc(s, &st.job_slot, S) && dalloc(s, &st.job_node, S) && dalloc(s, &st.job_var, S) && dalloc(s, &st.job_thr32, S)
-        && dalloc(s, &st.job_split, S) && dalloc(s, &st.job_seg_off, S) && dalloc(s, &st.job_len, S) && dalloc(s, &st.job_lo, S)
-        && dalloc(s, &st.job_hi, S) && dalloc(s, &st.job_vL, S) && dalloc(s, &st.job_vR, S) && dalloc(s, &st.job_order, S)
-        && dalloc(s, &st.grp_first, S + 1) && dalloc(s, &st.red_So, S) && dalloc(s, &st.red_Sr, S) && dalloc(s, &st.red_llL, S)
+        && dalloc(s, &st.job_slot, 2 * S) && dalloc(s, &st.job_node, 2 * S) && dalloc(s, &st.job_var, 2 * S) && dalloc(s, &st.job_thr32, 2 * S)
+        && dalloc(s, &st.job_split, 2 * S) && dalloc(s, &st.job_seg_off, 2 * S) && dalloc(s, &st.job_len, 2 * S) && dalloc(s, &st.job_lo, 2 * S)
+        && dalloc(s, &st.job_hi, 2 * S) && dalloc(s, &st.job_vL, 2 * S) && dalloc(s, &st.job_vR, 2 * S) && dalloc(s, &st.job_order, 2 * S)
+        && dalloc(s, &st.grp_first, 2 * (S + 1)) && dalloc(s, &st.red_So, S) && dalloc(s, &st.red_Sr, S) && dalloc(s, &st.red_llL, S)
         && dalloc(s, &st.red_llR, S) && dalloc(s, &st.red_cnt, S)
         && dalloc(s, &st.pj_anc, S) && dalloc(s, &st.pj_job, S) && dalloc(s, &st.pj_var, S) && dalloc(s, &st.pj_thr32, S)
         && dalloc(s, &st.pj_src_off, S) && dalloc(s, &st.pj_len, S) && dalloc(s, &st.pj_dst_off, S) && dalloc(s, &st.pj_cntL, S)
         && dalloc(s, &st.pj_warp_left, S * W) && dalloc(s, &st.pj_of_anc, S) && dalloc(s, &st.scan_tmp, PG_THREADS + 1)
-        && dalloc(s, &st.part_sum, G * S * 2) && dalloc(s, &st.part_cnt, W * S) && dalloc(s, &st.part_ccnt, G * S)
-        && dalloc(s, &st.part_tot, G * 4) && dalloc(s, &st.part_mm, G * S * 2) && dalloc(s, &st.part_ll, G * S * 2)
+        && dalloc(s, &st.part_sum, 2 * G * S * 2) && dalloc(s, &st.part_cnt, 2 * W * S) && dalloc(s, &st.part_ccnt, 2 * G * S)
+        && dalloc(s, &st.part_tot, 2 * G * 4) && dalloc(s, &st.part_mm, G * S * 2) && dalloc(s, &st.part_ll, G * S * 2)
         && dalloc(s, &st.info_depths, M) && dalloc(s, &st.ctrl, 1);
     if (!ok) return bail();
     {
@@ -514,6 +513,7 @@ int pgbart_get_profile(pgbart_handle h, double* out32) {
     if (!fetch_ctrl(s)) return 2;
     for (int i = 0; i < 32; ++i) out32[i] = (double)s->host_ctrl.prof[i];
     for (int i = 0; i < 16; ++i) out32[32 + i] = (double)s->host_ctrl.prof2[i];
+    out32[48] = (double)s->host_ctrl.n_spec;
     return 0;
 }
 

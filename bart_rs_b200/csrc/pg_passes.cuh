@@ -30,6 +30,35 @@
 // block and streams nothing (its SM keeps the control code in its instruction caches), so pass block = blockIdx - 1.
 #define PG_BID (sm.base->pass_bid)
 
+// Buffers a pass works on, selected by the command flags (PgCtrl.flags): which of the two A buffers it reads /
+// writes, and which parity of the job / partial-result buffers it uses.  The generic control code always
+// issues flags = 0 (in-place A, parity 0); the speculative root passes of pg_serial_fast.cuh use both parities.
+struct PgBuf {
+    const double* A_src; double* A_dst;
+    double* part_sum; unsigned* part_cnt; unsigned* part_ccnt; double* part_tot;
+    const int* job_var; const float* job_thr32; const int* job_order; const int* grp_first;
+    const unsigned* job_seg_off; const unsigned* job_len; const double* job_vL; const double* job_vR;
+};
+__host__ __device__ inline size_t pg_off_part_sum(const PgState& st, int pb) { return (size_t)pb * st.grid * st.S * 2; }
+__host__ __device__ inline size_t pg_off_part_cnt(const PgState& st, int pb) { return (size_t)pb * st.n_gwarps * st.S; }
+__host__ __device__ inline size_t pg_off_part_ccnt(const PgState& st, int pb) { return (size_t)pb * st.grid * st.S; }
+__host__ __device__ inline size_t pg_off_part_tot(const PgState& st, int pb) { return (size_t)pb * st.grid * 4; }
+__device__ __forceinline__ PgBuf pg_make_buf(const PgState& st, int flags) {
+    PgBuf b;
+    const int pb = (flags >> 2) & 1;
+    b.A_src = (flags & 1) ? st.A2 : st.A;
+    b.A_dst = (flags & 2) ? st.A2 : st.A;
+    b.part_sum = st.part_sum + pg_off_part_sum(st, pb);
+    b.part_cnt = st.part_cnt + pg_off_part_cnt(st, pb);
+    b.part_ccnt = st.part_ccnt + pg_off_part_ccnt(st, pb);
+    b.part_tot = st.part_tot + pg_off_part_tot(st, pb);
+    const size_t jo = (size_t)pb * st.S;
+    b.job_var = st.job_var + jo; b.job_thr32 = st.job_thr32 + jo; b.job_order = st.job_order + jo;
+    b.grp_first = st.grp_first + (size_t)pb * (st.S + 1);
+    b.job_seg_off = st.job_seg_off + jo; b.job_len = st.job_len + jo; b.job_vL = st.job_vL + jo; b.job_vR = st.job_vR + jo;
+    return b;
+}
+
 struct PgTreeSm {
     int size;
     int from_global;       // tree too large for shared memory
@@ -57,17 +86,21 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     unsigned rCnt[32], rMin[32], rMax[32];
     double wsA[PG_WARPS][32], wsB[PG_WARPS][32], wsT[PG_WARPS][4];   // per-warp stage of the reduction
     unsigned wsC[PG_WARPS][32], wsD[PG_WARPS][32];
-    // draws precomputed by idle warps: [update parity][round][slot]
-    double d_u1[2][FW_DR][32], d_u3[2][FW_DR][32], d_zL[2][FW_DR][32], d_zR[2][FW_DR][32];
-    int d_var[2][FW_DR][32];
-    double d_u6[2][FW_DR], d_u7[2];
-    int d_ok[2][FW_DR + 1];                      // draw source in range for (round) / for u7
-    int d0_status[2][32];                        // complete round-0 proposal: 1 depth reject, 3 min>=max, 5 live, 6 tape error, 7 depth error
-    float d0_lo[2][32], d0_hi[2][32], d0_thr[2][32];
-    double d0_split[2][32];
-    unsigned long long d_upd[2];                 // which tree update each buffer holds
-    volatile unsigned long long d_flag[2][FW_DR + 1];   // per helper warp: token (= update + 1) when its part is written
+    // draws precomputed by idle warps: [update mod 3][round][slot] (the update in progress and the next two)
+    double d_u1[3][FW_DR][32], d_u3[3][FW_DR][32], d_zL[3][FW_DR][32], d_zR[3][FW_DR][32];
+    int d_var[3][FW_DR][32];
+    double d_u6[3][FW_DR], d_u7[3];
+    int d_ok[3][FW_DR + 1];                      // draw source in range for (round) / for u7
+    int d0_status[3][32];                        // complete round-0 proposal: 1 depth reject, 3 min>=max, 5 live, 6 tape error, 7 depth error
+    float d0_lo[3][32], d0_hi[3][32], d0_thr[3][32];
+    double d0_split[3][32];
+    unsigned long long d_upd[3];                 // which tree update each buffer holds
+    volatile unsigned long long d_flag[3][FW_DR + 1];   // per helper warp: token (= update + 1) when its part is written
     int sn;
+    // control loop of the serial block: the pass that is in flight
+    unsigned issued;                             // commands issued so far (= value of bar_gen)
+    int out_phase, out_J, out_pb;                // phase / job count / buffer parity of the outstanding pass
+    int quit;
     unsigned scan[PG_THREADS + 1];
 };
 
@@ -197,14 +230,14 @@ __device__ __forceinline__ double pg_tree_eval(const PgState& st, int t, const P
 }
 
 // Stage the job list of the current pass into shared memory.
-__device__ __forceinline__ void pg_stage_jobs(const PgState& st, const PgSmemView& sm, int J, int G, bool with_values) {
+__device__ __forceinline__ void pg_stage_jobs(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int J, int G, bool with_values) {
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
-        sm.jvar[j] = __ldcg(&st.job_var[j]);
-        sm.jthr[j] = __ldcg(&st.job_thr32[j]);
-        sm.jorder[j] = __ldcg(&st.job_order[j]);
-        if (with_values) { sm.jvL[j] = __ldcg(&st.job_vL[j]); sm.jvR[j] = __ldcg(&st.job_vR[j]); }
+        sm.jvar[j] = __ldcg(&bf.job_var[j]);
+        sm.jthr[j] = __ldcg(&bf.job_thr32[j]);
+        sm.jorder[j] = __ldcg(&bf.job_order[j]);
+        if (with_values) { sm.jvL[j] = __ldcg(&bf.job_vL[j]); sm.jvR[j] = __ldcg(&bf.job_vR[j]); }
     }
-    for (int g = threadIdx.x; g <= G; g += blockDim.x) sm.grp[g] = __ldcg(&st.grp_first[g]);
+    for (int g = threadIdx.x; g <= G; g += blockDim.x) sm.grp[g] = __ldcg(&bf.grp_first[g]);
 }
 
 __device__ __forceinline__ void pg_zero_acc(const PgSmemView& sm, int S) {
@@ -212,19 +245,19 @@ __device__ __forceinline__ void pg_zero_acc(const PgSmemView& sm, int S) {
 }
 
 // Write the block's per-job results: fixed warp order => deterministic.
-__device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgSmemView& sm, int J, bool counts, bool as_ll) {
+__device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int J, bool counts, bool as_ll) {
     const int S = st.S;
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
         double a = 0.0, b = 0.0;
         unsigned cc = 0u;
         for (int w = 0; w < PG_WARPS; ++w) { a += sm.accA[w * S + j]; b += sm.accB[w * S + j]; cc += sm.accC[w * S + j]; }
-        double* dst = as_ll ? st.part_ll : st.part_sum;
+        double* dst = as_ll ? st.part_ll : bf.part_sum;
         dst[((size_t)PG_BID * S + j) * 2 + 0] = a;
         dst[((size_t)PG_BID * S + j) * 2 + 1] = b;
         if (counts) {
-            st.part_ccnt[(size_t)PG_BID * S + j] = cc;
+            bf.part_ccnt[(size_t)PG_BID * S + j] = cc;
             for (int w = 0; w < PG_WARPS; ++w)
-                st.part_cnt[((size_t)PG_BID * PG_WARPS + w) * S + j] = sm.accC[w * S + j];
+                bf.part_cnt[((size_t)PG_BID * PG_WARPS + w) * S + j] = sm.accC[w * S + j];
         }
     }
 }
@@ -234,7 +267,7 @@ __device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgSmemView
 // =============================================================================
 // Rows per lane per iteration: 8 (two float4 groups) => 256 rows per warp-iteration.
 template <bool BERN>
-__device__ void pg_pass_root(const PgState& st, const PgSmemView& sm) {
+__device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     const int J = __ldcg(&c->n_jobs) * (__ldcg(&c->phase) == PH_ROOT ? 1 : 0);
     const int t_add = __ldcg(&c->t_add), t_sub = __ldcg(&c->phase) == PH_ROOT ? __ldcg(&c->t_sub) : -1;
@@ -242,14 +275,14 @@ __device__ void pg_pass_root(const PgState& st, const PgSmemView& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
 
-    pg_stage_tree(st, t_add, sm.base->tadd);
+    pg_stage_tree(st, t_add, sm.base->tadd);   // t_add == -2: a stump (constant init_leaf), no forest read
     pg_stage_tree(st, t_sub, sm.base->tsub);
-    pg_stage_jobs(st, sm, J, 0, false);
+    pg_stage_jobs(st, bf, sm, J, 0, false);
     pg_zero_acc(sm, S);
     __syncthreads();
     const bool add_nontrivial = t_add >= 0 && sm.base->tadd.size > 1;
     const bool sub_nontrivial = t_sub >= 0 && sm.base->tsub.size > 1;
-    const double add_c = (t_add >= 0 && !add_nontrivial) ? sm.base->tadd.leaf_val[0] : 0.0;
+    const double add_c = t_add == -2 ? st.init_leaf : ((t_add >= 0 && !add_nontrivial) ? sm.base->tadd.leaf_val[0] : 0.0);
     const double sub_c = (t_sub >= 0 && !sub_nontrivial) ? sm.base->tsub.leaf_val[0] : 0.0;
 
     unsigned long long beg, end;
@@ -267,13 +300,13 @@ __device__ void pg_pass_root(const PgState& st, const PgSmemView& sm) {
             double2 a;
             float4 yy;
             if (g0) {
-                a = pg_ld_a2(st.A + r0); o[0] = a.x; o[1] = a.y;
-                a = pg_ld_a2(st.A + r0 + 2); o[2] = a.x; o[3] = a.y;
+                a = pg_ld_a2(bf.A_src + r0); o[0] = a.x; o[1] = a.y;
+                a = pg_ld_a2(bf.A_src + r0 + 2); o[2] = a.x; o[3] = a.y;
                 yy = pg_ld_x4(st.y + r0); yv[0] = yy.x; yv[1] = yy.y; yv[2] = yy.z; yv[3] = yy.w;
             } else { o[0] = o[1] = o[2] = o[3] = 0.0; yv[0] = yv[1] = yv[2] = yv[3] = 0.0f; }
             if (g1) {
-                a = pg_ld_a2(st.A + r1); o[4] = a.x; o[5] = a.y;
-                a = pg_ld_a2(st.A + r1 + 2); o[6] = a.x; o[7] = a.y;
+                a = pg_ld_a2(bf.A_src + r1); o[4] = a.x; o[5] = a.y;
+                a = pg_ld_a2(bf.A_src + r1 + 2); o[6] = a.x; o[7] = a.y;
                 yy = pg_ld_x4(st.y + r1); yv[4] = yy.x; yv[5] = yy.y; yv[6] = yy.z; yv[7] = yy.w;
             } else { o[4] = o[5] = o[6] = o[7] = 0.0; yv[4] = yv[5] = yv[6] = yv[7] = 0.0f; }
         }
@@ -281,7 +314,7 @@ __device__ void pg_pass_root(const PgState& st, const PgSmemView& sm) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) valid[q] = ((q < 4 ? r0 : r1 - 4) + q) < n && (q < 4 ? g0 : g1);
         // kernel.rs:99-102 then :84-87, each a separately rounded f64 operation
-        if (t_add >= 0) {
+        if (t_add >= 0 || t_add == -2) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const double v = add_nontrivial ? (valid[q] ? pg_tree_eval(st, t_add, sm.base->tadd, (q < 4 ? r0 : r1 - 4) + q) : 0.0) : add_c;
@@ -296,12 +329,12 @@ __device__ void pg_pass_root(const PgState& st, const PgSmemView& sm) {
             }
         }
         if (g0) {
-            __stcg(reinterpret_cast<double2*>(st.A + r0), make_double2(o[0], o[1]));
-            __stcg(reinterpret_cast<double2*>(st.A + r0 + 2), make_double2(o[2], o[3]));
+            __stcg(reinterpret_cast<double2*>(bf.A_dst + r0), make_double2(o[0], o[1]));
+            __stcg(reinterpret_cast<double2*>(bf.A_dst + r0 + 2), make_double2(o[2], o[3]));
         }
         if (g1) {
-            __stcg(reinterpret_cast<double2*>(st.A + r1), make_double2(o[4], o[5]));
-            __stcg(reinterpret_cast<double2*>(st.A + r1 + 2), make_double2(o[6], o[7]));
+            __stcg(reinterpret_cast<double2*>(bf.A_dst + r1), make_double2(o[4], o[5]));
+            __stcg(reinterpret_cast<double2*>(bf.A_dst + r1 + 2), make_double2(o[6], o[7]));
         }
         if (J == 0 && t_sub < 0) continue;   // PH_FINAL: commit only
         double r[8];
@@ -363,26 +396,26 @@ __device__ void pg_pass_root(const PgState& st, const PgSmemView& sm) {
     if (threadIdx.x < 4) {
         double v = 0.0;
         for (int w = 0; w < PG_WARPS; ++w) v += sm.base->tot[w][threadIdx.x];
-        st.part_tot[(size_t)PG_BID * 4 + threadIdx.x] = v;
+        bf.part_tot[(size_t)PG_BID * 4 + threadIdx.x] = v;
     }
-    pg_flush_acc(st, sm, J, true, false);
+    pg_flush_acc(st, bf, sm, J, true, false);
 }
 
 // =============================================================================
 // PH_MINMAX — splitting.rs:43-49 over index segments
 // =============================================================================
-__device__ void pg_pass_minmax(const PgState& st, const PgSmemView& sm) {
+__device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     const int J = __ldcg(&c->n_jobs);
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
-    for (int j = threadIdx.x; j < J; j += blockDim.x) { sm.mmin[j] = 0xFFFFFFFFu; sm.mmax[j] = 0u; sm.jvar[j] = __ldcg(&st.job_var[j]); }
+    for (int j = threadIdx.x; j < J; j += blockDim.x) { sm.mmin[j] = 0xFFFFFFFFu; sm.mmax[j] = 0u; sm.jvar[j] = __ldcg(&bf.job_var[j]); }
     __syncthreads();
     const size_t ld = (size_t)st.ld;
     for (int j = 0; j < J; ++j) {
-        const unsigned off = __ldcg(&st.job_seg_off[j]);
-        const unsigned long long L = __ldcg(&st.job_len[j]);
+        const unsigned off = __ldcg(&bf.job_seg_off[j]);
+        const unsigned long long L = __ldcg(&bf.job_len[j]);
         const float* col = st.X + (size_t)sm.jvar[j] * ld;
         unsigned long long beg, end;
         pg_warp_range(L, gw, st.n_gwarps, 1, &beg, &end);
@@ -412,13 +445,13 @@ __device__ void pg_pass_minmax(const PgState& st, const PgSmemView& sm) {
 // MODE 0: statistics (LEFT count, sum A, sum y-A).  MODE 1: Bernoulli child log-likelihoods
 // (A = left-child sum, B = right-child sum); identity segments allowed.
 template <int MODE>
-__device__ void pg_pass_seg(const PgState& st, const PgSmemView& sm) {
+__device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     const int J = __ldcg(&c->n_jobs), G = __ldcg(&c->n_groups);
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
-    pg_stage_jobs(st, sm, J, G, MODE == 1);
+    pg_stage_jobs(st, bf, sm, J, G, MODE == 1);
     pg_zero_acc(sm, S);
     __syncthreads();
     const size_t ld = (size_t)st.ld;
@@ -426,9 +459,9 @@ __device__ void pg_pass_seg(const PgState& st, const PgSmemView& sm) {
     for (int g = 0; g < G; ++g) {
         const int jb0 = sm.grp[g], jb1 = sm.grp[g + 1];
         const int j0 = sm.jorder[jb0];
-        const unsigned off = __ldcg(&st.job_seg_off[j0]);
+        const unsigned off = __ldcg(&bf.job_seg_off[j0]);
         const bool ident = off == PG_SEG_IDENTITY;
-        const unsigned long long L = __ldcg(&st.job_len[j0]);
+        const unsigned long long L = __ldcg(&bf.job_len[j0]);
         unsigned long long beg, end;
         pg_warp_range(L, gw, st.n_gwarps, ident ? 4 : 1, &beg, &end);
         for (unsigned long long base = beg; base < end; base += 32 * R) {
@@ -444,7 +477,7 @@ __device__ void pg_pass_seg(const PgState& st, const PgSmemView& sm) {
             }
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                o[k] = valid[k] ? __ldcg(&st.A[idx[k]]) : 0.0;
+                o[k] = valid[k] ? __ldcg(&bf.A_src[idx[k]]) : 0.0;
                 yv[k] = valid[k] ? __ldg(&st.y[idx[k]]) : 0.0f;
                 r[k] = valid[k] ? (double)yv[k] - o[k] : 0.0;
             }
@@ -490,13 +523,13 @@ __device__ void pg_pass_seg(const PgState& st, const PgSmemView& sm) {
         }
     }
     __syncthreads();
-    pg_flush_acc(st, sm, J, MODE == 0, MODE == 1);
+    pg_flush_acc(st, bf, sm, J, MODE == 0, MODE == 1);
 }
 
 // =============================================================================
 // PH_PART — stable partition of a segment by x[var] < split into the pool
 // =============================================================================
-__device__ void pg_pass_part(const PgState& st, const PgSmemView& sm) {
+__device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     const int K = __ldcg(&c->n_pjobs);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -534,22 +567,52 @@ __device__ void pg_pass_part(const PgState& st, const PgSmemView& sm) {
         }
         // the statistics pass counted the same predicate over the same range
         const int j = __ldcg(&st.pj_job[k]);
-        if (lane == 0 && (left_run - left0) != __ldcg(&st.part_cnt[(size_t)gw * st.S + j])) c->error = PG_ERR_INTERNAL;
+        if (lane == 0 && (left_run - left0) != __ldcg(&bf.part_cnt[(size_t)gw * st.S + j])) c->error = PG_ERR_INTERNAL;
     }
     (void)sm; (void)warp;
 }
 
 // Dispatch one grid pass.
 __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView& sm, int phase) {
+    const PgBuf bf = pg_make_buf(st, __ldcg(&st.ctrl->flags));
     switch (phase) {
         case PH_ROOT:
         case PH_FINAL:
-            if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true>(st, sm); else pg_pass_root<false>(st, sm);
+            if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true>(st, bf, sm); else pg_pass_root<false>(st, bf, sm);
             break;
-        case PH_MINMAX: pg_pass_minmax(st, sm); break;
-        case PH_STATS: pg_pass_seg<0>(st, sm); break;
-        case PH_BERN: pg_pass_seg<1>(st, sm); break;
-        case PH_PART: pg_pass_part(st, sm); break;
+        case PH_MINMAX: pg_pass_minmax(st, bf, sm); break;
+        case PH_STATS: pg_pass_seg<0>(st, bf, sm); break;
+        case PH_BERN: pg_pass_seg<1>(st, bf, sm); break;
+        case PH_PART: pg_pass_part(st, bf, sm); break;
         default: break;
     }
 }
+
+// ---- grid-level synchronisation primitives -------------------------------------------------------
+// Polling load: relaxed at gpu scope (served by L2, does not touch this SM's L1); the acquire is one
+// fence after the flag has flipped, so a spinning block does not keep invalidating the L1 that the
+// serial section running on the same SM depends on.
+__device__ __forceinline__ unsigned pg_ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pg_st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void pg_spin_until(const unsigned* p, unsigned target, PgCtrl* c) {
+    const long long t0 = clock64();
+    unsigned ns = 20;
+    while (pg_ld_relaxed(p) < target) {
+        __nanosleep(ns);
+        if (ns < 160) ns <<= 1;
+        if (clock64() - t0 > 40000000000ll) {   // ~20 s at 2 GHz: a lost block becomes an error, not a hang
+            c->error = PG_ERR_WATCHDOG;
+            __threadfence();
+            __trap();
+        }
+    }
+    __threadfence();   // acquire side of the fence/atomic/fence pattern
+}
+

@@ -183,31 +183,32 @@ PG_HDN inline void pg_compact_jobs_single(const PgState& st) {
 }
 
 // job_order: permutation with the jobs of one index segment adjacent (first-seen order);
-// grp_first: group boundaries in job_order.  J is small (<= S).
-PG_HDN inline void pg_group_jobs_single(const PgState& st, PgCtrl* c) {
-    const int J = c->n_jobs;
+// grp_first: group boundaries in job_order.  J is small (<= S).  Returns the number of groups.
+PG_HDN inline int pg_group_jobs_arrays(const unsigned int* seg_off, const unsigned int* seg_len, int* job_order, int* grp_first, int J) {
     int G = 0, filled = 0;
     bool one = true;   // common case (round 1, or all slots copies of one ancestor): a single segment
     for (int j = 1; j < J; ++j)
-        if (st.job_seg_off[j] != st.job_seg_off[0] || st.job_len[j] != st.job_len[0]) { one = false; break; }
+        if (seg_off[j] != seg_off[0] || seg_len[j] != seg_len[0]) { one = false; break; }
     if (one) {
-        for (int j = 0; j < J; ++j) st.job_order[j] = j;
-        st.grp_first[0] = 0; st.grp_first[J > 0 ? 1 : 0] = J;
-        c->n_groups = J > 0 ? 1 : 0;
-        return;
+        for (int j = 0; j < J; ++j) job_order[j] = j;
+        grp_first[0] = 0; grp_first[J > 0 ? 1 : 0] = J;
+        return J > 0 ? 1 : 0;
     }
-    for (int j = 0; j < J; ++j) st.job_order[j] = -1;
+    for (int j = 0; j < J; ++j) job_order[j] = -1;
     for (int j = 0; j < J; ++j) {
         bool placed = false;
-        for (int q = 0; q < filled; ++q) if (st.job_order[q] == j) { placed = true; break; }
+        for (int q = 0; q < filled; ++q) if (job_order[q] == j) { placed = true; break; }
         if (placed) continue;
-        st.grp_first[G++] = filled;
-        const unsigned int off = st.job_seg_off[j], len = st.job_len[j];
+        grp_first[G++] = filled;
+        const unsigned int off = seg_off[j], len = seg_len[j];
         for (int q = j; q < J; ++q)
-            if (st.job_seg_off[q] == off && st.job_len[q] == len) st.job_order[filled++] = q;
+            if (seg_off[q] == off && seg_len[q] == len) job_order[filled++] = q;
     }
-    st.grp_first[G] = filled;
-    c->n_groups = G;
+    grp_first[G] = filled;
+    return G;
+}
+PG_HDN inline void pg_group_jobs_single(const PgState& st, PgCtrl* c) {
+    c->n_groups = pg_group_jobs_arrays(st.job_seg_off, st.job_len, st.job_order, st.grp_first, c->n_jobs);
 }
 
 PG_HDN inline void pg_group_jobs_single(const PgState& st) { pg_group_jobs_single(st, st.ctrl); }

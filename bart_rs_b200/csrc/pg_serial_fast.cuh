@@ -62,8 +62,9 @@ __device__ void fw_load_state(const PgState& st, PgFastSm* f) {
         f->hsize[s] = __ldcg(&st.pt_size[s]); f->hqh[s] = __ldcg(&st.pt_qhead[s]);
         f->hqt[s] = __ldcg(&st.pt_qtail[s]); f->hG[s] = __ldcg(&st.pt_G[s]);
     }
-    if (threadIdx.x < 2) f->d_upd[threadIdx.x] = ~0ull;
-    if (threadIdx.x < 2 * (FW_DR + 1)) f->d_flag[threadIdx.x / (FW_DR + 1)][threadIdx.x % (FW_DR + 1)] = 0ull;
+    if (threadIdx.x < 3) f->d_upd[threadIdx.x] = ~0ull;
+    if (threadIdx.x < 3 * (FW_DR + 1)) f->d_flag[threadIdx.x / (FW_DR + 1)][threadIdx.x % (FW_DR + 1)] = 0ull;
+    if (threadIdx.x == 0) { f->issued = 0u; f->out_phase = PH_BEGIN; f->out_J = 0; f->out_pb = 0; f->quit = 0; }
 }
 
 __device__ void fw_store_state(const PgState& st, PgFastSm* f) {
@@ -88,12 +89,15 @@ __device__ __forceinline__ void fw_publish(const PgState& st, PgFastSm* f, int l
 // lane = job, warp = subset of blocks {warp, warp + PG_WARPS, ...}; rows of the [block][job] partial
 // arrays are contiguous in job: coalesced, and all of a warp's loads are in flight at once.
 #define FW_RB 10   // blocks per warp per batch (grid 148 / 16 warps = 9.25)
-__device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J) {
+__device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int pb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = st.grid, S = st.S;
+    const double* p_sum = st.part_sum + pg_off_part_sum(st, pb);
+    const unsigned* p_ccnt = st.part_ccnt + pg_off_part_ccnt(st, pb);
+    const double* p_tot = st.part_tot + pg_off_part_tot(st, pb);
     const bool sums = phase == PH_ROOT || phase == PH_STATS || phase == PH_BERN;
     if (sums) {
-        const double* src = phase == PH_BERN ? st.part_ll : st.part_sum;
+        const double* src = phase == PH_BERN ? st.part_ll : p_sum;
         const bool cnts = phase != PH_BERN;
         double a = 0.0, bsum = 0.0;
         unsigned cc = 0u;
@@ -107,7 +111,7 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J) {
                     const int b = b0 + q * PG_WARPS;
                     if (b < G) {
                         v[q] = __ldcg(reinterpret_cast<const double2*>(src + ((size_t)b * S + lane) * 2));
-                        k[q] = cnts ? __ldcg(&st.part_ccnt[(size_t)b * S + lane]) : 0u;
+                        k[q] = cnts ? __ldcg(&p_ccnt[(size_t)b * S + lane]) : 0u;
                     } else { v[q] = make_double2(0.0, 0.0); k[q] = 0u; }
                 }
 #pragma unroll
@@ -130,8 +134,8 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J) {
     if (phase == PH_ROOT) {   // root totals: thread = block
         double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
         for (int b = threadIdx.x; b < G; b += blockDim.x) {
-            const double2 u = __ldcg(reinterpret_cast<const double2*>(st.part_tot + (size_t)b * 4));
-            const double2 v = __ldcg(reinterpret_cast<const double2*>(st.part_tot + (size_t)b * 4 + 2));
+            const double2 u = __ldcg(reinterpret_cast<const double2*>(p_tot + (size_t)b * 4));
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(p_tot + (size_t)b * 4 + 2));
             t0 += u.x; t1 += u.y; t2 += v.x; t3 += v.y;
         }
 #pragma unroll 1
@@ -187,7 +191,7 @@ __device__ __forceinline__ bool fw_tape_ok(const PgState& st, unsigned long long
 // block: helpers must not raise errors for draws that may never be consumed.
 __device__ void fw_prefetch_draws(const PgState& st, const FwCx& x, unsigned long long upd, int hw, int lane, PgCtrl* scr) {
     PgFastSm* f = x.f;
-    const int buf = (int)(upd & 1ull);
+    const int buf = (int)(upd % 3ull);
     const int S = st.S;
     if (hw <= FW_DR) {
         const int r = hw - 1;
@@ -243,7 +247,7 @@ __device__ void fw_prefetch_draws(const PgState& st, const FwCx& x, unsigned lon
 }
 
 __device__ __forceinline__ void fw_wait_draws(PgFastSm* f, unsigned long long upd) {
-    const int buf = (int)(upd & 1ull);
+    const int buf = (int)(upd % 3ull);
 #pragma unroll 1
     for (int q = 0; q <= FW_DR; ++q)
         while (f->d_flag[buf][q] != upd + 1ull) __nanosleep(20);
@@ -252,12 +256,12 @@ __device__ __forceinline__ void fw_wait_draws(PgFastSm* f, unsigned long long up
 
 // draws as seen by warp 0: precomputed when in range, else the generic (error-raising) path
 __device__ __forceinline__ double fw_u6(const PgState& st, const FwCx& x, unsigned long long upd, int r) {
-    const int buf = (int)(upd & 1ull);
+    const int buf = (int)(upd % 3ull);
     if (r < FW_DR && x.f->d_ok[buf][r]) return x.f->d_u6[buf][r];
     return pg_uniform(st, x.c, PG_D_RESAMPLE, upd, r, 0);
 }
 __device__ __forceinline__ double fw_u7(const PgState& st, const FwCx& x, unsigned long long upd) {
-    const int buf = (int)(upd & 1ull);
+    const int buf = (int)(upd % 3ull);
     if (x.f->d_ok[buf][FW_DR]) return x.f->d_u7[buf];
     return pg_uniform(st, x.c, PG_D_SELECT, upd, 0, 0);
 }
@@ -271,42 +275,54 @@ struct FwJob {
     bool live;
 };
 
-// Compact live jobs (order preserved) into the GLOBAL job arrays (read by the next grid pass) and
-// into the shared job cache; slot_job goes to the shared slot scalars.  Returns the new J.
-__device__ __forceinline__ int fw_write_jobs(const PgState& st, const FwCx& x, const FwJob& jb, int lane, bool write_all) {
+// Compact live jobs (order preserved) into the GLOBAL job arrays of parity `pb` (read by the grid pass) and,
+// when `to_cache`, into the shared job cache + slot_job + the control block (the jobs of the update in progress).
+// Returns the new J; *ngroups_out = number of index segments the jobs span.
+__device__ __forceinline__ int fw_write_jobs(const PgState& st, const FwCx& x, const FwJob& jb, int lane, bool write_all,
+                                             int pb, bool to_global, bool to_cache, int* ngroups_out) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
+    const size_t jo = (size_t)pb * st.S;
     const unsigned live = __ballot_sync(PG_FULL, jb.live);
     const int J = __popc(live);
     const int pos = __popc(live & ((1u << lane) - 1u));
-    if (lane < st.S) f->hsjob[lane] = -1;
+    if (to_cache && lane < st.S) f->hsjob[lane] = -1;
     __syncwarp();
     if (jb.live) {
-        st.job_slot[pos] = jb.slot; st.job_node[pos] = jb.node; st.job_var[pos] = jb.var;
-        st.job_seg_off[pos] = jb.seg_off; st.job_len[pos] = jb.len;
-        f->jslot[pos] = jb.slot; f->jnode[pos] = jb.node; f->jvar[pos] = jb.var;
-        f->jseg[pos] = jb.seg_off; f->jlen[pos] = jb.len;
-        if (write_all) {
-            st.job_thr32[pos] = jb.thr; st.job_split[pos] = jb.split; st.job_lo[pos] = jb.lo; st.job_hi[pos] = jb.hi;
-            f->jthr[pos] = jb.thr; f->jsplit[pos] = jb.split;
+        if (to_global) {
+            st.job_slot[jo + pos] = jb.slot; st.job_node[jo + pos] = jb.node; st.job_var[jo + pos] = jb.var;
+            st.job_seg_off[jo + pos] = jb.seg_off; st.job_len[jo + pos] = jb.len;
+            st.job_order[jo + pos] = pos;
+            if (write_all) {
+                st.job_thr32[jo + pos] = jb.thr; st.job_split[jo + pos] = jb.split;
+                st.job_lo[jo + pos] = jb.lo; st.job_hi[jo + pos] = jb.hi;
+            }
         }
-        st.job_order[pos] = pos;
-        f->hsjob[jb.slot] = pos;
+        if (to_cache) {
+            f->jslot[pos] = jb.slot; f->jnode[pos] = jb.node; f->jvar[pos] = jb.var;
+            f->jseg[pos] = jb.seg_off; f->jlen[pos] = jb.len;
+            if (write_all) { f->jthr[pos] = jb.thr; f->jsplit[pos] = jb.split; }
+            f->hsjob[jb.slot] = pos;
+        }
     }
     const int first = __ffs(live) - 1;
     const unsigned off0 = __shfl_sync(PG_FULL, jb.seg_off, first < 0 ? 0 : first);
     const unsigned len0 = __shfl_sync(PG_FULL, jb.len, first < 0 ? 0 : first);
     const bool same = !jb.live || (jb.seg_off == off0 && jb.len == len0);
     const bool one = __all_sync(PG_FULL, same);
-    if (lane == 0) c->n_jobs = J;
+    int G = J > 0 ? 1 : 0;
     if (one) {
-        if (lane == 0) { st.grp_first[0] = 0; st.grp_first[J > 0 ? 1 : 0] = J; c->n_groups = J > 0 ? 1 : 0; }
+        if (lane == 0 && to_global) { int* gf = st.grp_first + (size_t)pb * (st.S + 1); gf[0] = 0; gf[J > 0 ? 1 : 0] = J; }
     } else {
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) pg_group_jobs_single(st, c);   // rare (several distinct survivors): generic grouping
+        if (lane == 0)   // rare (several distinct survivors): generic grouping on the global arrays
+            G = pg_group_jobs_arrays(st.job_seg_off + jo, st.job_len + jo, st.job_order + jo, st.grp_first + (size_t)pb * (st.S + 1), J);
+        G = __shfl_sync(PG_FULL, G, 0);
     }
+    if (to_cache && lane == 0) { c->n_jobs = J; c->n_groups = G; }
     __syncwarp();
+    *ngroups_out = G;
     return J;
 }
 
@@ -326,7 +342,7 @@ __device__ __forceinline__ void fw_decide(const PgState& st, const FwCx& x, FwJo
     if (tr) { tr[9] = (double)jb.lo; tr[10] = (double)jb.hi; }
     if (jb.lo >= jb.hi) { if (tr) tr[0] = 3; jb.live = false; return; }
     if (2 * jb.node + 2 >= st.maxn) { c->error = PG_ERR_DEPTH; jb.live = false; return; }
-    const int buf = (int)(c->upd & 1ull);
+    const int buf = (int)(c->upd % 3ull);
     bool done = false;
     if (r < FW_DR && x.f->d_ok[buf][r]) {
         const double lo = (double)jb.lo, hi = (double)jb.hi;
@@ -358,8 +374,29 @@ __device__ __forceinline__ int fw_begin_step(const PgState& st, const FwCx& x, i
     return SN_BEGIN_UPDATE;
 }
 
-// smc.rs:42-53 + round 0 of smc.rs:61-86: fresh particles; the precomputed root proposals become the job list
-__device__ __forceinline__ int fw_begin_update(const PgState& st, const FwCx& x, int lane) {
+// Round-0 proposals of tree update `upd` (precomputed by the helper warps) as a job lane view.
+__device__ __forceinline__ FwJob fw_root_job(const PgState& st, const FwCx& x, unsigned long long upd, int lane, bool* passed, int* status_out) {
+    PgFastSm* f = x.f;
+    const int buf = (int)(upd % 3ull);
+    FwJob jb;
+    jb.live = false; jb.slot = lane; jb.node = 0; jb.var = 0; jb.seg_off = PG_SEG_IDENTITY; jb.len = (unsigned)st.n;
+    jb.lo = jb.hi = jb.thr = 0.f; jb.split = 0.0;
+    *passed = false;
+    *status_out = 0;
+    if (lane < st.S) {
+        const int status = f->d0_status[buf][lane];
+        jb.var = f->d_var[buf][0][lane];
+        jb.lo = f->d0_lo[buf][lane]; jb.hi = f->d0_hi[buf][lane]; jb.thr = f->d0_thr[buf][lane]; jb.split = f->d0_split[buf][lane];
+        *passed = status != 1;
+        jb.live = status == 5;
+        *status_out = status;
+    }
+    return jb;
+}
+
+// smc.rs:42-53 + round 0 of smc.rs:61-86: fresh particles of the update that becomes current.  The precomputed
+// root proposals become the job list: written to the global job arrays unless a speculative root pass already did.
+__device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x, int lane, bool jobs_published) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
     const int S = st.S;
@@ -369,23 +406,16 @@ __device__ __forceinline__ int fw_begin_update(const PgState& st, const FwCx& x,
     }
     __syncwarp();
     const unsigned long long upd = c->upd;
-    const int buf = (int)(upd & 1ull);
+    const int buf = (int)(upd % 3ull);
     fw_wait_draws(f, upd);
-    FwJob jb;
-    jb.live = false; jb.slot = lane; jb.node = 0; jb.var = 0; jb.seg_off = PG_SEG_IDENTITY; jb.len = (unsigned)st.n;
-    jb.lo = jb.hi = jb.thr = 0.f; jb.split = 0.0;
-    bool passed = false;
+    bool passed;
+    int status;
+    const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
     if (lane < S) {
         const int s = lane;
         f->hw[s] = 0.0;       // smc.rs:53: once per update, never reset (Q1)
         f->hmut[s] = 0;
-        if (!f->d_ok[buf][0]) c->error = PG_ERR_TAPE;
-        const int status = f->d0_status[buf][s];
-        jb.var = f->d_var[buf][0][s];
-        jb.lo = f->d0_lo[buf][s]; jb.hi = f->d0_hi[buf][s]; jb.thr = f->d0_thr[buf][s]; jb.split = f->d0_split[buf][s];
-        passed = status != 1;
-        jb.live = status == 5;
-        if (status == 6) c->error = PG_ERR_TAPE;
+        if (!f->d_ok[buf][0] || status == 6) c->error = PG_ERR_TAPE;
         if (status == 7) c->error = PG_ERR_DEPTH;
         double* tr = pg_trace_slot(st, c, 0, s);
         if (tr) {
@@ -397,7 +427,8 @@ __device__ __forceinline__ int fw_begin_update(const PgState& st, const FwCx& x,
         }
     }
     const int J0 = __popc(__ballot_sync(PG_FULL, passed));
-    const int J = fw_write_jobs(st, x, jb, lane, true);
+    int G;
+    const int J = fw_write_jobs(st, x, jb, lane, true, (int)(upd & 1ull), !jobs_published, true, &G);
     const int uniq = fw_unique(jb.var, jb.live, lane);
     if (lane == 0) {
         const unsigned long long n = (unsigned long long)st.n;
@@ -407,7 +438,6 @@ __device__ __forceinline__ int fw_begin_update(const PgState& st, const FwCx& x,
         c->phase = PH_ROOT; c->n_phases += 1;
     }
     __syncwarp();
-    return SN_NONE;
 }
 
 // rounds >= 1: pop the next expandable node of every slot, depth-prior test, split variable (smc.rs:61-86 front half)
@@ -416,7 +446,7 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
     PgFastSm* f = x.f;
     const int cur = c->cur, r = c->round, S = st.S;
     const unsigned long long upd = c->upd;
-    const int buf = (int)(upd & 1ull);
+    const int buf = (int)(upd % 3ull);
     const bool pre = r < FW_DR && f->d_ok[buf][r];
     FwJob jb;
     jb.live = false; jb.slot = lane; jb.node = -1; jb.var = 0; jb.seg_off = 0; jb.len = 0; jb.lo = jb.hi = jb.thr = 0.f; jb.split = 0.0;
@@ -455,14 +485,18 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
             }
         }
     }
-    const int J = fw_write_jobs(st, x, jb, lane, false);
+    const int pb = (int)(upd & 1ull);
+    int G;
+    const int J = fw_write_jobs(st, x, jb, lane, false, pb, true, true, &G);
     if (J == 0) return SN_FINISH_ROUND;
     if (lane == 0) {
+        const int* jord = st.job_order + (size_t)pb * st.S;
+        const int* gf = st.grp_first + (size_t)pb * (st.S + 1);
         unsigned long long bm = 0, bc = 0;
 #pragma unroll 1
-        for (int g = 0; g < c->n_groups; ++g) {
-            const unsigned long long L = st.job_len[st.job_order[st.grp_first[g]]];
-            bm += 4ull * L + 4ull * L * (unsigned long long)(st.grp_first[g + 1] - st.grp_first[g]);
+        for (int g = 0; g < G; ++g) {
+            const unsigned long long L = f->jlen[jord[gf[g]]];
+            bm += 4ull * L + 4ull * L * (unsigned long long)(gf[g + 1] - gf[g]);
         }
 #pragma unroll 1
         for (int j = 0; j < J; ++j) bc += 8ull * f->jlen[j];
@@ -484,14 +518,18 @@ __device__ __forceinline__ int fw_after_minmax(const PgState& st, const FwCx& x,
     jb.thr = 0.f; jb.split = 0.0;
     jb.lo = jb.live ? pg_key2f(f->rMin[lane]) : 0.f; jb.hi = jb.live ? pg_key2f(f->rMax[lane]) : 0.f;
     fw_decide(st, x, jb);
-    const int J = fw_write_jobs(st, x, jb, lane, true);
+    const int pb = (int)(c->upd & 1ull);
+    int G;
+    const int J = fw_write_jobs(st, x, jb, lane, true, pb, true, true, &G);
     if (J == 0) return SN_FINISH_ROUND;
     if (lane == 0) {
+        const int* jord = st.job_order + (size_t)pb * st.S;
+        const int* gf = st.grp_first + (size_t)pb * (st.S + 1);
         unsigned long long bm = 0, bc = 0;
 #pragma unroll 1
-        for (int g = 0; g < c->n_groups; ++g) {
-            const unsigned long long L = st.job_len[st.job_order[st.grp_first[g]]];
-            bm += (4ull + 8ull + 4ull) * L + 4ull * L * (unsigned long long)(st.grp_first[g + 1] - st.grp_first[g]);
+        for (int g = 0; g < G; ++g) {
+            const unsigned long long L = f->jlen[jord[gf[g]]];
+            bm += (4ull + 8ull + 4ull) * L + 4ull * L * (unsigned long long)(gf[g + 1] - gf[g]);
         }
 #pragma unroll 1
         for (int j = 0; j < J; ++j) bc += 20ull * f->jlen[j];
@@ -553,7 +591,7 @@ __device__ __forceinline__ FwVals fw_values(const PgState& st, const FwCx& x, in
     FwVals v;
     const int s = f->jslot[j];
     const int r = c->round;
-    const int buf = (int)(c->upd & 1ull);
+    const int buf = (int)(c->upd % 3ull);
     const bool pre = r < FW_DR && f->d_ok[buf][r];
     v.cL = f->rCnt[j]; v.cR = nc - v.cL;
     v.SoL = f->rSo[j]; v.SoR = nSo - v.SoL;
@@ -569,13 +607,16 @@ __device__ __forceinline__ FwVals fw_values(const PgState& st, const FwCx& x, in
 
 __device__ __forceinline__ void fw_bern_bytes(const PgState& st, const FwCx& x, int J) {
     PgCtrl* c = x.c;
+    const int pb = (int)(c->upd & 1ull);
+    const int* jord = st.job_order + (size_t)pb * st.S;
+    const int* gf = st.grp_first + (size_t)pb * (st.S + 1);
     unsigned long long bm = 0, bc = 0;
 #pragma unroll 1
     for (int g = 0; g < c->n_groups; ++g) {
-        const int j0 = st.job_order[st.grp_first[g]];
+        const int j0 = jord[gf[g]];
         const unsigned long long L = x.f->jlen[j0];
         const unsigned long long fixed = x.f->jseg[j0] == PG_SEG_IDENTITY ? 12ull : 16ull;
-        bm += fixed * L + 4ull * L * (unsigned long long)(st.grp_first[g + 1] - st.grp_first[g]);
+        bm += fixed * L + 4ull * L * (unsigned long long)(gf[g + 1] - gf[g]);
     }
 #pragma unroll 1
     for (int j = 0; j < J; ++j) bc += 12ull * x.f->jlen[j];
@@ -605,7 +646,7 @@ __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, 
         f->jr_cL[lane] = v.cL;     // the partition reads the left count later
         if (bern) {
             f->jr_vL[lane] = v.vL; f->jr_vR[lane] = v.vR; f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL;
-            st.job_vL[lane] = v.vL; st.job_vR[lane] = v.vR;
+            { const size_t jo = (size_t)(c->upd & 1ull) * st.S; st.job_vL[jo + lane] = v.vL; st.job_vR[jo + lane] = v.vR; }
         } else fw_apply(st, x, lane, v.vL, v.vR, v.gL, v.gR, v.cL, v.cR, v.SoL, v.SoR, v.SrL, v.SrR);
     }
     __syncwarp();
@@ -751,6 +792,7 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
     const int K = c->n_pjobs, W = st.n_gwarps, S = st.S;
     const int tid = threadIdx.x, T = blockDim.x;
     const int chunk = (W + T - 1) / T;
+    const unsigned* p_cnt = st.part_cnt + pg_off_part_cnt(st, (int)(c->upd & 1ull));   // counts of this update's statistics pass
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
         const int j = st.pj_job[k];
@@ -759,7 +801,7 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
         if (chunk <= FB_CH) {
             unsigned v[FB_CH];
 #pragma unroll
-            for (int q = 0; q < FB_CH; ++q) v[q] = (q < chunk && b + q < W) ? __ldcg(&st.part_cnt[(size_t)(b + q) * S + j]) : 0u;
+            for (int q = 0; q < FB_CH; ++q) v[q] = (q < chunk && b + q < W) ? __ldcg(&p_cnt[(size_t)(b + q) * S + j]) : 0u;
 #pragma unroll
             for (int q = 0; q < FB_CH; ++q) local += v[q];
             f->scan[tid] = local;
@@ -783,13 +825,13 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
                 if (q < chunk && b + q < W) { st.pj_warp_left[(size_t)k * W + b + q] = run; run += v[q]; }
         } else {
             const int e = min(b + chunk, W);
-            for (int g = b; g < e; ++g) local += __ldcg(&st.part_cnt[(size_t)g * S + j]);
+            for (int g = b; g < e; ++g) local += __ldcg(&p_cnt[(size_t)g * S + j]);
             f->scan[tid] = local;
             __syncthreads();
             if (tid == 0) { unsigned run = 0; for (int q = 0; q < T; ++q) { const unsigned v = f->scan[q]; f->scan[q] = run; run += v; } }
             __syncthreads();
             unsigned run = f->scan[tid];
-            for (int g = b; g < e; ++g) { st.pj_warp_left[(size_t)k * W + g] = run; run += __ldcg(&st.part_cnt[(size_t)g * S + j]); }
+            for (int g = b; g < e; ++g) { st.pj_warp_left[(size_t)k * W + g] = run; run += __ldcg(&p_cnt[(size_t)g * S + j]); }
         }
         __syncthreads();
     }
@@ -918,7 +960,7 @@ __device__ __forceinline__ int fw_r0_values(const PgState& st, const FwCx& x, in
         const FwVals v = fw_values(st, x, lane, (unsigned)st.n, T_o, T_r);
         f->jr_vL[lane] = v.vL; f->jr_vR[lane] = v.vR; f->jr_gL[lane] = v.gL; f->jr_gR[lane] = v.gR;
         f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL; f->jr_cL[lane] = v.cL;
-        if (bern) { st.job_vL[lane] = v.vL; st.job_vR[lane] = v.vR; }
+        if (bern) { { const size_t jo = (size_t)(c->upd & 1ull) * st.S; st.job_vL[jo + lane] = v.vL; st.job_vR[jo + lane] = v.vR; } }
     }
     __syncwarp();
     if (bern && J > 0) {
@@ -1002,15 +1044,83 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
     return SN_PREP_PART;     // K >= 1 here; after PH_PART the general rounds continue
 }
 
-// ---- entry: the whole serial block (block 0) -------------------------------------------------------
-// phase / J: the pass that just completed (every block knows them: no load needed).
-// Returns the section's duration in SM cycles (thread 0).
-__device__ long long pg_serial_fast(const PgState& st, const PgSmemView& sm, int phase, int J) {
+// ---- commands to the pass blocks ---------------------------------------------------------------------
+// The pass blocks read the first 16 ints of the global PgCtrl (phase, t_add, t_sub, n_jobs, n_groups, n_pjobs,
+// flags, ...) after observing bar_gen; issuing = publish those words, then release-store the new generation.
+__device__ __forceinline__ void fw_issue(const PgState& st, const FwCx& x, int lane, int phase, int t_add, int t_sub,
+                                         int n_jobs, int n_groups, int n_pjobs, int flags) {
+    PgFastSm* f = x.f;
+    if (lane < 16) {
+        int v = reinterpret_cast<const int*>(&f->lc)[lane];
+        if (lane == 0) v = phase; else if (lane == 4) v = t_add; else if (lane == 5) v = t_sub; else if (lane == 7) v = n_jobs;
+        else if (lane == 8) v = n_groups; else if (lane == 9) v = n_pjobs; else if (lane == 15) v = flags;
+        reinterpret_cast<int*>(st.ctrl)[lane] = v;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+        f->issued += 1u;
+        f->out_phase = phase; f->out_J = n_jobs; f->out_pb = (flags >> 2) & 1;
+        pg_st_release(&st.ctrl->bar_gen, f->issued);
+    }
+    __syncwarp();
+}
+
+// Issue the pass the control block asks for (c->phase), on the buffers of the update in progress.
+__device__ __forceinline__ void fw_issue_ctrl(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    const int phase = c->phase;
+    const int pb = (int)(c->upd & 1ull);
+    int src = c->a_cur, dst = c->a_cur;
+    if (phase == PH_ROOT) dst = 1 - src;       // ping-pong: a discarded speculative pass never touches the live array
+    else if (phase == PH_FINAL) dst = 0;       // `predictions` always end in buffer 0
+    __syncwarp();
+    if (lane == 0 && (phase == PH_ROOT || phase == PH_FINAL)) c->a_cur = dst;
+    fw_issue(st, x, lane, phase, c->t_add, phase == PH_ROOT ? c->t_sub : -1, c->n_jobs, c->n_groups, c->n_pjobs,
+             src | (dst << 1) | (pb << 2));
+}
+
+// wait until the outstanding pass has completed on every pass block
+__device__ __forceinline__ void fw_await(const PgState& st, const FwCx& x, int lane) {
+    if (lane == 0) pg_spin_until(&st.ctrl->bar_count, x.f->issued * (gridDim.x - 1u), st.ctrl);
+    __syncwarp();
+}
+
+// Speculation: the root pass of update U+1 only needs (i) U+1's root proposals, which are
+// data-independent and already precomputed, and (ii) the tree update U commits.  When some slot of update U has no
+// proposal, U ends as a stump unless its grown particles out-weigh the stale weights (Q1) — so issue U+1's root pass
+// NOW, assuming "U commits a stump", and validate while it streams.  It reads the live A buffer and writes the other
+// one, with its own parity of job / partial buffers: a wrong guess costs nothing but the bandwidth of an idle GPU.
+__device__ __forceinline__ bool fw_try_speculate(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const unsigned long long U1 = c->upd + 1ull;
+    const int buf = (int)(U1 % 3ull);
+    bool ok = st.family != PG_BERNOULLI_LOGIT && c->k + 1 < c->batch && st.m >= 2 && c->n_jobs < st.S && c->error == PG_OK
+              && f->d_upd[buf] == U1 && f->d_ok[buf][0];
+#pragma unroll 1
+    for (int q = 0; q <= FW_DR && ok; ++q) ok = f->d_flag[buf][q] == U1 + 1ull;
+    if (!ok) return false;
+    __threadfence_block();
+    bool passed;
+    int status;
+    const FwJob jb = fw_root_job(st, x, U1, lane, &passed, &status);
+    if (__any_sync(PG_FULL, status == 6 || status == 7)) return false;   // let the regular path raise the error
+    int G;
+    const int pb1 = (int)(U1 & 1ull);
+    const int J1 = fw_write_jobs(st, x, jb, lane, true, pb1, true, false, &G);
+    const int t_sub1 = (c->next_tree_idx + c->k + 1) % st.m;
+    const int src = c->a_cur, dst = 1 - c->a_cur;
+    fw_issue(st, x, lane, PH_ROOT, -2 /* a stump */, t_sub1, J1, G, 0, src | (dst << 1) | (pb1 << 2));
+    if (lane == 0) c->n_spec += 1;
+    return true;
+}
+
+// ---- the serial block's whole-kernel control loop ------------------------------------------------------
+__device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
     __shared__ PgCtrl fw_scratch[FW_DR + 1];   // helpers must not raise errors for draws that may never be consumed
     PgFastSm* f = &sm.base->fast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long t_entry = clock64();
-
     FwCx x;
     x.f = f;
     x.c = &f->lc;
@@ -1021,76 +1131,116 @@ __device__ long long pg_serial_fast(const PgState& st, const PgSmemView& sm, int
     x.cmax = staged ? sm.cmax : st.col_max;
     PgCtrl* c = x.c;
 
-    const int gerr = threadIdx.x == 0 ? __ldcg(&st.ctrl->error) : PG_OK;   // a pass may have flagged an error
-    fw_reduce(st, f, phase, J);   // contains a __syncthreads before its combine step
-    if (threadIdx.x == 0 && gerr != PG_OK) c->error = gerr;
+    fw_load_state(st, f);
     __syncthreads();
-    const unsigned long long upd0 = c->upd;   // the update in progress at entry
-    const bool need_cur = f->d_upd[(int)(upd0 & 1ull)] != upd0;                    // draws missing (right after launch)
-    const bool need_next = f->d_upd[(int)((upd0 + 1ull) & 1ull)] != upd0 + 1ull;   // next update's draws not prefetched yet
-    __syncthreads();                           // ... all read by every warp before anything is advanced
+    if (threadIdx.x == 0) c->a_cur = 0;        // `predictions` live in buffer 0 between steps
+    bool first = true;
+#define FW_TICK(slot) do { if (lane == 0) { const long long now_ = clock64(); c->prof2[slot] += (unsigned long long)(now_ - tq); c->prof2[8 + slot] += 1ull; tq = now_; } } while (0)
 
-    long long tq = clock64();
-#define FW_TICK(slot) do { if (threadIdx.x == 0) { const long long now_ = clock64(); c->prof2[slot] += (unsigned long long)(now_ - tq); c->prof2[8 + slot] += 1ull; tq = now_; } } while (0)
-    if (threadIdx.x == 0) { c->prof2[0] += (unsigned long long)(tq - t_entry); c->prof2[8] += 1ull; }
-
-    // ---- helper warps: draws of the update in progress (only missing right after launch) and of the next one
-    if (warp >= 1 && warp <= FW_DR + 1) {
-        PgCtrl* scr = &fw_scratch[warp - 1];
-        if (need_cur) fw_prefetch_draws(st, x, upd0, warp, lane, scr);
-        if (need_next) fw_prefetch_draws(st, x, upd0 + 1ull, warp, lane, scr);
-    }
-
-    if (warp == 0) {
-        int sn = SN_NONE;
-        switch (phase) {
-            case PH_BEGIN: sn = fw_begin_step(st, x, lane); break;
-            case PH_ROOT:
-                sn = fw_r0_values(st, x, lane);
-                if (sn == SN_FINISH_ROUND) sn = fw_r0_finish(st, x, lane, false);
-                FW_TICK(1);
-                break;
-            case PH_STATS: sn = fw_after_stats(st, x, lane, phase); FW_TICK(1); break;
-            case PH_BERN:
-                if (c->round == 0) sn = fw_r0_finish(st, x, lane, true); else sn = fw_after_stats(st, x, lane, phase);
-                FW_TICK(1);
-                break;
-            case PH_MINMAX: sn = fw_after_minmax(st, x, lane); FW_TICK(2); break;
-            case PH_PART:
-                if (lane == 0) c->round += 1;
-                __syncwarp();
-                sn = SN_DRAW_ROUND;
-                break;
-            case PH_FINAL:
-                if (lane == 0) { c->next_tree_idx = (c->next_tree_idx + c->batch) % st.m; c->t_add = -1; c->phase = PH_DONE; }
-                break;
-            default: break;
-        }
-        // warp-only sub-steps chain without block barriers until a grid pass or a block-wide step is needed
 #pragma unroll 1
-        for (int guard = 0; guard < (1 << 20); ++guard) {
-            if (c->error != PG_OK) { sn = SN_NONE; break; }
-            if (sn == SN_NONE || sn == SN_PREP_PART) break;
-            if (sn == SN_BEGIN_UPDATE) { sn = fw_begin_update(st, x, lane); FW_TICK(6); }
-            else if (sn == SN_DRAW_ROUND) { sn = fw_draw_round(st, x, lane); FW_TICK(7); }
-            else if (sn == SN_FINISH_ROUND) { sn = fw_finish_round(st, x, lane); FW_TICK(3); }
-            else if (sn == SN_FINALIZE) { sn = fw_finalize(st, x, lane); FW_TICK(5); }
-            else { if (lane == 0) c->error = PG_ERR_INTERNAL; sn = SN_NONE; }
-        }
-        if (lane == 0) f->sn = sn;
-    }
-    __syncthreads();
-    if (f->sn == SN_PREP_PART) {
-        tq = clock64();
-        fb_prep_part(st, x);
-        FW_TICK(4);
+    for (long long guard = 0; guard < (1ll << 40); ++guard) {
+        // ---- (A) the outstanding pass (if any) completes
+        if (!first && threadIdx.x == 0) pg_spin_until(&st.ctrl->bar_count, f->issued * (gridDim.x - 1u), st.ctrl);
         __syncthreads();
-    }
-    if (warp == 0) {
-        if (lane == 0 && c->error != PG_OK) c->phase = PH_DONE;
-        __syncwarp();
-        fw_publish(st, f, lane);
+        const int phase = first ? PH_BEGIN : f->out_phase;
+        const int J = first ? 0 : f->out_J;
+        const int pb = first ? 0 : f->out_pb;
+        first = false;
+        const long long t_entry = clock64();
+        const int gerr = threadIdx.x == 0 ? __ldcg(&st.ctrl->error) : PG_OK;   // a pass may have flagged an error
+        fw_reduce(st, f, phase, J, pb);   // contains a __syncthreads before its combine step
+        if (threadIdx.x == 0 && gerr != PG_OK) c->error = gerr;
+        __syncthreads();
+        const unsigned long long upd0 = c->upd;   // the update in progress at entry
+        bool need[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) need[q] = f->d_upd[(int)((upd0 + q) % 3ull)] != upd0 + q;
+        __syncthreads();                           // ... all read by every warp before anything is advanced
+        long long tq = clock64();
+        if (threadIdx.x == 0) { c->prof2[0] += (unsigned long long)(tq - t_entry); c->prof2[8] += 1ull; }
+
+        // ---- (B) helper warps: draws of the update in progress (missing only right after launch) and of the next two
+        if (warp >= 1 && warp <= FW_DR + 1) {
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q)
+                if (need[q]) fw_prefetch_draws(st, x, upd0 + q, warp, lane, &fw_scratch[warp - 1]);
+        }
+
+        // ---- (C) warp 0: the control logic
+        if (warp == 0) {
+            int sn = SN_NONE;
+            bool spec = false;
+            switch (phase) {
+                case PH_BEGIN: sn = fw_begin_step(st, x, lane); break;
+                case PH_ROOT:
+                    spec = fw_try_speculate(st, x, lane);
+                    FW_TICK(6);
+                    sn = fw_r0_values(st, x, lane);
+                    if (sn == SN_FINISH_ROUND) sn = fw_r0_finish(st, x, lane, false);
+                    FW_TICK(1);
+                    break;
+                case PH_STATS: sn = fw_after_stats(st, x, lane, phase); FW_TICK(1); break;
+                case PH_BERN:
+                    if (c->round == 0) sn = fw_r0_finish(st, x, lane, true); else sn = fw_after_stats(st, x, lane, phase);
+                    FW_TICK(1);
+                    break;
+                case PH_MINMAX: sn = fw_after_minmax(st, x, lane); FW_TICK(2); break;
+                case PH_PART:
+                    if (lane == 0) c->round += 1;
+                    __syncwarp();
+                    sn = SN_DRAW_ROUND;
+                    break;
+                case PH_FINAL:
+                    if (lane == 0) { c->next_tree_idx = (c->next_tree_idx + c->batch) % st.m; c->t_add = -1; c->phase = PH_DONE; }
+                    __syncwarp();
+                    break;
+                default: break;
+            }
+            bool spec_commit = false;
+            // warp-only sub-steps chain without block barriers until a grid pass or a block-wide step is needed
+#pragma unroll 1
+            for (int it = 0; it < (1 << 20); ++it) {
+                if (c->error != PG_OK) { sn = SN_NONE; break; }
+                if (sn == SN_NONE || sn == SN_PREP_PART) break;
+                if (sn == SN_BEGIN_UPDATE) {
+                    if (spec) {   // the guess "this update commits a stump" held: the root pass in flight is the next update's
+                        if (lane == 0) c->a_cur = 1 - c->a_cur;
+                        __syncwarp();
+                        fw_start_update(st, x, lane, true);
+                        spec_commit = true;
+                    } else fw_start_update(st, x, lane, false);
+                    sn = SN_NONE;
+                    FW_TICK(7);
+                }
+                else if (sn == SN_DRAW_ROUND) { sn = fw_draw_round(st, x, lane); FW_TICK(7); }
+                else if (sn == SN_FINISH_ROUND) { sn = fw_finish_round(st, x, lane); FW_TICK(3); }
+                else if (sn == SN_FINALIZE) { sn = fw_finalize(st, x, lane); FW_TICK(5); }
+                else { if (lane == 0) c->error = PG_ERR_INTERNAL; sn = SN_NONE; }
+            }
+            if (c->error != PG_OK) { if (lane == 0) c->phase = PH_DONE; sn = SN_NONE; __syncwarp(); }
+            if (sn != SN_PREP_PART) {
+                if (spec && !spec_commit && c->phase != PH_DONE) fw_await(st, x, lane);   // drain a wrong guess (only on odd paths)
+                if (!spec_commit) fw_issue_ctrl(st, x, lane);                              // next pass, or PH_DONE
+            }
+            if (lane == 0) { f->sn = sn; f->quit = c->phase == PH_DONE ? 1 : 0; f->scan[PG_THREADS] = spec && !spec_commit ? 1u : 0u; }
+        }
+        __syncthreads();
+        if (f->sn == SN_PREP_PART) {   // survivors grew: partition offsets (block-wide), then the PART pass
+            tq = clock64();
+            const bool drain = f->scan[PG_THREADS] != 0u;
+            __syncthreads();
+            fb_prep_part(st, x);
+            __syncthreads();
+            if (warp == 0) {
+                if (drain) fw_await(st, x, lane);   // the speculative root pass guessed wrong: let it finish, ignore its output
+                fw_issue_ctrl(st, x, lane);
+                FW_TICK(4);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) st.ctrl->prof[16 + (phase & 7)] += (unsigned long long)(clock64() - t_entry);   // after the issue: off the critical path
+        if (f->quit) break;
     }
     __syncthreads();
-    return clock64() - t_entry;
+    fw_store_state(st, f);
 }

@@ -15,33 +15,6 @@
 
 namespace cg = cooperative_groups;
 
-// Polling load: relaxed at gpu scope (served by L2, does not touch this SM's L1); the acquire is one
-// fence after the flag has flipped, so a spinning block does not keep invalidating the L1 that the
-// serial section running on the same SM depends on.
-__device__ __forceinline__ unsigned pg_ld_relaxed(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void pg_st_release(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ void pg_spin_until(const unsigned* p, unsigned target, PgCtrl* c) {
-    const long long t0 = clock64();
-    unsigned ns = 20;
-    while (pg_ld_relaxed(p) < target) {
-        __nanosleep(ns);
-        if (ns < 160) ns <<= 1;
-        if (clock64() - t0 > 40000000000ll) {   // ~20 s at 2 GHz: a lost block becomes an error, not a hang
-            c->error = PG_ERR_WATCHDOG;
-            __threadfence();
-            __trap();
-        }
-    }
-    __threadfence();   // acquire side of the fence/atomic/fence pattern
-}
-
 // Grid barrier with a serial section.  Block 0 is ALWAYS the serial block: its SM keeps the (large,
 // straight-line) control code in its instruction caches, which is what the section's latency is made of.
 // Other blocks arrive (release fence + counter) and wait for the generation flag; block 0 waits for the
@@ -65,13 +38,13 @@ __device__ void pg_barrier_serial(const PgState& st, const PgSmemView& smv, unsi
         }
         __syncthreads();
         long long dur;
-        if (FAST) dur = pg_serial_fast(st, smv, phase, J);   // latency-organised control logic (one lane per particle)
-        else {                                               // generic team version (P > 32)
+        {                                                    // generic team version of the control logic
             PgTeam tm{(int)threadIdx.x, (int)blockDim.x};
             const long long ts = clock64();
             pg_serial(st, tm);
             dur = clock64() - ts;
         }
+        (void)smv; (void)J;
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -95,8 +68,36 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
             sm.cmin[i] = st.col_min[i];
             sm.cmax[i] = st.col_max[i];
         }
-    if (FAST && blockIdx.x == 0) fw_load_state(st, &sm.base->fast);   // the serial block keeps the control state in shared memory
     __syncthreads();
+    if (FAST) {
+        // ---- P <= 32: block 0 runs the whole control loop (pg_control_fast) and issues commands; the other blocks
+        // execute them.  A command = the published words of PgCtrl + a new generation in bar_gen; completion = every
+        // pass block adds 1 to bar_count.  The control block may issue the next root pass before it has finished
+        // digesting the previous one (speculation), so passes and control overlap.
+        if (blockIdx.x == 0) { pg_control_fast(st, sm); return; }
+        PgCtrl* c = st.ctrl;
+        unsigned gen = 0;
+        long long t_idle = clock64();
+        for (;;) {
+            if (threadIdx.x == 0) pg_spin_until(&c->bar_gen, gen + 1u, c);
+            __syncthreads();
+            const int phase = __ldcg(&c->phase);
+            if (phase == PH_DONE) break;
+            const long long t0 = clock64();
+            pg_run_pass(st, sm, phase);
+            __syncthreads();
+            const long long t1 = clock64();
+            if (threadIdx.x == 0) { __threadfence(); atomicAdd(&c->bar_count, 1u); }
+            if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // stopwatch kept by the last pass block
+                c->prof[phase & 7] += (unsigned long long)(t1 - t0);
+                c->prof[8 + (phase & 7)] += (unsigned long long)(t0 - t_idle);   // time spent waiting for this command
+                c->prof[24 + (phase & 7)] += 1ull;
+            }
+            t_idle = t1;
+            gen += 1u;
+        }
+        return;
+    }
     unsigned gen = 0;
     pg_barrier_serial<FAST>(st, sm, gen, PH_BEGIN, 0);   // serial section of PH_BEGIN prepares the first pass
     for (;;) {
@@ -115,7 +116,6 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
             c->prof[24 + (phase & 7)] += 1ull;
         }
     }
-    if (FAST && blockIdx.x == 0) { __syncthreads(); fw_store_state(st, &sm.base->fast); }
 }
 
 // P <= 32: latency-organised serial section; P > 32: generic team serial section.
@@ -133,25 +133,6 @@ extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_phase_kernel(cons
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_serial_kernel(const PgState st) {
     PgTeam tm{(int)threadIdx.x, (int)blockDim.x};
     pg_serial(st, tm);
-}
-
-// stepwise driver with the latency-organised serial section (isolates it for profiling)
-extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_serial_fast_kernel(const PgState st, int first) {
-    extern __shared__ __align__(16) unsigned char pg_smem_raw[];
-    const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
-    for (int i = threadIdx.x; i < st.max_depth + 2 && i < 16; i += blockDim.x) sm.base->cthr[i] = st.thr_depth[i];
-    if (threadIdx.x == 0) sm.base->cstaged = (st.p <= FW_MAXP && st.max_depth + 2 <= 16) ? 1 : 0;
-    if (st.p <= FW_MAXP)
-        for (int i = threadIdx.x; i < st.p; i += blockDim.x) {
-            sm.cprior[i] = st.prior ? st.prior[i] : 0.0;
-            sm.cmin[i] = st.col_min[i];
-            sm.cmax[i] = st.col_max[i];
-        }
-    fw_load_state(st, &sm.base->fast);
-    __syncthreads();
-    pg_serial_fast(st, sm, first ? PH_BEGIN : __ldcg(&st.ctrl->phase), first ? 0 : __ldcg(&st.ctrl->n_jobs));
-    __syncthreads();
-    fw_store_state(st, &sm.base->fast);
 }
 
 extern "C" __global__ void pg_prepare_step(const PgState st, int tune) {
@@ -205,7 +186,6 @@ int pg_query_grid(int device, int S, int* grid_out, size_t* smem_out, char* err,
         e = cudaFuncSetAttribute(pg_sweep_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_sweep_persistent_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_serial_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { snprintf(err, errlen, "shared memory request %zu B: %s", smem, cudaGetErrorString(e)); return 1; }
     }
     int per_sm = 0;
@@ -237,11 +217,6 @@ cudaError_t pg_launch_phase(const PgState& st, size_t smem, cudaStream_t s) {
 
 cudaError_t pg_launch_serial(const PgState& st, cudaStream_t s) {
     pg_serial_kernel<<<1, PG_THREADS, 0, s>>>(st);
-    return cudaGetLastError();
-}
-
-cudaError_t pg_launch_serial_fast(const PgState& st, size_t smem, int first, cudaStream_t s) {
-    pg_serial_fast_kernel<<<1, PG_THREADS, smem, s>>>(st, first);
     return cudaGetLastError();
 }
 

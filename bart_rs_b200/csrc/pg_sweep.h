@@ -8,7 +8,6 @@ cudaError_t pg_launch_prepare(const PgState& st, int tune, cudaStream_t s);
 cudaError_t pg_launch_persistent(const PgState& st, size_t smem, cudaStream_t s);
 cudaError_t pg_launch_phase(const PgState& st, size_t smem, cudaStream_t s);
 cudaError_t pg_launch_serial(const PgState& st, cudaStream_t s);
-cudaError_t pg_launch_serial_fast(const PgState& st, size_t smem, int first, cudaStream_t s);
 cudaError_t pg_launch_fill(double* p, long long n, double v, cudaStream_t s);
 cudaError_t pg_launch_init_forest(const PgState& st, cudaStream_t s);
 cudaError_t pg_launch_leaf_indices(const PgState& st, int t, unsigned* out, cudaStream_t s);

@@ -63,7 +63,7 @@ struct PgCtrl {
     int k;            // tree update index within this step's batch
     int batch;
     int t_cur;        // tree being updated
-    int t_add;        // tree whose (new) values the next ROOT/FINAL pass adds to A, -1 = none
+    int t_add;        // tree whose (new) values the next ROOT/FINAL pass adds to A, -1 = none, -2 = a stump (constant init_leaf)
     int t_sub;        // tree whose (old) values the next ROOT pass subtracts, -1 = none
     int round;
     int n_jobs;
@@ -74,7 +74,7 @@ struct PgCtrl {
     int snext;        // next serial sub-step (PgSerialNext), SN_NONE = run the grid pass `phase`
     int max_size;     // largest slot tree size (bounds the resampling copy)
     int t_add_internal;   // internal nodes of tree t_add (bytes accounting)
-    int pad1;
+    int flags;        // pass command flags: bit0 A source buffer, bit1 A destination buffer, bit2 job/partial buffer parity
     unsigned long long upd;       // tree-update counter since creation (RNG coordinate)
     unsigned long long pool_top;
     int next_tree_idx;
@@ -95,9 +95,10 @@ struct PgCtrl {
     unsigned long long bytes_contract;  // SURVEY.md §8(d) formula
     unsigned long long n_phases;        // grid passes executed
     unsigned long long n_updates;       // tree updates executed
+    unsigned long long n_spec;          // root passes issued speculatively (pg_serial_fast.cuh)
     unsigned long long trace_n;         // tree updates recorded in the trace
     int trace_overflow;
-    int pad0;
+    int a_cur;                      // which A buffer holds the running array of the update in progress
     // serial-section breakdown (cycles / calls): 0 reduce, 1 after_stats, 2 after_minmax, 3 finish_round, 4 prep_part,
     // 5 finalize, 6 begin_update, 7 draw_round; [8..15] call counts
     unsigned long long prof2[16];
@@ -120,7 +121,8 @@ struct PgState {
     // data
     const float* X;
     const float* y;
-    double* A;
+    double* A;                   // buffer 0: holds `predictions` between steps
+    double* A2;                  // buffer 1: ping-pong partner for speculatively issued root passes
     const float* col_min;
     const float* col_max;
     const double* prior;         // split prior used as raw weights (Q3); null = uniform integer draw

@@ -230,11 +230,11 @@ class PySampler:
 
     def profile(self) -> dict:
         """In-kernel stopwatch (SM cycles since creation), by phase; see include/pgbart.h."""
-        out = np.zeros(48)
+        out = np.zeros(49)
         self._check(self._L.pgbart_get_profile(self._h, out.ctypes.data_as(C.c_void_p)))
         names = ["begin", "root", "minmax", "stats", "bern", "part", "final", "done"]
         sub = ["reduce", "after_stats", "after_minmax", "finish_round", "prep_part", "finalize", "begin_update", "draw_round"]
-        return {"serial_sub_cycles": dict(zip(sub, out[32:40].tolist())), "serial_sub_calls": dict(zip(sub, out[40:48].tolist())),"pass_cycles": dict(zip(names, out[0:8].tolist())), "wait_serial_cycles": dict(zip(names, out[8:16].tolist())),
+        return {"speculative_root_passes": float(out[48]), "serial_sub_cycles": dict(zip(sub, out[32:40].tolist())), "serial_sub_calls": dict(zip(sub, out[40:48].tolist())),"pass_cycles": dict(zip(names, out[0:8].tolist())), "wait_serial_cycles": dict(zip(names, out[8:16].tolist())),
                 "serial_cycles": dict(zip(names, out[16:24].tolist())), "passes": dict(zip(names, out[24:32].tolist()))}
 
     def timer_start(self) -> None:

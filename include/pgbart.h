@@ -110,8 +110,8 @@ int pgbart_get_counters(pgbart_handle h, double* out8);
 /* In-kernel stopwatch, SM cycles since creation: out32[0..7] pass time by phase as seen by block 0,
  * [8..15] pass end -> barrier exit (wait for the slowest block + serial section), [16..23] serial section alone,
  * [24..31] passes by phase (phases: 1 ROOT, 2 MINMAX, 3 STATS, 4 BERN, 5 PART, 6 FINAL); [32..39] serial sub-step
- * cycles (reduce, after_stats, after_minmax, finish_round, prep_part, finalize, begin_update, draw_round), [40..47] calls. */
-int pgbart_get_profile(pgbart_handle h, double* out48);
+ * cycles (reduce, after_stats, after_minmax, finish_round, prep_part, finalize, begin_update, draw_round), [40..47] calls, [48] root passes issued speculatively. */
+int pgbart_get_profile(pgbart_handle h, double* out49);
 
 /* CUDA-event stopwatch on the sampler's own stream (the stream the sweep kernels are launched on):
  * start records an event, stop records a second one, synchronises and returns the milliseconds between. */

@@ -232,7 +232,7 @@ void* pgsim_create(const double* x_f, uint64_t n, uint64_t p, const double* y, c
     for (int d = 0; d < st.max_depth + 2; ++d) thr[d] = 1.0 - (cfg->alpha * std::pow(1.0 + (double)d, -cfg->beta));
     st.thr_depth = thr;
     const size_t S = st.S, MN = st.maxn, M = st.m, G = st.grid, W = st.n_gwarps;
-    st.A = halloc<double>(s, (size_t)st.ld);
+    st.A = halloc<double>(s, (size_t)st.ld); st.A2 = halloc<double>(s, (size_t)st.ld);
     st.f_split_var = halloc<int>(s, M * MN); st.f_thr32 = halloc<float>(s, M * MN); st.f_split_val = halloc<double>(s, M * MN);
     st.f_leaf_val = halloc<double>(s, M * MN); st.f_size = halloc<int>(s, M); st.f_internal = halloc<int>(s, M);
     st.pt_split_var = halloc<int>(s, 2 * S * MN); st.pt_thr32 = halloc<float>(s, 2 * S * MN); st.pt_split_val = halloc<double>(s, 2 * S * MN);

@@ -43,4 +43,6 @@ for n in p1["serial_sub_cycles"]:
     calls = (p1["serial_sub_calls"][n] - p0["serial_sub_calls"][n]) / steps
     if calls:
         print(f"  serial {n:14s} calls/sweep {calls:7.1f}  us/call {cyc / calls / ghz / 1e3:7.2f}  ms/sweep {cyc / ghz / 1e6:6.2f}")
+c = s.counters()
+print("counters", c, "speculative root passes per sweep", (p1["speculative_root_passes"] - p0["speculative_root_passes"]) / steps)
 print(f"sum of block-0 pass+wait time: {tot:.2f} ms per sweep; measured {ms / steps:.2f} ms")
