@@ -512,6 +512,7 @@ int pgbart_get_profile(pgbart_handle h, double* out32) {
     Sampler* s = &h->s;
     if (!fetch_ctrl(s)) return 2;
     for (int i = 0; i < 32; ++i) out32[i] = (double)s->host_ctrl.prof[i];
+    if (s->st.P <= 32 && !s->stepwise) for (int i = 0; i < 8; ++i) out32[16 + i] = (double)s->host_ctrl.prof_ser[i];
     for (int i = 0; i < 16; ++i) out32[32 + i] = (double)s->host_ctrl.prof2[i];
     out32[48] = (double)s->host_ctrl.n_spec;
     return 0;

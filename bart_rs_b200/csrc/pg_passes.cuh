@@ -68,6 +68,8 @@ struct PgTreeSm {
 };
 
 #define FW_DR 4            // SMC rounds whose data-independent draws are precomputed per tree update
+#define FW_GW (PG_WARPS - FW_DR - 1)          // warps of the control group: warp 0 + warps FW_DR+2 .. PG_WARPS-1
+#define FW_GT (FW_GW * 32)                   // threads of the control group (named barrier 1)
 
 struct PgFastSm {          // state of the latency-organised serial section (pg_serial_fast.cuh), P <= 32.
     // Lives in block 0's shared memory for the whole kernel: loaded at launch, stored at exit.
@@ -101,6 +103,11 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     unsigned issued;                             // commands issued so far (= value of bar_gen)
     int out_phase, out_J, out_pb;                // phase / job count / buffer parity of the outstanding pass
     int quit;
+    unsigned long long pre_upd;                  // update whose root jobs are already staged in the global job arrays
+    int pre_J, pre_G, spec_now;
+    volatile unsigned long long want_base, want_top;   // draw helpers: updates [want_base, want_top] are wanted
+    volatile int helpers_quit;
+    double stump_total, stump_cum[32];           // final selection when every particle is a stump: sequential sums of 1/P
     unsigned scan[PG_THREADS + 1];
 };
 

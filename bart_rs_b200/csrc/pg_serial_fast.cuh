@@ -64,7 +64,7 @@ __device__ void fw_load_state(const PgState& st, PgFastSm* f) {
     }
     if (threadIdx.x < 3) f->d_upd[threadIdx.x] = ~0ull;
     if (threadIdx.x < 3 * (FW_DR + 1)) f->d_flag[threadIdx.x / (FW_DR + 1)][threadIdx.x % (FW_DR + 1)] = 0ull;
-    if (threadIdx.x == 0) { f->issued = 0u; f->out_phase = PH_BEGIN; f->out_J = 0; f->out_pb = 0; f->quit = 0; }
+    if (threadIdx.x == 0) { f->issued = 0u; f->out_phase = PH_BEGIN; f->out_J = 0; f->out_pb = 0; f->quit = 0; f->pre_upd = ~0ull; f->spec_now = 0; }
 }
 
 __device__ void fw_store_state(const PgState& st, PgFastSm* f) {
@@ -598,8 +598,8 @@ __device__ __forceinline__ FwVals fw_values(const PgState& st, const FwCx& x, in
     v.SrL = f->rSr[j]; v.SrR = nSr - v.SrL;
     const double zL = pre ? f->d_zL[buf][r][s] : pg_normal(st, c, PG_D_ZLEFT, c->upd, r, s);   // drawn for both children, left first
     const double zR = pre ? f->d_zR[buf][r][s] : pg_normal(st, c, PG_D_ZRIGHT, c->upd, r, s);
-    v.vL = v.cL == 0u ? zL * st.leaf_sigma : pg_mul_add(zL, st.leaf_sigma, v.SoL / (double)v.cL / st.m_f);
-    v.vR = v.cR == 0u ? zR * st.leaf_sigma : pg_mul_add(zR, st.leaf_sigma, v.SoR / (double)v.cR / st.m_f);
+    v.vL = v.cL == 0u ? zL * st.leaf_sigma : pg_mul_add(zL, st.leaf_sigma, v.SoL / ((double)v.cL * st.m_f));   // cL*m is exact
+    v.vR = v.cR == 0u ? zR * st.leaf_sigma : pg_mul_add(zR, st.leaf_sigma, v.SoR / ((double)v.cR * st.m_f));
     v.gL = pg_gauss_g(v.vL, v.SrL, v.cL, c->inv_s2);
     v.gR = pg_gauss_g(v.vR, v.SrR, v.cR, c->inv_s2);
     return v;
@@ -851,6 +851,7 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
 __device__ __forceinline__ int fw_end_update(const PgState& st, const FwCx& x, int lane, int depth, int internal, double Wn0) {
     PgCtrl* c = x.c;
     int next = SN_NONE;
+    __syncwarp();   // every lane has finished reading this update's counters (trace_n, upd, round) before lane 0 advances them
     if (lane == 0) {
         const int t = c->t_cur;
         c->info_loglik += Wn0;
@@ -951,7 +952,7 @@ __device__ __forceinline__ int fw_r0_values(const PgState& st, const FwCx& x, in
     double C0, g_stump;
     if (bern) { C0 = 0.0; g_stump = T_ll0; }
     else if (st.family == PG_GAUSSIAN) {
-        C0 = c->Cconst - 0.5 * T_rr / (st.lik_sigma * st.lik_sigma);   // same expression as the generic path
+        C0 = c->Cconst - 0.5 * T_rr * c->inv_s2;
         g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n, c->inv_s2);
     } else { C0 = -0.5 * T_rr; g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n, 1.0); }
     if (lane == 0) { c->T_o = T_o; c->T_r = T_r; c->T_rr = T_rr; c->T_ll0 = T_ll0; c->C0 = C0; c->g_stump = g_stump; }
@@ -1001,10 +1002,21 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
     if (!__any_sync(PG_FULL, need)) {
         // every survivor is an untouched stump with an empty queue: the loop of smc.rs:61 ends here.  All P
         // particles are stumps with the same log-likelihood (smc.rs:105-111).
-        double Wn0;
-        (void)fw_select(st, x, lane, c->C0 + c->g_stump, &Wn0);
+        // exp(0) = 1 for everyone, the sequential sum of P ones is P, so every normalised weight is 1/P; the sequential
+        // partial sums of P copies of 1/P are launch constants (f->stump_cum) — same values the generic loops produce.
+        const int P = st.P;
+        const double Wn = 1.0 / (double)P;
+        const double chosen = fw_u7(st, x, c->upd) * f->stump_total;
+        const int sel = __popc(__ballot_sync(PG_FULL, lane + 1 < P && f->stump_cum[lane] <= chosen));
+        if (st.tr_upd) {
+            if ((long long)c->trace_n < st.tr_u_cap) {
+                double* tr = st.tr_upd + (size_t)c->trace_n * (size_t)(4 + 2 * P);
+                if (lane == 0) { tr[0] = (double)(c->round + 1); tr[1] = (double)sel; tr[2] = (double)c->t_cur; tr[3] = (double)c->acc_update; }
+                if (lane < P) { tr[4 + lane] = c->C0 + c->g_stump; tr[4 + P + lane] = Wn; }
+            } else if (lane == 0) c->trace_overflow = 1;
+        }
         if (lane == 0) fw_write_stump(st, c->t_cur);
-        return fw_end_update(st, x, lane, 0, 0, Wn0);
+        return fw_end_update(st, x, lane, 0, 0, Wn);
     }
     // ---- survivors that grew: write the slot tables of ALL slots (copies of their ancestors) into half `cur`
     unsigned off, cntL;
@@ -1116,6 +1128,41 @@ __device__ __forceinline__ bool fw_try_speculate(const PgState& st, const FwCx& 
     return true;
 }
 
+// Stage the root jobs of the NEXT update in the global job arrays of its parity while nothing waits for us, so that
+// the speculative command itself is only the 16 published words (fw_issue_prestaged).
+__device__ __forceinline__ void fw_prestage(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const unsigned long long U1 = c->upd + 1ull;
+    const int buf = (int)(U1 % 3ull);
+    bool ok = st.family != PG_BERNOULLI_LOGIT && c->k + 1 < c->batch && st.m >= 2 && c->error == PG_OK
+              && f->d_upd[buf] == U1 && f->d_ok[buf][0];
+#pragma unroll 1
+    for (int q = 0; q <= FW_DR && ok; ++q) ok = f->d_flag[buf][q] == U1 + 1ull;
+    if (!ok) return;
+    __threadfence_block();
+    bool passed;
+    int status;
+    const FwJob jb = fw_root_job(st, x, U1, lane, &passed, &status);
+    if (__any_sync(PG_FULL, status == 6 || status == 7)) return;
+    int G;
+    const int J1 = fw_write_jobs(st, x, jb, lane, true, (int)(U1 & 1ull), true, false, &G);
+    if (lane == 0) { f->pre_upd = U1; f->pre_J = J1; f->pre_G = G; }
+    __syncwarp();
+}
+
+__device__ __forceinline__ bool fw_issue_prestaged(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const unsigned long long U1 = c->upd + 1ull;
+    if (!(f->pre_upd == U1 && c->n_jobs < st.S && c->k + 1 < c->batch && c->error == PG_OK)) return false;
+    const int t_sub1 = (c->next_tree_idx + c->k + 1) % st.m;
+    const int src = c->a_cur, dst = 1 - c->a_cur;
+    fw_issue(st, x, lane, PH_ROOT, -2 /* a stump */, t_sub1, f->pre_J, f->pre_G, 0, src | (dst << 1) | ((int)(U1 & 1ull) << 2));
+    if (lane == 0) c->n_spec += 1;
+    return true;
+}
+
 // ---- the serial block's whole-kernel control loop ------------------------------------------------------
 __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
     __shared__ PgCtrl fw_scratch[FW_DR + 1];   // helpers must not raise errors for draws that may never be consumed
@@ -1132,6 +1179,12 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
     PgCtrl* c = x.c;
 
     fw_load_state(st, f);
+    if (threadIdx.x == 0) {   // final selection among P identical stumps: sequential sums of P copies of 1/P (smc.rs:105-114)
+        const double wn = 1.0 / (double)st.P;
+        double cum = 0.0;
+        for (int i = 0; i < st.P && i < 32; ++i) { cum += wn; f->stump_cum[i] = cum; }
+        f->stump_total = cum;
+    }
     __syncthreads();
     if (threadIdx.x == 0) c->a_cur = 0;        // `predictions` live in buffer 0 between steps
     bool first = true;
@@ -1148,6 +1201,10 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
         first = false;
         const long long t_entry = clock64();
         const int gerr = threadIdx.x == 0 ? __ldcg(&st.ctrl->error) : PG_OK;   // a pass may have flagged an error
+        if (warp == 0) {   // the next update's root pass, if its jobs are staged: issue it before anything else
+            const bool sp = phase == PH_ROOT && fw_issue_prestaged(st, x, lane);
+            if (lane == 0) f->spec_now = sp ? 1 : 0;
+        }
         fw_reduce(st, f, phase, J, pb);   // contains a __syncthreads before its combine step
         if (threadIdx.x == 0 && gerr != PG_OK) c->error = gerr;
         __syncthreads();
@@ -1173,7 +1230,8 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
             switch (phase) {
                 case PH_BEGIN: sn = fw_begin_step(st, x, lane); break;
                 case PH_ROOT:
-                    spec = fw_try_speculate(st, x, lane);
+                    spec = f->spec_now != 0;
+                    if (!spec) spec = fw_try_speculate(st, x, lane);
                     FW_TICK(6);
                     sn = fw_r0_values(st, x, lane);
                     if (sn == SN_FINISH_ROUND) sn = fw_r0_finish(st, x, lane, false);
@@ -1221,6 +1279,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
             if (sn != SN_PREP_PART) {
                 if (spec && !spec_commit && c->phase != PH_DONE) fw_await(st, x, lane);   // drain a wrong guess (only on odd paths)
                 if (!spec_commit) fw_issue_ctrl(st, x, lane);                              // next pass, or PH_DONE
+                if (c->phase == PH_ROOT && c->round == 0) fw_prestage(st, x, lane);        // an update just started: stage the one after it
             }
             if (lane == 0) { f->sn = sn; f->quit = c->phase == PH_DONE ? 1 : 0; f->scan[PG_THREADS] = spec && !spec_commit ? 1u : 0u; }
         }
@@ -1238,7 +1297,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) st.ctrl->prof[16 + (phase & 7)] += (unsigned long long)(clock64() - t_entry);   // after the issue: off the critical path
+        if (threadIdx.x == 0) c->prof_ser[phase & 7] += (unsigned long long)(clock64() - t_entry);
         if (f->quit) break;
     }
     __syncthreads();

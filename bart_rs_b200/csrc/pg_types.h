@@ -102,6 +102,7 @@ struct PgCtrl {
     // serial-section breakdown (cycles / calls): 0 reduce, 1 after_stats, 2 after_minmax, 3 finish_round, 4 prep_part,
     // 5 finalize, 6 begin_update, 7 draw_round; [8..15] call counts
     unsigned long long prof2[16];
+    unsigned long long prof_ser[8];     // serial section cycles by phase (kept by the control block)
     // ---- grid barrier
     unsigned int bar_count;
     unsigned int bar_pad[31];
