@@ -103,6 +103,11 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     unsigned issued;                             // commands issued so far (= value of bar_gen)
     int out_phase, out_J, out_pb;                // phase / job count / buffer parity of the outstanding pass
     int quit;
+    // look-ahead caches of the update in progress (rounds 1 and 2), indexed [round-1][slot]
+    int mm_valid[2][32]; unsigned mm_seg[2][32]; int mm_var[2][32]; float mm_lo[2][32], mm_hi[2][32];
+    int sc_valid[32]; unsigned sc_seg[32]; int sc_var[32]; float sc_thr[32]; unsigned sc_cnt[32]; double sc_So[32], sc_Sr[32];
+    int rq_r[64], rq_s[64]; unsigned rq_seg[64];  // request -> (round, slot, child segment)
+    int n_mq, pf_n, pf_slot[32];
     unsigned long long pre_upd;                  // update whose root jobs are already staged in the global job arrays
     int pre_J, pre_G, spec_now;
     volatile unsigned long long want_base, want_top;   // draw helpers: updates [want_base, want_top] are wanted
@@ -135,7 +140,7 @@ __host__ __device__ inline size_t pg_smem_bytes(int S) {
     b = (b + 15) & ~(size_t)15;
     b += (size_t)S * 16;                       // jvL, jvR
     b += (size_t)PG_WARPS * S * (8 + 8 + 4);   // accA, accB, accC
-    b += (size_t)S * 8;                        // mmin, mmax
+    b += (size_t)S * 16;                       // mmin, mmax (2S each)
     b = (b + 15) & ~(size_t)15;
     b += (size_t)FW_MAXP * (8 + 4 + 4);        // cprior, cmin, cmax
     return b + 64;
@@ -157,8 +162,8 @@ __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
     v.accA = reinterpret_cast<double*>(raw + off); off += (size_t)PG_WARPS * S * 8;
     v.accB = reinterpret_cast<double*>(raw + off); off += (size_t)PG_WARPS * S * 8;
     v.accC = reinterpret_cast<unsigned*>(raw + off); off += (size_t)PG_WARPS * S * 4;
-    v.mmin = reinterpret_cast<unsigned*>(raw + off); off += (size_t)S * 4;
-    v.mmax = reinterpret_cast<unsigned*>(raw + off); off += (size_t)S * 4;
+    v.mmin = reinterpret_cast<unsigned*>(raw + off); off += (size_t)S * 8;
+    v.mmax = reinterpret_cast<unsigned*>(raw + off); off += (size_t)S * 8;
     v.jvar = reinterpret_cast<int*>(raw + off); off += (size_t)S * 4;
     v.jthr = reinterpret_cast<float*>(raw + off); off += (size_t)S * 4;
     v.jorder = reinterpret_cast<int*>(raw + off); off += (size_t)S * 4;
@@ -441,8 +446,8 @@ __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemV
     }
     __syncthreads();
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
-        st.part_mm[((size_t)PG_BID * S + j) * 2 + 0] = sm.mmin[j];
-        st.part_mm[((size_t)PG_BID * S + j) * 2 + 1] = sm.mmax[j];
+        st.part_mm[((size_t)PG_BID * 2 * S + j) * 2 + 0] = sm.mmin[j];
+        st.part_mm[((size_t)PG_BID * 2 * S + j) * 2 + 1] = sm.mmax[j];
     }
 }
 
@@ -539,10 +544,15 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
 __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     const int K = __ldcg(&c->n_pjobs);
+    const int Q = __ldcg(&c->n_groups);     // look-ahead min/max requests riding on this pass (0 in the generic control code)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
     const unsigned lt_mask = (1u << lane) - 1u;
     const size_t ld = (size_t)st.ld;
+    if (Q > 0) {
+        for (int q = threadIdx.x; q < Q; q += blockDim.x) { sm.mmin[q] = 0xFFFFFFFFu; sm.mmax[q] = 0u; }
+        __syncthreads();
+    }
     for (int k = 0; k < K; ++k) {
         const unsigned src = __ldcg(&st.pj_src_off[k]);
         const bool ident = src == PG_SEG_IDENTITY;
@@ -575,8 +585,32 @@ __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemVie
         // the statistics pass counted the same predicate over the same range
         const int j = __ldcg(&st.pj_job[k]);
         if (lane == 0 && (left_run - left0) != __ldcg(&bf.part_cnt[(size_t)gw * st.S + j])) c->error = PG_ERR_INTERNAL;
+        // look-ahead: splitting.rs:43-49 for proposals the control block expects on the two children (their rows are
+        // streaming through this SM's caches right now: no gather pass later)
+        for (int q = 0; q < Q; ++q) {
+            if (__ldcg(&st.mq_pj[q]) != k) continue;
+            const bool want_left = __ldcg(&st.mq_side[q]) == 0;
+            const float* col2 = st.X + (size_t)__ldcg(&st.mq_var[q]) * ld;
+            float mn = INFINITY, mx = -INFINITY;
+            bool any = false;
+            for (unsigned long long e = beg + lane; e < end; e += 32) {
+                const unsigned idx = ident ? (unsigned)e : __ldcg(&st.pool[(size_t)src + e]);
+                const bool left = __ldg(&col[idx]) < thr;
+                if (left == want_left) { const float v = __ldg(&col2[idx]); mn = fminf(mn, v); mx = fmaxf(mx, v); any = true; }
+            }
+            unsigned kmn = any ? pg_f2key(mn) : 0xFFFFFFFFu, kmx = any ? pg_f2key(mx) : 0u;
+            kmn = __reduce_min_sync(PG_FULL, kmn);
+            kmx = __reduce_max_sync(PG_FULL, kmx);
+            if (lane == 0) { atomicMin(&sm.mmin[q], kmn); atomicMax(&sm.mmax[q], kmx); }
+        }
     }
-    (void)sm; (void)warp;
+    if (Q > 0) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+            st.part_mm[((size_t)PG_BID * 2 * st.S + q) * 2 + 0] = sm.mmin[q];
+            st.part_mm[((size_t)PG_BID * 2 * st.S + q) * 2 + 1] = sm.mmax[q];
+        }
+    }
 }
 
 // Dispatch one grid pass.

@@ -330,8 +330,8 @@ PG_HDN inline void pg_s_after_minmax(const PgState& st, const PgTeam& tm) {
     PG_FOR(j, J) {
         uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
         for (int b = 0; b < st.grid; ++b) {
-            const uint32_t a = st.part_mm[((size_t)b * st.S + j) * 2 + 0];
-            const uint32_t z = st.part_mm[((size_t)b * st.S + j) * 2 + 1];
+            const uint32_t a = st.part_mm[((size_t)b * 2 * st.S + j) * 2 + 0];
+            const uint32_t z = st.part_mm[((size_t)b * 2 * st.S + j) * 2 + 1];
             kmin = a < kmin ? a : kmin;
             kmax = z > kmax ? z : kmax;
         }
@@ -634,6 +634,7 @@ PG_HDN inline void pg_s_prep_part(const PgState& st, const PgTeam& tm) {
             bm += (st.pj_src_off[k] == PG_SEG_IDENTITY ? 0ull : 4ull * L) + 4ull * L + 4ull * L;
         }
         c->bytes_model += bm;
+        c->n_groups = 0;      // no look-ahead requests ride on the partition pass here
         c->phase = PH_PART;
         c->n_phases += 1;
         c->snext = SN_NONE;

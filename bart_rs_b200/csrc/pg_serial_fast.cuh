@@ -119,12 +119,12 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int 
             }
         }
         f->wsA[warp][lane] = a; f->wsB[warp][lane] = bsum; f->wsC[warp][lane] = cc;
-    } else if (phase == PH_MINMAX) {
+    } else if (phase == PH_MINMAX || phase == PH_PART) {
         unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
         if (lane < J) {
 #pragma unroll 1
             for (int b = warp; b < G; b += PG_WARPS) {
-                const uint2 v = __ldcg(reinterpret_cast<const uint2*>(st.part_mm + ((size_t)b * S + lane) * 2));
+                const uint2 v = __ldcg(reinterpret_cast<const uint2*>(st.part_mm + ((size_t)b * 2 * S + lane) * 2));
                 kmin = min(kmin, v.x); kmax = max(kmax, v.y);
             }
         }
@@ -155,7 +155,7 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int 
             if (phase == PH_BERN) { f->rllL[lane] = a; f->rllR[lane] = b; }
             else { f->rSo[lane] = a; f->rSr[lane] = b; f->rCnt[lane] = cc; }
         }
-        if (phase == PH_MINMAX && lane < J) {
+        if ((phase == PH_MINMAX || phase == PH_PART) && lane < J) {
             unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll 1
             for (int w = 0; w < PG_WARPS; ++w) { kmin = min(kmin, f->wsC[w][lane]); kmax = max(kmax, f->wsD[w][lane]); }
@@ -411,6 +411,8 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     bool passed;
     int status;
     const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
+    f->mm_valid[0][lane] = 0; f->mm_valid[1][lane] = 0; f->sc_valid[lane] = 0;
+    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; }
     if (lane < S) {
         const int s = lane;
         f->hw[s] = 0.0;       // smc.rs:53: once per update, never reset (Q1)
@@ -439,6 +441,8 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     }
     __syncwarp();
 }
+
+__device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, int lane, int phase);
 
 // rounds >= 1: pop the next expandable node of every slot, depth-prior test, split variable (smc.rs:61-86 front half)
 __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, int lane) {
@@ -487,21 +491,105 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
     }
     const int pb = (int)(upd & 1ull);
     int G;
-    const int J = fw_write_jobs(st, x, jb, lane, false, pb, true, true, &G);
-    if (J == 0) return SN_FINISH_ROUND;
+    if (!__any_sync(PG_FULL, jb.live)) {
+        (void)fw_write_jobs(st, x, jb, lane, false, pb, false, true, &G);
+        return SN_FINISH_ROUND;
+    }
+    // ---- look-ahead caches: min/max computed by the partition pass, statistics prefetched by the previous stats pass
+    const int ri = r - 1;
+    const bool mm_hit = (r == 1 || r == 2) && (!jb.live || (f->mm_valid[ri][lane] && f->mm_seg[ri][lane] == jb.seg_off && f->mm_var[ri][lane] == jb.var));
+    if (!__all_sync(PG_FULL, mm_hit)) {
+        // the regular way: a min/max pass over the nodes' index segments
+        const int J = fw_write_jobs(st, x, jb, lane, false, pb, true, true, &G);
+        if (lane == 0) {
+            const int* jord = st.job_order + (size_t)pb * st.S;
+            const int* gf = st.grp_first + (size_t)pb * (st.S + 1);
+            unsigned long long bm = 0, bc = 0;
+#pragma unroll 1
+            for (int g = 0; g < G; ++g) {
+                const unsigned long long L = f->jlen[jord[gf[g]]];
+                bm += 4ull * L + 4ull * L * (unsigned long long)(gf[g + 1] - gf[g]);
+            }
+#pragma unroll 1
+            for (int j = 0; j < J; ++j) bc += 8ull * f->jlen[j];
+            c->bytes_model += bm; c->bytes_contract += bc;
+            c->phase = PH_MINMAX; c->n_phases += 1;
+        }
+        __syncwarp();
+        return SN_NONE;
+    }
+    if (jb.live) { jb.lo = f->mm_lo[ri][lane]; jb.hi = f->mm_hi[ri][lane]; }
+    fw_decide(st, x, jb);                                  // splitting.rs:39-56 (may drop the job: min >= max)
+    if (lane == 0) { unsigned long long bc = 0; (void)bc; }
+    if (!__any_sync(PG_FULL, jb.live)) {
+        (void)fw_write_jobs(st, x, jb, lane, true, pb, false, true, &G);
+        return SN_FINISH_ROUND;
+    }
+    const bool sc_hit = !jb.live || (f->sc_valid[lane] && f->sc_seg[lane] == jb.seg_off && f->sc_var[lane] == jb.var && f->sc_thr[lane] == jb.thr);
+    if (__all_sync(PG_FULL, sc_hit)) {
+        // the statistics were prefetched too: no pass at all for this round
+        const int J = fw_write_jobs(st, x, jb, lane, true, pb, false, true, &G);
+        if (lane < J) {
+            const int s = f->jslot[lane];
+            f->rCnt[lane] = f->sc_cnt[s]; f->rSo[lane] = f->sc_So[s]; f->rSr[lane] = f->sc_Sr[s];
+        }
+        __syncwarp();
+        if (lane == 0) { unsigned long long bc = 0; for (int j = 0; j < J; ++j) bc += 28ull * f->jlen[j]; c->bytes_contract += bc; }
+        return fw_after_stats(st, x, lane, PH_STATS);
+    }
+    // statistics pass for this round's jobs ...
+    const int J = fw_write_jobs(st, x, jb, lane, true, pb, true, true, &G);
+    // ... carrying, for round 1, the round-2 proposals of every slot (node 2: the other child) as prefetch jobs
+    int Jp = 0;
+    if (r == 1 && G == 1) {
+        const int buf2 = buf;
+        bool want = lane < S && f->mm_valid[1][lane] && f->d_ok[buf2][2] && f->mm_lo[1][lane] < f->mm_hi[1][lane];
+        double split2 = 0.0;
+        float thr2 = 0.f;
+        if (want) {
+            const double lo = (double)f->mm_lo[1][lane], hi = (double)f->mm_hi[1][lane];
+            split2 = __dadd_rn(__dmul_rn(f->d_u3[buf2][2][lane], hi - lo), lo);
+            want = split2 < hi;
+            thr2 = pg_thr32(split2);
+        }
+        const unsigned wm = __ballot_sync(PG_FULL, want);
+        Jp = __popc(wm);
+        if (J + Jp > S) { Jp = 0; }
+        else if (want) {
+            const int q = __popc(wm & ((1u << lane) - 1u));
+            const size_t jo = (size_t)pb * st.S + (size_t)(J + q);
+            const unsigned len2 = (unsigned)st.n - 0u;
+            (void)len2;
+            st.job_var[jo] = f->mm_var[1][lane]; st.job_thr32[jo] = thr2; st.job_seg_off[jo] = f->mm_seg[1][lane];
+            st.job_len[jo] = st.pt_cnt[pg_tix(st, cur, lane, 2)];
+            st.job_slot[jo] = lane; st.job_node[jo] = 2; st.job_split[jo] = split2;
+            f->pf_slot[q] = lane;
+            f->sc_seg[lane] = f->mm_seg[1][lane]; f->sc_var[lane] = f->mm_var[1][lane]; f->sc_thr[lane] = thr2;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (Jp > 0 && lane == 0) {
+            const size_t jo = (size_t)pb * st.S;
+            G = pg_group_jobs_arrays(st.job_seg_off + jo, st.job_len + jo, st.job_order + jo, st.grp_first + (size_t)pb * (st.S + 1), J + Jp);
+        }
+        G = __shfl_sync(PG_FULL, G, 0);
+    }
     if (lane == 0) {
-        const int* jord = st.job_order + (size_t)pb * st.S;
+        f->pf_n = Jp;
+        const size_t jo = (size_t)pb * st.S;
+        const int* jord = st.job_order + jo;
         const int* gf = st.grp_first + (size_t)pb * (st.S + 1);
         unsigned long long bm = 0, bc = 0;
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
-            const unsigned long long L = f->jlen[jord[gf[g]]];
-            bm += 4ull * L + 4ull * L * (unsigned long long)(gf[g + 1] - gf[g]);
+            const unsigned long long L = st.job_len[jo + jord[gf[g]]];
+            bm += (4ull + 8ull + 4ull) * L + 4ull * L * (unsigned long long)(gf[g + 1] - gf[g]);
         }
 #pragma unroll 1
-        for (int j = 0; j < J; ++j) bc += 8ull * f->jlen[j];
+        for (int j = 0; j < J; ++j) bc += 28ull * f->jlen[j];
         c->bytes_model += bm; c->bytes_contract += bc;
-        c->phase = PH_MINMAX; c->n_phases += 1;
+        c->n_groups = G;
+        c->phase = PH_STATS; c->n_phases += 1;
     }
     __syncwarp();
     return SN_NONE;
@@ -776,7 +864,7 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
         st.pt_seg_off[pg_tix(st, dst, lane, 2 * node + 2)] = off + cntL;
     }
     const int any_queue = __any_sync(PG_FULL, act && qh < qt);
-    if (lane == 0) { c->acc_update += n_mut; c->cur = dst; c->n_pjobs = K; c->any_queue = any_queue; }
+    if (lane == 0) { c->acc_update += n_mut; c->cur = dst; c->n_pjobs = K; c->any_queue = any_queue; f->n_mq = 0; }
     __syncwarp();
     if (c->error != PG_OK) return SN_NONE;
     if (K > 0) return SN_PREP_PART;
@@ -842,7 +930,8 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
             const unsigned long long L = st.pj_len[k];
             bm += (st.pj_src_off[k] == PG_SEG_IDENTITY ? 0ull : 4ull * L) + 4ull * L + 4ull * L;
         }
-        c->bytes_model += bm;
+        c->bytes_model += bm + 4ull * (unsigned long long)f->n_mq * (K > 0 ? (unsigned long long)st.pj_len[0] : 0ull);
+        c->n_groups = f->n_mq;          // look-ahead min/max requests riding on the partition pass
         c->phase = PH_PART; c->n_phases += 1;
     }
 }
@@ -1051,6 +1140,31 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         }
     }
     if (lane == 0) { c->n_pjobs = K; c->any_queue = 1; }
+    // ---- look-ahead: when every slot is a copy of ONE grown particle, the proposals of rounds 1 and 2
+    // are known now — slot s will try node 1 with (u1, var)(round 1, s) and node 2 with (u1, var)(round 2, s), whatever
+    // the resampling does in between.  Let the partition pass compute the min/max those proposals need.
+    {
+        const int buf = (int)(c->upd % 3ull);
+        const bool single = K == 1 && st.family != PG_BERNOULLI_LOGIT && __all_sync(PG_FULL, !act || need) && st.maxn > 6;
+        int nq = 0;
+        if (single) {
+            const int j = f->hsjob[anc];
+            const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n - cL;
+#pragma unroll 1
+            for (int r = 1; r <= 2; ++r) {
+                const bool want = act && f->d_ok[buf][r] && !(x.thr[1] > f->d_u1[buf][r][lane]) && (r == 1 ? cL : cR) > 0u;
+                const unsigned m = __ballot_sync(PG_FULL, want);
+                const int q = nq + __popc(m & ((1u << lane) - 1u));
+                if (want && q < 32) {
+                    st.mq_pj[q] = 0; st.mq_side[q] = r - 1; st.mq_var[q] = f->d_var[buf][r][lane];
+                    f->rq_r[q] = r; f->rq_s[q] = lane; f->rq_seg[q] = r == 1 ? off : off + cL;
+                }
+                nq += __popc(m);
+            }
+            if (nq > 32) nq = 32;
+        }
+        if (lane == 0) f->n_mq = nq;
+    }
     __syncwarp();
     if (c->error != PG_OK) return SN_NONE;
     return SN_PREP_PART;     // K >= 1 here; after PH_PART the general rounds continue
@@ -1088,8 +1202,11 @@ __device__ __forceinline__ void fw_issue_ctrl(const PgState& st, const FwCx& x, 
     else if (phase == PH_FINAL) dst = 0;       // `predictions` always end in buffer 0
     __syncwarp();
     if (lane == 0 && (phase == PH_ROOT || phase == PH_FINAL)) c->a_cur = dst;
-    fw_issue(st, x, lane, phase, c->t_add, phase == PH_ROOT ? c->t_sub : -1, c->n_jobs, c->n_groups, c->n_pjobs,
+    const int nj = phase == PH_STATS ? c->n_jobs + x.f->pf_n : c->n_jobs;
+    fw_issue(st, x, lane, phase, c->t_add, phase == PH_ROOT ? c->t_sub : -1, nj, c->n_groups, c->n_pjobs,
              src | (dst << 1) | (pb << 2));
+    if (phase == PH_PART && lane == 0) x.f->out_J = x.f->n_mq;   // what the next section reduces: the look-ahead min/max
+    __syncwarp();
 }
 
 // wait until the outstanding pass has completed on every pass block
@@ -1237,17 +1354,39 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                     if (sn == SN_FINISH_ROUND) sn = fw_r0_finish(st, x, lane, false);
                     FW_TICK(1);
                     break;
-                case PH_STATS: sn = fw_after_stats(st, x, lane, phase); FW_TICK(1); break;
+                case PH_STATS:
+                    if (f->pf_n > 0) {   // results of the prefetch jobs (round-2 proposals) go to the statistics cache
+                        const int J0 = c->n_jobs;
+                        if (lane >= J0 && lane < J0 + f->pf_n) {
+                            const int s = f->pf_slot[lane - J0];
+                            f->sc_cnt[s] = f->rCnt[lane]; f->sc_So[s] = f->rSo[lane]; f->sc_Sr[s] = f->rSr[lane]; f->sc_valid[s] = 1;
+                        }
+                        __syncwarp();
+                        if (lane == 0) f->pf_n = 0;
+                        __syncwarp();
+                    }
+                    sn = fw_after_stats(st, x, lane, phase);
+                    FW_TICK(1);
+                    break;
                 case PH_BERN:
                     if (c->round == 0) sn = fw_r0_finish(st, x, lane, true); else sn = fw_after_stats(st, x, lane, phase);
                     FW_TICK(1);
                     break;
                 case PH_MINMAX: sn = fw_after_minmax(st, x, lane); FW_TICK(2); break;
-                case PH_PART:
-                    if (lane == 0) c->round += 1;
+                case PH_PART: {
+                    const int nq = f->n_mq;
+                    __syncwarp();
+                    if (lane < nq) {   // look-ahead min/max computed by the partition pass
+                        const int ri = f->rq_r[lane] - 1, s = f->rq_s[lane];
+                        f->mm_seg[ri][s] = f->rq_seg[lane]; f->mm_var[ri][s] = st.mq_var[lane];
+                        f->mm_lo[ri][s] = pg_key2f(f->rMin[lane]); f->mm_hi[ri][s] = pg_key2f(f->rMax[lane]);
+                        f->mm_valid[ri][s] = 1;
+                    }
+                    if (lane == 0) { c->round += 1; f->n_mq = 0; }
                     __syncwarp();
                     sn = SN_DRAW_ROUND;
                     break;
+                }
                 case PH_FINAL:
                     if (lane == 0) { c->next_tree_idx = (c->next_tree_idx + c->batch) % st.m; c->t_add = -1; c->phase = PH_DONE; }
                     __syncwarp();

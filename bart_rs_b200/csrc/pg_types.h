@@ -164,7 +164,8 @@ struct PgState {
     unsigned int* part_cnt;      // [n_gwarps][S] left count per global warp (prefix for the partition)
     unsigned int* part_ccnt;     // [grid][S]     left count per block
     double* part_tot;            // [grid][4]
-    unsigned int* part_mm;       // [grid][S][2]  ordered-uint keys of min / max
+    unsigned int* part_mm;       // [grid][2S][2] ordered-uint keys of min / max (2S: the partition pass may carry look-ahead requests)
+    int* mq_pj; int* mq_side; int* mq_var;   // [2S] look-ahead min/max requests of the partition pass: (partition job, child side, column)
     double* part_ll;             // [grid][S][2]  Bernoulli: log-likelihood of the left / right child
     // segment pool
     unsigned int* pool; unsigned long long pool_cap;

@@ -113,8 +113,8 @@ void pass_minmax(const PgState& st) {
                     if (x == x) { kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax; }
                 }
             }
-            st.part_mm[((size_t)b * S + j) * 2 + 0] = kmin;
-            st.part_mm[((size_t)b * S + j) * 2 + 1] = kmax;
+            st.part_mm[((size_t)b * 2 * S + j) * 2 + 0] = kmin;
+            st.part_mm[((size_t)b * 2 * S + j) * 2 + 1] = kmax;
         }
 }
 
@@ -253,7 +253,7 @@ void* pgsim_create(const double* x_f, uint64_t n, uint64_t p, const double* y, c
     st.pj_cntL = halloc<unsigned>(s, S); st.pj_warp_left = halloc<unsigned>(s, S * W); st.pj_of_anc = halloc<int>(s, S);
     st.scan_tmp = halloc<unsigned>(s, PG_THREADS + 1);
     st.part_sum = halloc<double>(s, G * S * 2); st.part_cnt = halloc<unsigned>(s, W * S); st.part_ccnt = halloc<unsigned>(s, G * S);
-    st.part_tot = halloc<double>(s, G * 4); st.part_mm = halloc<unsigned>(s, G * S * 2); st.part_ll = halloc<double>(s, G * S * 2);
+    st.part_tot = halloc<double>(s, G * 4); st.part_mm = halloc<unsigned>(s, G * 2 * S * 2); st.mq_pj = halloc<int>(s, 2 * S); st.mq_side = halloc<int>(s, 2 * S); st.mq_var = halloc<int>(s, 2 * S); st.part_ll = halloc<double>(s, G * S * 2);
     st.info_depths = halloc<unsigned char>(s, M);
     st.ctrl = halloc<PgCtrl>(s, 1);
     st.pool_cap = (unsigned long long)std::max<size_t>(2 * S, (size_t)st.max_depth + 2) * n;
