@@ -178,7 +178,9 @@ __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
 // ---- loads ------------------------------------------------------------------
 // X and y never change: read-only path.  A and the pool are rewritten between passes by other
 // SMs: read through L2 (ld.global.cg) so a stale L1 line can never be observed.
-__device__ __forceinline__ float4 pg_ld_x4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// X columns are streamed once per pass and are far larger than L2: load them with the streaming (evict-first) policy so
+// they do not push out what IS reused every pass — A, y, and the control block's code and tables.
+__device__ __forceinline__ float4 pg_ld_x4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ double2 pg_ld_a2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 
 // ---- warp-transposed reduction of 4 jobs' partial sums ----------------------
