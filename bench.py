@@ -11,8 +11,9 @@ GPU) every rank runs an independent chain of the same workload with its own seed
 SURVEY.md §8(e): no data-path collective, weak scaling; value = sweeps of all ranks / max-over-ranks time.
 
 One JSON line on stdout (rank 0).  Keys beyond the base contract:
-  roofline      dominant (and only) hot kernel pg_sweep_persistent: achieved = compulsory bytes of its passes
-                (device counters) / CUDA-event time on the sampler's stream; peak = MEASURED_PEAKS.json
+  roofline      dominant (and only) hot kernel pg_sweep_persistent: achieved = SURVEY.md §8(d) algorithmic bytes of the
+                sweep (device counters) / CUDA-event time on the sampler's stream; fused_* = bytes this
+                implementation must move; traffic = ncu dram bytes (profiles/ncu_traffic.json); peak = MEASURED_PEAKS.json
   cpu_baseline  the oracle (C++ restatement of the bart-rs CPU path, 1 core) timed here on a bounded sample
   e2e           same metric through PySampler.step() with host buffers (likelihood push H2D, predictions D2H)
 """
@@ -148,7 +149,8 @@ def run_reference(args):
         "impl": "reference", "metric": "PG sweeps/sec", "value": sweeps_per_s, "unit": "sweeps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: Friedman n={w['n']} p={w['p']} m={w['m']} P={w['P']} {w['family']}",
+        "config": {"workload": f"{args.workload}: Friedman n={w['n']} p={w['p']} m={w['m']} P={w['P']} {w['family']}, "
+                               "batch=(1,1) so one step = one sweep",
                    "sample": f"each step = {per_step} tree updates of the sweep, scaled to m={w['m']}"},
         "cpu_baseline": {"value": sweeps_per_s, "unit": "sweeps/s", "cores": 1, "kind": "port",
                          "sample": f"{done_total} tree updates in {total:.2f} s, scaled to m={w['m']}"},
@@ -175,8 +177,9 @@ def run_gpu(args):
 
     w = WORKLOADS[args.workload]
     X, y, prm = make_data(w)
-    st = PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, prm["sigma"], list(prm["split_prior"]),
-                        ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=rank)
+    from bart_rs_b200.chains import chain_settings, job_throughput
+    st = chain_settings(PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, prm["sigma"], list(prm["split_prior"]),
+                                       ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=0), rank)
     lik = DeviceLikelihood(w["family"], 1.0)
     smp = PySampler.init(X, y, lik, st, device=local_rank)   # X is float32 C-order: converted to column-major on upload
 
@@ -203,11 +206,7 @@ def run_gpu(args):
     barrier()
     clk = clocks.stop() if rank == 0 else None
     c1 = smp.counters()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * args.steps / (ms_max / 1000.0)
+    value, ms_max = job_throughput(ms, args.steps, world, device="cuda")
 
     # ---- end to end: PySampler.step() with host buffers (likelihood parameters H2D, predictions D2H each step)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -220,10 +219,7 @@ def run_gpu(args):
         pred = smp.step(False)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps / float(t2.item())
+    e2e_value, _ = job_throughput(1000.0 * e2e_s, e2e_steps, world, device="cuda")
     assert np.all(np.isfinite(pred))
 
     if rank == 0:
@@ -231,8 +227,15 @@ def run_gpu(args):
         k = args.steps
         bytes_per_launch = (c1["bytes_model"] - c0["bytes_model"]) / k
         contract_per_launch = (c1["bytes_contract"] - c0["bytes_contract"]) / k
-        achieved = bytes_per_launch / (ms / 1000.0 / k) / 1e9
-        contract_gbs = contract_per_launch / (ms / 1000.0 / k) / 1e9
+        fused_gbs = bytes_per_launch / (ms / 1000.0 / k) / 1e9
+        achieved = contract_per_launch / (ms / 1000.0 / k) / 1e9
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("workload") == args.workload:
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             done, dt = oracle_sample(X, y, prm, w, args.ref_updates)
@@ -250,12 +253,16 @@ def run_gpu(args):
                              else "working set fits L2 (L2-resident by design of this config)",
                        "storage": "X, y fp32; running sum-of-trees fp64; accumulation fp64"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "pg_sweep_persistent",
-                         "bytes_per_launch": bytes_per_launch,
-                         "contract_formula_gbs": contract_gbs, "contract_bytes_per_launch": contract_per_launch,
-                         "note": "achieved uses this implementation's compulsory bytes (A r/w, y, one read per distinct split "
-                                 "column per pass, index lists); contract_* uses SURVEY.md §8(d)'s per-slot formula, which "
-                                 "charges A/y once per slot — the fused root pass reads them once per tree"},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "pg_sweep_persistent (one launch = one sweep = m tree updates)",
+                         "algorithmic_bytes_per_launch": contract_per_launch,
+                         "fused_bytes_per_launch": bytes_per_launch, "fused_gbs": fused_gbs, "fused_frac": fused_gbs / peak,
+                         "note": "achieved = SURVEY.md 8(d) contract bytes (B_tree summed from device counters over the sweep's "
+                                 "grows: per-slot min/max + stats + partition passes, fp64 A, no credit for cross-particle "
+                                 "sharing) / CUDA-event time of the launch.  fused_* = the bytes this implementation must move "
+                                 "(A, y and each distinct split column read once per pass for all slots together); "
+                                 "traffic = ncu dram bytes of one launch (A and y stay L2-resident, so it is below both). "
+                                 "The launch is bound by its serial control sections, not by HBM: DESIGN.md section 6"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8 * w["n"],
                     "steps": e2e_steps},
@@ -276,7 +283,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-updates", type=int, default=24, help="tree updates per timed CPU sample")
+    ap.add_argument("--ref-updates", type=int, default=40, help="tree updates per timed CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

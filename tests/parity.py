@@ -133,3 +133,69 @@ def philox_parity(make_dev, X, y, cfg, family, lik_sigma, tunes, r_cap=24, rtol=
     assert_traces_match((tr.slot, tr.round, tr.upd), (ds, dr, du), n_upd, S, P, rtol)
     assert_forest_matches(orc, dev, m, rtol)
     return tr
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py): replay without the oracle.
+
+GOLDEN_NAMES = ["gauss_P20", "gauss_deep_P3", "bern_P6", "gauss_noprior_batch"]
+
+
+def load_golden(name):
+    import ast
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
+    z = np.load(path)
+    g = {k: z[k] for k in z.files if k != "meta"}
+    g["meta"] = ast.literal_eval(str(z["meta"]))
+    return g
+
+
+class GoldenForest:
+    """tree()/leaf_indices() view of a fixture, for assert_forest_matches."""
+
+    def __init__(self, g):
+        self.g = g
+
+    def tree(self, t):
+        sv = self.g["split_var"][t]
+        # stored padded to the largest tree of the fixture: cut back to this tree's own length
+        live = np.nonzero((sv >= 0) | ~np.isnan(self.g["leaf_val"][t]))[0]
+        size = int(live.max()) + 1 if live.size else 1
+        return sv[:size].astype(np.int32), self.g["split_val"][t][:size], self.g["leaf_val"][t][:size]
+
+    def leaf_indices(self, t):
+        return self.g["leaf_indices"][t].astype(np.uint32)
+
+
+def golden_parity(make_dev, g, rtol=RTOL):
+    """Replay a fixture's tape through `make_dev`'s implementation and compare with the stored trace."""
+    meta = g["meta"]
+    cfg = {k: meta[k] for k in ("n_trees", "n_particles", "max_depth", "alpha", "beta", "sigma", "split_prior",
+                                "batch_tune", "batch_post", "seed")}
+    m, P = cfg["n_trees"], cfg["n_particles"]
+    S = P - 1
+    dev = make_dev(g["X"], g["y"], cfg)
+    dev.set_likelihood_code(meta["family"], [meta["lik_sigma"]])
+    dev.set_rng_tape(g["tape_slot"], g["tape_round"], g["tape_upd"])
+    U = g["tape_upd"].shape[0]
+    dev.trace_enable(U, meta["r_cap"])
+    preds = np.stack([dev.step(t) for t in meta["tunes"]])
+    ds, dr, du, n_upd, ovf = dev.trace_read()
+    assert not ovf and n_upd == int(g["n_upd"])
+    assert_traces_match((g["trace_slot"], g["trace_round"], g["trace_upd"]), (ds, dr, du), n_upd, S, P, rtol)
+    np.testing.assert_allclose(preds, g["preds"], rtol=rtol, atol=0, err_msg="predictions")
+    gf = GoldenForest(g)
+    for t in range(m):
+        osv, osp, olv = gf.tree(t)
+        dsv, dsp, dlv = dev.tree(t)
+        k = min(len(osv), len(dsv))       # implementations may trim trailing unused nodes differently
+        assert np.all(dsv[k:] < 0) and np.all(osv[k:] < 0)
+        np.testing.assert_array_equal(dsv[:k], osv[:k], err_msg=f"tree {t} split_var")
+        np.testing.assert_array_equal(np.nan_to_num(dsp[:k], nan=-7e300), np.nan_to_num(osp[:k], nan=-7e300))
+        np.testing.assert_array_equal(np.isnan(dlv[:k]), np.isnan(olv[:k]))
+        np.testing.assert_allclose(np.nan_to_num(dlv[:k]), np.nan_to_num(olv[:k]), rtol=rtol, atol=1e-12)
+        np.testing.assert_array_equal(dev.leaf_indices(t), gf.leaf_indices(t), err_msg=f"tree {t} leaf_indices")
+    dll, dacc, ddep = dev.info()
+    assert dacc == int(g["info_acc"])
+    np.testing.assert_array_equal(ddep, g["info_depths"])
