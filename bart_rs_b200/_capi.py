@@ -21,7 +21,7 @@ EXPORTS = [
     "pgbart_step_device", "pgbart_sync", "pgbart_predictions_device", "pgbart_get_predictions", "pgbart_get_info",
     "pgbart_tree_size", "pgbart_get_tree", "pgbart_get_leaf_indices", "pgbart_get_state", "pgbart_set_rng_philox",
     "pgbart_set_rng_tape", "pgbart_trace_enable", "pgbart_trace_read", "pgbart_set_option", "pgbart_get_counters",
-    "pgbart_timer_start", "pgbart_timer_stop", "pgbart_get_profile",
+    "pgbart_timer_start", "pgbart_timer_stop", "pgbart_get_profile", "pgbart_debug_block_cycles",
 ]
 
 

@@ -207,8 +207,11 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
 
     char ebuf[256];
     int grid = 0;
-    if (pg_query_grid(device, st.S, &grid, &s->smem, ebuf, sizeof ebuf)) { s->err = ebuf; return bail(); }
+    int stage_bytes = 0;
+    if (pg_query_grid(device, st.S, &grid, &s->smem, &stage_bytes, ebuf, sizeof ebuf)) { s->err = ebuf; return bail(); }
     st.grid = grid;
+    st.stage_bytes = stage_bytes;
+    st.root_staged = 0;
     st.n_gwarps = grid * PG_WARPS;
 
     // ---- X -> column-major fp32 with per-column min/max; y -> fp32
@@ -225,7 +228,8 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
                 colbuf[i] = v;
                 mn = std::fmin(mn, v); mx = std::fmax(mx, v);
             }
-            for (uint64_t i = n; i < (uint64_t)st.ld; ++i) colbuf[i] = 0.0f;
+            // padding rows compare as "not left" for every threshold, so block-unit passes need no row masks on x
+            for (uint64_t i = n; i < (uint64_t)st.ld; ++i) colbuf[i] = std::numeric_limits<float>::infinity();
             cmin[j] = mn; cmax[j] = mx;
             if (!ck(s, cudaMemcpy(dX + (size_t)j * st.ld, colbuf.data(), (size_t)st.ld * 4, cudaMemcpyHostToDevice), "upload X")) return bail();
         }
@@ -235,6 +239,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         if (!ck(s, cudaMemcpy(dmin, cmin.data(), p * 4, cudaMemcpyHostToDevice), "upload") ||
             !ck(s, cudaMemcpy(dmax, cmax.data(), p * 4, cudaMemcpyHostToDevice), "upload")) return bail();
         for (uint64_t i = 0; i < n; ++i) colbuf[i] = (float)y[i];
+        for (uint64_t i = n; i < (uint64_t)st.ld; ++i) colbuf[i] = 0.0f;
         if (!ck(s, cudaMemcpy(dy, colbuf.data(), (size_t)st.ld * 4, cudaMemcpyHostToDevice), "upload y")) return bail();
         st.col_min = dmin; st.col_max = dmax; st.y = dy;
     }
@@ -277,7 +282,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         && dalloc(s, &st.pj_src_off, S) && dalloc(s, &st.pj_len, S) && dalloc(s, &st.pj_dst_off, S) && dalloc(s, &st.pj_cntL, S)
         && dalloc(s, &st.pj_warp_left, S * W) && dalloc(s, &st.pj_of_anc, S) && dalloc(s, &st.scan_tmp, PG_THREADS + 1)
         && dalloc(s, &st.part_sum, 2 * G * S * 2) && dalloc(s, &st.part_cnt, 2 * W * S) && dalloc(s, &st.part_ccnt, 2 * G * S)
-        && dalloc(s, &st.part_tot, 2 * G * 4) && dalloc(s, &st.part_mm, G * 2 * S * 2) && dalloc(s, &st.mq_pj, 2 * S) && dalloc(s, &st.mq_side, 2 * S) && dalloc(s, &st.mq_var, 2 * S) && dalloc(s, &st.part_ll, G * S * 2)
+        && dalloc(s, &st.part_tot, 2 * G * 4) && dalloc(s, &st.part_mm, G * 2 * S * 2) && dalloc(s, &st.mq_pj, 2 * S) && dalloc(s, &st.mq_side, 2 * S) && dalloc(s, &st.mq_var, 2 * S) && dalloc(s, &st.part_ll, G * S * 2) && dalloc(s, &st.diag_blocks, G * 16)
         && dalloc(s, &st.info_depths, M) && dalloc(s, &st.ctrl, 1);
     if (!ok) return bail();
     {
@@ -475,6 +480,12 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
         s->err = "driver must be 'persistent' or 'stepwise'";
         return 1;
     }
+    if (std::strcmp(key, "root_pass") == 0) {
+        if (std::strcmp(value, "staged") == 0) { s->st.root_staged = 1; return 0; }
+        if (std::strcmp(value, "direct") == 0) { s->st.root_staged = 0; return 0; }
+        s->err = "root_pass must be 'staged' or 'direct'";
+        return 1;
+    }
     if (std::strcmp(key, "pool_factor") == 0) {
         const long long f = std::atoll(value);
         if (f < 1) { s->err = "pool_factor must be >= 1"; return 1; }
@@ -515,6 +526,18 @@ int pgbart_get_profile(pgbart_handle h, double* out32) {
     if (s->st.P <= 32 && !s->stepwise) for (int i = 0; i < 8; ++i) out32[16 + i] = (double)s->host_ctrl.prof_ser[i];
     for (int i = 0; i < 16; ++i) out32[32 + i] = (double)s->host_ctrl.prof2[i];
     out32[48] = (double)s->host_ctrl.n_spec;
+    for (int i = 0; i < 16; ++i) out32[49 + i] = (double)s->host_ctrl.prof3[i];
+    for (int i = 0; i < 12; ++i) out32[57 + i] = (double)s->host_ctrl.dbg[4 + i];   // prof3[8..15] unused: diagnostics ride there
+    return 0;
+}
+
+int pgbart_debug_block_cycles(pgbart_handle h, double* out, int cap) {
+    Sampler* s = &h->s;
+    const int G = s->st.grid;
+    std::vector<unsigned long long> tmp((size_t)G * 16);
+    if (!ck(s, cudaStreamSynchronize(s->stream), "sync")) return 2;
+    if (!ck(s, cudaMemcpy(tmp.data(), s->st.diag_blocks, tmp.size() * 8, cudaMemcpyDeviceToHost), "copy diag")) return 2;
+    for (int i = 0; i < G * 16 && i < cap; ++i) out[i] = (double)tmp[i];
     return 0;
 }
 

@@ -20,10 +20,16 @@
 //                   compaction) appended to the segment pool; only for surviving particles.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include "pg_types.h"
 #include "pg_serial.h"
 
 #define PG_TREE_SM 63      // tree nodes staged in shared memory (depth <= 5); larger trees read global
+#define PGR_T 512          // staged root pass: rows per tile
+#define PGR_MAXST 8        //   stages of the ring (as many as the staging area holds, at least 3)
+#define PGR_MAXU 40        //   distinct columns per tile (S <= 31 job columns + tree columns)
+#define PGR_JW 8           //   jobs per warp: 4 job groups x 8 >= S
+#define PGR_KP 6           //   staged arrays per thread whose source pointers live in registers
 #define PG_FULL 0xFFFFFFFFu
 
 // Index of this block among the PASS blocks (st.grid of them).  In the persistent kernel block 0 is the serial
@@ -124,6 +130,15 @@ struct PgSmem {
     int cstaged;           // split prior / column min-max are staged in the dynamic area
     int pass_bid;          // this block's index among the pass blocks (-1: serial-only block)
     int is_last;
+    // ---- staged root pass (pg_pass_root_staged): bulk-copy ring in the staging area behind the dynamic arrays
+    int r_ucol[PGR_MAXU];                  // distinct columns staged per tile
+    int r_jslot[32];                       // job -> staged column
+    short r_add_slot[PG_TREE_SM], r_sub_slot[PG_TREE_SM];   // tree node -> staged column, -1 = gather from global
+    int r_U;
+    unsigned long long r_src[3 + PGR_MAXU];   // per staged array (A rows 0-255, A rows 256-511, y, columns...): address of tile row 0 at r0 = 0
+    double r_acc[4][32][2];                // [row quarter][job]: sum A, sum y-A over LEFT rows
+    unsigned r_cnt[4][32];
+    unsigned p_scan[2][PG_WARPS];          // block-unit identity partition: warp totals of a chunk, double-buffered
     // followed by dynamic arrays, see pg_smem_* accessors
 };
 
@@ -143,7 +158,7 @@ __host__ __device__ inline size_t pg_smem_bytes(int S) {
     b += (size_t)S * 16;                       // mmin, mmax (2S each)
     b = (b + 15) & ~(size_t)15;
     b += (size_t)FW_MAXP * (8 + 4 + 4);        // cprior, cmin, cmax
-    return b + 64;
+    return ((b + 127) & ~(size_t)127) + 128;   // the staging area starts 128-byte aligned behind this
 }
 
 struct PgSmemView {
@@ -151,6 +166,7 @@ struct PgSmemView {
     int* jvar; float* jthr; int* jorder; int* grp; double* jvL; double* jvR;
     double* accA; double* accB; unsigned* accC; unsigned* mmin; unsigned* mmax;
     double* cprior; float* cmin; float* cmax;
+    unsigned char* stage;      // staging area (st.stage_bytes), 128-byte aligned
 };
 
 __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
@@ -171,7 +187,8 @@ __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
     off = (off + 15) & ~(size_t)15;
     v.cprior = reinterpret_cast<double*>(raw + off); off += (size_t)FW_MAXP * 8;
     v.cmin = reinterpret_cast<float*>(raw + off); off += (size_t)FW_MAXP * 4;
-    v.cmax = reinterpret_cast<float*>(raw + off);
+    v.cmax = reinterpret_cast<float*>(raw + off); off += (size_t)FW_MAXP * 4;
+    v.stage = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw + off) + 127) & ~(uintptr_t)127);
     return v;
 }
 
@@ -280,7 +297,9 @@ __device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgBuf& bf,
 // PH_ROOT / PH_FINAL
 // =============================================================================
 // Rows per lane per iteration: 8 (two float4 groups) => 256 rows per warp-iteration.
-template <bool BERN>
+// BLOCKR: the block's rows are pg_block_range (the block-unit scheme of the P <= 32 persistent kernel), split among its
+// warps; otherwise every global warp owns one pg_warp_range (generic control code, stepwise driver).
+template <bool BERN, bool BLOCKR>
 __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     const int J = __ldcg(&c->n_jobs) * (__ldcg(&c->phase) == PH_ROOT ? 1 : 0);
@@ -300,7 +319,12 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
     const double sub_c = (t_sub >= 0 && !sub_nontrivial) ? sm.base->tsub.leaf_val[0] : 0.0;
 
     unsigned long long beg, end;
-    pg_warp_range((unsigned long long)st.n, gw, st.n_gwarps, 4, &beg, &end);
+    if (BLOCKR) {
+        long long B0, B1;
+        pg_block_range(st.n, PG_BID, st.grid, &B0, &B1);
+        pg_warp_range((unsigned long long)(B1 - B0), warp, PG_WARPS, 4, &beg, &end);
+        beg += (unsigned long long)B0; end += (unsigned long long)B0;
+    } else pg_warp_range((unsigned long long)st.n, gw, st.n_gwarps, 4, &beg, &end);
     const long long n = st.n;
     const size_t ld = (size_t)st.ld;
     double tot_o = 0.0, tot_r = 0.0, tot_rr = 0.0, tot_ll = 0.0;
@@ -413,6 +437,381 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
         bf.part_tot[(size_t)PG_BID * 4 + threadIdx.x] = v;
     }
     pg_flush_acc(st, bf, sm, J, true, false);
+}
+
+// =============================================================================
+// PH_ROOT / PH_FINAL, staged variant (P <= 32 persistent kernel)
+// =============================================================================
+// The warp-range pass above is latency bound: each warp walks its rows through dependent global loads with
+// little else in flight (measured 32 us per pass at n = 1M against ~12 us of HBM time).  Here the loads are decoupled
+// from the arithmetic: all threads keep a ring of tiles in flight with asynchronous copies into shared memory
+// (cp.async, 16 B per thread per copy, evict-first for X); a tile = PGR_T rows of A, y and every DISTINCT column the
+// pass needs (the slots' split variables plus the split variables of the trees being committed / opened, so tree
+// evaluation reads shared memory too).  Warp w = (row quarter w / 4, job group w % 4): a lane owns 4 consecutive rows
+// of its quarter and accumulates its group's jobs in registers across ALL tiles of the block, so the cross-lane
+// reduction happens once per pass instead of once per 256 rows.  Every sum is taken in a fixed order (lane-private
+// sequential, fixed shuffle tree, quarters in order) => bit-reproducible.  Emits per-BLOCK results only (part_tot,
+// part_sum, part_ccnt): partitions of the root segment use the block-unit scheme (pg_part_ident).
+// (Bulk copies — cp.async.bulk + mbarrier — were measured first: one thread needs ~87 cycles to issue each 2 KB
+// column copy, 17 per tile, which alone costs as much as the whole pass should.)
+__device__ __forceinline__ unsigned pg_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long pg_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void pg_cp16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pg_cp16_hint(unsigned dst, const void* src, unsigned long long pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 pg_lds_f4(unsigned addr) {     // explicit shared-space loads: the staging area is reached through a
+    float4 v;                                                      // generic pointer, which would otherwise compile to generic LD
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float pg_lds_f1(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 pg_lds_d2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void pg_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pg_cp_wait_pending(int n) {      // at most n of this thread's groups still in flight
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    }
+}
+
+// one row of one job: if (x < thr) { a += o; b += r; c += 1; } (smc.rs:201-217) without predication: the 0/1 mask
+// times a finite value is exact, so a = fma(m, o, a) is the same sum (ptxas turns predicated f64 adds into add + two
+// selects, twice the instructions)
+__device__ __forceinline__ void pg_acc_left(double& a, double& b, unsigned& c, float x, float thr, double o, double r) {
+    const bool left = x < thr;
+    const double m = left ? 1.0 : 0.0;
+    a = fma(m, o, a);
+    b = fma(m, r, b);
+    c += left ? 1u : 0u;
+}
+
+// tree value of a row whose columns are (mostly) staged: tile-local row `lr`, global row `row`
+__device__ __forceinline__ double pg_tree_eval_staged(const PgState& st, int t, const PgTreeSm& tr, const short* slot,
+                                                       unsigned cols_u32, int lr, long long row) {
+    if (tr.from_global) return pg_tree_eval(st, t, tr, row);
+    int node = 0, sv;
+    while ((sv = tr.split_var[node]) >= 0) {
+        const int sl = slot[node];
+        const float x = sl >= 0 ? pg_lds_f1(cols_u32 + (unsigned)(sl * PGR_T + lr) * 4u) : __ldg(&st.X[(size_t)sv * st.ld + row]);
+        node = 2 * node + 1 + (x < tr.thr32[node] ? 0 : 1);
+    }
+    return tr.leaf_val[node];
+}
+
+template <bool BERN, int JW>
+__device__ void pg_pass_root_staged(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+    PgCtrl* c = st.ctrl;
+    PgSmem* b = sm.base;
+    const bool is_root = __ldcg(&c->phase) == PH_ROOT;
+    const int J = is_root ? __ldcg(&c->n_jobs) : 0;
+    const int t_add = __ldcg(&c->t_add), t_sub = is_root ? __ldcg(&c->t_sub) : -1;
+    const int S = st.S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qd = warp >> 2, grp = warp & 3;
+#ifdef PG_DIAG
+    long long ck_t = clock64();
+    unsigned long long* ck_d = st.diag_blocks + (size_t)st.grid * 8 + (size_t)PG_BID * 8;
+#define PG_CK(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); ck_d[i] += (unsigned long long)(now_ - ck_t); ck_t = now_; } } while (0)
+#else
+#define PG_CK(i) do { } while (0)
+#endif
+
+    pg_stage_tree(st, t_add, b->tadd);
+    pg_stage_tree(st, t_sub, b->tsub);
+    for (int j = tid; j < J; j += blockDim.x) { sm.jvar[j] = __ldcg(&bf.job_var[j]); sm.jthr[j] = __ldcg(&bf.job_thr32[j]); }
+    __syncthreads();
+    PG_CK(0);
+    // ---- the distinct columns of this pass (warp 0)
+    if (warp == 0) {
+        const bool live = lane < J;
+        const int var = live ? sm.jvar[lane] : -1 - lane;
+        const unsigned same = __match_any_sync(PG_FULL, var);
+        const bool leader = live && (__ffs(same) - 1) == lane;
+        const unsigned leadm = __ballot_sync(PG_FULL, leader);
+        const int slot_l = __popc(leadm & ((1u << lane) - 1u));
+        if (leader) b->r_ucol[slot_l] = var;
+        const int slot = __shfl_sync(PG_FULL, slot_l, live ? (__ffs(same) - 1) : 0);
+        if (live) b->r_jslot[lane] = slot;
+        int U = __popc(leadm);
+        const int ucap = min(PGR_MAXU, (st.stage_bytes / 3 - PGR_T * 12) / (PGR_T * 4));   // at least three stages must fit
+        __syncwarp();
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            const PgTreeSm& tr = which == 0 ? b->tadd : b->tsub;
+            short* slots = which == 0 ? b->r_add_slot : b->r_sub_slot;
+            const int sz = (which == 0 ? t_add : t_sub) >= 0 && !tr.from_global ? tr.size : 0;
+#pragma unroll 1
+            for (int node = 0; node < sz; ++node) {
+                const int sv = tr.split_var[node];
+                if (sv < 0) { if (lane == 0) slots[node] = -1; continue; }
+                const bool hit0 = lane < U && b->r_ucol[lane] == sv;
+                const bool hit1 = lane + 32 < U && b->r_ucol[lane + 32] == sv;
+                const unsigned m0 = __ballot_sync(PG_FULL, hit0), m1 = __ballot_sync(PG_FULL, hit1);
+                int sl = m0 ? (__ffs(m0) - 1) : (m1 ? 32 + (__ffs(m1) - 1) : -1);
+                if (sl < 0 && U < ucap) { sl = U; if (lane == 0) b->r_ucol[U] = sv; U += 1; }
+                if (lane == 0) slots[node] = (short)sl;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) b->r_U = U;
+    }
+    __syncthreads();
+    PG_CK(1);
+    const int U = b->r_U;
+    const bool add_nontrivial = t_add >= 0 && b->tadd.size > 1;
+    const bool sub_nontrivial = t_sub >= 0 && b->tsub.size > 1;
+    const double add_c = t_add == -2 ? st.init_leaf : ((t_add >= 0 && !add_nontrivial) ? b->tadd.leaf_val[0] : 0.0);
+    const double sub_c = (t_sub >= 0 && !sub_nontrivial) ? b->tsub.leaf_val[0] : 0.0;
+    const bool do_add = t_add >= 0 || t_add == -2, do_sub = t_sub >= 0;
+    const bool commit_only = J == 0 && t_sub < 0;      // PH_FINAL
+
+    long long B0, B1;
+    pg_block_range(st.n, PG_BID, st.grid, &B0, &B1);
+    const int n_tiles = (int)((B1 - B0 + PGR_T - 1) / PGR_T);
+    const unsigned stage_bytes = (unsigned)PGR_T * (12u + 4u * (unsigned)U);
+    const int NST = min(PGR_MAXST, (int)((unsigned)st.stage_bytes / stage_bytes));
+    const size_t ld = (size_t)st.ld;
+    const unsigned long long pol = pg_policy_evict_first();
+    const unsigned stage0 = pg_smem_u32(sm.stage);
+    // staged arrays a = 0, 1: A (rows 0-255 / 256-511 of the tile), 2: y, 3 + u: column u — each 2048 bytes of a full
+    // tile, at stage offset 2048 a.  Thread (a0 = tid / 128, q = tid % 128) copies 16-byte piece q of arrays a0, a0 + 4, ...
+    const int n_arr = 3 + U;
+    for (int a = tid; a < n_arr; a += blockDim.x)
+        b->r_src[a] = a < 2 ? (unsigned long long)(bf.A_src + 256 * a) : a == 2 ? (unsigned long long)st.y
+                                                                                : (unsigned long long)(st.X + (size_t)b->r_ucol[a - 3] * ld);
+    __syncthreads();
+    const int a0 = tid >> 7, q16 = (tid & 127) * 16;
+    // running source pointers of this thread's first PGR_KP arrays (advanced by one tile per issue)
+    const char* sp[PGR_KP];
+#pragma unroll
+    for (int k = 0; k < PGR_KP; ++k) {
+        const int a = a0 + 4 * k;
+        sp[k] = a < n_arr ? reinterpret_cast<const char*>(b->r_src[a]) + B0 * (a < 2 ? 8 : 4) + q16 : nullptr;
+    }
+    const int step0 = a0 < 2 ? PGR_T * 8 : PGR_T * 4;
+    auto issue = [&](int t, int stage_of_t) {
+        if (t < n_tiles) {
+            const long long r0 = B0 + (long long)t * PGR_T;
+            const int rows = (int)min((long long)PGR_T, B1 - r0);
+            const unsigned dst0 = stage0 + (unsigned)stage_of_t * stage_bytes + (unsigned)q16 + (unsigned)a0 * 2048u;
+            if (rows == PGR_T) {
+                if (a0 < 3) pg_cp16(dst0, sp[0]); else if (n_arr > 3) pg_cp16_hint(dst0, sp[0], pol);
+#pragma unroll
+                for (int k = 1; k < PGR_KP; ++k)
+                    if (a0 + 4 * k < n_arr) pg_cp16_hint(dst0 + (unsigned)k * 8192u, sp[k], pol);
+#pragma unroll 1
+                for (int a = a0 + 4 * PGR_KP; a < n_arr; a += 4)
+                    pg_cp16_hint(dst0 + (unsigned)(a - a0) * 2048u, reinterpret_cast<const char*>(b->r_src[a]) + r0 * 4 + q16, pol);
+            } else {
+#pragma unroll 1
+                for (int a = a0; a < n_arr; a += 4) {
+                    const int first_row = a < 2 ? a * 256 + (tid & 127) * 2 : (tid & 127) * 4;
+                    if (first_row < rows) pg_cp16(dst0 + (unsigned)(a - a0) * 2048u, reinterpret_cast<const char*>(b->r_src[a]) + r0 * (a < 2 ? 8 : 4) + q16);
+                }
+            }
+        }
+        sp[0] += step0;
+#pragma unroll
+        for (int k = 1; k < PGR_KP; ++k) sp[k] += PGR_T * 4;
+        pg_cp_commit();
+    };
+    for (int t = 0; t < NST - 1; ++t) issue(t, t);
+    PG_CK(2);
+
+    // my jobs: group g takes jobs j with (j + 1) % 4 == g, so group 0 (which also writes A and keeps the totals) gets the fewest
+    const int jfirst = (grp + 3) & 3;
+    const int myJ = J > jfirst ? (J - jfirst + 3) / 4 : 0;
+    unsigned coff[JW];
+    float jthr[JW];
+    double accA[JW], accB[JW];
+    unsigned accC[JW];
+#pragma unroll
+    for (int q = 0; q < JW; ++q) {
+        const int j = jfirst + 4 * q;
+        const bool lv = j < J;
+        coff[q] = lv ? (unsigned)b->r_jslot[j] * (PGR_T * 4u) : 0u;
+        jthr[q] = lv ? sm.jthr[j] : 0.0f;
+        accA[q] = 0.0; accB[q] = 0.0; accC[q] = 0u;
+    }
+    double tot_o = 0.0, tot_r = 0.0, tot_rr = 0.0, tot_ll = 0.0;
+    const int lr = qd * 128 + lane * 4;     // tile-local first row of this lane
+    int stg = 0;
+
+#pragma unroll 1
+    for (int t = 0; t < n_tiles; ++t) {
+#ifdef PG_DIAG
+        const long long tw0 = clock64();
+#endif
+        pg_cp_wait_pending(NST - 2);                        // this thread's copies of tile t have landed
+#ifdef PG_DIAG
+        const long long tw1 = clock64();
+#endif
+        __syncthreads();                                    // ... and everyone's; everyone is done with tile t - 1
+#ifdef PG_DIAG
+        const long long tw2 = clock64();
+        if (tid == 0 && t > 0) { ck_d[6] += (unsigned long long)(tw1 - tw0); ck_d[7] += (unsigned long long)(tw2 - tw1); }
+#endif
+        if (t == 0) PG_CK(3);
+        issue(t + NST - 1, stg == 0 ? NST - 1 : stg - 1);   // refill the stage tile t - 1 occupied
+#ifdef PG_DIAG
+        if (tid == 0 && t > 0) ck_d[2] += (unsigned long long)(clock64() - tw2);
+#endif
+        const unsigned sbase = stage0 + (unsigned)stg * stage_bytes;
+        stg = stg + 1 == NST ? 0 : stg + 1;
+        const long long r0 = B0 + (long long)t * PGR_T;
+        const int rows = (int)min((long long)PGR_T, B1 - r0);
+        if (lr >= rows) continue;
+        const long long row = r0 + lr;
+#ifdef PG_DIAG
+        const long long tc0 = clock64();
+#endif
+        const int nv = (int)min(4ll, st.n - row);           // valid rows of this lane's four (>= 1 except past n)
+        const unsigned cols = sbase + PGR_T * 12u;          // shared-space address of the staged columns
+        double o0, o1, o2, o3;
+        float4 yy;
+        {
+            const double2 a01 = pg_lds_d2(sbase + (unsigned)lr * 8u);
+            const double2 a23 = pg_lds_d2(sbase + (unsigned)lr * 8u + 16u);
+            yy = pg_lds_f4(sbase + PGR_T * 8u + (unsigned)lr * 4u);
+            o0 = a01.x; o1 = a01.y; o2 = a23.x; o3 = a23.y;
+        }
+        // kernel.rs:99-102 then :84-87, each a separately rounded f64 operation
+        if (do_add) {
+            if (add_nontrivial) {
+                o0 = o0 + (nv > 0 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, lr + 0, row + 0) : 0.0);
+                o1 = o1 + (nv > 1 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, lr + 1, row + 1) : 0.0);
+                o2 = o2 + (nv > 2 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, lr + 2, row + 2) : 0.0);
+                o3 = o3 + (nv > 3 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, lr + 3, row + 3) : 0.0);
+            } else { o0 = o0 + add_c; o1 = o1 + add_c; o2 = o2 + add_c; o3 = o3 + add_c; }
+        }
+        if (do_sub) {
+            if (sub_nontrivial) {
+                o0 = o0 - (nv > 0 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, lr + 0, row + 0) : 0.0);
+                o1 = o1 - (nv > 1 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, lr + 1, row + 1) : 0.0);
+                o2 = o2 - (nv > 2 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, lr + 2, row + 2) : 0.0);
+                o3 = o3 - (nv > 3 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, lr + 3, row + 3) : 0.0);
+            } else { o0 = o0 - sub_c; o1 = o1 - sub_c; o2 = o2 - sub_c; o3 = o3 - sub_c; }
+        }
+#ifdef PG_DIAG
+        const long long tc1 = clock64();
+#endif
+        if (grp == 0) {
+            __stcg(reinterpret_cast<double2*>(bf.A_dst + row), make_double2(o0, o1));
+            __stcg(reinterpret_cast<double2*>(bf.A_dst + row + 2), make_double2(o2, o3));
+        }
+#ifdef PG_DIAG
+        const long long tc2 = clock64();
+        if (tid == 0 && t > 0) { ck_d[0] += (unsigned long long)(tc1 - tc0); ck_d[1] += (unsigned long long)(tc2 - tc1); }
+#endif
+        if (commit_only) continue;
+        double r0v = (double)yy.x - o0, r1v = (double)yy.y - o1, r2v = (double)yy.z - o2, r3v = (double)yy.w - o3;
+        if (grp == 0) {
+            if (nv >= 4) {
+                tot_o += o0; tot_o += o1; tot_o += o2; tot_o += o3;
+                tot_r += r0v; tot_r += r1v; tot_r += r2v; tot_r += r3v;
+                tot_rr += r0v * r0v; tot_rr += r1v * r1v; tot_rr += r2v * r2v; tot_rr += r3v * r3v;
+                if (BERN) {
+                    const double m0 = o0 + st.init_leaf, m1 = o1 + st.init_leaf, m2 = o2 + st.init_leaf, m3 = o3 + st.init_leaf;
+                    tot_ll += (double)yy.x * m0 - pg_softplus(m0); tot_ll += (double)yy.y * m1 - pg_softplus(m1);
+                    tot_ll += (double)yy.z * m2 - pg_softplus(m2); tot_ll += (double)yy.w * m3 - pg_softplus(m3);
+                }
+            } else {                                        // the lane that straddles n: rows row .. row + nv - 1 are real
+                const double ov[4] = {o0, o1, o2, o3}, rv[4] = {r0v, r1v, r2v, r3v};
+                const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll 1
+                for (int e = 0; e < nv; ++e) {
+                    tot_o += ov[e]; tot_r += rv[e]; tot_rr += rv[e] * rv[e];
+                    if (BERN) { const double mu = ov[e] + st.init_leaf; tot_ll += (double)yv[e] * mu - pg_softplus(mu); }
+                }
+            }
+        }
+        // smc.rs:201-217 for this warp's slots of round 1 (padding rows hold x = +inf: never LEFT).  Dispatch on the
+        // warp-uniform job count so that the unrolled bodies carry no per-job branches.
+        const unsigned xb = sbase + PGR_T * 12u + (unsigned)lr * 4u;
+        auto jobs = [&](auto njc) {
+            constexpr int NJ = decltype(njc)::value;
+#pragma unroll
+            for (int q = 0; q < NJ; ++q) {
+                const float4 xv = pg_lds_f4(xb + coff[q]);
+                pg_acc_left(accA[q], accB[q], accC[q], xv.x, jthr[q], o0, r0v);
+                pg_acc_left(accA[q], accB[q], accC[q], xv.y, jthr[q], o1, r1v);
+                pg_acc_left(accA[q], accB[q], accC[q], xv.z, jthr[q], o2, r2v);
+                pg_acc_left(accA[q], accB[q], accC[q], xv.w, jthr[q], o3, r3v);
+            }
+        };
+        switch (myJ) {
+            case 0: break;
+            case 1: jobs(std::integral_constant<int, 1>{}); break;
+            case 2: jobs(std::integral_constant<int, 2>{}); break;
+            case 3: jobs(std::integral_constant<int, 3>{}); break;
+            case 4: jobs(std::integral_constant<int, 4>{}); break;
+            case 5: jobs(std::integral_constant<int, 5>{}); break;
+            default:
+                if constexpr (JW > 5) {
+                    if (myJ == 6) jobs(std::integral_constant<int, 6>{});
+                    else if (myJ == 7) jobs(std::integral_constant<int, 7>{});
+                    else jobs(std::integral_constant<int, JW>{});
+                }
+                break;
+        }
+#ifdef PG_DIAG
+        if (tid == 0 && t > 0) ck_d[3] += (unsigned long long)(clock64() - tc2);
+#endif
+    }
+    pg_cp_wait_pending(0);
+    PG_CK(4);
+
+    // ---- block results
+    if (!commit_only) {
+#pragma unroll
+        for (int q = 0; q < JW; ++q) {
+            if (q < myJ) {                                  // warp-uniform
+                const double a = pg_warp_sum(accA[q]), bb = pg_warp_sum(accB[q]);
+                const unsigned cc = __reduce_add_sync(PG_FULL, accC[q]);
+                if (lane == 0) { const int j = jfirst + 4 * q; b->r_acc[qd][j][0] = a; b->r_acc[qd][j][1] = bb; b->r_cnt[qd][j] = cc; }
+            }
+        }
+        if (grp == 0) {
+            tot_o = pg_warp_sum(tot_o); tot_r = pg_warp_sum(tot_r); tot_rr = pg_warp_sum(tot_rr); tot_ll = pg_warp_sum(tot_ll);
+            if (lane == 0) { b->tot[qd][0] = tot_o; b->tot[qd][1] = tot_r; b->tot[qd][2] = tot_rr; b->tot[qd][3] = tot_ll; }
+        }
+    }
+    __syncthreads();
+    if (commit_only) return;
+    if (tid < 4) {
+        double v = 0.0;
+        for (int q = 0; q < 4; ++q) v += b->tot[q][tid];
+        bf.part_tot[(size_t)PG_BID * 4 + tid] = v;
+    }
+    for (int j = tid; j < J; j += blockDim.x) {
+        double a = 0.0, bb = 0.0;
+        unsigned cc = 0u;
+        for (int q = 0; q < 4; ++q) { a += b->r_acc[q][j][0]; bb += b->r_acc[q][j][1]; cc += b->r_cnt[q][j]; }
+        bf.part_sum[((size_t)PG_BID * S + j) * 2 + 0] = a;
+        bf.part_sum[((size_t)PG_BID * S + j) * 2 + 1] = bb;
+        bf.part_ccnt[(size_t)PG_BID * S + j] = cc;
+    }
+    PG_CK(5);
 }
 
 // =============================================================================
@@ -543,6 +942,111 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
 // =============================================================================
 // PH_PART — stable partition of a segment by x[var] < split into the pool
 // =============================================================================
+// Identity segment (the root's rows), block-unit scheme of the P <= 32 persistent kernel: block b compacts its own
+// contiguous rows (pg_block_range, the same ranges as the staged root pass, whose per-block LEFT counts give the
+// block's output offsets).  Rows are taken 4 per thread with coalesced float4 loads, 4 chunks in flight; order is
+// kept by a warp scan + a 16-entry cross-warp prefix per chunk.  Look-ahead min/max requests stream the two columns
+// the same way (no gathers: the segment is the identity).
+#define PGP_CH (PG_THREADS * 4)      // rows per chunk
+__device__ void pg_part_ident(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int k, int Q,
+                              const float* col, float thr, unsigned long long L) {
+    PgCtrl* c = st.ctrl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const size_t ld = (size_t)st.ld;
+    long long B0, B1;
+    pg_block_range((long long)L, PG_BID, st.grid, &B0, &B1);
+    const long long n = (long long)L;
+    unsigned* scanw = &sm.base->p_scan[0][0];                    // [2][PG_WARPS] warp totals, double-buffered by chunk parity
+    unsigned left_run = __ldcg(&st.pj_warp_left[(size_t)k * st.n_gwarps + PG_BID]);   // block-unit: indexed by block
+    const unsigned left0 = left_run;
+    unsigned right_run = (unsigned)min(B0, n) - left_run;
+    unsigned* dstL = st.pool + (size_t)__ldcg(&st.pj_dst_off[k]);
+    unsigned* dstR = dstL + __ldcg(&st.pj_cntL[k]);
+    int par = 0;
+#pragma unroll 1
+    for (long long cb = B0; cb < B1; cb += 4 * PGP_CH) {
+        float4 xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long row = cb + (long long)u * PGP_CH + tid * 4;
+            xv[u] = row < B1 ? __ldg(reinterpret_cast<const float4*>(col + row)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long cs = cb + (long long)u * PGP_CH;      // chunk start (block-uniform)
+            if (cs >= B1) break;
+            const long long row = cs + tid * 4;
+            const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+            bool vl[4], lf[4];
+            int cl = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { vl[e] = row + e < n && row < B1; lf[e] = vl[e] && xs[e] < thr; cl += lf[e] ? 1 : 0; }
+            int incl = cl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(PG_FULL, incl, o); if (lane >= o) incl += y; }
+            if (lane == 31) scanw[par * PG_WARPS + warp] = (unsigned)incl;
+            __syncthreads();
+            unsigned wpre = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < PG_WARPS; ++w) { const unsigned v = scanw[par * PG_WARPS + w]; tot += v; wpre += w < warp ? v : 0u; }
+            const unsigned before_left = wpre + (unsigned)(incl - cl);
+            unsigned wl = left_run + before_left;
+            unsigned wr = right_run + ((unsigned)(tid * 4) - before_left);      // rows before mine in the chunk are all valid if mine are
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (vl[e]) {
+                    if (lf[e]) __stcg(&dstL[wl++], (unsigned)(row + e));
+                    else __stcg(&dstR[wr++], (unsigned)(row + e));
+                }
+            }
+            const long long ce = min(min(cs + PGP_CH, B1), n);
+            const unsigned nvalid = ce > cs ? (unsigned)(ce - cs) : 0u;
+            left_run += tot;
+            right_run += nvalid - tot;
+            par ^= 1;
+        }
+    }
+    // the root pass counted the same predicate over the same rows
+    const int j = __ldcg(&st.pj_job[k]);
+    if (tid == 0 && (left_run - left0) != __ldcg(&bf.part_ccnt[(size_t)PG_BID * st.S + j])) c->error = PG_ERR_INTERNAL;
+    // look-ahead: splitting.rs:43-49 for the proposals expected on the two children
+    for (int q = 0; q < Q; ++q) {
+        if (__ldcg(&st.mq_pj[q]) != k) continue;
+        const bool want_left = __ldcg(&st.mq_side[q]) == 0;
+        const float* col2 = st.X + (size_t)__ldcg(&st.mq_var[q]) * ld;
+        float mn = INFINITY, mx = -INFINITY;
+        bool any = false;
+#pragma unroll 1
+        for (long long cb = B0; cb < B1; cb += 4 * PGP_CH) {
+            float4 xv[4], zv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long row = cb + (long long)u * PGP_CH + tid * 4;
+                const bool in = row < B1;
+                xv[u] = in ? __ldg(reinterpret_cast<const float4*>(col + row)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                zv[u] = in ? __ldg(reinterpret_cast<const float4*>(col2 + row)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long row = cb + (long long)u * PGP_CH + tid * 4;
+                const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                const float zs[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool ok = row + e < n && row < B1 && ((xs[e] < thr) == want_left);
+                    if (ok) { mn = fminf(mn, zs[e]); mx = fmaxf(mx, zs[e]); any = true; }
+                }
+            }
+        }
+        unsigned kmn = any ? pg_f2key(mn) : 0xFFFFFFFFu, kmx = any ? pg_f2key(mx) : 0u;
+        kmn = __reduce_min_sync(PG_FULL, kmn);
+        kmx = __reduce_max_sync(PG_FULL, kmx);
+        if (lane == 0) { atomicMin(&sm.mmin[q], kmn); atomicMax(&sm.mmax[q], kmx); }
+    }
+    __syncthreads();      // scanw is reused by the next job
+}
+
+template <bool FASTP>
 __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     const int K = __ldcg(&c->n_pjobs);
@@ -553,14 +1057,15 @@ __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemVie
     const size_t ld = (size_t)st.ld;
     if (Q > 0) {
         for (int q = threadIdx.x; q < Q; q += blockDim.x) { sm.mmin[q] = 0xFFFFFFFFu; sm.mmax[q] = 0u; }
-        __syncthreads();
     }
+    __syncthreads();
     for (int k = 0; k < K; ++k) {
         const unsigned src = __ldcg(&st.pj_src_off[k]);
         const bool ident = src == PG_SEG_IDENTITY;
         const unsigned long long L = __ldcg(&st.pj_len[k]);
         const float* col = st.X + (size_t)__ldcg(&st.pj_var[k]) * ld;
         const float thr = __ldcg(&st.pj_thr32[k]);
+        if (FASTP && ident) { pg_part_ident(st, bf, sm, k, Q, col, thr, L); continue; }
         unsigned long long beg, end;
         pg_warp_range(L, gw, st.n_gwarps, ident ? 4 : 1, &beg, &end);
         unsigned left_run = __ldcg(&st.pj_warp_left[(size_t)k * st.n_gwarps + gw]);
@@ -616,17 +1121,26 @@ __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemVie
 }
 
 // Dispatch one grid pass.
+// FASTP: the block-unit passes of the P <= 32 persistent kernel (staged root pass, block-unit identity partitions);
+// otherwise the warp-range passes the generic control code, the stepwise driver and the host simulation share.
+template <bool FASTP>
 __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView& sm, int phase) {
     const PgBuf bf = pg_make_buf(st, __ldcg(&st.ctrl->flags));
     switch (phase) {
         case PH_ROOT:
         case PH_FINAL:
-            if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true>(st, bf, sm); else pg_pass_root<false>(st, bf, sm);
+            if (FASTP && st.root_staged) {
+                if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root_staged<true, PGR_JW>(st, bf, sm);
+                else if (st.S <= 20) pg_pass_root_staged<false, 5>(st, bf, sm);      // <= 5 jobs per warp: fewer live registers
+                else pg_pass_root_staged<false, PGR_JW>(st, bf, sm);
+            }
+            else if (FASTP) { if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true, true>(st, bf, sm); else pg_pass_root<false, true>(st, bf, sm); }
+            else { if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true, false>(st, bf, sm); else pg_pass_root<false, false>(st, bf, sm); }
             break;
         case PH_MINMAX: pg_pass_minmax(st, bf, sm); break;
         case PH_STATS: pg_pass_seg<0>(st, bf, sm); break;
         case PH_BERN: pg_pass_seg<1>(st, bf, sm); break;
-        case PH_PART: pg_pass_part(st, bf, sm); break;
+        case PH_PART: pg_pass_part<FASTP>(st, bf, sm); break;
         default: break;
     }
 }
@@ -642,6 +1156,12 @@ __device__ __forceinline__ unsigned pg_ld_relaxed(const unsigned* p) {
 }
 __device__ __forceinline__ void pg_st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long pg_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ void pg_spin_until(const unsigned* p, unsigned target, PgCtrl* c) {

@@ -881,8 +881,31 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
     const int tid = threadIdx.x, T = blockDim.x;
     const int chunk = (W + T - 1) / T;
     const unsigned* p_cnt = st.part_cnt + pg_off_part_cnt(st, (int)(c->upd & 1ull));   // counts of this update's statistics pass
+    // identity segments (the root's rows) are partitioned in block units: exclusive prefix, over pass blocks, of the
+    // root pass's per-block left counts — one warp per job
+    {
+        const unsigned* p_ccnt = st.part_ccnt + pg_off_part_ccnt(st, (int)(c->upd & 1ull));
+        const int lane = tid & 31, warp = tid >> 5, G = st.grid;
+#pragma unroll 1
+        for (int k = warp; k < K; k += PG_WARPS) {
+            if (st.pj_src_off[k] != PG_SEG_IDENTITY) continue;
+            const int j = st.pj_job[k];
+            unsigned carry = 0;
+#pragma unroll 1
+            for (int base = 0; base < G; base += 32) {
+                const int bq = base + lane;
+                const unsigned v = bq < G ? __ldcg(&p_ccnt[(size_t)bq * S + j]) : 0u;
+                unsigned xx = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(PG_FULL, xx, o); if (lane >= o) xx += y; }
+                if (bq < G) st.pj_warp_left[(size_t)k * W + bq] = carry + xx - v;
+                carry += __shfl_sync(PG_FULL, xx, 31);
+            }
+        }
+    }
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
+        if (st.pj_src_off[k] == PG_SEG_IDENTITY) continue;      // block-uniform
         const int j = st.pj_job[k];
         const int b = tid * chunk;
         unsigned local = 0;
@@ -1182,6 +1205,9 @@ __device__ __forceinline__ void fw_issue(const PgState& st, const FwCx& x, int l
         else if (lane == 8) v = n_groups; else if (lane == 9) v = n_pjobs; else if (lane == 15) v = flags;
         reinterpret_cast<int*>(st.ctrl)[lane] = v;
     }
+#ifdef PG_DIAG
+    if (lane == 0) { st.ctrl->dbg[1] = 0ull; st.ctrl->dbg[2] = 0ull; st.ctrl->dbg[3] = 0ull; st.ctrl->dbg[0] = pg_globaltimer(); }
+#endif
     __threadfence();
     __syncwarp();
     if (lane == 0) {
@@ -1310,7 +1336,21 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
 #pragma unroll 1
     for (long long guard = 0; guard < (1ll << 40); ++guard) {
         // ---- (A) the outstanding pass (if any) completes
-        if (!first && threadIdx.x == 0) pg_spin_until(&st.ctrl->bar_count, f->issued * (gridDim.x - 1u), st.ctrl);
+        if (!first && threadIdx.x == 0) {
+            const long long tw = clock64();
+            pg_spin_until(&st.ctrl->bar_count, f->issued * (gridDim.x - 1u), st.ctrl);
+            const int ph = f->out_phase;
+            c->prof3[ph == PH_ROOT ? 4 : ph == PH_STATS ? 5 : ph == PH_PART ? 6 : 7] += (unsigned long long)(clock64() - tw);
+#ifdef PG_DIAG
+            const int cls = ph == PH_ROOT ? 0 : ph == PH_STATS ? 1 : ph == PH_PART ? 2 : -1;
+            if (cls >= 0) {
+                const unsigned long long now = pg_globaltimer();
+                volatile unsigned long long* d = st.ctrl->dbg;
+                const unsigned long long t_is = d[0];
+                d[4 + 4 * cls] += d[1] - t_is; d[5 + 4 * cls] += d[2] - t_is; d[6 + 4 * cls] += now - t_is; d[7 + 4 * cls] += d[3];
+            }
+#endif
+        }
         __syncthreads();
         const int phase = first ? PH_BEGIN : f->out_phase;
         const int J = first ? 0 : f->out_J;
@@ -1348,7 +1388,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                 case PH_BEGIN: sn = fw_begin_step(st, x, lane); break;
                 case PH_ROOT:
                     spec = f->spec_now != 0;
-                    if (!spec) spec = fw_try_speculate(st, x, lane);
+                    if (!spec) { spec = fw_try_speculate(st, x, lane); if (spec && lane == 0) f->spec_now = 1; }
                     FW_TICK(6);
                     sn = fw_r0_values(st, x, lane);
                     if (sn == SN_FINISH_ROUND) sn = fw_r0_finish(st, x, lane, false);
@@ -1436,7 +1476,11 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) c->prof_ser[phase & 7] += (unsigned long long)(clock64() - t_entry);
+        if (threadIdx.x == 0) {
+            const unsigned long long d = (unsigned long long)(clock64() - t_entry);
+            c->prof_ser[phase & 7] += d;
+            if (phase == PH_ROOT) { const int q = f->spec_now ? 0 : 2; c->prof3[q] += d; c->prof3[q + 1] += 1ull; }
+        }
         if (f->quit) break;
     }
     __syncthreads();

@@ -57,7 +57,7 @@ __device__ void pg_barrier_serial(const PgState& st, const PgSmemView& smv, unsi
 
 template <bool FAST>
 __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
-    extern __shared__ __align__(16) unsigned char pg_smem_raw[];
+    extern __shared__ __align__(128) unsigned char pg_smem_raw[];
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     // sampler constants the serial section reads: staged once per launch
     for (int i = threadIdx.x; i < st.max_depth + 2 && i < 16; i += blockDim.x) sm.base->cthr[i] = st.thr_depth[i];
@@ -79,15 +79,27 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
         unsigned gen = 0;
         long long t_idle = clock64();
         for (;;) {
-            if (threadIdx.x == 0) pg_spin_until(&c->bar_gen, gen + 1u, c);
+            if (threadIdx.x == 0) {
+                pg_spin_until(&c->bar_gen, gen + 1u, c);
+#ifdef PG_DIAG
+                atomicMax(&c->dbg[1], pg_globaltimer());
+#endif
+            }
             __syncthreads();
             const int phase = __ldcg(&c->phase);
             if (phase == PH_DONE) break;
             const long long t0 = clock64();
-            pg_run_pass(st, sm, phase);
+            pg_run_pass<true>(st, sm, phase);
             __syncthreads();
             const long long t1 = clock64();
-            if (threadIdx.x == 0) { __threadfence(); atomicAdd(&c->bar_count, 1u); }
+            if (threadIdx.x == 0) {
+#ifdef PG_DIAG
+                atomicMax(&c->dbg[3], (unsigned long long)(t1 - t0));
+                st.diag_blocks[(size_t)(blockIdx.x - 1) * 8 + (phase & 7)] += (unsigned long long)(t1 - t0);
+                atomicMax(&c->dbg[2], pg_globaltimer());
+#endif
+                __threadfence(); atomicAdd(&c->bar_count, 1u);
+            }
             if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // stopwatch kept by the last pass block
                 c->prof[phase & 7] += (unsigned long long)(t1 - t0);
                 c->prof[8 + (phase & 7)] += (unsigned long long)(t0 - t_idle);   // time spent waiting for this command
@@ -105,7 +117,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
         const int J = __ldcg(&st.ctrl->n_jobs);
         if (phase == PH_DONE) break;
         const long long t0 = clock64();
-        if (blockIdx.x != 0) pg_run_pass(st, sm, phase);   // block 0 = serial block: streams nothing
+        if (blockIdx.x != 0) pg_run_pass<false>(st, sm, phase);   // block 0 = serial block: streams nothing
         __syncthreads();
         const long long t1 = clock64();
         pg_barrier_serial<FAST>(st, sm, gen, phase, J);
@@ -123,11 +135,11 @@ extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent(
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_generic(const PgState st) { pg_sweep_body<false>(st); }
 
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_phase_kernel(const PgState st) {
-    extern __shared__ __align__(16) unsigned char pg_smem_raw[];
+    extern __shared__ __align__(128) unsigned char pg_smem_raw[];
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     if (threadIdx.x == 0) sm.base->pass_bid = (int)blockIdx.x;
     __syncthreads();
-    pg_run_pass(st, sm, __ldcg(&st.ctrl->phase));
+    pg_run_pass<false>(st, sm, __ldcg(&st.ctrl->phase));
 }
 
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_serial_kernel(const PgState st) {
@@ -177,17 +189,24 @@ extern "C" __global__ void pg_leaf_indices_kernel(const PgState st, int t, unsig
 // launchers
 // ---------------------------------------------------------------------------
 
-int pg_query_grid(int device, int S, int* grid_out, size_t* smem_out, char* err, size_t errlen) {
+int pg_query_grid(int device, int S, int* grid_out, size_t* smem_out, int* stage_out, char* err, size_t errlen) {
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return 1; }
-    const size_t smem = pg_smem_bytes(S);
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(pg_sweep_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_sweep_persistent_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { snprintf(err, errlen, "shared memory request %zu B: %s", smem, cudaGetErrorString(e)); return 1; }
-    }
+    // dynamic shared memory = the pass arrays + a staging area (bulk-copy ring of the staged root pass) that takes
+    // whatever one block per SM can have
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, pg_sweep_persistent);
+    if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncGetAttributes: %s", cudaGetErrorString(e)); return 1; }
+    const size_t base = pg_smem_bytes(S);
+    const size_t optin = prop.sharedMemPerBlockOptin;
+    if (base + fa.sharedSizeBytes + 16 * 1024 > optin) { snprintf(err, errlen, "shared memory: %zu B needed, %zu B available", base + fa.sharedSizeBytes + 16 * 1024, optin); return 1; }
+    const size_t stage = ((optin - fa.sharedSizeBytes - base - 1024) / 1024) * 1024;
+    const size_t smem = base + stage;
+    e = cudaFuncSetAttribute(pg_sweep_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_sweep_persistent_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { snprintf(err, errlen, "shared memory request %zu B: %s", smem, cudaGetErrorString(e)); return 1; }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_sweep_persistent, PG_THREADS, smem);
     if (e != cudaSuccess || per_sm < 1) { snprintf(err, errlen, "occupancy query failed: %s", cudaGetErrorString(e)); return 1; }
@@ -196,6 +215,7 @@ int pg_query_grid(int device, int S, int* grid_out, size_t* smem_out, char* err,
     *grid_out = per_sm * prop.multiProcessorCount - 1;   // pass blocks; one more SM hosts the serial block
     if (*grid_out < 1) { snprintf(err, errlen, "device has too few SMs"); return 1; }
     *smem_out = smem;
+    *stage_out = (int)stage;
     return 0;
 }
 

@@ -103,6 +103,8 @@ struct PgCtrl {
     // 5 finalize, 6 begin_update, 7 draw_round; [8..15] call counts
     unsigned long long prof2[16];
     unsigned long long prof_ser[8];     // serial section cycles by phase (kept by the control block)
+    unsigned long long prof3[16];       // control block: [0,1] root sections with speculation (cycles, count), [2,3] without,
+                                        // [4..7] cycles spent waiting for a ROOT / STATS / PART / other pass to complete
     // ---- grid barrier
     unsigned int bar_count;
     unsigned int bar_pad[31];
@@ -112,6 +114,11 @@ struct PgCtrl {
     // [0..7] pass time by phase, [8..15] pass end -> barrier exit (wait for the slowest block + serial section),
     // [16..23] serial section alone (written by the serial block), [24..31] number of passes by phase
     unsigned long long prof[32];
+    // ---- signalling diagnostics (globaltimer ns): [0] time of the last issue, [1] latest command observation,
+    // [2] latest arrival, [3] longest pass body (SM cycles) of the pass in flight; [4..] per phase class c = 0 ROOT,
+    // 1 STATS, 2 PART: [4+4c] sum issue->last observed, [5+4c] sum issue->last arrival, [6+4c] sum issue->completion seen
+    // by the control block, [7+4c] sum of the longest pass body (cycles)
+    unsigned long long dbg[16];
 };
 
 struct PgState {
@@ -119,6 +126,8 @@ struct PgState {
     long long n, ld;
     int p, m, P, S, max_depth, maxn;
     int grid, n_gwarps;          // CTAs in the sweep grid, global warps (= grid * PG_WARPS)
+    int stage_bytes;             // shared-memory staging area per block behind the pass arrays (async-copy ring)
+    int root_staged;             // P <= 32 persistent kernel: 1 = staged root pass (pg_pass_root_staged), 0 = warp-range loads
     // data
     const float* X;
     const float* y;
@@ -167,6 +176,7 @@ struct PgState {
     unsigned int* part_mm;       // [grid][2S][2] ordered-uint keys of min / max (2S: the partition pass may carry look-ahead requests)
     int* mq_pj; int* mq_side; int* mq_var;   // [2S] look-ahead min/max requests of the partition pass: (partition job, child side, column)
     double* part_ll;             // [grid][S][2]  Bernoulli: log-likelihood of the left / right child
+    unsigned long long* diag_blocks;   // [grid][8] per pass block, by phase: cycles spent in pass bodies (-DPG_DIAG only)
     // segment pool
     unsigned int* pool; unsigned long long pool_cap;
     // rng
@@ -215,6 +225,18 @@ PG_HD float pg_key2f(uint32_t k) {
 
 // Contiguous range of segment entries owned by one global warp.  Identity
 // segments use granule 4 (float4 loads), index segments granule 1.
+// Rows of pass block `bid` in the block-unit passes (staged root pass, identity partitions): contiguous, a multiple of
+// 4 rows (16 B of a column) so every tile is a legal bulk copy; the last range ends at n rounded up to 4 (<= ld).
+PG_HD void pg_block_range(long long n, int bid, int grid, long long* b0, long long* b1) {
+    const long long units = (n + 3) / 4;
+    const long long per = (units + grid - 1) / grid;
+    long long b = (long long)bid * per * 4, e = b + per * 4;
+    const long long n4 = units * 4;
+    if (b > n4) b = n4;
+    if (e > n4) e = n4;
+    *b0 = b; *b1 = e;
+}
+
 PG_HD void pg_warp_range(unsigned long long L, int gw, int n_gwarps, int granule,
                          unsigned long long* beg, unsigned long long* end) {
     unsigned long long units = (L + (unsigned long long)granule - 1) / (unsigned long long)granule;

@@ -230,12 +230,23 @@ class PySampler:
 
     def profile(self) -> dict:
         """In-kernel stopwatch (SM cycles since creation), by phase; see include/pgbart.h."""
-        out = np.zeros(49)
+        out = np.zeros(69)
         self._check(self._L.pgbart_get_profile(self._h, out.ctypes.data_as(C.c_void_p)))
         names = ["begin", "root", "minmax", "stats", "bern", "part", "final", "done"]
         sub = ["reduce", "after_stats", "after_minmax", "finish_round", "prep_part", "finalize", "begin_update", "draw_round"]
-        return {"speculative_root_passes": float(out[48]), "serial_sub_cycles": dict(zip(sub, out[32:40].tolist())), "serial_sub_calls": dict(zip(sub, out[40:48].tolist())),"pass_cycles": dict(zip(names, out[0:8].tolist())), "wait_serial_cycles": dict(zip(names, out[8:16].tolist())),
+        return {"diag": {n: dict(zip(["issue_to_last_seen_ns", "issue_to_last_arrival_ns", "issue_to_completion_ns", "longest_body_cycles"],
+                                      out[57 + 4 * i:61 + 4 * i].tolist())) for i, n in enumerate(["root", "stats", "part"])},
+                "control": dict(zip(["root_spec_cycles", "root_spec_n", "root_nospec_cycles", "root_nospec_n", "wait_root", "wait_stats",
+                                     "wait_part", "wait_other"], out[49:57].tolist())),
+                "speculative_root_passes": float(out[48]), "serial_sub_cycles": dict(zip(sub, out[32:40].tolist())), "serial_sub_calls": dict(zip(sub, out[40:48].tolist())),"pass_cycles": dict(zip(names, out[0:8].tolist())), "wait_serial_cycles": dict(zip(names, out[8:16].tolist())),
                 "serial_cycles": dict(zip(names, out[16:24].tolist())), "passes": dict(zip(names, out[24:32].tolist()))}
+
+    def block_cycles(self) -> np.ndarray:
+        """[pass block][phase] cycles spent in pass bodies (only filled by -DPG_DIAG builds)."""
+        g = int(self.counters()["grid_blocks"])
+        out = np.zeros(g * 16)
+        self._check(self._L.pgbart_debug_block_cycles(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return np.concatenate([out[:g * 8].reshape(g, 8), out[g * 8:].reshape(g, 8)], axis=1)
 
     def timer_start(self) -> None:
         """CUDA-event stopwatch on the sampler's stream (the stream the kernels run on)."""

@@ -98,7 +98,8 @@ int pgbart_set_rng_tape(pgbart_handle h, const double* slot, const double* round
 int pgbart_trace_enable(pgbart_handle h, int64_t u_cap, int r_cap);
 int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd, int64_t* n_upd, int* overflow);
 
-/* Options: "driver" = "persistent" (default) | "stepwise"; "pool_factor" = integer >= 1. */
+/* Options: "driver" = "persistent" (default) | "stepwise"; "pool_factor" = integer >= 1;
+ * "root_pass" = "direct" (default: register loads over warp ranges) | "staged" (async-copy ring in shared memory). */
 int pgbart_set_option(pgbart_handle h, const char* key, const char* value);
 
 /* Counters since creation: [0] compulsory bytes of this implementation's passes, [1] bytes by the
@@ -110,8 +111,16 @@ int pgbart_get_counters(pgbart_handle h, double* out8);
 /* In-kernel stopwatch, SM cycles since creation: out32[0..7] pass time by phase as seen by block 0,
  * [8..15] pass end -> barrier exit (wait for the slowest block + serial section), [16..23] serial section alone,
  * [24..31] passes by phase (phases: 1 ROOT, 2 MINMAX, 3 STATS, 4 BERN, 5 PART, 6 FINAL); [32..39] serial sub-step
- * cycles (reduce, after_stats, after_minmax, finish_round, prep_part, finalize, begin_update, draw_round), [40..47] calls, [48] root passes issued speculatively. */
-int pgbart_get_profile(pgbart_handle h, double* out49);
+ * cycles (reduce, after_stats, after_minmax, finish_round, prep_part, finalize, begin_update, draw_round), [40..47] calls, [48] root passes issued speculatively,
+ * [49..64] control block: root sections with / without a speculative issue (cycles, count, cycles, count), then cycles spent
+ * waiting for a ROOT / STATS / PART / other pass to complete; [57..68] signalling diagnostics, filled only when the library
+ * is built with -DPG_DIAG: for ROOT, STATS, PART: ns issue -> last block saw the command, issue -> last arrival,
+ * issue -> control block saw completion, and cycles of the longest pass body, all summed over passes. */
+int pgbart_get_profile(pgbart_handle h, double* out69);
+
+/* Diagnostics (-DPG_DIAG builds): out[b*8 + phase] = SM cycles pass block b has spent in pass bodies of that phase;
+ * out[G*8 + b*8 + i] = cycles between checkpoints i of the staged root pass (G = pass blocks; cap >= 16 G). */
+int pgbart_debug_block_cycles(pgbart_handle h, double* out, int cap);
 
 /* CUDA-event stopwatch on the sampler's own stream (the stream the sweep kernels are launched on):
  * start records an event, stop records a second one, synchronises and returns the milliseconds between. */

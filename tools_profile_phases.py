@@ -14,6 +14,8 @@ X, y, prm = bench.make_data(w)
 st = PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, prm["sigma"], list(prm["split_prior"]),
                     ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=0)
 s = PySampler.init(X, y, DeviceLikelihood(w["family"], 1.0), st)
+if len(sys.argv) > 3:
+    s.set_option("root_pass", sys.argv[3])
 for _ in range(2):
     s.step_device(False)
 s.sync()
@@ -46,3 +48,26 @@ for n in p1["serial_sub_cycles"]:
 c = s.counters()
 print("counters", c, "speculative root passes per sweep", (p1["speculative_root_passes"] - p0["speculative_root_passes"]) / steps)
 print(f"sum of block-0 pass+wait time: {tot:.2f} ms per sweep; measured {ms / steps:.2f} ms")
+ctl = {k: (p1["control"][k] - p0["control"][k]) / steps for k in p1["control"]}
+us = lambda cyc: cyc / ghz / 1e3
+print(f"control block: root sections with speculative issue {ctl['root_spec_n']:.1f}/sweep x {us(ctl['root_spec_cycles']) / max(ctl['root_spec_n'], 1):.2f} us; "
+      f"without {ctl['root_nospec_n']:.1f}/sweep x {us(ctl['root_nospec_cycles']) / max(ctl['root_nospec_n'], 1):.2f} us")
+print("control block idle (ms/sweep) waiting for: " + ", ".join(f"{k[5:]} {us(ctl[k]) / 1e3:.2f}" for k in ("wait_root", "wait_stats", "wait_part", "wait_other")))
+for n in ("root", "stats", "part"):
+    d = {k: (p1["diag"][n][k] - p0["diag"][n][k]) / steps for k in p1["diag"][n]}
+    cnt = out["passes"][n]
+    if cnt and d["issue_to_completion_ns"]:
+        print(f"diag {n}: issue->last block saw command {d['issue_to_last_seen_ns'] / cnt / 1e3:.2f} us, issue->last arrival "
+              f"{d['issue_to_last_arrival_ns'] / cnt / 1e3:.2f} us, issue->completion seen {d['issue_to_completion_ns'] / cnt / 1e3:.2f} us, "
+              f"longest pass body {d['longest_body_cycles'] / cnt / ghz / 1e3:.2f} us")
+bc = s.block_cycles()
+if bc.any():
+    for ph, n in ((1, "root"), (3, "stats"), (5, "part")):
+        v = bc[:, ph] / ghz / 1e3
+        order = np.argsort(v)
+        print(f"per-block total {n} body time (us): min {v.min():.0f} median {np.median(v):.0f} max {v.max():.0f}; slowest blocks {order[-6:].tolist()} "
+              f"-> {np.round(v[order[-6:]]).tolist()}; fastest {order[:4].tolist()} -> {np.round(v[order[:4]]).tolist()}")
+if bc.any() and bc.shape[1] >= 16:
+    nroot = out["passes"]["root"] * (steps + 2)
+    for b in (0, 73, 146):
+        print(f"staged root pass checkpoints, block {b} (us/pass): " + ", ".join(f"{n} {bc[b, 8 + i] / nroot / ghz / 1e3:.2f}" for i, n in enumerate(["prologue + (in loop) A/y->o incl. tree eval", "prologue + (in loop) A store", "issue first tiles (+ in-loop issue)", "first tile lands + (in loop) totals+jobs", "tile loop", "epilogue", "(in loop) wait own copies", "(in loop) block sync"])))
