@@ -208,10 +208,15 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     char ebuf[256];
     int grid = 0;
     int stage_bytes = 0;
-    if (pg_query_grid(device, st.S, &grid, &s->smem, &stage_bytes, ebuf, sizeof ebuf)) { s->err = ebuf; return bail(); }
+    const char* env_root = std::getenv("PGBART_ROOT_PASS");      // experiments: "staged" reserves the staging area and selects the staged pass
+    const bool want_stage = env_root && std::strcmp(env_root, "staged") == 0;
+    if (pg_query_grid(device, st.S, want_stage, &grid, &s->smem, &stage_bytes, ebuf, sizeof ebuf)) { s->err = ebuf; return bail(); }
     st.grid = grid;
     st.stage_bytes = stage_bytes;
     st.root_staged = 0;
+    st.prefetch_next = 0;
+    st.root_staged = want_stage ? 1 : 0;
+    if (const char* e = std::getenv("PGBART_PREFETCH_NEXT")) st.prefetch_next = std::atoi(e) != 0;
     st.n_gwarps = grid * PG_WARPS;
 
     // ---- X -> column-major fp32 with per-column min/max; y -> fp32
@@ -481,11 +486,15 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
         return 1;
     }
     if (std::strcmp(key, "root_pass") == 0) {
-        if (std::strcmp(value, "staged") == 0) { s->st.root_staged = 1; return 0; }
+        if (std::strcmp(value, "staged") == 0) {
+            if (s->st.stage_bytes < 64 * 1024) { s->err = "the staged root pass needs its staging area: create the sampler with PGBART_ROOT_PASS=staged"; return 1; }
+            s->st.root_staged = 1; return 0;
+        }
         if (std::strcmp(value, "direct") == 0) { s->st.root_staged = 0; return 0; }
         s->err = "root_pass must be 'staged' or 'direct'";
         return 1;
     }
+    if (std::strcmp(key, "prefetch_next") == 0) { s->st.prefetch_next = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "pool_factor") == 0) {
         const long long f = std::atoll(value);
         if (f < 1) { s->err = "pool_factor must be >= 1"; return 1; }

@@ -1120,6 +1120,27 @@ __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemVie
     }
 }
 
+// After a root pass: the control block has usually staged the NEXT tree update's root jobs already (pg_serial_fast.cuh,
+// fw_prestage), so this block asks L2 for its own rows of those columns now — one bulk prefetch per distinct column,
+// issued after the block has reported completion, i.e. off the critical path.  The next root pass then streams from
+// L2 instead of waiting on HBM round trips.  Purely a hint: stale job arrays only cost a useless prefetch.
+__device__ __forceinline__ void pg_prefetch_next_root(const PgState& st, int flags) {
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int pb_next = 1 - ((flags >> 2) & 1);
+    const int J = min(__ldcg(&st.ctrl->pre_J[pb_next]), 32);
+    const bool live = lane < J;
+    const int var = live ? __ldcg(&st.job_var[(size_t)pb_next * st.S + lane]) : -1 - lane;
+    const unsigned same = __match_any_sync(PG_FULL, var);
+    if (!live || (__ffs(same) - 1) != lane || var < 0 || var >= st.p) return;
+    long long B0, B1;
+    pg_block_range(st.n, (int)blockIdx.x - 1, st.grid, &B0, &B1);
+    if (B1 <= B0) return;
+    const float* src = st.X + (size_t)var * st.ld + B0;
+    const unsigned bytes = (unsigned)(B1 - B0) * 4u;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // Dispatch one grid pass.
 // FASTP: the block-unit passes of the P <= 32 persistent kernel (staged root pass, block-unit identity partitions);
 // otherwise the warp-range passes the generic control code, the stepwise driver and the host simulation share.

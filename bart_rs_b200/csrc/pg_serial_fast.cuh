@@ -1290,7 +1290,7 @@ __device__ __forceinline__ void fw_prestage(const PgState& st, const FwCx& x, in
     if (__any_sync(PG_FULL, status == 6 || status == 7)) return;
     int G;
     const int J1 = fw_write_jobs(st, x, jb, lane, true, (int)(U1 & 1ull), true, false, &G);
-    if (lane == 0) { f->pre_upd = U1; f->pre_J = J1; f->pre_G = G; }
+    if (lane == 0) { f->pre_upd = U1; f->pre_J = J1; f->pre_G = G; st.ctrl->pre_J[(int)(U1 & 1ull)] = J1; }
     __syncwarp();
 }
 

@@ -89,6 +89,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
             const int phase = __ldcg(&c->phase);
             if (phase == PH_DONE) break;
             const long long t0 = clock64();
+            const int flags = __ldcg(&c->flags);
             pg_run_pass<true>(st, sm, phase);
             __syncthreads();
             const long long t1 = clock64();
@@ -100,6 +101,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
 #endif
                 __threadfence(); atomicAdd(&c->bar_count, 1u);
             }
+            if (phase == PH_ROOT && st.prefetch_next) pg_prefetch_next_root(st, flags);
             if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // stopwatch kept by the last pass block
                 c->prof[phase & 7] += (unsigned long long)(t1 - t0);
                 c->prof[8 + (phase & 7)] += (unsigned long long)(t0 - t_idle);   // time spent waiting for this command
@@ -189,7 +191,7 @@ extern "C" __global__ void pg_leaf_indices_kernel(const PgState st, int t, unsig
 // launchers
 // ---------------------------------------------------------------------------
 
-int pg_query_grid(int device, int S, int* grid_out, size_t* smem_out, int* stage_out, char* err, size_t errlen) {
+int pg_query_grid(int device, int S, bool want_stage, int* grid_out, size_t* smem_out, int* stage_out, char* err, size_t errlen) {
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return 1; }
@@ -200,8 +202,9 @@ int pg_query_grid(int device, int S, int* grid_out, size_t* smem_out, int* stage
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncGetAttributes: %s", cudaGetErrorString(e)); return 1; }
     const size_t base = pg_smem_bytes(S);
     const size_t optin = prop.sharedMemPerBlockOptin;
-    if (base + fa.sharedSizeBytes + 16 * 1024 > optin) { snprintf(err, errlen, "shared memory: %zu B needed, %zu B available", base + fa.sharedSizeBytes + 16 * 1024, optin); return 1; }
-    const size_t stage = ((optin - fa.sharedSizeBytes - base - 1024) / 1024) * 1024;
+    if (base + fa.sharedSizeBytes + (want_stage ? 16 * 1024 : 0) > optin) { snprintf(err, errlen, "shared memory: %zu B needed, %zu B available", base + fa.sharedSizeBytes + 16 * 1024, optin); return 1; }
+    // (only when the staged root pass is requested: a large carve-out leaves the control block almost no L1)
+    const size_t stage = want_stage ? ((optin - fa.sharedSizeBytes - base - 1024) / 1024) * 1024 : 0;
     const size_t smem = base + stage;
     e = cudaFuncSetAttribute(pg_sweep_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_sweep_persistent_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

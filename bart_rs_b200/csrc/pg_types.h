@@ -119,6 +119,9 @@ struct PgCtrl {
     // 1 STATS, 2 PART: [4+4c] sum issue->last observed, [5+4c] sum issue->last arrival, [6+4c] sum issue->completion seen
     // by the control block, [7+4c] sum of the longest pass body (cycles)
     unsigned long long dbg[16];
+    // ---- hint for the pass blocks: number of root jobs staged ahead in the job arrays of each buffer parity
+    // (written by the control block when it pre-stages the next tree update; read after a root pass to prefetch)
+    int pre_J[2];
 };
 
 struct PgState {
@@ -127,6 +130,7 @@ struct PgState {
     int p, m, P, S, max_depth, maxn;
     int grid, n_gwarps;          // CTAs in the sweep grid, global warps (= grid * PG_WARPS)
     int stage_bytes;             // shared-memory staging area per block behind the pass arrays (async-copy ring)
+    int prefetch_next;           // pass blocks prefetch the next update's root columns into L2 after a root pass
     int root_staged;             // P <= 32 persistent kernel: 1 = staged root pass (pg_pass_root_staged), 0 = warp-range loads
     // data
     const float* X;

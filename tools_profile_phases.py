@@ -16,6 +16,8 @@ st = PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, prm["sigma"], l
 s = PySampler.init(X, y, DeviceLikelihood(w["family"], 1.0), st)
 if len(sys.argv) > 3:
     s.set_option("root_pass", sys.argv[3])
+if len(sys.argv) > 4:
+    s.set_option("prefetch_next", sys.argv[4])
 for _ in range(2):
     s.step_device(False)
 s.sync()
