@@ -293,6 +293,17 @@ __device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgBuf& bf,
     }
 }
 
+// one row of one job: if (x < thr) { a += o; b += r; c += 1; } (smc.rs:201-217) without predication: the 0/1 mask
+// times a finite value is exact, so a = fma(m, o, a) is the same sum (ptxas turns predicated f64 adds into add + two
+// selects, twice the instructions)
+__device__ __forceinline__ void pg_acc_left(double& a, double& b, unsigned& c, float x, float thr, double o, double r) {
+    const bool left = x < thr;
+    const double m = left ? 1.0 : 0.0;
+    a = fma(m, o, a);
+    b = fma(m, r, b);
+    c += left ? 1u : 0u;
+}
+
 // =============================================================================
 // PH_ROOT / PH_FINAL
 // =============================================================================
@@ -397,24 +408,20 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
             for (int q = 0; q < 4; ++q) {
                 const bool live = jb + q < J;
                 const float* col = st.X + (size_t)(live ? sm.jvar[jb + q] : 0) * ld;
-                xa[q] = (live && g0) ? pg_ld_x4(col + r0) : make_float4(0.f, 0.f, 0.f, 0.f);
-                xb[q] = (live && g1) ? pg_ld_x4(col + r1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // rows outside this warp's range read as +inf, like the padding rows of X: never LEFT
+                xa[q] = (live && g0) ? pg_ld_x4(col + r0) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                xb[q] = (live && g1) ? pg_ld_x4(col + r1) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const bool live = jb + q < J;
-                const float thr = live ? sm.jthr[jb + q] : 0.0f;
+                const float thr = live ? sm.jthr[jb + q] : -INFINITY;
                 const float xs[8] = {xa[q].x, xa[q].y, xa[q].z, xa[q].w, xb[q].x, xb[q].y, xb[q].z, xb[q].w};
                 double a = 0.0, b = 0.0;
-                int cc = 0;
+                unsigned cc = 0;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const bool left = live && valid[e] && (xs[e] < thr);
-                    a += left ? o[e] : 0.0;
-                    b += left ? r[e] : 0.0;
-                    cc += left ? 1 : 0;
-                }
-                so[q] = a; sr[q] = b; cn[q] = cc;
+                for (int e = 0; e < 8; ++e) pg_acc_left(a, b, cc, xs[e], thr, o[e], r[e]);   // o = r = 0 on rows >= n
+                so[q] = a; sr[q] = b; cn[q] = (int)cc;
             }
             const double ta = pg_xreduce4(so[0], so[1], so[2], so[3], lane);
             const double tb = pg_xreduce4(sr[0], sr[1], sr[2], sr[3], lane);
@@ -492,17 +499,6 @@ __device__ __forceinline__ void pg_cp_wait_pending(int n) {      // at most n of
         case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
         default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
     }
-}
-
-// one row of one job: if (x < thr) { a += o; b += r; c += 1; } (smc.rs:201-217) without predication: the 0/1 mask
-// times a finite value is exact, so a = fma(m, o, a) is the same sum (ptxas turns predicated f64 adds into add + two
-// selects, twice the instructions)
-__device__ __forceinline__ void pg_acc_left(double& a, double& b, unsigned& c, float x, float thr, double o, double r) {
-    const bool left = x < thr;
-    const double m = left ? 1.0 : 0.0;
-    a = fma(m, o, a);
-    b = fma(m, r, b);
-    c += left ? 1u : 0u;
 }
 
 // tree value of a row whose columns are (mostly) staged: tile-local row `lr`, global row `row`
@@ -911,8 +907,9 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
                         const float x = ok ? __ldg(&col[idx[k]]) : 0.0f;
                         const bool left = ok && (x < thr);
                         if (MODE == 0) {
-                            a += left ? o[k] : 0.0;
-                            b += left ? r[k] : 0.0;
+                            const double m = left ? 1.0 : 0.0;      // exact 0/1 mask (see pg_acc_left)
+                            a = fma(m, o[k], a);
+                            b = fma(m, r[k], b);
                             cc += left ? 1 : 0;
                         } else if (ok) {
                             const double mu = o[k] + (left ? sm.jvL[j] : sm.jvR[j]);
