@@ -209,13 +209,18 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     int grid = 0;
     int stage_bytes = 0;
     const char* env_root = std::getenv("PGBART_ROOT_PASS");      // experiments: "staged" reserves the staging area and selects the staged pass
+#ifdef PGBART_WITH_STAGED
     const bool want_stage = env_root && std::strcmp(env_root, "staged") == 0;
+#else
+    const bool want_stage = false;   // the staged root pass is compiled only with -DPGBART_WITH_STAGED (it is slower than the default)
+#endif
     if (pg_query_grid(device, st.S, want_stage, &grid, &s->smem, &stage_bytes, ebuf, sizeof ebuf)) { s->err = ebuf; return bail(); }
     st.grid = grid;
     st.stage_bytes = stage_bytes;
     st.root_staged = 0;
     st.prefetch_next = 0;
     st.root_staged = want_stage ? 1 : 0;
+    st.root_quarters = (env_root && std::strcmp(env_root, "quarters") == 0) ? 1 : 0;
     if (const char* e = std::getenv("PGBART_PREFETCH_NEXT")) st.prefetch_next = std::atoi(e) != 0;
     st.n_gwarps = grid * PG_WARPS;
 
@@ -490,7 +495,8 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
             if (s->st.stage_bytes < 64 * 1024) { s->err = "the staged root pass needs its staging area: create the sampler with PGBART_ROOT_PASS=staged"; return 1; }
             s->st.root_staged = 1; return 0;
         }
-        if (std::strcmp(value, "direct") == 0) { s->st.root_staged = 0; return 0; }
+        if (std::strcmp(value, "direct") == 0) { s->st.root_staged = 0; s->st.root_quarters = 0; return 0; }
+        if (std::strcmp(value, "quarters") == 0) { s->st.root_staged = 0; s->st.root_quarters = 1; return 0; }
         s->err = "root_pass must be 'staged' or 'direct'";
         return 1;
     }

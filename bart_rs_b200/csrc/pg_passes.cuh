@@ -447,6 +447,174 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
 }
 
 // =============================================================================
+// PH_ROOT / PH_FINAL, quarter/group variant (P <= 32 persistent kernel, default)
+// =============================================================================
+// Same arithmetic as pg_pass_root on a different work split.  The block's rows (pg_block_range) are cut into four
+// contiguous quarters; warp w = (quarter w / 4, job group w % 4) streams its quarter 128 rows at a time (4 consecutive
+// rows per lane, float4 loads) and accumulates ITS jobs (every fourth one) in per-lane registers for the whole pass:
+// no cross-lane reduction and no shared memory inside the loop, one reduction at the end.  The split columns of the
+// next 128 rows are loaded before the current ones are consumed (register double buffer), so every warp always has
+// ~2.5 KB in flight.  A and y come from L2 (they are re-read every tree update and stay resident).  Each of the four
+// groups of a quarter re-derives A -> "others" for its rows (a dozen instructions); only group 0 writes A back and keeps
+// the totals.  Fixed summation order => bit-reproducible.  Emits per-BLOCK results (part_tot, part_sum, part_ccnt).
+template <bool BERN, int JW>
+__device__ void pg_pass_root_quarters(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+    PgCtrl* c = st.ctrl;
+    PgSmem* b = sm.base;
+    const bool is_root = __ldcg(&c->phase) == PH_ROOT;
+    const int J = is_root ? __ldcg(&c->n_jobs) : 0;
+    const int t_add = __ldcg(&c->t_add), t_sub = is_root ? __ldcg(&c->t_sub) : -1;
+    const int S = st.S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qd = warp >> 2, grp = warp & 3;
+
+    pg_stage_tree(st, t_add, b->tadd);
+    pg_stage_tree(st, t_sub, b->tsub);
+    for (int j = tid; j < J; j += blockDim.x) { sm.jvar[j] = __ldcg(&bf.job_var[j]); sm.jthr[j] = __ldcg(&bf.job_thr32[j]); }
+    __syncthreads();
+    const bool add_nontrivial = t_add >= 0 && b->tadd.size > 1;
+    const bool sub_nontrivial = t_sub >= 0 && b->tsub.size > 1;
+    const double add_c = t_add == -2 ? st.init_leaf : ((t_add >= 0 && !add_nontrivial) ? b->tadd.leaf_val[0] : 0.0);
+    const double sub_c = (t_sub >= 0 && !sub_nontrivial) ? b->tsub.leaf_val[0] : 0.0;
+    const bool do_add = t_add >= 0 || t_add == -2, do_sub = t_sub >= 0;
+    const bool commit_only = J == 0 && t_sub < 0;      // PH_FINAL
+
+    long long B0, B1;
+    pg_block_range(st.n, PG_BID, st.grid, &B0, &B1);
+    unsigned long long qb, qe;
+    pg_warp_range((unsigned long long)(B1 - B0), qd, 4, 128, &qb, &qe);     // quarters in units of one warp-iteration
+    const long long Q0 = B0 + (long long)qb, Q1 = B0 + (long long)qe;
+    const long long n = st.n;
+    const size_t ld = (size_t)st.ld;
+
+    // my jobs: group g takes jobs j with (j + 1) % 4 == g, so group 0 (which also writes A and keeps the totals) gets the fewest
+    const int jfirst = (grp + 3) & 3;
+    const int myJ = J > jfirst ? min((J - jfirst + 3) / 4, JW) : 0;
+    const float* colp[JW];
+    float jthr[JW];
+    double accA[JW], accB[JW];
+    unsigned accC[JW];
+#pragma unroll
+    for (int q = 0; q < JW; ++q) {
+        const int j = jfirst + 4 * q;
+        const bool lv = q < myJ;
+        colp[q] = st.X + (size_t)(lv ? sm.jvar[j] : 0) * ld + Q0 + 4 * lane;
+        jthr[q] = lv ? sm.jthr[j] : -INFINITY;
+        accA[q] = 0.0; accB[q] = 0.0; accC[q] = 0u;
+    }
+    double tot_o = 0.0, tot_r = 0.0, tot_rr = 0.0, tot_ll = 0.0;
+    const float4 finf = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+
+    float4 xc[JW], xn[JW];
+    {
+        const bool in0 = Q0 + 4 * lane < Q1;
+#pragma unroll
+        for (int q = 0; q < JW; ++q) xc[q] = (q < myJ && in0) ? pg_ld_x4(colp[q]) : finf;
+    }
+#pragma unroll 1
+    for (long long base = Q0; base < Q1; base += 128) {
+        const long long row = base + 4 * lane;
+        const bool in = row < Q1;
+        const bool in_next = row + 128 < Q1;
+        // the next iteration's columns: in flight while this one is consumed
+#pragma unroll
+        for (int q = 0; q < JW; ++q) xn[q] = (q < myJ && in_next) ? pg_ld_x4(colp[q] + (base - Q0) + 128) : finf;
+        double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
+        float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) {
+            const double2 a01 = pg_ld_a2(bf.A_src + row), a23 = pg_ld_a2(bf.A_src + row + 2);
+            yy = __ldg(reinterpret_cast<const float4*>(st.y + row));
+            o0 = a01.x; o1 = a01.y; o2 = a23.x; o3 = a23.y;
+            const int nv = (int)min(4ll, n - row);
+            // kernel.rs:99-102 then :84-87, each a separately rounded f64 operation
+            if (do_add) {
+                if (add_nontrivial) {
+                    o0 = o0 + (nv > 0 ? pg_tree_eval(st, t_add, b->tadd, row + 0) : 0.0);
+                    o1 = o1 + (nv > 1 ? pg_tree_eval(st, t_add, b->tadd, row + 1) : 0.0);
+                    o2 = o2 + (nv > 2 ? pg_tree_eval(st, t_add, b->tadd, row + 2) : 0.0);
+                    o3 = o3 + (nv > 3 ? pg_tree_eval(st, t_add, b->tadd, row + 3) : 0.0);
+                } else { o0 = o0 + add_c; o1 = o1 + add_c; o2 = o2 + add_c; o3 = o3 + add_c; }
+            }
+            if (do_sub) {
+                if (sub_nontrivial) {
+                    o0 = o0 - (nv > 0 ? pg_tree_eval(st, t_sub, b->tsub, row + 0) : 0.0);
+                    o1 = o1 - (nv > 1 ? pg_tree_eval(st, t_sub, b->tsub, row + 1) : 0.0);
+                    o2 = o2 - (nv > 2 ? pg_tree_eval(st, t_sub, b->tsub, row + 2) : 0.0);
+                    o3 = o3 - (nv > 3 ? pg_tree_eval(st, t_sub, b->tsub, row + 3) : 0.0);
+                } else { o0 = o0 - sub_c; o1 = o1 - sub_c; o2 = o2 - sub_c; o3 = o3 - sub_c; }
+            }
+            if (grp == 0) {
+                __stcg(reinterpret_cast<double2*>(bf.A_dst + row), make_double2(o0, o1));
+                __stcg(reinterpret_cast<double2*>(bf.A_dst + row + 2), make_double2(o2, o3));
+            }
+            if (nv < 4) {                                   // the lane that straddles n (padding rows: x = +inf already)
+                if (nv < 2) { o1 = 0.0; yy.y = 0.f; }
+                if (nv < 3) { o2 = 0.0; yy.z = 0.f; }
+                o3 = 0.0; yy.w = 0.f;
+                if (nv < 1) { o0 = 0.0; yy.x = 0.f; }
+            }
+        }
+        if (!commit_only) {
+            const double r0v = (double)yy.x - o0, r1v = (double)yy.y - o1, r2v = (double)yy.z - o2, r3v = (double)yy.w - o3;
+            if (grp == 0) {                                 // rows past the range / past n contribute exact zeros
+                tot_o += o0; tot_o += o1; tot_o += o2; tot_o += o3;
+                tot_r += r0v; tot_r += r1v; tot_r += r2v; tot_r += r3v;
+                tot_rr += r0v * r0v; tot_rr += r1v * r1v; tot_rr += r2v * r2v; tot_rr += r3v * r3v;
+                if (BERN && in) {
+                    const int nv = (int)min(4ll, n - row);
+                    const double ov[4] = {o0, o1, o2, o3};
+                    const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (e < nv) { const double mu = ov[e] + st.init_leaf; tot_ll += (double)yv[e] * mu - pg_softplus(mu); }
+                }
+            }
+            // smc.rs:201-217 for this warp's slots of round 1; +inf never compares LEFT
+#pragma unroll
+            for (int q = 0; q < JW; ++q) {
+                pg_acc_left(accA[q], accB[q], accC[q], xc[q].x, jthr[q], o0, r0v);
+                pg_acc_left(accA[q], accB[q], accC[q], xc[q].y, jthr[q], o1, r1v);
+                pg_acc_left(accA[q], accB[q], accC[q], xc[q].z, jthr[q], o2, r2v);
+                pg_acc_left(accA[q], accB[q], accC[q], xc[q].w, jthr[q], o3, r3v);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < JW; ++q) xc[q] = xn[q];
+    }
+
+    // ---- block results
+    if (!commit_only) {
+#pragma unroll
+        for (int q = 0; q < JW; ++q) {
+            if (q < myJ) {                                  // warp-uniform
+                const double a = pg_warp_sum(accA[q]), bb = pg_warp_sum(accB[q]);
+                const unsigned cc = __reduce_add_sync(PG_FULL, accC[q]);
+                if (lane == 0) { const int j = jfirst + 4 * q; b->r_acc[qd][j][0] = a; b->r_acc[qd][j][1] = bb; b->r_cnt[qd][j] = cc; }
+            }
+        }
+        if (grp == 0) {
+            tot_o = pg_warp_sum(tot_o); tot_r = pg_warp_sum(tot_r); tot_rr = pg_warp_sum(tot_rr); tot_ll = pg_warp_sum(tot_ll);
+            if (lane == 0) { b->tot[qd][0] = tot_o; b->tot[qd][1] = tot_r; b->tot[qd][2] = tot_rr; b->tot[qd][3] = tot_ll; }
+        }
+    }
+    __syncthreads();
+    if (commit_only) return;
+    if (tid < 4) {
+        double v = 0.0;
+        for (int q = 0; q < 4; ++q) v += b->tot[q][tid];
+        bf.part_tot[(size_t)PG_BID * 4 + tid] = v;
+    }
+    for (int j = tid; j < J; j += blockDim.x) {
+        double a = 0.0, bb = 0.0;
+        unsigned cc = 0u;
+        for (int q = 0; q < 4; ++q) { a += b->r_acc[q][j][0]; bb += b->r_acc[q][j][1]; cc += b->r_cnt[q][j]; }
+        bf.part_sum[((size_t)PG_BID * S + j) * 2 + 0] = a;
+        bf.part_sum[((size_t)PG_BID * S + j) * 2 + 1] = bb;
+        bf.part_ccnt[(size_t)PG_BID * S + j] = cc;
+    }
+}
+
+// =============================================================================
 // PH_ROOT / PH_FINAL, staged variant (P <= 32 persistent kernel)
 // =============================================================================
 // The warp-range pass above is latency bound: each warp walks its rows through dependent global loads with
@@ -1139,25 +1307,31 @@ __device__ __forceinline__ void pg_prefetch_next_root(const PgState& st, int fla
 }
 
 // Dispatch one grid pass.
-// FASTP: the block-unit passes of the P <= 32 persistent kernel (staged root pass, block-unit identity partitions);
-// otherwise the warp-range passes the generic control code, the stepwise driver and the host simulation share.
-template <bool FASTP>
+// Pass variants.  Every persistent kernel instantiates exactly one, so that the register allocation and code size of
+// one variant never disturb another (the kernels are monoliths: control block + every pass inlined):
+//   PGV_GENERIC   warp-range passes, both likelihood families at run time: generic control code (P > 32), stepwise driver
+//   PGV_DIRECT    P <= 32, Gaussian families: block-unit scheme, root pass = register loads over warp sub-ranges
+//   PGV_QUARTERS  P <= 32, Gaussian families, S <= 20: block-unit scheme, quarter/group root pass (default)
+//   PGV_STAGED    P <= 32, Gaussian families: block-unit scheme, async-copy ring root pass (needs the staging area)
+//   PGV_BERN      P <= 32, Bernoulli-logit: block-unit scheme, direct root pass with the stump log-likelihood
+enum { PGV_GENERIC = 0, PGV_DIRECT = 1, PGV_QUARTERS = 2, PGV_STAGED = 3, PGV_BERN = 4 };
+
+template <int VAR>
 __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView& sm, int phase) {
     const PgBuf bf = pg_make_buf(st, __ldcg(&st.ctrl->flags));
+    constexpr bool FASTP = VAR != PGV_GENERIC;
     switch (phase) {
         case PH_ROOT:
         case PH_FINAL:
-            if (FASTP && st.root_staged) {
-                if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root_staged<true, PGR_JW>(st, bf, sm);
-                else if (st.S <= 20) pg_pass_root_staged<false, 5>(st, bf, sm);      // <= 5 jobs per warp: fewer live registers
-                else pg_pass_root_staged<false, PGR_JW>(st, bf, sm);
-            }
-            else if (FASTP) { if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true, true>(st, bf, sm); else pg_pass_root<false, true>(st, bf, sm); }
-            else { if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true, false>(st, bf, sm); else pg_pass_root<false, false>(st, bf, sm); }
+            if (VAR == PGV_GENERIC) { if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true, false>(st, bf, sm); else pg_pass_root<false, false>(st, bf, sm); }
+            else if (VAR == PGV_BERN) pg_pass_root<true, true>(st, bf, sm);
+            else if (VAR == PGV_QUARTERS) pg_pass_root_quarters<false, 5>(st, bf, sm);
+            else if (VAR == PGV_STAGED) { if (st.S <= 20) pg_pass_root_staged<false, 5>(st, bf, sm); else pg_pass_root_staged<false, PGR_JW>(st, bf, sm); }
+            else pg_pass_root<false, true>(st, bf, sm);
             break;
         case PH_MINMAX: pg_pass_minmax(st, bf, sm); break;
         case PH_STATS: pg_pass_seg<0>(st, bf, sm); break;
-        case PH_BERN: pg_pass_seg<1>(st, bf, sm); break;
+        case PH_BERN: if (VAR == PGV_GENERIC || VAR == PGV_BERN) pg_pass_seg<1>(st, bf, sm); break;
         case PH_PART: pg_pass_part<FASTP>(st, bf, sm); break;
         default: break;
     }

@@ -55,8 +55,9 @@ __device__ void pg_barrier_serial(const PgState& st, const PgSmemView& smv, unsi
     gen += 1u;
 }
 
-template <bool FAST>
+template <int VAR>
 __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
+    constexpr bool FAST = VAR != PGV_GENERIC;
     extern __shared__ __align__(128) unsigned char pg_smem_raw[];
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     // sampler constants the serial section reads: staged once per launch
@@ -90,7 +91,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
             if (phase == PH_DONE) break;
             const long long t0 = clock64();
             const int flags = __ldcg(&c->flags);
-            pg_run_pass<true>(st, sm, phase);
+            pg_run_pass<VAR>(st, sm, phase);
             __syncthreads();
             const long long t1 = clock64();
             if (threadIdx.x == 0) {
@@ -119,7 +120,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
         const int J = __ldcg(&st.ctrl->n_jobs);
         if (phase == PH_DONE) break;
         const long long t0 = clock64();
-        if (blockIdx.x != 0) pg_run_pass<false>(st, sm, phase);   // block 0 = serial block: streams nothing
+        if (blockIdx.x != 0) pg_run_pass<PGV_GENERIC>(st, sm, phase);   // block 0 = serial block: streams nothing
         __syncthreads();
         const long long t1 = clock64();
         pg_barrier_serial<FAST>(st, sm, gen, phase, J);
@@ -132,16 +133,21 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
     }
 }
 
-// P <= 32: latency-organised serial section; P > 32: generic team serial section.
-extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent(const PgState st) { pg_sweep_body<true>(st); }
-extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_generic(const PgState st) { pg_sweep_body<false>(st); }
+// P <= 32: latency-organised control block, one kernel per pass variant; P > 32: generic team serial section.
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent(const PgState st) { pg_sweep_body<PGV_QUARTERS>(st); }
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_direct(const PgState st) { pg_sweep_body<PGV_DIRECT>(st); }
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_bern(const PgState st) { pg_sweep_body<PGV_BERN>(st); }
+#ifdef PGBART_WITH_STAGED
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_staged(const PgState st) { pg_sweep_body<PGV_STAGED>(st); }
+#endif
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_generic(const PgState st) { pg_sweep_body<PGV_GENERIC>(st); }
 
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_phase_kernel(const PgState st) {
     extern __shared__ __align__(128) unsigned char pg_smem_raw[];
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     if (threadIdx.x == 0) sm.base->pass_bid = (int)blockIdx.x;
     __syncthreads();
-    pg_run_pass<false>(st, sm, __ldcg(&st.ctrl->phase));
+    pg_run_pass<PGV_GENERIC>(st, sm, __ldcg(&st.ctrl->phase));
 }
 
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_serial_kernel(const PgState st) {
@@ -197,19 +203,28 @@ int pg_query_grid(int device, int S, bool want_stage, int* grid_out, size_t* sme
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return 1; }
     // dynamic shared memory = the pass arrays + a staging area (bulk-copy ring of the staged root pass) that takes
     // whatever one block per SM can have
-    cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, pg_sweep_persistent);
-    if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncGetAttributes: %s", cudaGetErrorString(e)); return 1; }
+    const void* kernels[] = {(const void*)pg_sweep_persistent, (const void*)pg_sweep_persistent_direct, (const void*)pg_sweep_persistent_bern,
+#ifdef PGBART_WITH_STAGED
+                             (const void*)pg_sweep_persistent_staged,
+#endif
+                             (const void*)pg_sweep_persistent_generic, (const void*)pg_phase_kernel};
+    size_t static_smem = 0;
+    for (const void* k : kernels) {
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, k);
+        if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncGetAttributes: %s", cudaGetErrorString(e)); return 1; }
+        if (fa.sharedSizeBytes > static_smem) static_smem = fa.sharedSizeBytes;
+    }
     const size_t base = pg_smem_bytes(S);
     const size_t optin = prop.sharedMemPerBlockOptin;
-    if (base + fa.sharedSizeBytes + (want_stage ? 16 * 1024 : 0) > optin) { snprintf(err, errlen, "shared memory: %zu B needed, %zu B available", base + fa.sharedSizeBytes + 16 * 1024, optin); return 1; }
+    if (base + static_smem + (want_stage ? 16 * 1024 : 0) > optin) { snprintf(err, errlen, "shared memory: %zu B needed, %zu B available", base + static_smem + (want_stage ? 16 * 1024 : 0), optin); return 1; }
     // (only when the staged root pass is requested: a large carve-out leaves the control block almost no L1)
-    const size_t stage = want_stage ? ((optin - fa.sharedSizeBytes - base - 1024) / 1024) * 1024 : 0;
+    const size_t stage = want_stage ? ((optin - static_smem - base - 1024) / 1024) * 1024 : 0;
     const size_t smem = base + stage;
-    e = cudaFuncSetAttribute(pg_sweep_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_sweep_persistent_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pg_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { snprintf(err, errlen, "shared memory request %zu B: %s", smem, cudaGetErrorString(e)); return 1; }
+    for (const void* k : kernels) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { snprintf(err, errlen, "shared memory request %zu B: %s", smem, cudaGetErrorString(e)); return 1; }
+    }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_sweep_persistent, PG_THREADS, smem);
     if (e != cudaSuccess || per_sm < 1) { snprintf(err, errlen, "occupancy query failed: %s", cudaGetErrorString(e)); return 1; }
@@ -229,7 +244,15 @@ cudaError_t pg_launch_prepare(const PgState& st, int tune, cudaStream_t s) {
 
 cudaError_t pg_launch_persistent(const PgState& st, size_t smem, cudaStream_t s) {
     void* args[] = {(void*)&st};
-    void* fn = st.P <= 32 ? (void*)pg_sweep_persistent : (void*)pg_sweep_persistent_generic;
+    void* fn = (void*)pg_sweep_persistent_generic;
+    if (st.P <= 32) {
+        if (st.family == PG_BERNOULLI_LOGIT) fn = (void*)pg_sweep_persistent_bern;
+#ifdef PGBART_WITH_STAGED
+        else if (st.root_staged) fn = (void*)pg_sweep_persistent_staged;
+#endif
+        else if (st.root_quarters && st.S <= 20) fn = (void*)pg_sweep_persistent;
+        else fn = (void*)pg_sweep_persistent_direct;
+    }
     return cudaLaunchCooperativeKernel(fn, dim3(st.grid + 1), dim3(PG_THREADS), args, smem, s);   // + the serial block
 }
 

@@ -131,6 +131,7 @@ struct PgState {
     int grid, n_gwarps;          // CTAs in the sweep grid, global warps (= grid * PG_WARPS)
     int stage_bytes;             // shared-memory staging area per block behind the pass arrays (async-copy ring)
     int prefetch_next;           // pass blocks prefetch the next update's root columns into L2 after a root pass
+    int root_quarters;           // P <= 32 persistent kernel: 1 = quarter/group root pass (pg_pass_root_quarters)
     int root_staged;             // P <= 32 persistent kernel: 1 = staged root pass (pg_pass_root_staged), 0 = warp-range loads
     // data
     const float* X;

@@ -99,7 +99,9 @@ int pgbart_trace_enable(pgbart_handle h, int64_t u_cap, int r_cap);
 int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd, int64_t* n_upd, int* overflow);
 
 /* Options: "driver" = "persistent" (default) | "stepwise"; "pool_factor" = integer >= 1;
- * "root_pass" = "direct" (default: register loads over warp ranges) | "staged" (async-copy ring in shared memory). */
+ * "root_pass" = "direct" (default: register loads over warp sub-ranges of the block's rows) | "quarters" (row quarter x job
+ * group, per-lane accumulators) | "staged" (async-copy ring in shared memory; only in -DPGBART_WITH_STAGED builds);
+ * "prefetch_next" = 0 | 1 (L2 prefetch of the next tree update's root columns after a root pass). */
 int pgbart_set_option(pgbart_handle h, const char* key, const char* value);
 
 /* Counters since creation: [0] compulsory bytes of this implementation's passes, [1] bytes by the
