@@ -254,7 +254,7 @@ def run_gpu(args):
                        "storage": "X, y fp32; running sum-of-trees fp64; accumulation fp64"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": "pg_sweep_persistent (one launch = one sweep = m tree updates)",
+                         "kernel": "pg_sweep_persistent_direct (one launch = one sweep = m tree updates)",
                          "algorithmic_bytes_per_launch": contract_per_launch,
                          "fused_bytes_per_launch": bytes_per_launch, "fused_gbs": fused_gbs, "fused_frac": fused_gbs / peak,
                          "note": "achieved = SURVEY.md 8(d) contract bytes (B_tree summed from device counters over the sweep's "
@@ -262,7 +262,7 @@ def run_gpu(args):
                                  "sharing) / CUDA-event time of the launch.  fused_* = the bytes this implementation must move "
                                  "(A, y and each distinct split column read once per pass for all slots together); "
                                  "traffic = ncu dram bytes of one launch (A and y stay L2-resident, so it is below both). "
-                                 "The launch is bound by its serial control sections, not by HBM: DESIGN.md section 6"},
+                                 "The launch is bound by latency (control sections and per-pass instruction issue), not by HBM: DESIGN.md section 4-5"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8 * w["n"],
                     "steps": e2e_steps},
