@@ -82,6 +82,8 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     PgCtrl lc;                                   // working copy of the control block
     double hw[32], hG[64];                       // slot scalars: weights; [2][S] particle log-lik sums
     int hmut[32], hanc[32], hsjob[32], hsize[64], hqh[64], hqt[64];
+    int hlin[32];                                // lineage id of each slot: equal ids <=> identical slot tables
+    double hGp[32];                              // rounds >= 1: log-lik sum a slot would have with its pending (deferred) mutation
     int jslot[32], jnode[32], jvar[32];          // job list of the current round
     unsigned jseg[32], jlen[32];
     float jthr[32];

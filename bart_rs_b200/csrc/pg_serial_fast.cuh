@@ -629,12 +629,12 @@ __device__ __forceinline__ int fw_after_minmax(const PgState& st, const FwCx& x,
 }
 
 // particle.rs:91-148 bookkeeping half + smc.rs:76-81 for rounds >= 1 (mirrors pg_apply_mutation on the shared scalars)
-__device__ __forceinline__ void fw_apply(const PgState& st, const FwCx& x, int j, double vL, double vR, double gL, double gR,
+// `cur`/`s`: the table (half, slot) the mutation is written to — the proposing slot itself, or (deferred mutations) the
+// fresh copy a surviving descendant received; `record` = also set the slot's weight / trace (immediate application).
+__device__ __forceinline__ void fw_apply(const PgState& st, const FwCx& x, int cur, int s, bool record, int j, double vL, double vR, double gL, double gR,
                                          unsigned cL, unsigned cR, double SoL, double SoR, double SrL, double SrR) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
-    const int cur = c->cur;
-    const int s = f->jslot[j];
     const int node = f->jnode[j];
     const int L = 2 * node + 1, R = 2 * node + 2;
     const size_t iN = pg_tix(st, cur, s, node), iL = pg_tix(st, cur, s, L), iR = pg_tix(st, cur, s, R);
@@ -664,11 +664,13 @@ __device__ __forceinline__ void fw_apply(const PgState& st, const FwCx& x, int j
     st.pt_queue[pg_tix(st, cur, s, qt)] = L;           // particle.rs:146-147
     st.pt_queue[pg_tix(st, cur, s, qt + 1)] = R;
     f->hqt[ss] = qt + 2;
-    f->hmut[s] = 1;
-    const double w = c->C0 + G;                        // smc.rs:89-95
-    f->hw[s] = w;
-    double* tr = pg_trace_slot(st, c, c->round, s);
-    if (tr) { tr[0] = 4; tr[4] = vL; tr[5] = vR; tr[6] = (double)cL; tr[7] = (double)cR; tr[8] = w; tr[11] = SoL; }
+    if (record) {
+        f->hmut[s] = 1;
+        const double w = c->C0 + G;                    // smc.rs:89-95
+        f->hw[s] = w;
+        double* tr = pg_trace_slot(st, c, c->round, s);
+        if (tr) { tr[0] = 4; tr[4] = vL; tr[5] = vR; tr[6] = (double)cL; tr[7] = (double)cR; tr[8] = w; tr[11] = SoL; }
+    }
 }
 
 // Leaf values of one job (smc.rs:219-239) and, for the Gaussian families, the leaf terms of the log-likelihood.
@@ -722,7 +724,7 @@ __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, 
         if (lane < J) {
             const size_t iN = pg_tix(st, cur, f->jslot[lane], f->jnode[lane]);
             const unsigned cL = f->jr_cL[lane];
-            fw_apply(st, x, lane, f->jr_vL[lane], f->jr_vR[lane], f->rllL[lane], f->rllR[lane], cL, st.pt_cnt[iN] - cL,
+            fw_apply(st, x, cur, f->jslot[lane], true, lane, f->jr_vL[lane], f->jr_vR[lane], f->rllL[lane], f->rllR[lane], cL, st.pt_cnt[iN] - cL,
                      f->jr_SoL[lane], st.pt_So[iN] - f->jr_SoL[lane], f->jr_SrL[lane], st.pt_Sr[iN] - f->jr_SrL[lane]);
         }
         __syncwarp();
@@ -735,7 +737,22 @@ __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, 
         if (bern) {
             f->jr_vL[lane] = v.vL; f->jr_vR[lane] = v.vR; f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL;
             { const size_t jo = (size_t)(c->upd & 1ull) * st.S; st.job_vL[jo + lane] = v.vL; st.job_vR[jo + lane] = v.vR; }
-        } else fw_apply(st, x, lane, v.vL, v.vR, v.gL, v.gR, v.cL, v.cR, v.SoL, v.SoR, v.SrL, v.SrR);
+        } else {
+            // Deferred (particle.rs:91-148 is applied lazily): the mutated particle's weight is all resampling needs.  Its
+            // table is written only if a copy of it survives (fw_finish_round) — under the stale-weight rule (Q1) it
+            // almost never does, and then no slot table moves at all.
+            const int s = f->jslot[lane];
+            const int ss = pg_six(st, cur, s);
+            f->jr_vL[lane] = v.vL; f->jr_vR[lane] = v.vR; f->jr_gL[lane] = v.gL; f->jr_gR[lane] = v.gR;
+            f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL;
+            const double G = (f->hG[ss] - st.pt_g[iN]) + (v.gL + v.gR);
+            const double w = c->C0 + G;                // smc.rs:89-95
+            f->hGp[s] = G;
+            f->hw[s] = w;
+            f->hmut[s] = 1;
+            double* tr = pg_trace_slot(st, c, c->round, s);
+            if (tr) { tr[0] = 4; tr[4] = v.vL; tr[5] = v.vR; tr[6] = (double)v.cL; tr[7] = (double)v.cR; tr[8] = w; tr[11] = v.SoL; }
+        }
     }
     __syncwarp();
     if (bern && J > 0) {
@@ -827,15 +844,33 @@ __device__ __forceinline__ int fw_plan_partitions(const PgState& st, const FwCx&
     return K;
 }
 
-// smc.rs:96-102 for rounds >= 1: clone survivors' tables, plan the lazy partitions
+// smc.rs:96-102 for rounds >= 1: clone survivors' tables (only when a table actually changes owner), apply the deferred
+// mutations of survivors, plan the lazy partitions
 __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x, int lane) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
     const int S = st.S;
-    const int src = c->cur, dst = 1 - c->cur;
     const bool act = lane < S;
+    const bool bern = st.family == PG_BERNOULLI_LOGIT;    // Bernoulli mutations are applied immediately (fw_after_stats)
     int n_mut, mut;
     const int anc = fw_normalize_resample(st, x, lane, &n_mut, &mut);
+    const int mut_a = __shfl_sync(PG_FULL, mut, anc);
+    const int my_lin = act ? f->hlin[lane] : 0;
+    const int lin_a = __shfl_sync(PG_FULL, my_lin, anc);
+    const bool moves = act && (mut_a != 0 || lin_a != my_lin || (bern && mut != 0));
+    if (!__any_sync(PG_FULL, moves)) {
+        // Every slot keeps a table identical to its ancestor's: same lineage, nobody's pending mutation survived, and the
+        // per-slot scalars (size, queue head / tail, log-lik sum) of one lineage are equal because every slot pops one
+        // node per round.  Nothing to copy.
+        const int ss = pg_six(st, c->cur, lane);
+        const int any_queue = __any_sync(PG_FULL, act && f->hqh[ss] < f->hqt[ss]);
+        if (lane == 0) { c->acc_update += n_mut; c->n_pjobs = 0; c->any_queue = any_queue; f->n_mq = 0; }
+        __syncwarp();
+        if (c->error != PG_OK) return SN_NONE;
+        if (any_queue) { if (lane == 0) c->round += 1; __syncwarp(); return SN_DRAW_ROUND; }
+        return SN_FINALIZE;
+    }
+    const int src = c->cur, dst = 1 - c->cur;
     const int fs = pg_six(st, src, anc), ts = pg_six(st, dst, lane);
     const int sz = act ? f->hsize[fs] : 0;
     const int qh = act ? f->hqh[fs] : 0, qt = act ? f->hqt[fs] : 0;
@@ -853,9 +888,17 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
         }
     }
     __syncwarp();
-    if (act) { f->hsize[ts] = sz; f->hqh[ts] = qh; f->hqt[ts] = qt; f->hG[ts] = Gs; }
-    const int mut_a = __shfl_sync(PG_FULL, mut, anc);
+    if (act) { f->hsize[ts] = sz; f->hqh[ts] = qh; f->hqt[ts] = qt; f->hG[ts] = Gs; f->hlin[lane] = mut_a ? 64 + 32 * (c->round & 0xffff) + anc : lin_a; }
+    __syncwarp();
     const bool need = act && mut_a != 0;
+    if (need && !bern) {                                   // the ancestor's deferred mutation, on this slot's fresh copy
+        const int j = f->hsjob[anc];
+        const size_t iN = pg_tix(st, dst, lane, f->jnode[j]);
+        const unsigned cL = f->jr_cL[j];
+        fw_apply(st, x, dst, lane, false, j, f->jr_vL[j], f->jr_vR[j], f->jr_gL[j], f->jr_gR[j], cL, st.pt_cnt[iN] - cL,
+                 f->jr_SoL[j], st.pt_So[iN] - f->jr_SoL[j], f->jr_SrL[j], st.pt_Sr[iN] - f->jr_SrL[j]);
+    }
+    __syncwarp();
     unsigned off, cntL;
     int node;
     const int K = fw_plan_partitions(st, x, lane, anc, need, &off, &cntL, &node);
@@ -863,7 +906,7 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
         st.pt_seg_off[pg_tix(st, dst, lane, 2 * node + 1)] = off;
         st.pt_seg_off[pg_tix(st, dst, lane, 2 * node + 2)] = off + cntL;
     }
-    const int any_queue = __any_sync(PG_FULL, act && qh < qt);
+    const int any_queue = __any_sync(PG_FULL, act && f->hqh[ts] < f->hqt[ts]);
     if (lane == 0) { c->acc_update += n_mut; c->cur = dst; c->n_pjobs = K; c->any_queue = any_queue; f->n_mq = 0; }
     __syncwarp();
     if (c->error != PG_OK) return SN_NONE;
@@ -1154,7 +1197,9 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
             st.pt_queue[i0] = 1; st.pt_queue[i1] = 2;      // particle.rs:146-147: left then right
             f->hsize[ss] = 3; f->hqh[ss] = 0; f->hqt[ss] = 2;
             f->hG[ss] = (c->g_stump - c->g_stump) + (f->jr_gL[j] + f->jr_gR[j]);
+            f->hlin[lane] = anc;                           // copies of one grown particle share a lineage
         } else {
+            f->hlin[lane] = 32;                            // the untouched stump
             st.pt_split_var[i0] = -1; st.pt_split_val[i0] = pg_nan(); st.pt_thr32[i0] = 0.0f; st.pt_leaf_val[i0] = st.init_leaf;
             st.pt_seg_off[i0] = PG_SEG_IDENTITY; st.pt_cnt[i0] = (unsigned)st.n;
             st.pt_So[i0] = c->T_o; st.pt_Sr[i0] = c->T_r; st.pt_g[i0] = c->g_stump;
