@@ -50,6 +50,7 @@ const char* pg_error_text(int code) {
         case PG_ERR_WATCHDOG: return "grid barrier watchdog fired";
         case PG_ERR_WEIGHTS: return "final particle weights are not finite (the reference panics in WeightedIndex::new)";
         case PG_ERR_INTERNAL: return "internal consistency check failed";
+        case PG_ERR_PRUNE: return "prune_dead_proposals: residual sum of squares too large for the weight bound (disable the option)";
         default: return "unknown device error";
     }
 }
@@ -219,6 +220,8 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     st.stage_bytes = stage_bytes;
     st.root_staged = 0;
     st.prefetch_next = 0;
+    st.prune = 0;
+    if (const char* e = std::getenv("PGBART_PRUNE")) st.prune = std::atoi(e) != 0;
     st.root_staged = want_stage ? 1 : 0;
     st.root_quarters = (env_root && std::strcmp(env_root, "quarters") == 0) ? 1 : 0;
     if (const char* e = std::getenv("PGBART_PREFETCH_NEXT")) st.prefetch_next = std::atoi(e) != 0;
@@ -500,6 +503,7 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
         s->err = "root_pass must be 'staged' or 'direct'";
         return 1;
     }
+    if (std::strcmp(key, "prune_dead_proposals") == 0) { s->st.prune = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "prefetch_next") == 0) { s->st.prefetch_next = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "pool_factor") == 0) {
         const long long f = std::atoll(value);

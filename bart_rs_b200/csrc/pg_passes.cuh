@@ -118,6 +118,7 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     int n_mq, pf_n, pf_slot[32];
     unsigned long long pre_upd;                  // update whose root jobs are already staged in the global job arrays
     int pre_J, pre_G, spec_now;
+    int lazy_J;                                  // pruned round 0: accepted root proposals that were not evaluated (they count as grows)
     volatile unsigned long long want_base, want_top;   // draw helpers: updates [want_base, want_top] are wanted
     volatile int helpers_quit;
     double stump_total, stump_cum[32];           // final selection when every particle is a stump: sequential sums of 1/P
@@ -508,25 +509,30 @@ __device__ void pg_pass_root_quarters(const PgState& st, const PgBuf& bf, const 
     const float4 finf = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
 
     float4 xc[JW], xn[JW];
+    double2 ac01 = make_double2(0.0, 0.0), ac23 = make_double2(0.0, 0.0), an01, an23;
+    float4 yc = make_float4(0.f, 0.f, 0.f, 0.f), yn;
     {
-        const bool in0 = Q0 + 4 * lane < Q1;
+        const long long row0 = Q0 + 4 * lane;
+        const bool in0 = row0 < Q1;
 #pragma unroll
         for (int q = 0; q < JW; ++q) xc[q] = (q < myJ && in0) ? pg_ld_x4(colp[q]) : finf;
+        if (in0) { ac01 = pg_ld_a2(bf.A_src + row0); ac23 = pg_ld_a2(bf.A_src + row0 + 2); yc = __ldg(reinterpret_cast<const float4*>(st.y + row0)); }
     }
 #pragma unroll 1
     for (long long base = Q0; base < Q1; base += 128) {
         const long long row = base + 4 * lane;
         const bool in = row < Q1;
         const bool in_next = row + 128 < Q1;
-        // the next iteration's columns: in flight while this one is consumed
+        // the next iteration's inputs: in flight while this one is consumed
 #pragma unroll
         for (int q = 0; q < JW; ++q) xn[q] = (q < myJ && in_next) ? pg_ld_x4(colp[q] + (base - Q0) + 128) : finf;
+        an01 = make_double2(0.0, 0.0); an23 = make_double2(0.0, 0.0); yn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in_next) { an01 = pg_ld_a2(bf.A_src + row + 128); an23 = pg_ld_a2(bf.A_src + row + 130); yn = __ldg(reinterpret_cast<const float4*>(st.y + row + 128)); }
         double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
         float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in) {
-            const double2 a01 = pg_ld_a2(bf.A_src + row), a23 = pg_ld_a2(bf.A_src + row + 2);
-            yy = __ldg(reinterpret_cast<const float4*>(st.y + row));
-            o0 = a01.x; o1 = a01.y; o2 = a23.x; o3 = a23.y;
+            yy = yc;
+            o0 = ac01.x; o1 = ac01.y; o2 = ac23.x; o3 = ac23.y;
             const int nv = (int)min(4ll, n - row);
             // kernel.rs:99-102 then :84-87, each a separately rounded f64 operation
             if (do_add) {
@@ -582,6 +588,7 @@ __device__ void pg_pass_root_quarters(const PgState& st, const PgBuf& bf, const 
         }
 #pragma unroll
         for (int q = 0; q < JW; ++q) xc[q] = xn[q];
+        ac01 = an01; ac23 = an23; yc = yn;
     }
 
     // ---- block results

@@ -64,7 +64,7 @@ __device__ void fw_load_state(const PgState& st, PgFastSm* f) {
     }
     if (threadIdx.x < 3) f->d_upd[threadIdx.x] = ~0ull;
     if (threadIdx.x < 3 * (FW_DR + 1)) f->d_flag[threadIdx.x / (FW_DR + 1)][threadIdx.x % (FW_DR + 1)] = 0ull;
-    if (threadIdx.x == 0) { f->issued = 0u; f->out_phase = PH_BEGIN; f->out_J = 0; f->out_pb = 0; f->quit = 0; f->pre_upd = ~0ull; f->spec_now = 0; }
+    if (threadIdx.x == 0) { f->issued = 0u; f->out_phase = PH_BEGIN; f->out_J = 0; f->out_pb = 0; f->quit = 0; f->pre_upd = ~0ull; f->spec_now = 0; f->lazy_J = 0; }
 }
 
 __device__ void fw_store_state(const PgState& st, PgFastSm* f) {
@@ -394,6 +394,37 @@ __device__ __forceinline__ FwJob fw_root_job(const PgState& st, const FwCx& x, u
     return jb;
 }
 
+// Option prune_dead_proposals.  Stale-weight rule (Q1): in round 0 a slot that proposes nothing keeps the
+// log-weight 0.0 while a slot that grew gets its particle's log-likelihood.  For the Gaussian families that log-likelihood
+// is at most Cconst = -n (log sigma + 0.5 log 2 pi) whatever the data (the leaf terms are bounded by half the residual sum
+// of squares, by Cauchy-Schwarz), so when Cconst < -800 every grown particle's normalised weight is exp(w - 0) = 0.0
+// EXACTLY and only the resampling pointer overrunning the end of the weights can still select it.  This checks, with the
+// reference's arithmetic (smc.rs:257-268, resampling.rs:24-44), that no grown slot is anybody's ancestor: then the update
+// ends as a stump whatever the proposals' statistics are, and they need not be computed.
+__device__ __forceinline__ bool fw_round0_all_dead(const PgState& st, const FwCx& x, unsigned long long upd, int lane, bool live) {
+    PgCtrl* c = x.c;
+    const int S = st.S;
+    if (!st.prune || st.family != PG_GAUSSIAN || !(c->Cconst < -800.0) || st.tr_slot || st.tr_round || st.tr_upd) return false;
+    const unsigned lm = __ballot_sync(PG_FULL, live);
+    if (lm == 0u || __popc(lm) >= S) return false;          // nothing to prune / every slot grows: weights matter
+    const bool act = lane < S;
+    const double e = act ? (live ? 0.0 : 1.0) : 0.0;          // exp(w - max): max = 0.0 (a non-growing slot), exp(-1e6) = 0.0
+    const double sum = fw_sum_seq(e, S);
+    const double wn = e / sum;
+    const double u6 = fw_u6(st, x, upd, 0);
+    const double target = ((double)lane + u6) / (double)S;
+    int cidx = 0;
+    double cum = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < S; ++k) {
+        if (cum < target) cidx = k + 1;
+        cum += __shfl_sync(PG_FULL, wn, k);
+    }
+    const int anc = act ? (cidx == 0 ? 0 : cidx - 1) : 0;
+    const bool anc_live = (lm >> anc) & 1u;
+    return !__any_sync(PG_FULL, act && anc_live);
+}
+
 // smc.rs:42-53 + round 0 of smc.rs:61-86: fresh particles of the update that becomes current.  The precomputed
 // root proposals become the job list: written to the global job arrays unless a speculative root pass already did.
 __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x, int lane, bool jobs_published) {
@@ -432,12 +463,15 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     int G;
     const int J = fw_write_jobs(st, x, jb, lane, true, (int)(upd & 1ull), !jobs_published, true, &G);
     const int uniq = fw_unique(jb.var, jb.live, lane);
+    const bool lazy = fw_round0_all_dead(st, x, upd, lane, jb.live);   // same decision the speculative issue took (fw_prestage)
     if (lane == 0) {
         const unsigned long long n = (unsigned long long)st.n;
-        const int cols = uniq + c->t_add_internal + st.f_internal[c->t_sub];
+        const int cols = (lazy ? 0 : uniq) + c->t_add_internal + st.f_internal[c->t_sub];
         c->bytes_model += n * (8 + 8 + 4) + 4ull * n * (unsigned long long)cols;
-        c->bytes_contract += 20ull * n + 4ull * n * (unsigned long long)J0 + 16ull * n * (unsigned long long)J;
+        c->bytes_contract += 20ull * n + (lazy ? 0ull : 4ull * n * (unsigned long long)J0 + 16ull * n * (unsigned long long)J);
         c->phase = PH_ROOT; c->n_phases += 1;
+        f->lazy_J = lazy ? J : 0;
+        if (lazy) c->n_jobs = 0;                             // the root pass only commits / opens the trees and sums the residuals
     }
     __syncwarp();
 }
@@ -1152,7 +1186,11 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
     const int anc = fw_normalize_resample(st, x, lane, &n_mut, &mut);
     const int mut_a = __shfl_sync(PG_FULL, mut, anc);
     const bool need = act && mut_a != 0;
-    if (lane == 0) c->acc_update += n_mut;
+    if (lane == 0) {
+        c->acc_update += n_mut + f->lazy_J;                  // pruned proposals were accepted grows all the same (smc.rs:79-81)
+        // the bound w <= Cconst holds up to the rounding of terms of size T_rr / (2 sigma^2): keep 50 units of margin honest
+        if (f->lazy_J > 0 && !(0.5 * c->T_rr * c->inv_s2 < 1.0e13)) c->error = PG_ERR_PRUNE;
+    }
     __syncwarp();
     if (!__any_sync(PG_FULL, need)) {
         // every survivor is an untouched stump with an empty queue: the loop of smc.rs:61 ends here.  All P
@@ -1308,7 +1346,8 @@ __device__ __forceinline__ bool fw_try_speculate(const PgState& st, const FwCx& 
     if (__any_sync(PG_FULL, status == 6 || status == 7)) return false;   // let the regular path raise the error
     int G;
     const int pb1 = (int)(U1 & 1ull);
-    const int J1 = fw_write_jobs(st, x, jb, lane, true, pb1, true, false, &G);
+    int J1 = fw_write_jobs(st, x, jb, lane, true, pb1, true, false, &G);
+    if (fw_round0_all_dead(st, x, U1, lane, jb.live)) J1 = 0;
     const int t_sub1 = (c->next_tree_idx + c->k + 1) % st.m;
     const int src = c->a_cur, dst = 1 - c->a_cur;
     fw_issue(st, x, lane, PH_ROOT, -2 /* a stump */, t_sub1, J1, G, 0, src | (dst << 1) | (pb1 << 2));
@@ -1334,7 +1373,8 @@ __device__ __forceinline__ void fw_prestage(const PgState& st, const FwCx& x, in
     const FwJob jb = fw_root_job(st, x, U1, lane, &passed, &status);
     if (__any_sync(PG_FULL, status == 6 || status == 7)) return;
     int G;
-    const int J1 = fw_write_jobs(st, x, jb, lane, true, (int)(U1 & 1ull), true, false, &G);
+    int J1 = fw_write_jobs(st, x, jb, lane, true, (int)(U1 & 1ull), true, false, &G);
+    if (fw_round0_all_dead(st, x, U1, lane, jb.live)) J1 = 0;
     if (lane == 0) { f->pre_upd = U1; f->pre_J = J1; f->pre_G = G; st.ctrl->pre_J[(int)(U1 & 1ull)] = J1; }
     __syncwarp();
 }

@@ -48,7 +48,8 @@ enum PgError : int {
     PG_ERR_TAPE = 3,       // RNG tape exhausted / split draw not below max
     PG_ERR_WATCHDOG = 4,   // grid barrier timed out
     PG_ERR_WEIGHTS = 5,    // non-finite weights (reference: WeightedIndex::new(..).unwrap() panics)
-    PG_ERR_INTERNAL = 6
+    PG_ERR_INTERNAL = 6,
+    PG_ERR_PRUNE = 7       // prune_dead_proposals: the rounding slack of the weight bound is not negligible for this data
 };
 
 #define PG_SEG_IDENTITY 0xFFFFFFFFu  // node's samples are 0..n (root): no index list is read
@@ -130,6 +131,7 @@ struct PgState {
     int p, m, P, S, max_depth, maxn;
     int grid, n_gwarps;          // CTAs in the sweep grid, global warps (= grid * PG_WARPS)
     int stage_bytes;             // shared-memory staging area per block behind the pass arrays (async-copy ring)
+    int prune;                   // option prune_dead_proposals: do not evaluate proposals whose particle provably gets weight 0
     int prefetch_next;           // pass blocks prefetch the next update's root columns into L2 after a root pass
     int root_quarters;           // P <= 32 persistent kernel: 1 = quarter/group root pass (pg_pass_root_quarters)
     int root_staged;             // P <= 32 persistent kernel: 1 = staged root pass (pg_pass_root_staged), 0 = warp-range loads

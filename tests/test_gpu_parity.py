@@ -145,3 +145,39 @@ def test_gpu_large_n_properties():
         dev.close()
     np.testing.assert_array_equal(outs[0], outs[1])              # run-to-run bit reproducibility
     np.testing.assert_allclose(outs[0], outs[2], rtol=1e-9)       # stepwise driver: generic serial code, other reduction order
+
+
+@pytest.mark.gpu
+def test_gpu_pruned_dead_proposals_same_forest():
+    """Option prune_dead_proposals: proposals of particles whose weight is provably 0 are not evaluated.
+    Forest, predictions and BartInfo must still equal the oracle's, which evaluates everything."""
+    from oracle import pyoracle as po
+    n, p, m, P = 3000, 6, 20, 20
+    X, y = datagen.small(n, p, seed=11)
+    cfg = cfg_for(y, m, P, p, seed=5)
+    orc = po.OracleSampler(X.astype(np.float64), y, **cfg)
+    orc.set_likelihood(po.FAM_GAUSSIAN, [1.0])
+    orc.set_rng(po.RNG_PHILOX, 5)
+    outs = {}
+    for prune in ("0", "1"):
+        dev = make_gpu()(X, y, cfg)
+        dev.set_likelihood_code(0, [1.0])
+        dev.set_rng_philox(5)
+        dev.set_option("prune_dead_proposals", prune)
+        preds = [dev.step(t) for t in (True, True, False)]
+        outs[prune] = (preds, dev.counters()["bytes_contract"], dev)
+    opreds = [orc.step(t) for t in (True, True, False)]
+    for prune in ("0", "1"):
+        preds, _, dev = outs[prune]
+        for a, b in zip(opreds, preds):
+            np.testing.assert_allclose(b, a, rtol=parity.RTOL, atol=0)
+        parity.assert_forest_matches(orc, dev, m)
+        oll, oacc, odep = orc.info()
+        dll, dacc, ddep = dev.info()
+        assert oacc == dacc
+        np.testing.assert_array_equal(ddep, odep)
+        np.testing.assert_allclose(dll, oll, rtol=1e-4, atol=1e-12)
+    # bit-identical between the two modes, and the pruned run really skipped work
+    for a, b in zip(outs["0"][0], outs["1"][0]):
+        np.testing.assert_array_equal(a, b)
+    assert outs["1"][1] < 0.8 * outs["0"][1]
