@@ -222,6 +222,24 @@ def run_gpu(args):
     e2e_value, _ = job_throughput(1000.0 * e2e_s, e2e_steps, world, device="cuda")
     assert np.all(np.isfinite(pred))
 
+    # ---- reported beside the headline, never instead of it: the same sweep with option prune_dead_proposals
+    # (proposals of particles whose weight is provably exactly 0 are not evaluated; identical forest and predictions)
+    pruned = None
+    if world == 1 and w["family"] == "gaussian":
+        smp.set_option("prune_dead_proposals", "1")
+        for _ in range(3):
+            smp.step_device(False)
+        smp.sync()
+        smp.timer_start()
+        for _ in range(args.steps):
+            smp.step_device(False)
+        pms = smp.timer_stop()
+        smp.sync()
+        smp.set_option("prune_dead_proposals", "0")
+        pruned = {"value": args.steps / (pms / 1000.0), "unit": "sweeps/s", "ms_per_step": pms / args.steps,
+                  "note": "option prune_dead_proposals=1 (off by default; DESIGN.md section 4b): same forest and predictions, "
+                          "dead proposals not evaluated; NOT the headline value"}
+
     if rank == 0:
         peak, peak_src = peaks()
         k = args.steps
@@ -266,6 +284,7 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8 * w["n"],
                     "steps": e2e_steps},
+            "pruned": pruned,
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
             "grid_passes_per_step": (c1["grid_passes"] - c0["grid_passes"]) / k,
             "clocks": clk,
