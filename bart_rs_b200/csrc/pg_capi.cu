@@ -40,6 +40,8 @@ struct Sampler {
     long long tr_u_cap = 0;
     int tr_r_cap = 0;
     PgCtrl host_ctrl{};
+    std::vector<void*> ipc_open;     // peer mailboxes opened through CUDA IPC (observation sharding)
+    long long steps_done = 0;
 };
 
 const char* pg_error_text(int code) {
@@ -91,6 +93,8 @@ double unrolled_mean(const double* xs, size_t n) {
 }
 
 void free_all(Sampler* s) {
+    for (void* p : s->ipc_open) cudaIpcCloseMemHandle(p);
+    s->ipc_open.clear();
     for (void* p : s->allocs) cudaFree(p);
     s->allocs.clear();
     for (double* p : {s->tape_slot, s->tape_round, s->tape_upd, s->tr_slot, s->tr_round, s->tr_upd})
@@ -280,7 +284,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         && dalloc(s, &st.f_split_var, M * MN) && dalloc(s, &st.f_thr32, M * MN) && dalloc(s, &st.f_split_val, M * MN)
         && dalloc(s, &st.f_leaf_val, M * MN) && dalloc(s, &st.f_size, M) && dalloc(s, &st.f_internal, M)
         && dalloc(s, &st.pt_split_var, 2 * S * MN) && dalloc(s, &st.pt_thr32, 2 * S * MN) && dalloc(s, &st.pt_split_val, 2 * S * MN)
-        && dalloc(s, &st.pt_leaf_val, 2 * S * MN) && dalloc(s, &st.pt_seg_off, 2 * S * MN) && dalloc(s, &st.pt_cnt, 2 * S * MN)
+        && dalloc(s, &st.pt_leaf_val, 2 * S * MN) && dalloc(s, &st.pt_seg_off, 2 * S * MN) && dalloc(s, &st.pt_cnt, 2 * S * MN) && dalloc(s, &st.pt_len, 2 * S * MN)
         && dalloc(s, &st.pt_So, 2 * S * MN) && dalloc(s, &st.pt_Sr, 2 * S * MN) && dalloc(s, &st.pt_g, 2 * S * MN)
         && dalloc(s, &st.pt_queue, 2 * S * MN) && dalloc(s, &st.pt_size, 2 * S) && dalloc(s, &st.pt_qhead, 2 * S)
         && dalloc(s, &st.pt_qtail, 2 * S) && dalloc(s, &st.pt_G, 2 * S)
@@ -307,6 +311,8 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         st.pool_cap = cap;
         if (!dalloc(s, &st.pool, (size_t)cap, false)) return bail();
     }
+    st.rank = 0; st.world = 1; st.n_global = st.n;
+    for (int r = 0; r < PG_MAX_RANKS; ++r) st.mail[r] = nullptr;
     st.rng_mode = PG_RNG_PHILOX;
     st.philox_key0 = (unsigned)cfg->seed;
     st.philox_key1 = (unsigned)(cfg->seed >> 32);
@@ -345,12 +351,13 @@ int pgbart_set_likelihood(pgbart_handle h, int family, const double* params, int
     return 0;
 }
 
-int pgbart_step_device(pgbart_handle h, int tune) { return enqueue_step(&h->s, tune); }
+int pgbart_step_device(pgbart_handle h, int tune) { h->s.steps_done += 1; return enqueue_step(&h->s, tune); }
 
 int pgbart_sync(pgbart_handle h) { return finish_step(&h->s); }
 
 int pgbart_step(pgbart_handle h, int tune, double* out_pred) {
     Sampler* s = &h->s;
+    s->steps_done += 1;
     int rc = enqueue_step(s, tune);
     if (rc) return rc;
     if (out_pred && !ck(s, cudaMemcpyAsync(out_pred, s->st.A, (size_t)s->st.n * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions")) return 2;
@@ -557,6 +564,58 @@ int pgbart_debug_block_cycles(pgbart_handle h, double* out, int cap) {
     if (!ck(s, cudaStreamSynchronize(s->stream), "sync")) return 2;
     if (!ck(s, cudaMemcpy(tmp.data(), s->st.diag_blocks, tmp.size() * 8, cudaMemcpyDeviceToHost), "copy diag")) return 2;
     for (int i = 0; i < G * 16 && i < cap; ++i) out[i] = (double)tmp[i];
+    return 0;
+}
+
+// ---- observation sharding (include/pgbart.h) ---------------------------------------------------------
+int pgbart_shard_config(pgbart_handle h, int rank, int world, uint64_t n_global, double y_mean_global,
+                        const float* col_min_global, const float* col_max_global) {
+    Sampler* s = &h->s;
+    PgState& st = s->st;
+    if (world < 1 || world > PG_MAX_RANKS || rank < 0 || rank >= world) { s->err = "shard_config: need 0 <= rank < world <= 8"; return 1; }
+    if (st.P > 32) { s->err = "observation sharding is implemented for n_particles <= 32"; return 1; }
+    if (s->stepwise) { s->err = "observation sharding needs the persistent driver"; return 1; }
+    if (s->steps_done != 0) { s->err = "shard_config must precede the first step"; return 1; }
+    cudaSetDevice(s->device);
+    st.rank = rank; st.world = world; st.n_global = (long long)n_global;
+    st.y_mean = y_mean_global;
+    st.init_leaf = st.y_mean / (double)st.m;
+    if (!ck(s, cudaMemcpyAsync((void*)st.col_min, col_min_global, (size_t)st.p * 4, cudaMemcpyHostToDevice, s->stream), "upload col_min") ||
+        !ck(s, cudaMemcpyAsync((void*)st.col_max, col_max_global, (size_t)st.p * 4, cudaMemcpyHostToDevice, s->stream), "upload col_max")) return 2;
+    if (!ck(s, pg_launch_fill(st.A, st.n, st.y_mean, s->stream), "fill predictions")) return 2;
+    if (!ck(s, pg_launch_init_forest(st, s->stream), "init forest")) return 2;
+    if (!st.mail[rank]) {
+        double* mb = nullptr;
+        if (!dalloc(s, &mb, PG_MAIL_BYTES / 8)) return 2;
+        st.mail[rank] = mb;
+    }
+    return ck(s, cudaStreamSynchronize(s->stream), "synchronize") ? 0 : 2;
+}
+
+int pgbart_shard_mailbox(pgbart_handle h, unsigned char* handle64) {
+    Sampler* s = &h->s;
+    if (!s->st.mail[s->st.rank]) { s->err = "shard_mailbox: call shard_config first"; return 1; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    cudaSetDevice(s->device);
+    if (!ck(s, cudaIpcGetMemHandle(&hd, s->st.mail[s->st.rank]), "cudaIpcGetMemHandle")) return 2;
+    std::memcpy(handle64, &hd, 64);
+    return 0;
+}
+
+int pgbart_shard_connect(pgbart_handle h, const unsigned char* handles) {
+    Sampler* s = &h->s;
+    PgState& st = s->st;
+    cudaSetDevice(s->device);
+    for (int r = 0; r < st.world; ++r) {
+        if (r == st.rank) continue;
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        if (!ck(s, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return 2;
+        st.mail[r] = (double*)p;
+        s->ipc_open.push_back(p);
+    }
     return 0;
 }
 

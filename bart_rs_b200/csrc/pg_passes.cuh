@@ -91,9 +91,11 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     // round-0 proposals' results, kept in registers/shared memory until resampling decides who survives
     double jr_vL[32], jr_vR[32], jr_gL[32], jr_gR[32], jr_SoL[32], jr_SrL[32];
     unsigned jr_cL[32];
+    unsigned jr_cLl[32];                         // left count among THIS rank's rows (= jr_cL on one GPU)
     double rSo[32], rSr[32], rllL[32], rllR[32]; // reduced per-job partials
     double tot[4];
     unsigned rCnt[32], rMin[32], rMax[32];
+    unsigned rCntL[32];                          // rCnt before the exchange between ranks: this rank's rows only
     double wsA[PG_WARPS][32], wsB[PG_WARPS][32], wsT[PG_WARPS][4];   // per-warp stage of the reduction
     unsigned wsC[PG_WARPS][32], wsD[PG_WARPS][32];
     // draws precomputed by idle warps: [update mod 3][round][slot] (the update in progress and the next two)
@@ -113,7 +115,7 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     int quit;
     // look-ahead caches of the update in progress (rounds 1 and 2), indexed [round-1][slot]
     int mm_valid[2][32]; unsigned mm_seg[2][32]; int mm_var[2][32]; float mm_lo[2][32], mm_hi[2][32];
-    int sc_valid[32]; unsigned sc_seg[32]; int sc_var[32]; float sc_thr[32]; unsigned sc_cnt[32]; double sc_So[32], sc_Sr[32];
+    int sc_valid[32]; unsigned sc_seg[32]; int sc_var[32]; float sc_thr[32]; unsigned sc_cnt[32], sc_cntL[32]; double sc_So[32], sc_Sr[32];
     int rq_r[64], rq_s[64]; unsigned rq_seg[64];  // request -> (round, slot, child segment)
     int n_mq, pf_n, pf_slot[32];
     unsigned long long pre_upd;                  // update whose root jobs are already staged in the global job arrays

@@ -153,7 +153,7 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int 
 #pragma unroll 1
             for (int w = 0; w < PG_WARPS; ++w) { a += f->wsA[w][lane]; b += f->wsB[w][lane]; cc += f->wsC[w][lane]; }
             if (phase == PH_BERN) { f->rllL[lane] = a; f->rllR[lane] = b; }
-            else { f->rSo[lane] = a; f->rSr[lane] = b; f->rCnt[lane] = cc; }
+            else { f->rSo[lane] = a; f->rSr[lane] = b; f->rCnt[lane] = cc; f->rCntL[lane] = cc; }
         }
         if ((phase == PH_MINMAX || phase == PH_PART) && lane < J) {
             unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
@@ -169,6 +169,89 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int 
         }
         __syncwarp();
     }
+}
+
+// ---- stage A': observation sharding — exchange the reduced values between the ranks' control blocks ------------
+// Every rank holds a contiguous block of rows and runs the identical control code on identical draws; the only
+// data-dependent inputs of that code are the values fw_reduce produces.  Each rank writes its values into every peer's
+// mailbox (plain stores into peer memory over NVLink, then a system-scope release of a sequence flag), waits for the
+// peers' flags, and combines all ranks' contributions IN RANK ORDER, so every rank computes bit-identical totals and
+// takes bit-identical decisions; no host round trip, no collective launch.  Mailbox slots alternate with the parity of
+// the sequence number: a rank can be at most one exchange ahead of a peer that still reads the previous slot.
+__device__ __forceinline__ void fw_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long fw_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, int lane) {
+    const int W = st.world, me = st.rank;
+    const bool sums = phase == PH_ROOT || phase == PH_STATS || phase == PH_BERN;
+    const bool mm = phase == PH_MINMAX || phase == PH_PART;
+    if (!sums && !mm) return;
+    // payload: [0..3] root totals, then per job three values
+    const int n_val = 4 + 3 * J;
+    const unsigned long long seq = f->lc.xseq + 1ull;
+    const int par = (int)(seq & 1ull);
+    double mine[4];                                          // this lane's values: indices lane, lane + 32, ...
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = lane + 32 * q;
+        double v = 0.0;
+        if (i < 4) v = phase == PH_ROOT ? f->tot[i] : 0.0;
+        else if (i < n_val) {
+            const int j = (i - 4) / 3, k = (i - 4) % 3;
+            if (phase == PH_BERN) v = k == 0 ? f->rllL[j] : k == 1 ? f->rllR[j] : 0.0;
+            else if (sums) v = k == 0 ? f->rSo[j] : k == 1 ? f->rSr[j] : (double)f->rCnt[j];
+            else v = k == 0 ? (double)f->rMin[j] : k == 1 ? (double)f->rMax[j] : 0.0;      // ordered keys: exact in a double
+        }
+        mine[q] = v;
+    }
+    for (int r = 0; r < W; ++r) {                            // my slot in every rank's mailbox (my own included)
+        double* dst = st.mail[r] + ((size_t)par * PG_MAX_RANKS + me) * PG_MAIL_DOUBLES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n_val) dst[i] = mine[q]; }
+    }
+    __threadfence_system();
+    __syncwarp();
+    unsigned long long* my_flags = reinterpret_cast<unsigned long long*>(st.mail[me] + (size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES);
+    if (lane < W && lane != me) {
+        unsigned long long* peer_flags = reinterpret_cast<unsigned long long*>(st.mail[lane] + (size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES);
+        fw_st_release_sys(&peer_flags[par * PG_MAX_RANKS + me], seq);
+    }
+    if (lane < W && lane != me) {
+        const long long t0 = clock64();
+        while (fw_ld_acquire_sys(&my_flags[par * PG_MAX_RANKS + lane]) < seq) {
+            __nanosleep(100);
+            if (clock64() - t0 > 40000000000ll) { f->lc.error = PG_ERR_WATCHDOG; break; }   // a lost peer becomes an error
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+    const double* box = st.mail[me] + (size_t)par * PG_MAX_RANKS * PG_MAIL_DOUBLES;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = lane + 32 * q;
+        if (i >= n_val) continue;
+        const volatile double* col = box + i;
+        double acc = sums ? 0.0 : col[0];
+        if (sums) { for (int r = 0; r < W; ++r) acc += col[(size_t)r * PG_MAIL_DOUBLES]; }
+        else {
+            const int k = (i - 4) % 3;
+            for (int r = 1; r < W; ++r) { const double v = col[(size_t)r * PG_MAIL_DOUBLES]; acc = k == 0 ? fmin(acc, v) : fmax(acc, v); }
+        }
+        if (i < 4) { if (phase == PH_ROOT) f->tot[i] = acc; }
+        else {
+            const int j = (i - 4) / 3, k = (i - 4) % 3;
+            if (phase == PH_BERN) { if (k == 0) f->rllL[j] = acc; else if (k == 1) f->rllR[j] = acc; }
+            else if (sums) { if (k == 0) f->rSo[j] = acc; else if (k == 1) f->rSr[j] = acc; else f->rCnt[j] = (unsigned)acc; }
+            else { if (k == 0) f->rMin[j] = (unsigned)acc; else if (k == 1) f->rMax[j] = (unsigned)acc; }
+        }
+    }
+    if (lane == 0) f->lc.xseq = seq;
+    __syncwarp();
 }
 
 // smc.rs:242-254 (prior in shared memory when staged), same subtraction order as the reference
@@ -367,7 +450,7 @@ __device__ __forceinline__ int fw_begin_step(const PgState& st, const FwCx& x, i
         c->info_loglik = 0.0; c->info_acc = 0; c->info_n = 0;
         if (st.family == PG_GAUSSIAN) {
             c->inv_s2 = 1.0 / (st.lik_sigma * st.lik_sigma);
-            c->Cconst = -(double)st.n * (log(st.lik_sigma) + 0.5 * log(6.283185307179586476925286766559));
+            c->Cconst = -(double)st.n_global * (log(st.lik_sigma) + 0.5 * log(6.283185307179586476925286766559));
         } else { c->inv_s2 = 1.0; c->Cconst = 0.0; }
     }
     __syncwarp();
@@ -517,7 +600,7 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
                         else { var = (int)(u2 * (double)st.p); if (var > st.p - 1) var = st.p - 1; }
                     }
                     if (tr) tr[2] = (double)var;
-                    jb.live = true; jb.node = node; jb.var = var; jb.len = cnt;
+                    jb.live = true; jb.node = node; jb.var = var; jb.len = st.pt_len[iN];
                     jb.seg_off = st.pt_seg_off[iN];
                 }
             }
@@ -565,7 +648,7 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
         const int J = fw_write_jobs(st, x, jb, lane, true, pb, false, true, &G);
         if (lane < J) {
             const int s = f->jslot[lane];
-            f->rCnt[lane] = f->sc_cnt[s]; f->rSo[lane] = f->sc_So[s]; f->rSr[lane] = f->sc_Sr[s];
+            f->rCnt[lane] = f->sc_cnt[s]; f->rCntL[lane] = f->sc_cntL[s]; f->rSo[lane] = f->sc_So[s]; f->rSr[lane] = f->sc_Sr[s];
         }
         __syncwarp();
         if (lane == 0) { unsigned long long bc = 0; for (int j = 0; j < J; ++j) bc += 28ull * f->jlen[j]; c->bytes_contract += bc; }
@@ -595,7 +678,7 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
             const unsigned len2 = (unsigned)st.n - 0u;
             (void)len2;
             st.job_var[jo] = f->mm_var[1][lane]; st.job_thr32[jo] = thr2; st.job_seg_off[jo] = f->mm_seg[1][lane];
-            st.job_len[jo] = st.pt_cnt[pg_tix(st, cur, lane, 2)];
+            st.job_len[jo] = st.pt_len[pg_tix(st, cur, lane, 2)];
             st.job_slot[jo] = lane; st.job_node[jo] = 2; st.job_split[jo] = split2;
             f->pf_slot[q] = lane;
             f->sc_seg[lane] = f->mm_seg[1][lane]; f->sc_var[lane] = f->mm_var[1][lane]; f->sc_thr[lane] = thr2;
@@ -666,7 +749,7 @@ __device__ __forceinline__ int fw_after_minmax(const PgState& st, const FwCx& x,
 // `cur`/`s`: the table (half, slot) the mutation is written to — the proposing slot itself, or (deferred mutations) the
 // fresh copy a surviving descendant received; `record` = also set the slot's weight / trace (immediate application).
 __device__ __forceinline__ void fw_apply(const PgState& st, const FwCx& x, int cur, int s, bool record, int j, double vL, double vR, double gL, double gR,
-                                         unsigned cL, unsigned cR, double SoL, double SoR, double SrL, double SrR) {
+                                         unsigned cL, unsigned cR, double SoL, double SoR, double SrL, double SrR, unsigned lenL) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
     const int node = f->jnode[j];
@@ -679,7 +762,7 @@ __device__ __forceinline__ void fw_apply(const PgState& st, const FwCx& x, int c
     for (int q = old_size; q < R + 1; ++q) {          // tree.rs:105-110 filler nodes
         const size_t iq = pg_tix(st, cur, s, q);
         st.pt_split_var[iq] = -1; st.pt_split_val[iq] = pg_nan(); st.pt_thr32[iq] = 0.0f; st.pt_leaf_val[iq] = 0.0;
-        st.pt_seg_off[iq] = PG_SEG_NONE; st.pt_cnt[iq] = 0u; st.pt_So[iq] = 0.0; st.pt_Sr[iq] = 0.0; st.pt_g[iq] = 0.0;
+        st.pt_seg_off[iq] = PG_SEG_NONE; st.pt_cnt[iq] = 0u; st.pt_len[iq] = 0u; st.pt_So[iq] = 0.0; st.pt_Sr[iq] = 0.0; st.pt_g[iq] = 0.0;
     }
     st.pt_split_var[iN] = f->jvar[j];
     st.pt_split_val[iN] = f->jsplit[j];
@@ -689,6 +772,7 @@ __device__ __forceinline__ void fw_apply(const PgState& st, const FwCx& x, int c
     st.pt_split_var[iR] = -1; st.pt_split_val[iR] = pg_nan(); st.pt_thr32[iR] = 0.0f; st.pt_leaf_val[iR] = vR;
     st.pt_seg_off[iL] = PG_SEG_NONE; st.pt_seg_off[iR] = PG_SEG_NONE;
     st.pt_cnt[iL] = cL; st.pt_cnt[iR] = cR;
+    st.pt_len[iL] = lenL; st.pt_len[iR] = st.pt_len[iN] - lenL;
     st.pt_So[iL] = SoL; st.pt_So[iR] = SoR; st.pt_Sr[iL] = SrL; st.pt_Sr[iR] = SrR;
     st.pt_g[iL] = gL; st.pt_g[iR] = gR;
     if (R + 1 > old_size) f->hsize[ss] = R + 1;
@@ -759,7 +843,7 @@ __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, 
             const size_t iN = pg_tix(st, cur, f->jslot[lane], f->jnode[lane]);
             const unsigned cL = f->jr_cL[lane];
             fw_apply(st, x, cur, f->jslot[lane], true, lane, f->jr_vL[lane], f->jr_vR[lane], f->rllL[lane], f->rllR[lane], cL, st.pt_cnt[iN] - cL,
-                     f->jr_SoL[lane], st.pt_So[iN] - f->jr_SoL[lane], f->jr_SrL[lane], st.pt_Sr[iN] - f->jr_SrL[lane]);
+                     f->jr_SoL[lane], st.pt_So[iN] - f->jr_SoL[lane], f->jr_SrL[lane], st.pt_Sr[iN] - f->jr_SrL[lane], f->jr_cLl[lane]);
         }
         __syncwarp();
         return SN_FINISH_ROUND;
@@ -768,6 +852,7 @@ __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, 
         const size_t iN = pg_tix(st, cur, f->jslot[lane], f->jnode[lane]);
         const FwVals v = fw_values(st, x, lane, st.pt_cnt[iN], st.pt_So[iN], st.pt_Sr[iN]);
         f->jr_cL[lane] = v.cL;     // the partition reads the left count later
+        f->jr_cLl[lane] = f->rCntL[lane];
         if (bern) {
             f->jr_vL[lane] = v.vL; f->jr_vR[lane] = v.vR; f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL;
             { const size_t jo = (size_t)(c->upd & 1ull) * st.S; st.job_vL[jo + lane] = v.vL; st.job_vR[jo + lane] = v.vR; }
@@ -847,7 +932,7 @@ __device__ __forceinline__ int fw_plan_partitions(const PgState& st, const FwCx&
     const int k = __popc(leadm & ((1u << lane) - 1u));
     int j = 0, node = 0;
     unsigned len = 0u, cntL = 0u;
-    if (need) { j = f->hsjob[anc]; node = f->jnode[j]; len = f->jlen[j]; cntL = f->jr_cL[j]; }
+    if (need) { j = f->hsjob[anc]; node = f->jnode[j]; len = f->jlen[j]; cntL = f->jr_cLl[j]; }   // this rank's rows: segment layout is local
     unsigned long long off = 0;
     {
         const unsigned long long mylen = leader ? (unsigned long long)len : 0ull;
@@ -916,7 +1001,7 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
             const size_t a = pg_tix(st, src, anc, node), t = pg_tix(st, dst, lane, node);
             st.pt_split_var[t] = st.pt_split_var[a]; st.pt_thr32[t] = st.pt_thr32[a];
             st.pt_split_val[t] = st.pt_split_val[a]; st.pt_leaf_val[t] = st.pt_leaf_val[a];
-            st.pt_seg_off[t] = st.pt_seg_off[a]; st.pt_cnt[t] = st.pt_cnt[a];
+            st.pt_seg_off[t] = st.pt_seg_off[a]; st.pt_cnt[t] = st.pt_cnt[a]; st.pt_len[t] = st.pt_len[a];
             st.pt_So[t] = st.pt_So[a]; st.pt_Sr[t] = st.pt_Sr[a]; st.pt_g[t] = st.pt_g[a];
             st.pt_queue[t] = st.pt_queue[a];
         }
@@ -930,7 +1015,7 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
         const size_t iN = pg_tix(st, dst, lane, f->jnode[j]);
         const unsigned cL = f->jr_cL[j];
         fw_apply(st, x, dst, lane, false, j, f->jr_vL[j], f->jr_vR[j], f->jr_gL[j], f->jr_gR[j], cL, st.pt_cnt[iN] - cL,
-                 f->jr_SoL[j], st.pt_So[iN] - f->jr_SoL[j], f->jr_SrL[j], st.pt_Sr[iN] - f->jr_SrL[j]);
+                 f->jr_SoL[j], st.pt_So[iN] - f->jr_SoL[j], f->jr_SrL[j], st.pt_Sr[iN] - f->jr_SrL[j], f->jr_cLl[j]);
     }
     __syncwarp();
     unsigned off, cntL;
@@ -1142,14 +1227,14 @@ __device__ __forceinline__ int fw_r0_values(const PgState& st, const FwCx& x, in
     if (bern) { C0 = 0.0; g_stump = T_ll0; }
     else if (st.family == PG_GAUSSIAN) {
         C0 = c->Cconst - 0.5 * T_rr * c->inv_s2;
-        g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n, c->inv_s2);
-    } else { C0 = -0.5 * T_rr; g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n, 1.0); }
+        g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n_global, c->inv_s2);
+    } else { C0 = -0.5 * T_rr; g_stump = pg_gauss_g(st.init_leaf, T_r, (unsigned)st.n_global, 1.0); }
     if (lane == 0) { c->T_o = T_o; c->T_r = T_r; c->T_rr = T_rr; c->T_ll0 = T_ll0; c->C0 = C0; c->g_stump = g_stump; }
     __syncwarp();
     if (lane < J) {
-        const FwVals v = fw_values(st, x, lane, (unsigned)st.n, T_o, T_r);
+        const FwVals v = fw_values(st, x, lane, (unsigned)st.n_global, T_o, T_r);
         f->jr_vL[lane] = v.vL; f->jr_vR[lane] = v.vR; f->jr_gL[lane] = v.gL; f->jr_gR[lane] = v.gR;
-        f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL; f->jr_cL[lane] = v.cL;
+        f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL; f->jr_cL[lane] = v.cL; f->jr_cLl[lane] = f->rCntL[lane];
         if (bern) { { const size_t jo = (size_t)(c->upd & 1ull) * st.S; st.job_vL[jo + lane] = v.vL; st.job_vR[jo + lane] = v.vR; } }
     }
     __syncwarp();
@@ -1178,7 +1263,7 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         double* tr = pg_trace_slot(st, c, 0, s);
         if (tr) {
             tr[0] = 4; tr[4] = f->jr_vL[lane]; tr[5] = f->jr_vR[lane]; tr[6] = (double)f->jr_cL[lane];
-            tr[7] = (double)((unsigned)st.n - f->jr_cL[lane]); tr[8] = w; tr[11] = f->jr_SoL[lane];
+            tr[7] = (double)((unsigned)st.n_global - f->jr_cL[lane]); tr[8] = w; tr[11] = f->jr_SoL[lane];
         }
     }
     __syncwarp();
@@ -1221,14 +1306,15 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         if (need) {
             const int j = f->hsjob[anc];
             const size_t i1 = i0 + 1, i2 = i0 + 2;
-            const unsigned cL = f->jr_cL[j], cR = (unsigned)st.n - cL;
+            const unsigned cL = f->jr_cL[j], cR = (unsigned)st.n_global - cL, cLl = f->jr_cLl[j];
             st.pt_split_var[i0] = f->jvar[j]; st.pt_split_val[i0] = f->jsplit[j]; st.pt_thr32[i0] = f->jthr[j];
-            st.pt_leaf_val[i0] = pg_nan(); st.pt_seg_off[i0] = PG_SEG_IDENTITY; st.pt_cnt[i0] = (unsigned)st.n;
+            st.pt_leaf_val[i0] = pg_nan(); st.pt_seg_off[i0] = PG_SEG_IDENTITY; st.pt_cnt[i0] = (unsigned)st.n_global; st.pt_len[i0] = (unsigned)st.n;
             st.pt_So[i0] = c->T_o; st.pt_Sr[i0] = c->T_r; st.pt_g[i0] = c->g_stump;
             st.pt_split_var[i1] = -1; st.pt_split_val[i1] = pg_nan(); st.pt_thr32[i1] = 0.0f; st.pt_leaf_val[i1] = f->jr_vL[j];
             st.pt_split_var[i2] = -1; st.pt_split_val[i2] = pg_nan(); st.pt_thr32[i2] = 0.0f; st.pt_leaf_val[i2] = f->jr_vR[j];
-            st.pt_seg_off[i1] = off; st.pt_seg_off[i2] = off + cL;
+            st.pt_seg_off[i1] = off; st.pt_seg_off[i2] = off + cLl;
             st.pt_cnt[i1] = cL; st.pt_cnt[i2] = cR;
+            st.pt_len[i1] = cLl; st.pt_len[i2] = (unsigned)st.n - cLl;
             st.pt_So[i1] = f->jr_SoL[j]; st.pt_So[i2] = c->T_o - f->jr_SoL[j];
             st.pt_Sr[i1] = f->jr_SrL[j]; st.pt_Sr[i2] = c->T_r - f->jr_SrL[j];
             st.pt_g[i1] = f->jr_gL[j]; st.pt_g[i2] = f->jr_gR[j];
@@ -1239,7 +1325,7 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         } else {
             f->hlin[lane] = 32;                            // the untouched stump
             st.pt_split_var[i0] = -1; st.pt_split_val[i0] = pg_nan(); st.pt_thr32[i0] = 0.0f; st.pt_leaf_val[i0] = st.init_leaf;
-            st.pt_seg_off[i0] = PG_SEG_IDENTITY; st.pt_cnt[i0] = (unsigned)st.n;
+            st.pt_seg_off[i0] = PG_SEG_IDENTITY; st.pt_cnt[i0] = (unsigned)st.n_global; st.pt_len[i0] = (unsigned)st.n;
             st.pt_So[i0] = c->T_o; st.pt_Sr[i0] = c->T_r; st.pt_g[i0] = c->g_stump;
             f->hsize[ss] = 1; f->hqh[ss] = 1; f->hqt[ss] = 1;
             f->hG[ss] = c->g_stump;
@@ -1255,7 +1341,7 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         int nq = 0;
         if (single) {
             const int j = f->hsjob[anc];
-            const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n - cL;
+            const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n_global - cL, cLl = f->jr_cLl[act ? j : 0];
 #pragma unroll 1
             for (int r = 1; r <= 2; ++r) {
                 const bool want = act && f->d_ok[buf][r] && !(x.thr[1] > f->d_u1[buf][r][lane]) && (r == 1 ? cL : cR) > 0u;
@@ -1263,7 +1349,7 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
                 const int q = nq + __popc(m & ((1u << lane) - 1u));
                 if (want && q < 32) {
                     st.mq_pj[q] = 0; st.mq_side[q] = r - 1; st.mq_var[q] = f->d_var[buf][r][lane];
-                    f->rq_r[q] = r; f->rq_s[q] = lane; f->rq_seg[q] = r == 1 ? off : off + cL;
+                    f->rq_r[q] = r; f->rq_s[q] = lane; f->rq_seg[q] = r == 1 ? off : off + cLl;
                 }
                 nq += __popc(m);
             }
@@ -1448,6 +1534,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
             if (lane == 0) f->spec_now = sp ? 1 : 0;
         }
         fw_reduce(st, f, phase, J, pb);   // contains a __syncthreads before its combine step
+        if (st.world > 1 && warp == 0) fw_exchange(st, f, phase, J, lane);
         if (threadIdx.x == 0 && gerr != PG_OK) c->error = gerr;
         __syncthreads();
         const unsigned long long upd0 = c->upd;   // the update in progress at entry
@@ -1484,7 +1571,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                         const int J0 = c->n_jobs;
                         if (lane >= J0 && lane < J0 + f->pf_n) {
                             const int s = f->pf_slot[lane - J0];
-                            f->sc_cnt[s] = f->rCnt[lane]; f->sc_So[s] = f->rSo[lane]; f->sc_Sr[s] = f->rSr[lane]; f->sc_valid[s] = 1;
+                            f->sc_cnt[s] = f->rCnt[lane]; f->sc_cntL[s] = f->rCntL[lane]; f->sc_So[s] = f->rSo[lane]; f->sc_Sr[s] = f->rSr[lane]; f->sc_valid[s] = 1;
                         }
                         __syncwarp();
                         if (lane == 0) f->pf_n = 0;

@@ -58,6 +58,11 @@ enum PgError : int {
 #define PG_THREADS 512
 #define PG_WARPS (PG_THREADS / 32)
 
+#define PG_MAX_RANKS 8
+#define PG_MAIL_DOUBLES 128                    // payload of one exchange
+// mailbox of one rank: [2 parities][PG_MAX_RANKS senders][PG_MAIL_DOUBLES] doubles, then [2][PG_MAX_RANKS] u64 flags
+#define PG_MAIL_BYTES ((size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES * 8 + (size_t)2 * PG_MAX_RANKS * 8)
+
 struct PgCtrl {
     // ---- state machine (written by the serial section, read by all CTAs after the barrier)
     int phase;
@@ -100,6 +105,7 @@ struct PgCtrl {
     unsigned long long trace_n;         // tree updates recorded in the trace
     int trace_overflow;
     int a_cur;                      // which A buffer holds the running array of the update in progress
+    unsigned long long xseq;        // observation sharding: exchanges between ranks done so far (same on every rank)
     // serial-section breakdown (cycles / calls): 0 reduce, 1 after_stats, 2 after_minmax, 3 finish_round, 4 prep_part,
     // 5 finalize, 6 begin_update, 7 draw_round; [8..15] call counts
     unsigned long long prof2[16];
@@ -131,6 +137,11 @@ struct PgState {
     int p, m, P, S, max_depth, maxn;
     int grid, n_gwarps;          // CTAs in the sweep grid, global warps (= grid * PG_WARPS)
     int stage_bytes;             // shared-memory staging area per block behind the pass arrays (async-copy ring)
+    // ---- observation sharding: this rank holds n of n_global rows; reductions are exchanged
+    // between the ranks' control blocks through peer mailboxes (pg_serial_fast.cuh, fw_exchange)
+    int rank, world;
+    long long n_global;
+    double* mail[PG_MAX_RANKS];  // mail[r] = rank r's mailbox (peer memory for r != rank)
     int prune;                   // option prune_dead_proposals: do not evaluate proposals whose particle provably gets weight 0
     int prefetch_next;           // pass blocks prefetch the next update's root columns into L2 after a root pass
     int root_quarters;           // P <= 32 persistent kernel: 1 = quarter/group root pass (pg_pass_root_quarters)
@@ -156,6 +167,7 @@ struct PgState {
     // particle slot tables, [2][S][maxn] / [2][S]
     int* pt_split_var; float* pt_thr32; double* pt_split_val; double* pt_leaf_val;
     unsigned int* pt_seg_off; unsigned int* pt_cnt;
+    unsigned int* pt_len;        // rows of the node held by THIS rank (= pt_cnt on one GPU; pt_cnt is the global count)
     double* pt_So; double* pt_Sr; double* pt_g;
     int* pt_queue; int* pt_size; int* pt_qhead; int* pt_qtail; double* pt_G;
     double* w; int* mutated; int* anc; int* slot_job;   // [S]

@@ -120,6 +120,22 @@ int pgbart_get_counters(pgbart_handle h, double* out8);
  * issue -> control block saw completion, and cycles of the longest pass body, all summed over passes. */
 int pgbart_get_profile(pgbart_handle h, double* out69);
 
+/* Observation sharding: the rows of one chain are split across `world` GPUs of one node, one process and
+ * one handle per GPU, each created with its own rows.  Every rank runs the same control code on the same draws; the
+ * reductions (root totals, per-proposal counts and sums, min/max, Bernoulli log-likelihoods) are exchanged inside the
+ * persistent kernel through peer mailboxes over NVLink and combined in rank order, so all ranks take bit-identical
+ * decisions.  Replaces nothing in the reference (it is single-process CPU); north_star asks for it.
+ *   1. pgbart_shard_config: before the first step.  n_global, the mean of all y and the global per-column min / max
+ *      (the reference's root split candidates, splitting.rs:43-49) replace the values create() derived from the local rows.
+ *   2. pgbart_shard_mailbox: 64-byte CUDA IPC handle of this rank's mailbox — exchange the handles between ranks
+ *      (torch.distributed all_gather; bart_rs_b200/sharded.py).
+ *   3. pgbart_shard_connect: handles = world x 64 bytes, in rank order.
+ * pgbart_step* then returns this rank's rows of the predictions.  n_particles <= 32, persistent driver only. */
+int pgbart_shard_config(pgbart_handle h, int rank, int world, uint64_t n_global, double y_mean_global,
+                        const float* col_min_global, const float* col_max_global);
+int pgbart_shard_mailbox(pgbart_handle h, unsigned char* handle64);
+int pgbart_shard_connect(pgbart_handle h, const unsigned char* handles);
+
 /* Diagnostics (-DPG_DIAG builds): out[b*8 + phase] = SM cycles pass block b has spent in pass bodies of that phase;
  * out[G*8 + b*8 + i] = cycles between checkpoints i of the staged root pass (G = pass blocks; cap >= 16 G). */
 int pgbart_debug_block_cycles(pgbart_handle h, double* out, int cap);

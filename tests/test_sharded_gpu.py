@@ -1,0 +1,21 @@
+"""Observation sharding across GPUs: needs at least two GPUs; skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_two_rank_observation_sharding_matches_oracle():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "run_sharded.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=850)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("sharded parity OK") == 4, r.stdout[-3000:]
