@@ -38,12 +38,19 @@ WORKLOADS = {
     "C2": dict(n=100_000, p=20, m=200, P=20, family="gaussian"),
     "C3": dict(n=1_000_000, p=50, m=200, P=20, family="gaussian"),
     "C5": dict(n=1_000_000, p=50, m=200, P=256, family="bernoulli_logit"),
+    # observation-sharded: ONE chain, rows split across the GPUs; strong scaling
+    "C4": dict(n=10_000_000, p=100, m=200, P=20, family="gaussian", sharded=True),
+    "C3s": dict(n=1_000_000, p=50, m=200, P=20, family="gaussian", sharded=True),
 }
 
 
-def make_data(w, seed=0):
+def make_data(w, seed=0, rows=None):
+    """rows = (lo, hi): only this rank's rows of a sharded workload (generated from a per-shard seed; the leaf sd is
+    derived from the local rows, which is the same number to three digits and only needs to agree across ranks)."""
     from tests import datagen
-    X, y = datagen.friedman(w["n"], w["p"], seed=seed, bernoulli=(w["family"] == "bernoulli_logit"))
+    n = w["n"] if rows is None else rows[1] - rows[0]
+    X, y = datagen.friedman(n, w["p"], seed=seed if rows is None else seed + 1000 + rows[0] % 9973,
+                            bernoulli=(w["family"] == "bernoulli_logit"))
     prm = datagen.pgbart_params(y, w["m"], w["p"])
     return X, y, prm
 
@@ -176,12 +183,24 @@ def run_gpu(args):
     from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
 
     w = WORKLOADS[args.workload]
-    X, y, prm = make_data(w)
     from bart_rs_b200.chains import chain_settings, job_throughput
-    st = chain_settings(PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, prm["sigma"], list(prm["split_prior"]),
-                                       ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=0), rank)
+    sharded = bool(w.get("sharded")) and world > 1
     lik = DeviceLikelihood(w["family"], 1.0)
-    smp = PySampler.init(X, y, lik, st, device=local_rank)   # X is float32 C-order: converted to column-major on upload
+    if sharded:
+        # one chain over all rows: rank r generates and keeps rows [lo, hi); sigma must be the same number on every rank
+        from bart_rs_b200.sharded import ShardedSampler, row_range
+        lo, hi = row_range(w["n"], rank, world)
+        X, y, prm = make_data(w, rows=(lo, hi))
+        sig = torch.tensor([prm["sigma"]], dtype=torch.float64, device="cuda")
+        dist.broadcast(sig, 0)
+        st = PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, float(sig.item()), list(prm["split_prior"]),
+                            ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=0)
+        smp = ShardedSampler.init(X, y, lik, st, device=local_rank)
+    else:
+        X, y, prm = make_data(w)
+        st = chain_settings(PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, prm["sigma"], list(prm["split_prior"]),
+                                           ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=0), rank)
+        smp = PySampler.init(X, y, lik, st, device=local_rank)   # X is float32 C-order: converted to column-major on upload
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,6 +226,8 @@ def run_gpu(args):
     clk = clocks.stop() if rank == 0 else None
     c1 = smp.counters()
     value, ms_max = job_throughput(ms, args.steps, world, device="cuda")
+    if sharded:
+        value /= world            # all ranks worked on the SAME sweeps
 
     # ---- end to end: PySampler.step() with host buffers (likelihood parameters H2D, predictions D2H each step)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -220,6 +241,8 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_value, _ = job_throughput(1000.0 * e2e_s, e2e_steps, world, device="cuda")
+    if sharded:
+        e2e_value /= world
     assert np.all(np.isfinite(pred))
 
     # ---- reported beside the headline, never instead of it: the same sweep with option prune_dead_proposals
@@ -262,17 +285,20 @@ def run_gpu(args):
                              "(C++ restatement of the bart-rs CPU path; the Rust crate cannot be built in this image)"}
         line = {
             "metric": "PG sweeps/sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: Friedman n={w['n']} p={w['p']} m={w['m']} P={w['P']} {w['family']}, "
                                    "batch=(1,1) so one step = one sweep",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent chains, one per GPU, no collective",
-                       "l2": "inputs larger than L2 (X 200 MB fp32 + A/y 12 MB vs 126 MB L2); no flush" if w["n"] * w["p"] * 4 > 126e6
+                       "parallelism": "1 GPU" if world == 1 else (f"one chain, rows sharded over {world} GPUs, in-kernel exchange of sufficient "
+                                                                    "statistics over NVLink peer memory" if sharded
+                                                                    else f"{world} independent chains, one per GPU, no collective"),
+                       "l2": f"inputs larger than L2 (X {X.shape[0] * w['p'] * 4 / 1e6:.0f} MB fp32 per GPU vs 126 MB L2); no flush" if X.shape[0] * w["p"] * 4 > 126e6
                              else "working set fits L2 (L2-resident by design of this config)",
                        "storage": "X, y fp32; running sum-of-trees fp64; accumulation fp64"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": "pg_sweep_persistent_direct (one launch = one sweep = m tree updates)",
+                         "kernel": "pg_sweep_persistent_direct (one launch = one sweep = m tree updates)"
+                                   + (f"; rank 0 of {world}: bytes of its own rows, per-GPU figure" if sharded else ""),
                          "algorithmic_bytes_per_launch": contract_per_launch,
                          "fused_bytes_per_launch": bytes_per_launch, "fused_gbs": fused_gbs, "fused_frac": fused_gbs / peak,
                          "note": "achieved = SURVEY.md 8(d) contract bytes (B_tree summed from device counters over the sweep's "
@@ -282,7 +308,7 @@ def run_gpu(args):
                                  "traffic = ncu dram bytes of one launch (A and y stay L2-resident, so it is below both). "
                                  "The launch is bound by latency (control sections and per-pass instruction issue), not by HBM: DESIGN.md section 4-5"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8 * w["n"],
+            "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8 * X.shape[0],
                     "steps": e2e_steps},
             "pruned": pruned,
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
