@@ -22,7 +22,7 @@ EXPORTS = [
     "pgbart_tree_size", "pgbart_get_tree", "pgbart_get_leaf_indices", "pgbart_get_state", "pgbart_set_rng_philox",
     "pgbart_set_rng_tape", "pgbart_trace_enable", "pgbart_trace_read", "pgbart_set_option", "pgbart_get_counters",
     "pgbart_timer_start", "pgbart_timer_stop", "pgbart_get_profile", "pgbart_debug_block_cycles",
-    "pgbart_shard_config", "pgbart_shard_mailbox", "pgbart_shard_connect",
+    "pgbart_shard_config", "pgbart_shard_mailbox", "pgbart_shard_connect", "pgbart_predict", "pgbart_variable_inclusion",
 ]
 
 
@@ -80,5 +80,7 @@ def lib():
     L.pgbart_shard_config.argtypes = [vp, i32, i32, u64, dbl, vp, vp]
     L.pgbart_shard_mailbox.argtypes = [vp, vp]
     L.pgbart_shard_connect.argtypes = [vp, vp]
+    L.pgbart_predict.argtypes = [vp, vp, i32, i32, u64, vp]
+    L.pgbart_variable_inclusion.argtypes = [vp, vp]
     _lib = L
     return L

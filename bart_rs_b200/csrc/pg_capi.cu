@@ -619,6 +619,50 @@ int pgbart_shard_connect(pgbart_handle h, const unsigned char* handles) {
     return 0;
 }
 
+// Out-of-sample prediction (tree.rs:169-192 summed over the forest) and variable inclusion (state.rs:10, declared by
+// the reference and never filled): the "next" rows of SURVEY.md 8(f).
+int pgbart_predict(pgbart_handle h, const void* x, int x_dtype, int x_order, uint64_t n_new, double* out) {
+    Sampler* s = &h->s;
+    const PgState& st = s->st;
+    if (!x || !out) { s->err = "predict: null argument"; return 1; }
+    if (x_dtype != PGBART_X_F32 && x_dtype != PGBART_X_F64) { s->err = "predict: x_dtype must be f32 or f64"; return 1; }
+    if (n_new == 0) return 0;
+    cudaSetDevice(s->device);
+    const uint64_t p = (uint64_t)st.p;
+    std::vector<double> col((size_t)n_new * p);
+    for (uint64_t j = 0; j < p; ++j)
+        for (uint64_t i = 0; i < n_new; ++i) {
+            const size_t src = x_order == PGBART_ORDER_F ? (size_t)j * n_new + i : (size_t)i * p + j;
+            col[(size_t)j * n_new + i] = x_dtype == PGBART_X_F32 ? (double)((const float*)x)[src] : ((const double*)x)[src];
+        }
+    double *dx = nullptr, *dout = nullptr;
+    if (!ck(s, cudaMalloc(&dx, col.size() * 8), "cudaMalloc") || !ck(s, cudaMalloc(&dout, (size_t)n_new * 8), "cudaMalloc")) { if (dx) cudaFree(dx); return 2; }
+    bool ok = ck(s, cudaMemcpyAsync(dx, col.data(), col.size() * 8, cudaMemcpyHostToDevice, s->stream), "upload x")
+           && ck(s, pg_launch_predict(st, dx, (long long)n_new, (long long)n_new, dout, s->stream), "launch predict")
+           && ck(s, cudaMemcpyAsync(out, dout, (size_t)n_new * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions")
+           && ck(s, cudaStreamSynchronize(s->stream), "synchronize");
+    s->launches += 1;
+    cudaFree(dx); cudaFree(dout);
+    return ok ? 0 : 2;
+}
+
+int pgbart_variable_inclusion(pgbart_handle h, uint32_t* out_p) {
+    Sampler* s = &h->s;
+    const PgState& st = s->st;
+    cudaSetDevice(s->device);
+    std::vector<int> sv((size_t)st.m * st.maxn), size((size_t)st.m);
+    if (!ck(s, cudaStreamSynchronize(s->stream), "synchronize") ||
+        !ck(s, cudaMemcpy(sv.data(), st.f_split_var, sv.size() * 4, cudaMemcpyDeviceToHost), "copy forest") ||
+        !ck(s, cudaMemcpy(size.data(), st.f_size, size.size() * 4, cudaMemcpyDeviceToHost), "copy forest")) return 2;
+    for (int j = 0; j < st.p; ++j) out_p[j] = 0u;
+    for (int t = 0; t < st.m; ++t)
+        for (int q = 0; q < size[(size_t)t]; ++q) {
+            const int v = sv[(size_t)t * st.maxn + q];
+            if (v >= 0 && v < st.p) out_p[v] += 1u;
+        }
+    return 0;
+}
+
 int pgbart_timer_start(pgbart_handle h) {
     Sampler* s = &h->s;
     return ck(s, cudaEventRecord(s->tm0, s->stream), "event record") ? 0 : 2;

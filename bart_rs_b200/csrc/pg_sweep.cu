@@ -193,6 +193,23 @@ extern "C" __global__ void pg_leaf_indices_kernel(const PgState st, int t, unsig
     }
 }
 
+// Out-of-sample prediction of the whole forest (tree.rs:169-192 per tree, summed over trees in tree order):
+// x is column-major f64 [p][ldx]; the comparison is the reference's `sample[sv] < split_val` in f64.
+extern "C" __global__ void pg_predict_kernel(const PgState st, const double* x, long long n_new, long long ldx, double* out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_new; i += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int t = 0; t < st.m; ++t) {
+            const size_t fb = (size_t)t * st.maxn;
+            const int size = st.f_size[t];
+            int node = 0, sv;
+            while (node < size && (sv = st.f_split_var[fb + node]) >= 0)
+                node = 2 * node + 1 + (x[(size_t)sv * ldx + i] < st.f_split_val[fb + node] ? 0 : 1);
+            if (node < size) acc += st.f_leaf_val[fb + node];
+        }
+        out[i] = acc;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -273,6 +290,11 @@ cudaError_t pg_launch_fill(double* p, long long n, double v, cudaStream_t s) {
 
 cudaError_t pg_launch_init_forest(const PgState& st, cudaStream_t s) {
     pg_init_forest<<<(st.m + 127) / 128, 128, 0, s>>>(st);
+    return cudaGetLastError();
+}
+
+cudaError_t pg_launch_predict(const PgState& st, const double* x, long long n_new, long long ldx, double* out, cudaStream_t s) {
+    pg_predict_kernel<<<592, 256, 0, s>>>(st, x, n_new, ldx, out);
     return cudaGetLastError();
 }
 

@@ -79,8 +79,14 @@ class PGBART:
         self.pg_bart.set_likelihood(self.likelihood)     # the reference refreshes shared likelihood inputs here (pgbart.py:190)
         sum_trees = self.pg_bart.step(self.tune)
         t1 = perf_counter()
-        stats = {"variable_inclusion": np.array([0.0]), "tune": self.tune, "time": t1 - t0}   # pgbart.py:195-199
+        # pgbart.py:195-199 reports the placeholder np.array([0.0]) for variable_inclusion (the Rust side never fills
+        # state.rs:10); here it is the real per-variable split count of the current forest
+        stats = {"variable_inclusion": self.pg_bart.variable_inclusion().astype(np.float64), "tune": self.tune, "time": t1 - t0}
         return sum_trees, [stats]
+
+    def predict(self, X_new):
+        """Sum of trees of the current forest at new rows (reference TreeArrays::predict_batch_test, src/tree.rs:169-192)."""
+        return self.pg_bart.predict(np.asarray(X_new))
 
     def stop_tuning(self):
         self.tune = False

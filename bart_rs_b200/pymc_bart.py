@@ -241,6 +241,32 @@ class PySampler:
                 "speculative_root_passes": float(out[48]), "serial_sub_cycles": dict(zip(sub, out[32:40].tolist())), "serial_sub_calls": dict(zip(sub, out[40:48].tolist())),"pass_cycles": dict(zip(names, out[0:8].tolist())), "wait_serial_cycles": dict(zip(names, out[8:16].tolist())),
                 "serial_cycles": dict(zip(names, out[16:24].tolist())), "passes": dict(zip(names, out[24:32].tolist()))}
 
+    def predict(self, x) -> np.ndarray:
+        """Sum of trees at new rows (reference TreeArrays::predict_batch_test, src/tree.rs:169-192, over the forest)."""
+        x = np.asarray(x)
+        if x.ndim != 2:
+            raise TypeError("x must be a 2-D array")
+        if x.dtype == np.float32:
+            dtype = _capi.X_F32
+        else:
+            x = x.astype(np.float64, copy=False)
+            dtype = _capi.X_F64
+        if x.flags.f_contiguous:
+            order = _capi.ORDER_F
+        else:
+            x = np.ascontiguousarray(x)
+            order = _capi.ORDER_C
+        out = np.empty(x.shape[0], dtype=np.float64)
+        self._check(self._L.pgbart_predict(self._h, x.ctypes.data_as(C.c_void_p), dtype, order, x.shape[0], out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def variable_inclusion(self) -> np.ndarray:
+        """Splits per variable in the current forest (reference BartState.variable_inclusion, src/state.rs:10)."""
+        p = int(self.p)
+        out = np.zeros(p, dtype=np.uint32)
+        self._check(self._L.pgbart_variable_inclusion(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def block_cycles(self) -> np.ndarray:
         """[pass block][phase] cycles spent in pass bodies (only filled by -DPG_DIAG builds)."""
         g = int(self.counters()["grid_blocks"])

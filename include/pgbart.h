@@ -120,6 +120,15 @@ int pgbart_get_counters(pgbart_handle h, double* out8);
  * issue -> control block saw completion, and cycles of the longest pass body, all summed over passes. */
 int pgbart_get_profile(pgbart_handle h, double* out69);
 
+/* Out-of-sample prediction: out[i] = sum over the forest's trees, in tree order, of the leaf value row i of x reaches
+ * (reference TreeArrays::predict_batch_test, src/tree.rs:169-192, applied to every tree; comparison `x < split_val` in
+ * f64).  x: n_new x p, dtype / order as in pgbart_create.  Under observation sharding every rank holds the whole forest. */
+int pgbart_predict(pgbart_handle h, const void* x, int x_dtype, int x_order, uint64_t n_new, double* out);
+
+/* Split counts per variable over the current forest (reference BartState.variable_inclusion, src/state.rs:10 — declared
+ * and zero-initialised at src/kernel.rs:49, never updated; python/pymc_bart/pgbart.py:56,196 reports a placeholder). */
+int pgbart_variable_inclusion(pgbart_handle h, uint32_t* out_p);
+
 /* Observation sharding: the rows of one chain are split across `world` GPUs of one node, one process and
  * one handle per GPU, each created with its own rows.  Every rank runs the same control code on the same draws; the
  * reductions (root totals, per-proposal counts and sums, min/max, Bernoulli log-likelihoods) are exchanged inside the

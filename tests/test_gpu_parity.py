@@ -181,3 +181,46 @@ def test_gpu_pruned_dead_proposals_same_forest():
     for a, b in zip(outs["0"][0], outs["1"][0]):
         np.testing.assert_array_equal(a, b)
     assert outs["1"][1] < 0.8 * outs["0"][1]
+
+
+def _numpy_forest_predict(dev, m, Xnew):
+    """tree.rs:169-192 per tree, summed in tree order (restated with numpy on the exported forest)."""
+    out = np.zeros(Xnew.shape[0])
+    for t in range(m):
+        sv, sp, lv = dev.tree(t)
+        for i in range(Xnew.shape[0]):
+            node = 0
+            while node < len(sv) and sv[node] >= 0:
+                node = 2 * node + 1 if Xnew[i, sv[node]] < sp[node] else 2 * node + 2
+            if node < len(sv):
+                out[i] += lv[node]
+    return out
+
+
+@pytest.mark.gpu
+def test_gpu_out_of_sample_predict_and_variable_inclusion():
+    """forest prediction at new rows (tree.rs:169-192) and split counts per variable (state.rs:10)."""
+    n, p, m, P = 800, 4, 8, 3
+    X, y = datagen.small(n, p, seed=2)
+    cfg = cfg_for(y, m, P, p, seed=9, beta=0.7, max_depth=10)
+    dev = make_gpu()(X, y, cfg)
+    dev.set_rng_philox(9)
+    for t in (True, True, True):
+        pred = dev.step(t)
+    # on the training rows the traversal must reproduce the running sum of trees (fp32 X widened: same comparisons)
+    np.testing.assert_allclose(dev.predict(X), pred, rtol=1e-12, atol=1e-12)
+    rng = np.random.default_rng(4)
+    Xnew = rng.random((257, p))                       # float64, C order
+    ref = _numpy_forest_predict(dev, m, Xnew)
+    np.testing.assert_array_equal(dev.predict(Xnew), ref)
+    np.testing.assert_array_equal(dev.predict(np.asfortranarray(Xnew)), ref)
+    np.testing.assert_array_equal(dev.predict(Xnew.astype(np.float32)), _numpy_forest_predict(dev, m, Xnew.astype(np.float32).astype(np.float64)))
+    vi = dev.variable_inclusion()
+    cnt = np.zeros(p, dtype=np.uint32)
+    for t in range(m):
+        sv, _, _ = dev.tree(t)
+        for v in sv:
+            if v >= 0:
+                cnt[v] += 1
+    np.testing.assert_array_equal(vi, cnt)
+    assert vi.sum() > 0
