@@ -1,6 +1,9 @@
-"""Phase breakdown of the persistent kernel (in-kernel cycle counters): python tools_profile_phases.py [workload] [steps]"""
+"""Phase breakdown of the persistent kernel (in-kernel cycle counters): python tools/profile_phases.py [workload] [steps]"""
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
