@@ -508,6 +508,36 @@ __device__ __forceinline__ bool fw_round0_all_dead(const PgState& st, const FwCx
     return !__any_sync(PG_FULL, act && anc_live);
 }
 
+// The same argument in rounds >= 1 (option prune_dead_proposals): a slot that does not grow keeps its previous NORMALISED
+// weight (in [0, 1]) as log-weight, so the maximum is >= 0 and every growing particle (log-likelihood <= Cconst < -800)
+// gets exp(w - max) = 0.0 exactly.  True when, with those exact zeros, no growing slot is anybody's ancestor.
+__device__ __forceinline__ bool fw_round_all_dead(const PgState& st, const FwCx& x, int lane, bool live) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const int S = st.S;
+    if (!st.prune || st.family != PG_GAUSSIAN || !(c->Cconst < -800.0) || st.tr_slot || st.tr_round || st.tr_upd) return false;
+    if (!(0.5 * c->T_rr * c->inv_s2 < 1.0e13)) return false;
+    const unsigned lm = __ballot_sync(PG_FULL, live);
+    if (lm == 0u || __popc(lm) >= S) return false;
+    const bool act = lane < S;
+    const double w = act ? (live ? -INFINITY : f->hw[lane]) : -INFINITY;
+    const double mx = fw_max(w);
+    const double e = act ? exp(w - mx) : 0.0;
+    const double sum = fw_sum_seq(e, S);
+    const double wn = e / sum;
+    const double u6 = fw_u6(st, x, c->upd, c->round);
+    const double target = ((double)lane + u6) / (double)S;
+    int cidx = 0;
+    double cum = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < S; ++k) {
+        if (cum < target) cidx = k + 1;
+        cum += __shfl_sync(PG_FULL, wn, k);
+    }
+    const int anc = act ? (cidx == 0 ? 0 : cidx - 1) : 0;
+    return !__any_sync(PG_FULL, act && ((lm >> anc) & 1u));
+}
+
 // smc.rs:42-53 + round 0 of smc.rs:61-86: fresh particles of the update that becomes current.  The precomputed
 // root proposals become the job list: written to the global job arrays unless a speculative root pass already did.
 __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x, int lane, bool jobs_published) {
@@ -640,6 +670,13 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
     if (lane == 0) { unsigned long long bc = 0; (void)bc; }
     if (!__any_sync(PG_FULL, jb.live)) {
         (void)fw_write_jobs(st, x, jb, lane, true, pb, false, true, &G);
+        return SN_FINISH_ROUND;
+    }
+    if (fw_round_all_dead(st, x, lane, jb.live)) {
+        // pruned: the proposals are accepted grows (they count) of particles that cannot be resampled; their statistics,
+        // leaf values and weights are never looked at (the same normalisation runs below with exact zeros)
+        if (jb.live) { f->hw[lane] = -INFINITY; f->hmut[lane] = 1; }
+        __syncwarp();
         return SN_FINISH_ROUND;
     }
     const bool sc_hit = !jb.live || (f->sc_valid[lane] && f->sc_seg[lane] == jb.seg_off && f->sc_var[lane] == jb.var && f->sc_thr[lane] == jb.thr);
