@@ -574,9 +574,9 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     }
     const int J0 = __popc(__ballot_sync(PG_FULL, passed));
     int G;
-    const int J = fw_write_jobs(st, x, jb, lane, true, (int)(upd & 1ull), !jobs_published, true, &G);
-    const int uniq = fw_unique(jb.var, jb.live, lane);
     const bool lazy = fw_round0_all_dead(st, x, upd, lane, jb.live);   // same decision the speculative issue took (fw_prestage)
+    const int J = fw_write_jobs(st, x, jb, lane, true, (int)(upd & 1ull), !jobs_published && !lazy, true, &G);
+    const int uniq = fw_unique(jb.var, jb.live, lane);
     if (lane == 0) {
         const unsigned long long n = (unsigned long long)st.n;
         const int cols = (lazy ? 0 : uniq) + c->t_add_internal + st.f_internal[c->t_sub];
@@ -1304,14 +1304,15 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         }
     }
     __syncwarp();
-    int n_mut, mut;
-    const int anc = fw_normalize_resample(st, x, lane, &n_mut, &mut);
+    int n_mut = 0, mut = 0, anc = lane;
+    const bool lazy = f->lazy_J > 0;                         // pruned round 0: fw_round0_all_dead already ran the resampling
+    if (!lazy) anc = fw_normalize_resample(st, x, lane, &n_mut, &mut);
     const int mut_a = __shfl_sync(PG_FULL, mut, anc);
     const bool need = act && mut_a != 0;
     if (lane == 0) {
         c->acc_update += n_mut + f->lazy_J;                  // pruned proposals were accepted grows all the same (smc.rs:79-81)
         // the bound w <= Cconst holds up to the rounding of terms of size T_rr / (2 sigma^2): keep 50 units of margin honest
-        if (f->lazy_J > 0 && !(0.5 * c->T_rr * c->inv_s2 < 1.0e13)) c->error = PG_ERR_PRUNE;
+        if (lazy && !(0.5 * c->T_rr * c->inv_s2 < 1.0e13)) c->error = PG_ERR_PRUNE;
     }
     __syncwarp();
     if (!__any_sync(PG_FULL, need)) {
@@ -1469,8 +1470,9 @@ __device__ __forceinline__ bool fw_try_speculate(const PgState& st, const FwCx& 
     if (__any_sync(PG_FULL, status == 6 || status == 7)) return false;   // let the regular path raise the error
     int G;
     const int pb1 = (int)(U1 & 1ull);
-    int J1 = fw_write_jobs(st, x, jb, lane, true, pb1, true, false, &G);
-    if (fw_round0_all_dead(st, x, U1, lane, jb.live)) J1 = 0;
+    int J1 = 0;
+    G = 0;
+    if (!fw_round0_all_dead(st, x, U1, lane, jb.live)) J1 = fw_write_jobs(st, x, jb, lane, true, pb1, true, false, &G);
     const int t_sub1 = (c->next_tree_idx + c->k + 1) % st.m;
     const int src = c->a_cur, dst = 1 - c->a_cur;
     fw_issue(st, x, lane, PH_ROOT, -2 /* a stump */, t_sub1, J1, G, 0, src | (dst << 1) | (pb1 << 2));
@@ -1496,8 +1498,9 @@ __device__ __forceinline__ void fw_prestage(const PgState& st, const FwCx& x, in
     const FwJob jb = fw_root_job(st, x, U1, lane, &passed, &status);
     if (__any_sync(PG_FULL, status == 6 || status == 7)) return;
     int G;
-    int J1 = fw_write_jobs(st, x, jb, lane, true, (int)(U1 & 1ull), true, false, &G);
-    if (fw_round0_all_dead(st, x, U1, lane, jb.live)) J1 = 0;
+    int J1 = 0;
+    G = 0;
+    if (!fw_round0_all_dead(st, x, U1, lane, jb.live)) J1 = fw_write_jobs(st, x, jb, lane, true, (int)(U1 & 1ull), true, false, &G);
     if (lane == 0) { f->pre_upd = U1; f->pre_J = J1; f->pre_G = G; st.ctrl->pre_J[(int)(U1 & 1ull)] = J1; }
     __syncwarp();
 }
