@@ -1357,6 +1357,11 @@ __device__ __forceinline__ unsigned pg_ld_relaxed(const unsigned* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// arrival: add with release semantics at gpu scope (the block's results, ordered before by __syncthreads, become visible
+// to whoever acquires the counter) — one instruction instead of a full fence followed by a relaxed atomic
+__device__ __forceinline__ void pg_red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void pg_st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

@@ -1415,8 +1415,7 @@ __device__ __forceinline__ void fw_issue(const PgState& st, const FwCx& x, int l
 #ifdef PG_DIAG
     if (lane == 0) { st.ctrl->dbg[1] = 0ull; st.ctrl->dbg[2] = 0ull; st.ctrl->dbg[3] = 0ull; st.ctrl->dbg[0] = pg_globaltimer(); }
 #endif
-    __threadfence();
-    __syncwarp();
+    __syncwarp();                                            // the lanes' stores are ordered before lane 0's release store
     if (lane == 0) {
         f->issued += 1u;
         f->out_phase = phase; f->out_J = n_jobs; f->out_pb = (flags >> 2) & 1;

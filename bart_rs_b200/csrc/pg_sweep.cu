@@ -100,7 +100,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
                 st.diag_blocks[(size_t)(blockIdx.x - 1) * 8 + (phase & 7)] += (unsigned long long)(t1 - t0);
                 atomicMax(&c->dbg[2], pg_globaltimer());
 #endif
-                __threadfence(); atomicAdd(&c->bar_count, 1u);
+                pg_red_release_add(&c->bar_count, 1u);
             }
             if (phase == PH_ROOT && st.prefetch_next) pg_prefetch_next_root(st, flags);
             if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // stopwatch kept by the last pass block
