@@ -214,8 +214,7 @@ __device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, in
 #pragma unroll
         for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n_val) dst[i] = mine[q]; }
     }
-    __threadfence_system();
-    __syncwarp();
+    __syncwarp();                                            // every lane's payload stores are ordered before the release stores below
     unsigned long long* my_flags = reinterpret_cast<unsigned long long*>(st.mail[me] + (size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES);
     if (lane < W && lane != me) {
         unsigned long long* peer_flags = reinterpret_cast<unsigned long long*>(st.mail[lane] + (size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES);
@@ -228,8 +227,7 @@ __device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, in
             if (clock64() - t0 > 40000000000ll) { f->lc.error = PG_ERR_WATCHDOG; break; }   // a lost peer becomes an error
         }
     }
-    __syncwarp();
-    __threadfence_system();
+    __syncwarp();                                            // the acquiring lanes' loads are ordered before every lane's reads below
     const double* box = st.mail[me] + (size_t)par * PG_MAX_RANKS * PG_MAIL_DOUBLES;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
