@@ -261,6 +261,64 @@ __device__ __forceinline__ int fw_feature_from_probs(const PgState& st, const do
     return p - 1;
 }
 
+// ---- cold draws -----------------------------------------------------------------------------------------
+// Warp 0 normally finds its draws precomputed by the helper warps; the generator itself (ten Philox rounds, log / cos
+// for the normals, the tape bounds checks) is needed only for rounds beyond FW_DR.  Inlined at every call site it
+// would sit in the middle of the control block's hot code, which is instruction-fetch bound — so the fallback lives in
+// one out-of-line function that takes the generator's few fields by value (taking the address of the kernel parameter
+// `st` would force the whole struct into local memory).
+struct FwRngView {
+    int rng_mode, S, tape_r_cap;
+    unsigned k0, k1;
+    const double *tape_slot, *tape_round, *tape_upd;
+    long long tape_n_upd;
+    unsigned long long tape_base_upd;
+};
+__device__ __forceinline__ FwRngView fw_rng_view(const PgState& st) {
+    FwRngView v;
+    v.rng_mode = st.rng_mode; v.S = st.S; v.tape_r_cap = st.tape_r_cap; v.k0 = st.philox_key0; v.k1 = st.philox_key1;
+    v.tape_slot = st.tape_slot; v.tape_round = st.tape_round; v.tape_upd = st.tape_upd;
+    v.tape_n_upd = st.tape_n_upd; v.tape_base_upd = st.tape_base_upd;
+    return v;
+}
+// what = 0 uniform, 1 normal, 2 split value in [lo, hi) (pg_rng.h: pg_uniform / pg_normal / pg_split_draw)
+__device__ __noinline__ double fw_cold_draw(FwRngView v, PgCtrl* c, int what, int kind, unsigned long long upd, int round, int slot,
+                                            double lo, double hi) {
+    if (v.rng_mode == PG_RNG_TAPE) {
+        const double* p = nullptr;
+        if (upd >= v.tape_base_upd) {
+            const unsigned long long u = upd - v.tape_base_upd;
+            if ((long long)u < v.tape_n_upd && round < v.tape_r_cap) {
+                if (kind <= PG_D_ZRIGHT)
+                    p = v.tape_slot + (((u * (unsigned long long)v.tape_r_cap + (unsigned long long)round) * (unsigned long long)v.S
+                                        + (unsigned long long)slot) * 5ull + (unsigned long long)kind);
+                else if (kind == PG_D_RESAMPLE) p = v.tape_round + (u * (unsigned long long)v.tape_r_cap + (unsigned long long)round);
+                else p = v.tape_upd + u;
+            }
+        }
+        if (!p) { c->error = PG_ERR_TAPE; return 0.0; }
+        const double u = *p;
+        if (what != 2) return u;
+        const double r = __dadd_rn(__dmul_rn(u, hi - lo), lo);
+        if (!(r < hi)) c->error = PG_ERR_TAPE;
+        return r;
+    }
+    uint32_t o[4];
+    if (what != 2) {
+        pg_philox4x32_10((uint32_t)upd, (uint32_t)(upd >> 32), (uint32_t)round, ((uint32_t)slot << 16) | ((uint32_t)kind << 8), v.k0, v.k1, o);
+        const double ua = pg_bits53(o[0], o[1]);
+        if (what == 0) return ua;
+        return sqrt(-2.0 * log(1.0 - ua)) * cos(6.283185307179586476925286766559 * pg_bits53(o[2], o[3]));
+    }
+    for (int attempt = 0; attempt < 64; ++attempt) {
+        pg_philox4x32_10((uint32_t)upd, (uint32_t)(upd >> 32), (uint32_t)round,
+                         ((uint32_t)slot << 16) | ((uint32_t)PG_D_SPLIT << 8) | (uint32_t)(attempt & 0xff), v.k0, v.k1, o);
+        const double r = __dadd_rn(__dmul_rn(pg_bits53(o[0], o[1]), hi - lo), lo);
+        if (r < hi) return r;
+    }
+    return lo;
+}
+
 // ---- helper warps: draws of one tree update (data-independent) --------------------------------------
 __device__ __forceinline__ bool fw_tape_ok(const PgState& st, unsigned long long upd, int round) {
     if (st.rng_mode != PG_RNG_TAPE) return true;
@@ -339,12 +397,12 @@ __device__ __forceinline__ void fw_wait_draws(PgFastSm* f, unsigned long long up
 __device__ __forceinline__ double fw_u6(const PgState& st, const FwCx& x, unsigned long long upd, int r) {
     const int buf = (int)(upd % 3ull);
     if (r < FW_DR && x.f->d_ok[buf][r]) return x.f->d_u6[buf][r];
-    return pg_uniform(st, x.c, PG_D_RESAMPLE, upd, r, 0);
+    return fw_cold_draw(fw_rng_view(st), x.c, 0, PG_D_RESAMPLE, upd, r, 0, 0.0, 0.0);
 }
 __device__ __forceinline__ double fw_u7(const PgState& st, const FwCx& x, unsigned long long upd) {
     const int buf = (int)(upd % 3ull);
     if (x.f->d_ok[buf][FW_DR]) return x.f->d_u7[buf];
-    return pg_uniform(st, x.c, PG_D_SELECT, upd, 0, 0);
+    return fw_cold_draw(fw_rng_view(st), x.c, 0, PG_D_SELECT, upd, 0, 0, 0.0, 0.0);
 }
 
 // ---- per-lane job view ------------------------------------------------------------------------
@@ -430,7 +488,7 @@ __device__ __forceinline__ void fw_decide(const PgState& st, const FwCx& x, FwJo
         const double v = __dadd_rn(__dmul_rn(x.f->d_u3[buf][r][jb.slot], hi - lo), lo);
         if (v < hi) { jb.split = v; done = true; }
     }
-    if (!done) jb.split = pg_split_draw(st, c, c->upd, r, jb.slot, (double)jb.lo, (double)jb.hi);
+    if (!done) jb.split = fw_cold_draw(fw_rng_view(st), c, 2, PG_D_SPLIT, c->upd, r, jb.slot, (double)jb.lo, (double)jb.hi);
     jb.thr = pg_thr32(jb.split);
     if (tr) tr[3] = jb.split;
 }
@@ -614,7 +672,7 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
             const int node = st.pt_queue[pg_tix(st, cur, s, qh)];
             f->hqh[ss] = qh + 1;
             if (tr) { tr[0] = 1; tr[1] = (double)node; tr[2] = -1; }
-            const double u1 = pre ? f->d_u1[buf][r][s] : pg_uniform(st, c, PG_D_GROW, upd, r, s);
+            const double u1 = pre ? f->d_u1[buf][r][s] : fw_cold_draw(fw_rng_view(st), c, 0, PG_D_GROW, upd, r, s, 0.0, 0.0);
             if (!(x.thr[pg_depth_of(node)] > u1)) {
                 const size_t iN = pg_tix(st, cur, s, node);
                 const unsigned cnt = st.pt_cnt[iN];
@@ -623,7 +681,7 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
                     int var;
                     if (pre) var = f->d_var[buf][r][s];
                     else {
-                        const double u2 = pg_uniform(st, c, PG_D_VAR, upd, r, s);
+                        const double u2 = fw_cold_draw(fw_rng_view(st), c, 0, PG_D_VAR, upd, r, s, 0.0, 0.0);
                         if (x.prior) var = fw_feature_from_probs(st, x.prior, u2);
                         else { var = (int)(u2 * (double)st.p); if (var > st.p - 1) var = st.p - 1; }
                     }
@@ -839,8 +897,8 @@ __device__ __forceinline__ FwVals fw_values(const PgState& st, const FwCx& x, in
     v.cL = f->rCnt[j]; v.cR = nc - v.cL;
     v.SoL = f->rSo[j]; v.SoR = nSo - v.SoL;
     v.SrL = f->rSr[j]; v.SrR = nSr - v.SrL;
-    const double zL = pre ? f->d_zL[buf][r][s] : pg_normal(st, c, PG_D_ZLEFT, c->upd, r, s);   // drawn for both children, left first
-    const double zR = pre ? f->d_zR[buf][r][s] : pg_normal(st, c, PG_D_ZRIGHT, c->upd, r, s);
+    const double zL = pre ? f->d_zL[buf][r][s] : fw_cold_draw(fw_rng_view(st), c, 1, PG_D_ZLEFT, c->upd, r, s, 0.0, 0.0);   // drawn for both children, left first
+    const double zR = pre ? f->d_zR[buf][r][s] : fw_cold_draw(fw_rng_view(st), c, 1, PG_D_ZRIGHT, c->upd, r, s, 0.0, 0.0);
     v.vL = v.cL == 0u ? zL * st.leaf_sigma : pg_mul_add(zL, st.leaf_sigma, v.SoL / ((double)v.cL * st.m_f));   // cL*m is exact
     v.vR = v.cR == 0u ? zR * st.leaf_sigma : pg_mul_add(zR, st.leaf_sigma, v.SoR / ((double)v.cR * st.m_f));
     v.gL = pg_gauss_g(v.vL, v.SrL, v.cL, c->inv_s2);
