@@ -29,7 +29,6 @@ struct Sampler {
     std::string err;
     bool dead = false;
     bool stepwise = false;
-    bool stepwise_fast = false;   // stepwise driver, but with the latency-organised serial section (P <= 32)
     size_t smem = 0;
     double launches = 0;
     bool timing_pending = false;
@@ -494,9 +493,8 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
     Sampler* s = &h->s;
     if (!key || !value) { s->err = "null option"; return 1; }
     if (std::strcmp(key, "driver") == 0) {
-        if (std::strcmp(value, "persistent") == 0) { s->stepwise = false; s->stepwise_fast = false; return 0; }
-        if (std::strcmp(value, "stepwise") == 0) { s->stepwise = true; s->stepwise_fast = false; return 0; }
-        if (std::strcmp(value, "stepwise_fast") == 0) { s->stepwise = true; s->stepwise_fast = true; return 0; }
+        if (std::strcmp(value, "persistent") == 0) { s->stepwise = false; return 0; }
+        if (std::strcmp(value, "stepwise") == 0 || std::strcmp(value, "stepwise_fast") == 0) { s->stepwise = true; return 0; }
         s->err = "driver must be 'persistent' or 'stepwise'";
         return 1;
     }

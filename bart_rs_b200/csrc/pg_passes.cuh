@@ -74,8 +74,6 @@ struct PgTreeSm {
 };
 
 #define FW_DR 4            // SMC rounds whose data-independent draws are precomputed per tree update
-#define FW_GW (PG_WARPS - FW_DR - 1)          // warps of the control group: warp 0 + warps FW_DR+2 .. PG_WARPS-1
-#define FW_GT (FW_GW * 32)                   // threads of the control group (named barrier 1)
 
 struct PgFastSm {          // state of the latency-organised serial section (pg_serial_fast.cuh), P <= 32.
     // Lives in block 0's shared memory for the whole kernel: loaded at launch, stored at exit.
@@ -121,8 +119,6 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     unsigned long long pre_upd;                  // update whose root jobs are already staged in the global job arrays
     int pre_J, pre_G, spec_now;
     int lazy_J;                                  // pruned round 0: accepted root proposals that were not evaluated (they count as grows)
-    volatile unsigned long long want_base, want_top;   // draw helpers: updates [want_base, want_top] are wanted
-    volatile int helpers_quit;
     double stump_total, stump_cum[32];           // final selection when every particle is a stump: sequential sums of 1/P
     unsigned scan[PG_THREADS + 1];
 };
@@ -144,6 +140,7 @@ struct PgSmem {
     double r_acc[4][32][2];                // [row quarter][job]: sum A, sum y-A over LEFT rows
     unsigned r_cnt[4][32];
     unsigned p_scan[2][PG_WARPS];          // block-unit identity partition: warp totals of a chunk, double-buffered
+    int p_rq_idx[64], p_rq_side[64], p_rq_var[64], p_nreq;   // look-ahead requests of the partition job in progress
     // followed by dynamic arrays, see pg_smem_* accessors
 };
 
@@ -1185,39 +1182,76 @@ __device__ void pg_part_ident(const PgState& st, const PgBuf& bf, const PgSmemVi
     // the root pass counted the same predicate over the same rows
     const int j = __ldcg(&st.pj_job[k]);
     if (tid == 0 && (left_run - left0) != __ldcg(&bf.part_ccnt[(size_t)PG_BID * st.S + j])) c->error = PG_ERR_INTERNAL;
-    // look-ahead: splitting.rs:43-49 for the proposals expected on the two children
-    for (int q = 0; q < Q; ++q) {
-        if (__ldcg(&st.mq_pj[q]) != k) continue;
-        const bool want_left = __ldcg(&st.mq_side[q]) == 0;
-        const float* col2 = st.X + (size_t)__ldcg(&st.mq_var[q]) * ld;
-        float mn = INFINITY, mx = -INFINITY;
-        bool any = false;
+    // look-ahead: splitting.rs:43-49 for the proposals expected on the two children.  The requests of this job are staged
+    // in shared memory once, then taken three at a time with four chunks in flight each (16 independent float4 loads per
+    // thread), so the pass pays a memory round trip per group of requests instead of several per request.
+    int* rq_idx = sm.base->p_rq_idx; int* rq_side = sm.base->p_rq_side; int* rq_var = sm.base->p_rq_var;
+    __syncthreads();
+    if (warp == 0) {
+        int nreq = 0;
+        for (int q0 = 0; q0 < Q; q0 += 32) {
+            const int q = q0 + lane;
+            const bool mine = q < Q && __ldcg(&st.mq_pj[q]) == k;
+            const unsigned m = __ballot_sync(PG_FULL, mine);
+            if (mine) {
+                const int pos = nreq + __popc(m & ((1u << lane) - 1u));
+                rq_idx[pos] = q; rq_side[pos] = __ldcg(&st.mq_side[q]); rq_var[pos] = __ldcg(&st.mq_var[q]);
+            }
+            nreq += __popc(m);
+        }
+        if (lane == 0) sm.base->p_nreq = nreq;
+    }
+    __syncthreads();
+    const int nreq = sm.base->p_nreq;
+#pragma unroll 1
+    for (int g0 = 0; g0 < nreq; g0 += 3) {
+        const float* c2[3];
+        bool wl[3];
+        float mn[3], mx[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int gi = min(g0 + u, nreq - 1);            // a short last group repeats its last request (result discarded)
+            c2[u] = st.X + (size_t)rq_var[gi] * ld;
+            wl[u] = rq_side[gi] == 0;
+            mn[u] = INFINITY; mx[u] = -INFINITY;
+        }
 #pragma unroll 1
         for (long long cb = B0; cb < B1; cb += 4 * PGP_CH) {
-            float4 xv[4], zv[4];
+            float4 xv[4], zv[3][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const long long row = cb + (long long)u * PGP_CH + tid * 4;
                 const bool in = row < B1;
                 xv[u] = in ? __ldg(reinterpret_cast<const float4*>(col + row)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                zv[u] = in ? __ldg(reinterpret_cast<const float4*>(col2 + row)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int w = 0; w < 3; ++w) zv[w][u] = in ? __ldg(reinterpret_cast<const float4*>(c2[w] + row)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const long long row = cb + (long long)u * PGP_CH + tid * 4;
+                const int nv = row < B1 ? (int)min(4ll, n - row) : 0;
                 const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-                const float zs[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const bool ok = row + e < n && row < B1 && ((xs[e] < thr) == want_left);
-                    if (ok) { mn = fminf(mn, zs[e]); mx = fmaxf(mx, zs[e]); any = true; }
+                    const bool valid = e < nv, left = xs[e] < thr;
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) {
+                        const float z = e == 0 ? zv[w][u].x : e == 1 ? zv[w][u].y : e == 2 ? zv[w][u].z : zv[w][u].w;
+                        if (valid && left == wl[w]) { mn[w] = fminf(mn[w], z); mx[w] = fmaxf(mx[w], z); }
+                    }
                 }
             }
         }
-        unsigned kmn = any ? pg_f2key(mn) : 0xFFFFFFFFu, kmx = any ? pg_f2key(mx) : 0u;
-        kmn = __reduce_min_sync(PG_FULL, kmn);
-        kmx = __reduce_max_sync(PG_FULL, kmx);
-        if (lane == 0) { atomicMin(&sm.mmin[q], kmn); atomicMax(&sm.mmax[q], kmx); }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            if (g0 + u < nreq) {                             // block-uniform
+                // an untouched (+inf, -inf) pair maps to the identity keys of min / max
+                unsigned kmn = mn[u] <= mx[u] ? pg_f2key(mn[u]) : 0xFFFFFFFFu, kmx = mn[u] <= mx[u] ? pg_f2key(mx[u]) : 0u;
+                kmn = __reduce_min_sync(PG_FULL, kmn);
+                kmx = __reduce_max_sync(PG_FULL, kmx);
+                if (lane == 0) { atomicMin(&sm.mmin[rq_idx[g0 + u]], kmn); atomicMax(&sm.mmax[rq_idx[g0 + u]], kmx); }
+            }
+        }
     }
     __syncthreads();      // scanw is reused by the next job
 }

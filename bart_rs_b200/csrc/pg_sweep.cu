@@ -1,12 +1,13 @@
 // pg_sweep.cu — kernels of the PGBART sweep for sm_100a and their launchers.
 //
-//   pg_sweep_persistent  one cooperative launch per PySampler.step(): all tree updates of the
-//                        step's batch (kernel.rs:81-115) run inside it.  Grid passes alternate
-//                        with a serial section executed by the last block to reach the grid
-//                        barrier (pg_serial.h); no host round trip inside a step.
-//   pg_phase_kernel /    the same passes / serial section as separate launches with a host
-//   pg_serial_kernel     read-back between them ("stepwise" driver: slow, used to cross-check
-//                        the persistent kernel and under compute-sanitizer).
+//   pg_sweep_persistent*  one launch per PySampler.step(): all tree updates of the step's batch (kernel.rs:81-115)
+//                         run inside it, no host round trip.  P <= 32: block 0 is the control block
+//                         (pg_serial_fast.cuh) and issues commands that the other 147 blocks execute as grid passes
+//                         (pg_passes.cuh); one kernel per pass variant (PGV_*).  P > 32 (_generic): every block runs
+//                         the passes and block 0 runs the team-based serial section of pg_serial.h between them.
+//   pg_phase_kernel /     the same passes / serial section as separate launches with a host read-back between them
+//   pg_serial_kernel      ("stepwise" driver: slow, used to cross-check the persistent kernels).
+//   pg_predict_kernel     out-of-sample forest prediction (tree.rs:169-192).
 #include <cooperative_groups.h>
 #include <cstdio>
 #include "pg_passes.cuh"
