@@ -114,6 +114,7 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     // look-ahead caches of the update in progress (rounds 1 and 2), indexed [round-1][slot]
     int mm_valid[2][32]; unsigned mm_seg[2][32]; int mm_var[2][32]; float mm_lo[2][32], mm_hi[2][32];
     int sc_valid[32]; unsigned sc_seg[32]; int sc_var[32]; float sc_thr[32]; unsigned sc_cnt[32], sc_cntL[32]; double sc_So[32], sc_Sr[32];
+    int sc_job[32], from_cache;                  // job index the prefetched statistics had in their pass (its per-block counts live there)
     int rq_r[64], rq_s[64]; unsigned rq_seg[64];  // request -> (round, slot, child segment)
     int n_mq, pf_n, pf_slot[32];
     unsigned long long pre_upd;                  // update whose root jobs are already staged in the global job arrays
@@ -1115,6 +1116,91 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
 // =============================================================================
 // PH_PART — stable partition of a segment by x[var] < split into the pool
 // =============================================================================
+// =============================================================================
+// PH_STATS, block-unit variant (P <= 32 persistent kernels, Gaussian families)
+// =============================================================================
+// Same sums as pg_pass_seg<0>, but a block takes its contiguous entries of the segment (pg_seg_block_range) 8 per
+// thread at once: 8 index loads in flight, then the gathers of A, y and up to four jobs' columns for all 8 entries
+// together — three memory round trips per 4096 entries instead of three per 128 per warp.  Emits per-block results.
+__device__ void pg_pass_seg_block(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+    PgCtrl* c = st.ctrl;
+    const int J = __ldcg(&c->n_jobs), G = __ldcg(&c->n_groups);
+    const int S = st.S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pg_stage_jobs(st, bf, sm, J, G, false);
+    pg_zero_acc(sm, S);
+    __syncthreads();
+    const size_t ld = (size_t)st.ld;
+    constexpr int E = 8;
+    for (int g = 0; g < G; ++g) {
+        const int jb0 = sm.grp[g], jb1 = sm.grp[g + 1];
+        const int j0 = sm.jorder[jb0];
+        const unsigned off = __ldcg(&bf.job_seg_off[j0]);
+        const bool ident = off == PG_SEG_IDENTITY;
+        const unsigned long long L = __ldcg(&bf.job_len[j0]);
+        unsigned long long S0, S1;
+        pg_seg_block_range(L, PG_BID, st.n_gwarps, PG_WARPS, &S0, &S1);
+#pragma unroll 1
+        for (unsigned long long cb = S0; cb < S1; cb += (unsigned long long)E * PG_THREADS) {
+            unsigned idx[E];
+            bool valid[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                const unsigned long long e = cb + (unsigned long long)tid + (unsigned long long)k * PG_THREADS;
+                valid[k] = e < S1;
+                idx[k] = valid[k] ? (ident ? (unsigned)e : __ldcg(&st.pool[(size_t)off + e])) : 0u;
+            }
+            double o[E], r[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                o[k] = valid[k] ? __ldcg(&bf.A_src[idx[k]]) : 0.0;
+                r[k] = valid[k] ? (double)__ldg(&st.y[idx[k]]) : 0.0;
+            }
+            float x0[E][4];                                  // the first four jobs' columns ride with the A / y gathers
+            auto gather = [&](int jb) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool live = jb + q < jb1;
+                    const float* col = st.X + (size_t)sm.jvar[live ? sm.jorder[jb + q] : j0] * ld;
+#pragma unroll
+                    for (int k = 0; k < E; ++k) x0[k][q] = (live && valid[k]) ? __ldg(&col[idx[k]]) : INFINITY;
+                }
+            };
+            gather(jb0);
+#pragma unroll
+            for (int k = 0; k < E; ++k) r[k] = valid[k] ? r[k] - o[k] : 0.0;
+#pragma unroll 1
+            for (int jb = jb0; jb < jb1; jb += 4) {
+                if (jb != jb0) gather(jb);
+                double va[4], vb[4];
+                int cn[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool live = jb + q < jb1;
+                    const float thr = live ? sm.jthr[sm.jorder[jb + q]] : -INFINITY;
+                    double a = 0.0, b2 = 0.0;
+                    unsigned cc = 0u;
+#pragma unroll
+                    for (int k = 0; k < E; ++k) pg_acc_left(a, b2, cc, x0[k][q], thr, o[k], r[k]);
+                    va[q] = a; vb[q] = b2; cn[q] = (int)cc;
+                }
+                const double ta = pg_xreduce4(va[0], va[1], va[2], va[3], lane);
+                const double tb = pg_xreduce4(vb[0], vb[1], vb[2], vb[3], lane);
+                const int tc = pg_xreduce4(cn[0], cn[1], cn[2], cn[3], lane);
+                const int q = pg_xreduce4_job(lane);
+                if (lane < 4 && jb + q < jb1) {
+                    const int j = sm.jorder[jb + q];
+                    sm.accA[warp * S + j] += ta;
+                    sm.accB[warp * S + j] += tb;
+                    sm.accC[warp * S + j] += (unsigned)tc;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    pg_flush_acc(st, bf, sm, J, true, false);
+}
+
 // Identity segment (the root's rows), block-unit scheme of the P <= 32 persistent kernel: block b compacts its own
 // contiguous rows (pg_block_range, the same ranges as the staged root pass, whose per-block LEFT counts give the
 // block's output offsets).  Rows are taken 4 per thread with coalesced float4 loads, 4 chunks in flight; order is
@@ -1256,6 +1342,79 @@ __device__ void pg_part_ident(const PgState& st, const PgBuf& bf, const PgSmemVi
     __syncthreads();      // scanw is reused by the next job
 }
 
+// Pool segment (a non-root node's rows), block-unit scheme: block b compacts its own contiguous entries
+// (pg_seg_block_range; the statistics pass's per-block LEFT counts give the offsets) — 4 entries per thread, 2 chunks in
+// flight, same scan as pg_part_ident; the split column is gathered through the index list.
+__device__ void pg_part_seg(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int k, unsigned src,
+                            const float* col, float thr, unsigned long long L) {
+    PgCtrl* c = st.ctrl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    unsigned long long S0, S1;
+    pg_seg_block_range(L, PG_BID, st.n_gwarps, PG_WARPS, &S0, &S1);
+    unsigned* scanw = &sm.base->p_scan[0][0];
+    unsigned left_run = __ldcg(&st.pj_warp_left[(size_t)k * st.n_gwarps + PG_BID]);
+    const unsigned left0 = left_run;
+    unsigned right_run = (unsigned)S0 - left_run;
+    unsigned* dstL = st.pool + (size_t)__ldcg(&st.pj_dst_off[k]);
+    unsigned* dstR = dstL + __ldcg(&st.pj_cntL[k]);
+    const unsigned* seg = st.pool + (size_t)src;
+    int par = 0;
+#pragma unroll 1
+    for (unsigned long long cb = S0; cb < S1; cb += 2 * PGP_CH) {
+        unsigned idx[2][4];
+        float xs[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned long long en = cb + (unsigned long long)u * PGP_CH + (unsigned long long)tid * 4 + e;
+                idx[u][e] = en < S1 ? __ldcg(&seg[en]) : 0u;
+            }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned long long en = cb + (unsigned long long)u * PGP_CH + (unsigned long long)tid * 4 + e;
+                xs[u][e] = en < S1 ? __ldg(&col[idx[u][e]]) : INFINITY;
+            }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const unsigned long long cs = cb + (unsigned long long)u * PGP_CH;
+            if (cs >= S1) break;
+            const unsigned long long e0 = cs + (unsigned long long)tid * 4;
+            bool vl[4], lf[4];
+            int cl = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { vl[e] = e0 + e < S1; lf[e] = vl[e] && xs[u][e] < thr; cl += lf[e] ? 1 : 0; }
+            int incl = cl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(PG_FULL, incl, o); if (lane >= o) incl += y; }
+            if (lane == 31) scanw[par * PG_WARPS + warp] = (unsigned)incl;
+            __syncthreads();
+            unsigned wpre = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < PG_WARPS; ++w) { const unsigned v = scanw[par * PG_WARPS + w]; tot += v; wpre += w < warp ? v : 0u; }
+            const unsigned before_left = wpre + (unsigned)(incl - cl);
+            unsigned wl = left_run + before_left;
+            unsigned wr = right_run + ((unsigned)(tid * 4) - before_left);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (vl[e]) {
+                    if (lf[e]) __stcg(&dstL[wl++], idx[u][e]);
+                    else __stcg(&dstR[wr++], idx[u][e]);
+                }
+            }
+            const unsigned long long ce = cs + PGP_CH < S1 ? cs + PGP_CH : S1;
+            left_run += tot;
+            right_run += (unsigned)(ce - cs) - tot;
+            par ^= 1;
+        }
+    }
+    const int j = __ldcg(&st.pj_job[k]);
+    if (tid == 0 && (left_run - left0) != __ldcg(&bf.part_ccnt[(size_t)PG_BID * st.S + j])) c->error = PG_ERR_INTERNAL;
+    __syncthreads();      // scanw is reused by the next job
+}
+
 template <bool FASTP>
 __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
@@ -1275,7 +1434,10 @@ __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemVie
         const unsigned long long L = __ldcg(&st.pj_len[k]);
         const float* col = st.X + (size_t)__ldcg(&st.pj_var[k]) * ld;
         const float thr = __ldcg(&st.pj_thr32[k]);
-        if (FASTP && ident) { pg_part_ident(st, bf, sm, k, Q, col, thr, L); continue; }
+        if (FASTP) {                                         // block-unit scheme for every segment
+            if (ident) pg_part_ident(st, bf, sm, k, Q, col, thr, L); else pg_part_seg(st, bf, sm, k, src, col, thr, L);
+            continue;
+        }
         unsigned long long beg, end;
         pg_warp_range(L, gw, st.n_gwarps, ident ? 4 : 1, &beg, &end);
         unsigned left_run = __ldcg(&st.pj_warp_left[(size_t)k * st.n_gwarps + gw]);
@@ -1375,7 +1537,7 @@ __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView&
             else pg_pass_root<false, true>(st, bf, sm);
             break;
         case PH_MINMAX: pg_pass_minmax(st, bf, sm); break;
-        case PH_STATS: pg_pass_seg<0>(st, bf, sm); break;
+        case PH_STATS: if (FASTP && VAR != PGV_BERN) pg_pass_seg_block(st, bf, sm); else pg_pass_seg<0>(st, bf, sm); break;
         case PH_BERN: if (VAR == PGV_GENERIC || VAR == PGV_BERN) pg_pass_seg<1>(st, bf, sm); break;
         case PH_PART: pg_pass_part<FASTP>(st, bf, sm); break;
         default: break;

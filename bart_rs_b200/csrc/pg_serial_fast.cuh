@@ -612,7 +612,7 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     int status;
     const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
     f->mm_valid[0][lane] = 0; f->mm_valid[1][lane] = 0; f->sc_valid[lane] = 0;
-    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; }
+    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; }
     if (lane < S) {
         const int s = lane;
         f->hw[s] = 0.0;       // smc.rs:53: once per update, never reset (Q1)
@@ -694,6 +694,8 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
     }
     const int pb = (int)(upd & 1ull);
     int G;
+    if (lane == 0) f->from_cache = 0;
+    __syncwarp();
     if (!__any_sync(PG_FULL, jb.live)) {
         (void)fw_write_jobs(st, x, jb, lane, false, pb, false, true, &G);
         return SN_FINISH_ROUND;
@@ -739,6 +741,7 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
     if (__all_sync(PG_FULL, sc_hit)) {
         // the statistics were prefetched too: no pass at all for this round
         const int J = fw_write_jobs(st, x, jb, lane, true, pb, false, true, &G);
+        if (lane == 0) f->from_cache = 1;       // per-block counts of these jobs sit at the prefetch jobs' indices (sc_job)
         if (lane < J) {
             const int s = f->jslot[lane];
             f->rCnt[lane] = f->sc_cnt[s]; f->rCntL[lane] = f->sc_cntL[s]; f->rSo[lane] = f->sc_So[s]; f->rSr[lane] = f->sc_Sr[s];
@@ -1046,7 +1049,8 @@ __device__ __forceinline__ int fw_plan_partitions(const PgState& st, const FwCx&
     __syncwarp();
     if (leader) {
         st.pj_of_anc[anc] = k;
-        st.pj_anc[k] = anc; st.pj_job[k] = j; st.pj_var[k] = f->jvar[j]; st.pj_thr32[k] = f->jthr[j];
+        st.pj_anc[k] = anc; st.pj_job[k] = f->from_cache ? f->sc_job[f->jslot[j]] : j;   // where the pass left this job's per-block counts
+        st.pj_var[k] = f->jvar[j]; st.pj_thr32[k] = f->jthr[j];
         st.pj_src_off[k] = f->jseg[j]; st.pj_len[k] = len; st.pj_cntL[k] = cntL; st.pj_dst_off[k] = (unsigned)off;
     }
     const int lead_lane = need ? (__ffs(same & needm) - 1) : 0;
@@ -1127,23 +1131,19 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
     return SN_FINALIZE;
 }
 
-// block-wide: exclusive prefix, over global warps, of each partition job's per-warp left counts
-#define FB_CH 8
+// block-wide: the partition jobs' block offsets
 __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
     const int K = c->n_pjobs, W = st.n_gwarps, S = st.S;
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int chunk = (W + T - 1) / T;
-    const unsigned* p_cnt = st.part_cnt + pg_off_part_cnt(st, (int)(c->upd & 1ull));   // counts of this update's statistics pass
-    // identity segments (the root's rows) are partitioned in block units: exclusive prefix, over pass blocks, of the
-    // root pass's per-block left counts — one warp per job
+    const int tid = threadIdx.x;
+    // every segment is partitioned in block units (pg_part_ident / pg_part_seg): exclusive prefix, over pass blocks, of the
+    // per-block left counts of the pass that computed the job's statistics — one warp per job
     {
         const unsigned* p_ccnt = st.part_ccnt + pg_off_part_ccnt(st, (int)(c->upd & 1ull));
         const int lane = tid & 31, warp = tid >> 5, G = st.grid;
 #pragma unroll 1
         for (int k = warp; k < K; k += PG_WARPS) {
-            if (st.pj_src_off[k] != PG_SEG_IDENTITY) continue;
             const int j = st.pj_job[k];
             unsigned carry = 0;
 #pragma unroll 1
@@ -1158,49 +1158,7 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
             }
         }
     }
-#pragma unroll 1
-    for (int k = 0; k < K; ++k) {
-        if (st.pj_src_off[k] == PG_SEG_IDENTITY) continue;      // block-uniform
-        const int j = st.pj_job[k];
-        const int b = tid * chunk;
-        unsigned local = 0;
-        if (chunk <= FB_CH) {
-            unsigned v[FB_CH];
-#pragma unroll
-            for (int q = 0; q < FB_CH; ++q) v[q] = (q < chunk && b + q < W) ? __ldcg(&p_cnt[(size_t)(b + q) * S + j]) : 0u;
-#pragma unroll
-            for (int q = 0; q < FB_CH; ++q) local += v[q];
-            f->scan[tid] = local;
-            __syncthreads();
-            if (tid < 32) {
-                unsigned carry = 0;
-#pragma unroll 1
-                for (int base = 0; base < T; base += 32) {
-                    const unsigned x0 = f->scan[base + tid];
-                    unsigned xx = x0;
-#pragma unroll 1
-                    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(PG_FULL, xx, o); if (tid >= o) xx += y; }
-                    f->scan[base + tid] = carry + xx - x0;
-                    carry += __shfl_sync(PG_FULL, xx, 31);
-                }
-            }
-            __syncthreads();
-            unsigned run = f->scan[tid];
-#pragma unroll
-            for (int q = 0; q < FB_CH; ++q)
-                if (q < chunk && b + q < W) { st.pj_warp_left[(size_t)k * W + b + q] = run; run += v[q]; }
-        } else {
-            const int e = min(b + chunk, W);
-            for (int g = b; g < e; ++g) local += __ldcg(&p_cnt[(size_t)g * S + j]);
-            f->scan[tid] = local;
-            __syncthreads();
-            if (tid == 0) { unsigned run = 0; for (int q = 0; q < T; ++q) { const unsigned v = f->scan[q]; f->scan[q] = run; run += v; } }
-            __syncthreads();
-            unsigned run = f->scan[tid];
-            for (int g = b; g < e; ++g) { st.pj_warp_left[(size_t)k * W + g] = run; run += __ldcg(&p_cnt[(size_t)g * S + j]); }
-        }
-        __syncthreads();
-    }
+    __syncthreads();
     if (tid == 0) {
         unsigned long long bm = 0;
 #pragma unroll 1
@@ -1666,7 +1624,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                         const int J0 = c->n_jobs;
                         if (lane >= J0 && lane < J0 + f->pf_n) {
                             const int s = f->pf_slot[lane - J0];
-                            f->sc_cnt[s] = f->rCnt[lane]; f->sc_cntL[s] = f->rCntL[lane]; f->sc_So[s] = f->rSo[lane]; f->sc_Sr[s] = f->rSr[lane]; f->sc_valid[s] = 1;
+                            f->sc_cnt[s] = f->rCnt[lane]; f->sc_cntL[s] = f->rCntL[lane]; f->sc_So[s] = f->rSo[lane]; f->sc_Sr[s] = f->rSr[lane]; f->sc_job[s] = lane; f->sc_valid[s] = 1;
                         }
                         __syncwarp();
                         if (lane == 0) f->pf_n = 0;

@@ -256,6 +256,19 @@ PG_HD void pg_block_range(long long n, int bid, int grid, long long* b0, long lo
     *b0 = b; *b1 = e;
 }
 
+// Entries of an index segment of length L owned by pass block `bid` in the block-unit scheme: the union of the 16 warp
+// ranges pg_warp_range(L, gw, n_gwarps, 1) of its warps, so per-block counts agree whichever statistics pass (warp-range
+// or block-unit) produced them.
+PG_HD void pg_seg_block_range(unsigned long long L, int bid, int n_gwarps, int warps_per_block,
+                              unsigned long long* b0, unsigned long long* b1) {
+    const unsigned long long per = (L + (unsigned long long)n_gwarps - 1) / (unsigned long long)n_gwarps;
+    unsigned long long b = (unsigned long long)bid * (unsigned long long)warps_per_block * per;
+    unsigned long long e = b + (unsigned long long)warps_per_block * per;
+    if (b > L) b = L;
+    if (e > L) e = L;
+    *b0 = b; *b1 = e;
+}
+
 PG_HD void pg_warp_range(unsigned long long L, int gw, int n_gwarps, int granule,
                          unsigned long long* beg, unsigned long long* end) {
     unsigned long long units = (L + (unsigned long long)granule - 1) / (unsigned long long)granule;

@@ -59,6 +59,10 @@ CASES = [
     (33, 2, 4, 6, 0, 1.0, dict(), [True]),                                   # ragged: fewer rows than warps
     (1, 2, 3, 4, 0, 1.0, dict(), [True]),                                    # single row
     (20000, 12, 8, 40, 0, 1.0, dict(), [True]),                              # more particles
+    # two growing particles, shallow prior: both often grow in rounds 1-2, so prefetched statistics, deferred mutations that
+    # survive, and partitions of non-root segments all occur
+    (2003, 3, 10, 3, 0, 1.0, dict(beta=0.3, max_depth=10), [True, True, True, True]),
+    (1501, 4, 8, 4, 0, 1.0, dict(beta=0.3, max_depth=10), [True, True, True]),
 ]
 
 
