@@ -279,7 +279,8 @@ __device__ __forceinline__ void pg_zero_acc(const PgSmemView& sm, int S) {
 }
 
 // Write the block's per-job results: fixed warp order => deterministic.
-__device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int J, bool counts, bool as_ll) {
+__device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int J, bool counts, bool as_ll,
+                                             bool warp_counts = true) {
     const int S = st.S;
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
         double a = 0.0, b = 0.0;
@@ -290,8 +291,9 @@ __device__ __forceinline__ void pg_flush_acc(const PgState& st, const PgBuf& bf,
         dst[((size_t)PG_BID * S + j) * 2 + 1] = b;
         if (counts) {
             bf.part_ccnt[(size_t)PG_BID * S + j] = cc;
-            for (int w = 0; w < PG_WARPS; ++w)
-                bf.part_cnt[((size_t)PG_BID * PG_WARPS + w) * S + j] = sm.accC[w * S + j];
+            if (warp_counts)                                 // only the warp-range partitions of the generic kernels read these
+                for (int w = 0; w < PG_WARPS; ++w)
+                    bf.part_cnt[((size_t)PG_BID * PG_WARPS + w) * S + j] = sm.accC[w * S + j];
         }
     }
 }
@@ -446,7 +448,7 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
         for (int w = 0; w < PG_WARPS; ++w) v += sm.base->tot[w][threadIdx.x];
         bf.part_tot[(size_t)PG_BID * 4 + threadIdx.x] = v;
     }
-    pg_flush_acc(st, bf, sm, J, true, false);
+    pg_flush_acc(st, bf, sm, J, true, false, !BLOCKR);
 }
 
 // =============================================================================
@@ -1198,7 +1200,7 @@ __device__ void pg_pass_seg_block(const PgState& st, const PgBuf& bf, const PgSm
         }
     }
     __syncthreads();
-    pg_flush_acc(st, bf, sm, J, true, false);
+    pg_flush_acc(st, bf, sm, J, true, false, false);
 }
 
 // Identity segment (the root's rows), block-unit scheme of the P <= 32 persistent kernel: block b compacts its own
