@@ -234,14 +234,16 @@ __device__ __forceinline__ double pg_warp_sum(double v) {
 // ---- tree staging / evaluation (tree.rs:169-192 traversal on training rows) ------------------
 __device__ __forceinline__ void pg_stage_tree(const PgState& st, int t, PgTreeSm& sm) {
     if (t < 0) { if (threadIdx.x == 0) { sm.size = 0; sm.from_global = 0; } return; }
+    // the size and the first PG_TREE_SM nodes are requested together (the node arrays have maxn entries per tree, so the
+    // addresses are valid whatever the size turns out to be): one memory round trip instead of two
+    const int i = threadIdx.x;
+    const bool in = i < PG_TREE_SM && i < st.maxn;
     const int sz = __ldcg(&st.f_size[t]);
-    if (threadIdx.x == 0) { sm.size = sz; sm.from_global = sz > PG_TREE_SM; }
-    if (sz <= PG_TREE_SM)
-        for (int i = threadIdx.x; i < sz; i += blockDim.x) {
-            sm.split_var[i] = __ldcg(&st.f_split_var[(size_t)t * st.maxn + i]);
-            sm.thr32[i] = __ldcg(&st.f_thr32[(size_t)t * st.maxn + i]);
-            sm.leaf_val[i] = __ldcg(&st.f_leaf_val[(size_t)t * st.maxn + i]);
-        }
+    const int sv = in ? __ldcg(&st.f_split_var[(size_t)t * st.maxn + i]) : -1;
+    const float th = in ? __ldcg(&st.f_thr32[(size_t)t * st.maxn + i]) : 0.0f;
+    const double lv = in ? __ldcg(&st.f_leaf_val[(size_t)t * st.maxn + i]) : 0.0;
+    if (i == 0) { sm.size = sz; sm.from_global = sz > PG_TREE_SM; }
+    if (in && i < sz && sz <= PG_TREE_SM) { sm.split_var[i] = sv; sm.thr32[i] = th; sm.leaf_val[i] = lv; }
 }
 
 __device__ __forceinline__ double pg_tree_eval(const PgState& st, int t, const PgTreeSm& sm, long long row) {
