@@ -142,6 +142,7 @@ struct PgSmem {
     unsigned r_cnt[4][32];
     unsigned p_scan[2][PG_WARPS];          // block-unit identity partition: warp totals of a chunk, double-buffered
     int p_rq_idx[64], p_rq_side[64], p_rq_var[64], p_nreq;   // look-ahead requests of the partition job in progress
+    unsigned s_seg[32], s_len[32];         // block-unit statistics pass: the jobs' segments, staged with the job list
     // followed by dynamic arrays, see pg_smem_* accessors
 };
 
@@ -1132,6 +1133,7 @@ __device__ void pg_pass_seg_block(const PgState& st, const PgBuf& bf, const PgSm
     const int S = st.S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pg_stage_jobs(st, bf, sm, J, G, false);
+    for (int j = tid; j < J && j < 32; j += blockDim.x) { sm.base->s_seg[j] = __ldcg(&bf.job_seg_off[j]); sm.base->s_len[j] = __ldcg(&bf.job_len[j]); }
     pg_zero_acc(sm, S);
     __syncthreads();
     const size_t ld = (size_t)st.ld;
@@ -1139,9 +1141,9 @@ __device__ void pg_pass_seg_block(const PgState& st, const PgBuf& bf, const PgSm
     for (int g = 0; g < G; ++g) {
         const int jb0 = sm.grp[g], jb1 = sm.grp[g + 1];
         const int j0 = sm.jorder[jb0];
-        const unsigned off = __ldcg(&bf.job_seg_off[j0]);
+        const unsigned off = j0 < 32 ? sm.base->s_seg[j0] : __ldcg(&bf.job_seg_off[j0]);
         const bool ident = off == PG_SEG_IDENTITY;
-        const unsigned long long L = __ldcg(&bf.job_len[j0]);
+        const unsigned long long L = j0 < 32 ? sm.base->s_len[j0] : __ldcg(&bf.job_len[j0]);
         unsigned long long S0, S1;
         pg_seg_block_range(L, PG_BID, st.n_gwarps, PG_WARPS, &S0, &S1);
 #pragma unroll 1
