@@ -143,6 +143,10 @@ struct PgSmem {
     unsigned p_scan[2][PG_WARPS];          // block-unit identity partition: warp totals of a chunk, double-buffered
     int p_rq_idx[64], p_rq_side[64], p_rq_var[64], p_nreq;   // look-ahead requests of the partition job in progress
     unsigned s_seg[32], s_len[32];         // block-unit statistics pass: the jobs' segments, staged with the job list
+    // block-unit partition pass: every job's parameters and the look-ahead requests, staged in one round trip
+    unsigned pp_src[32], pp_len[32], pp_left[32], pp_dst[32], pp_cntL[32], pp_exp[32];
+    int pp_var[32], pp_mq_pj[64], pp_mq_side[64], pp_mq_var[64];
+    float pp_thr[32];
     // followed by dynamic arrays, see pg_smem_* accessors
 };
 
@@ -1222,11 +1226,11 @@ __device__ void pg_part_ident(const PgState& st, const PgBuf& bf, const PgSmemVi
     pg_block_range((long long)L, PG_BID, st.grid, &B0, &B1);
     const long long n = (long long)L;
     unsigned* scanw = &sm.base->p_scan[0][0];                    // [2][PG_WARPS] warp totals, double-buffered by chunk parity
-    unsigned left_run = __ldcg(&st.pj_warp_left[(size_t)k * st.n_gwarps + PG_BID]);   // block-unit: indexed by block
+    unsigned left_run = sm.base->pp_left[k];                     // block-unit: this block's offset among the LEFT rows
     const unsigned left0 = left_run;
     unsigned right_run = (unsigned)min(B0, n) - left_run;
-    unsigned* dstL = st.pool + (size_t)__ldcg(&st.pj_dst_off[k]);
-    unsigned* dstR = dstL + __ldcg(&st.pj_cntL[k]);
+    unsigned* dstL = st.pool + (size_t)sm.base->pp_dst[k];
+    unsigned* dstR = dstL + sm.base->pp_cntL[k];
     int par = 0;
 #pragma unroll 1
     for (long long cb = B0; cb < B1; cb += 4 * PGP_CH) {
@@ -1272,8 +1276,7 @@ __device__ void pg_part_ident(const PgState& st, const PgBuf& bf, const PgSmemVi
         }
     }
     // the root pass counted the same predicate over the same rows
-    const int j = __ldcg(&st.pj_job[k]);
-    if (tid == 0 && (left_run - left0) != __ldcg(&bf.part_ccnt[(size_t)PG_BID * st.S + j])) c->error = PG_ERR_INTERNAL;
+    if (tid == 0 && (left_run - left0) != sm.base->pp_exp[k]) c->error = PG_ERR_INTERNAL;
     // look-ahead: splitting.rs:43-49 for the proposals expected on the two children.  The requests of this job are staged
     // in shared memory once, then taken three at a time with four chunks in flight each (16 independent float4 loads per
     // thread), so the pass pays a memory round trip per group of requests instead of several per request.
@@ -1283,11 +1286,11 @@ __device__ void pg_part_ident(const PgState& st, const PgBuf& bf, const PgSmemVi
         int nreq = 0;
         for (int q0 = 0; q0 < Q; q0 += 32) {
             const int q = q0 + lane;
-            const bool mine = q < Q && __ldcg(&st.mq_pj[q]) == k;
+            const bool mine = q < Q && sm.base->pp_mq_pj[q] == k;
             const unsigned m = __ballot_sync(PG_FULL, mine);
             if (mine) {
                 const int pos = nreq + __popc(m & ((1u << lane) - 1u));
-                rq_idx[pos] = q; rq_side[pos] = __ldcg(&st.mq_side[q]); rq_var[pos] = __ldcg(&st.mq_var[q]);
+                rq_idx[pos] = q; rq_side[pos] = sm.base->pp_mq_side[q]; rq_var[pos] = sm.base->pp_mq_var[q];
             }
             nreq += __popc(m);
         }
@@ -1358,11 +1361,11 @@ __device__ void pg_part_seg(const PgState& st, const PgBuf& bf, const PgSmemView
     unsigned long long S0, S1;
     pg_seg_block_range(L, PG_BID, st.n_gwarps, PG_WARPS, &S0, &S1);
     unsigned* scanw = &sm.base->p_scan[0][0];
-    unsigned left_run = __ldcg(&st.pj_warp_left[(size_t)k * st.n_gwarps + PG_BID]);
+    unsigned left_run = sm.base->pp_left[k];
     const unsigned left0 = left_run;
     unsigned right_run = (unsigned)S0 - left_run;
-    unsigned* dstL = st.pool + (size_t)__ldcg(&st.pj_dst_off[k]);
-    unsigned* dstR = dstL + __ldcg(&st.pj_cntL[k]);
+    unsigned* dstL = st.pool + (size_t)sm.base->pp_dst[k];
+    unsigned* dstR = dstL + sm.base->pp_cntL[k];
     const unsigned* seg = st.pool + (size_t)src;
     int par = 0;
 #pragma unroll 1
@@ -1416,8 +1419,7 @@ __device__ void pg_part_seg(const PgState& st, const PgBuf& bf, const PgSmemView
             par ^= 1;
         }
     }
-    const int j = __ldcg(&st.pj_job[k]);
-    if (tid == 0 && (left_run - left0) != __ldcg(&bf.part_ccnt[(size_t)PG_BID * st.S + j])) c->error = PG_ERR_INTERNAL;
+    if (tid == 0 && (left_run - left0) != sm.base->pp_exp[k]) c->error = PG_ERR_INTERNAL;
     __syncthreads();      // scanw is reused by the next job
 }
 
@@ -1433,13 +1435,27 @@ __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemVie
     if (Q > 0) {
         for (int q = threadIdx.x; q < Q; q += blockDim.x) { sm.mmin[q] = 0xFFFFFFFFu; sm.mmax[q] = 0u; }
     }
+    if (FASTP) {   // every job's parameters and the look-ahead requests in one round trip (K <= S <= 31, Q <= 64)
+        PgSmem* b = sm.base;
+        const int t = threadIdx.x;
+        if (t < K && t < 32) {
+            b->pp_src[t] = __ldcg(&st.pj_src_off[t]); b->pp_len[t] = __ldcg(&st.pj_len[t]); b->pp_var[t] = __ldcg(&st.pj_var[t]);
+            b->pp_thr[t] = __ldcg(&st.pj_thr32[t]); b->pp_left[t] = __ldcg(&st.pj_warp_left[(size_t)t * st.n_gwarps + PG_BID]);
+            b->pp_dst[t] = __ldcg(&st.pj_dst_off[t]); b->pp_cntL[t] = __ldcg(&st.pj_cntL[t]);
+            b->pp_exp[t] = __ldcg(&bf.part_ccnt[(size_t)PG_BID * st.S + __ldcg(&st.pj_job[t])]);
+        }
+        if (t >= 64 && t - 64 < Q && t - 64 < 64) {
+            const int q = t - 64;
+            b->pp_mq_pj[q] = __ldcg(&st.mq_pj[q]); b->pp_mq_side[q] = __ldcg(&st.mq_side[q]); b->pp_mq_var[q] = __ldcg(&st.mq_var[q]);
+        }
+    }
     __syncthreads();
     for (int k = 0; k < K; ++k) {
-        const unsigned src = __ldcg(&st.pj_src_off[k]);
+        const unsigned src = FASTP ? sm.base->pp_src[k] : __ldcg(&st.pj_src_off[k]);
         const bool ident = src == PG_SEG_IDENTITY;
-        const unsigned long long L = __ldcg(&st.pj_len[k]);
-        const float* col = st.X + (size_t)__ldcg(&st.pj_var[k]) * ld;
-        const float thr = __ldcg(&st.pj_thr32[k]);
+        const unsigned long long L = FASTP ? sm.base->pp_len[k] : __ldcg(&st.pj_len[k]);
+        const float* col = st.X + (size_t)(FASTP ? sm.base->pp_var[k] : __ldcg(&st.pj_var[k])) * ld;
+        const float thr = FASTP ? sm.base->pp_thr[k] : __ldcg(&st.pj_thr32[k]);
         if (FASTP) {                                         // block-unit scheme for every segment
             if (ident) pg_part_ident(st, bf, sm, k, Q, col, thr, L); else pg_part_seg(st, bf, sm, k, src, col, thr, L);
             continue;
