@@ -41,6 +41,7 @@ WORKLOADS = {
     # observation-sharded: ONE chain, rows split across the GPUs; strong scaling
     "C4": dict(n=10_000_000, p=100, m=200, P=20, family="gaussian", sharded=True),
     "C3s": dict(n=1_000_000, p=50, m=200, P=20, family="gaussian", sharded=True),
+    "C3x20": dict(n=20_000_000, p=50, m=200, P=20, family="gaussian"),     # how close to the HBM roofline large n gets
 }
 
 
