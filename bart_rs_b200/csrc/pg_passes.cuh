@@ -132,7 +132,8 @@ struct PgSmem {
     int cstaged;           // split prior / column min-max are staged in the dynamic area
     int pass_bid;          // this block's index among the pass blocks (-1: serial-only block)
     int is_last;
-    // ---- staged root pass (pg_pass_root_staged): bulk-copy ring in the staging area behind the dynamic arrays
+    // ---- staged root pass (pg_pass_root_tma): bulk-copy ring in the staging area behind the dynamic arrays
+    unsigned long long mbar_full[PGR_MAXST], mbar_empty[PGR_MAXST];   // per stage: tile landed / every warp done with it
     int r_ucol[PGR_MAXU];                  // distinct columns staged per tile
     int r_jslot[32];                       // job -> staged column
     short r_add_slot[PG_TREE_SM], r_sub_slot[PG_TREE_SM];   // tree node -> staged column, -1 = gather from global
@@ -633,31 +634,26 @@ __device__ void pg_pass_root_quarters(const PgState& st, const PgBuf& bf, const 
 }
 
 // =============================================================================
-// PH_ROOT / PH_FINAL, staged variant (P <= 32 persistent kernel)
+// PH_ROOT / PH_FINAL, staged variant (P <= 32 persistent kernel; -DPGBART_WITH_STAGED, root_pass = "staged")
 // =============================================================================
-// The warp-range pass above is latency bound: each warp walks its rows through dependent global loads with
-// little else in flight (measured 32 us per pass at n = 1M against ~12 us of HBM time).  Here the loads are decoupled
-// from the arithmetic: all threads keep a ring of tiles in flight with asynchronous copies into shared memory
-// (cp.async, 16 B per thread per copy, evict-first for X); a tile = PGR_T rows of A, y and every DISTINCT column the
-// pass needs (the slots' split variables plus the split variables of the trees being committed / opened, so tree
-// evaluation reads shared memory too).  Warp w = (row quarter w / 4, job group w % 4): a lane owns 4 consecutive rows
-// of its quarter and accumulates its group's jobs in registers across ALL tiles of the block, so the cross-lane
-// reduction happens once per pass instead of once per 256 rows.  Every sum is taken in a fixed order (lane-private
-// sequential, fixed shuffle tree, quarters in order) => bit-reproducible.  Emits per-BLOCK results only (part_tot,
-// part_sum, part_ccnt): partitions of the root segment use the block-unit scheme (pg_part_ident).
-// (Bulk copies — cp.async.bulk + mbarrier — were measured first: one thread needs ~87 cycles to issue each 2 KB
-// column copy, 17 per tile, which alone costs as much as the whole pass should.)
+// The direct pass is latency / issue bound: each warp walks its rows through dependent global loads with loads only
+// one job group ahead.  Here the loads are decoupled from the arithmetic: a ring of tiles is kept in flight with bulk
+// asynchronous copies into shared memory (cp.async.bulk, completion on an mbarrier, evict-first for X); a tile = PGR_T
+// rows of A, y and every DISTINCT column the pass needs (the slots' split variables plus the split variables of the trees
+// being committed / opened, so tree evaluation reads shared memory too).  Warp w = (row quarter w / 4, job group
+// w % 4): a lane owns 4 consecutive rows of its quarter and accumulates its group's jobs in registers across ALL tiles of
+// the block, so the cross-lane reduction happens once per pass.  Every warp issues the copies of "its" arrays (one lane,
+// 1-2 bulk copies per tile) and the warps synchronise only through the per-stage "landed" / "done" mbarriers.  Fixed
+// summation order => bit-reproducible.  Emits per-BLOCK results only (part_tot, part_sum, part_ccnt).
+// Measured: parity-green, 15.1 ms per sweep at C3 against 13.9 for the direct pass (an earlier
+// version that copied with cp.async from all threads and synchronised the block per tile: 16.5).  Its arithmetic is lean
+// (26 K warp-instructions per SM per pass in the job loop); it waits for tiles — 17 bulk copies of 2 KB per tile do not
+// reach the rate a few large copies would.  Kept selectable for the next round (TMA gather4 tiles).
 __device__ __forceinline__ unsigned pg_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned long long pg_policy_evict_first() {
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
-}
-__device__ __forceinline__ void pg_cp16(unsigned dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void pg_cp16_hint(unsigned dst, const void* src, unsigned long long pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ float4 pg_lds_f4(unsigned addr) {     // explicit shared-space loads: the staging area is reached through a
     float4 v;                                                      // generic pointer, which would otherwise compile to generic LD
@@ -674,17 +670,34 @@ __device__ __forceinline__ double2 pg_lds_d2(unsigned addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void pg_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void pg_cp_wait_pending(int n) {      // at most n of this thread's groups still in flight
-    switch (n) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-    }
+__device__ __forceinline__ void pg_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pg_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_inval(unsigned long long* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(pg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {      // expect `bytes`, then arrive
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = pg_smem_u32(bar);
+    unsigned done, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");      // (a suspend-time hint made waits last the whole hint: 40 % slower)
+        if (!done && ++spins > (1u << 24)) __trap();     // a lost copy becomes an error, not a hang
+    } while (!done);
+}
+__device__ __forceinline__ void pg_bulk_g2s_u32(unsigned dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(pg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pg_bulk_g2s_hint_u32(unsigned dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(pg_smem_u32(bar)), "l"(pol) : "memory");
 }
 
 // tree value of a row whose columns are (mostly) staged: tile-local row `lr`, global row `row`
@@ -701,7 +714,7 @@ __device__ __forceinline__ double pg_tree_eval_staged(const PgState& st, int t, 
 }
 
 template <bool BERN, int JW>
-__device__ void pg_pass_root_staged(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+__device__ void pg_pass_root_tma(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     PgSmem* b = sm.base;
     const bool is_root = __ldcg(&c->phase) == PH_ROOT;
@@ -721,6 +734,11 @@ __device__ void pg_pass_root_staged(const PgState& st, const PgBuf& bf, const Pg
     pg_stage_tree(st, t_add, b->tadd);
     pg_stage_tree(st, t_sub, b->tsub);
     for (int j = tid; j < J; j += blockDim.x) { sm.jvar[j] = __ldcg(&bf.job_var[j]); sm.jthr[j] = __ldcg(&bf.job_thr32[j]); }
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < PGR_MAXST; ++q) { pg_mbar_init(&b->mbar_full[q], PG_WARPS); pg_mbar_init(&b->mbar_empty[q], PG_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     PG_CK(0);
     // ---- the distinct columns of this pass (warp 0)
@@ -775,49 +793,39 @@ __device__ void pg_pass_root_staged(const PgState& st, const PgBuf& bf, const Pg
     const size_t ld = (size_t)st.ld;
     const unsigned long long pol = pg_policy_evict_first();
     const unsigned stage0 = pg_smem_u32(sm.stage);
-    // staged arrays a = 0, 1: A (rows 0-255 / 256-511 of the tile), 2: y, 3 + u: column u — each 2048 bytes of a full
-    // tile, at stage offset 2048 a.  Thread (a0 = tid / 128, q = tid % 128) copies 16-byte piece q of arrays a0, a0 + 4, ...
-    const int n_arr = 3 + U;
+    // staged arrays a = 0: A (4096 B of a full tile), 1: y (2048 B), 2 + u: column u (2048 B each).  Warp w issues the bulk
+    // copies of arrays w, w + 16, w + 32 (one lane, a couple of instructions per tile) and every warp arrives once per stage
+    // on the "landed" barrier with the bytes it asked for; a warp arrives on the "done" barrier of a stage when it has
+    // consumed it, and refills a stage only after all 16 have.  No block-wide barrier inside the loop: warps drift apart
+    // by up to NST - 1 tiles.
+    const int n_arr = 2 + U;
     for (int a = tid; a < n_arr; a += blockDim.x)
-        b->r_src[a] = a < 2 ? (unsigned long long)(bf.A_src + 256 * a) : a == 2 ? (unsigned long long)st.y
-                                                                                : (unsigned long long)(st.X + (size_t)b->r_ucol[a - 3] * ld);
+        b->r_src[a] = a == 0 ? (unsigned long long)bf.A_src : a == 1 ? (unsigned long long)st.y
+                                                                    : (unsigned long long)(st.X + (size_t)b->r_ucol[a - 2] * ld);
     __syncthreads();
-    const int a0 = tid >> 7, q16 = (tid & 127) * 16;
-    // running source pointers of this thread's first PGR_KP arrays (advanced by one tile per issue)
-    const char* sp[PGR_KP];
-#pragma unroll
-    for (int k = 0; k < PGR_KP; ++k) {
-        const int a = a0 + 4 * k;
-        sp[k] = a < n_arr ? reinterpret_cast<const char*>(b->r_src[a]) + B0 * (a < 2 ? 8 : 4) + q16 : nullptr;
-    }
-    const int step0 = a0 < 2 ? PGR_T * 8 : PGR_T * 4;
-    auto issue = [&](int t, int stage_of_t) {
-        if (t < n_tiles) {
-            const long long r0 = B0 + (long long)t * PGR_T;
-            const int rows = (int)min((long long)PGR_T, B1 - r0);
-            const unsigned dst0 = stage0 + (unsigned)stage_of_t * stage_bytes + (unsigned)q16 + (unsigned)a0 * 2048u;
-            if (rows == PGR_T) {
-                if (a0 < 3) pg_cp16(dst0, sp[0]); else if (n_arr > 3) pg_cp16_hint(dst0, sp[0], pol);
-#pragma unroll
-                for (int k = 1; k < PGR_KP; ++k)
-                    if (a0 + 4 * k < n_arr) pg_cp16_hint(dst0 + (unsigned)k * 8192u, sp[k], pol);
+    auto issue = [&](int t) {                                // lane 0 of every warp
+        const int s_ = t % NST;
+        const long long r0 = B0 + (long long)t * PGR_T;
+        const unsigned rows = (unsigned)min((long long)PGR_T, B1 - r0);
+        const unsigned sbase = stage0 + (unsigned)s_ * stage_bytes;
+        unsigned bytes = 0;
 #pragma unroll 1
-                for (int a = a0 + 4 * PGR_KP; a < n_arr; a += 4)
-                    pg_cp16_hint(dst0 + (unsigned)(a - a0) * 2048u, reinterpret_cast<const char*>(b->r_src[a]) + r0 * 4 + q16, pol);
-            } else {
+        for (int a = warp; a < n_arr; a += PG_WARPS) bytes += rows * (a == 0 ? 8u : 4u);
+        if (bytes) pg_mbar_expect_tx(&b->mbar_full[s_], bytes); else pg_mbar_arrive(&b->mbar_full[s_]);
 #pragma unroll 1
-                for (int a = a0; a < n_arr; a += 4) {
-                    const int first_row = a < 2 ? a * 256 + (tid & 127) * 2 : (tid & 127) * 4;
-                    if (first_row < rows) pg_cp16(dst0 + (unsigned)(a - a0) * 2048u, reinterpret_cast<const char*>(b->r_src[a]) + r0 * (a < 2 ? 8 : 4) + q16);
-                }
-            }
+        for (int a = warp; a < n_arr; a += PG_WARPS) {
+            const unsigned es = a == 0 ? 8u : 4u;
+            const unsigned dst = sbase + (a == 0 ? 0u : a == 1 ? PGR_T * 8u : PGR_T * 12u + (unsigned)(a - 2) * (PGR_T * 4u));
+            const char* src = reinterpret_cast<const char*>(b->r_src[a]) + r0 * es;
+            if (a < 2) pg_bulk_g2s_u32(dst, src, rows * es, &b->mbar_full[s_]);
+            else pg_bulk_g2s_hint_u32(dst, src, rows * es, &b->mbar_full[s_], pol);
         }
-        sp[0] += step0;
-#pragma unroll
-        for (int k = 1; k < PGR_KP; ++k) sp[k] += PGR_T * 4;
-        pg_cp_commit();
     };
-    for (int t = 0; t < NST - 1; ++t) issue(t, t);
+    if (lane == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");    // A was written with ordinary stores by the previous pass
+        for (int t = 0; t < NST && t < n_tiles; ++t) issue(t);
+    }
+    __syncwarp();
     PG_CK(2);
 
     // my jobs: group g takes jobs j with (j + 1) % 4 == g, so group 0 (which also writes A and keeps the totals) gets the fewest
@@ -841,32 +849,20 @@ __device__ void pg_pass_root_staged(const PgState& st, const PgBuf& bf, const Pg
 
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
-#ifdef PG_DIAG
-        const long long tw0 = clock64();
-#endif
-        pg_cp_wait_pending(NST - 2);                        // this thread's copies of tile t have landed
-#ifdef PG_DIAG
-        const long long tw1 = clock64();
-#endif
-        __syncthreads();                                    // ... and everyone's; everyone is done with tile t - 1
-#ifdef PG_DIAG
-        const long long tw2 = clock64();
-        if (tid == 0 && t > 0) { ck_d[6] += (unsigned long long)(tw1 - tw0); ck_d[7] += (unsigned long long)(tw2 - tw1); }
-#endif
+        if (lane == 0 && t >= 1 && t - 1 + NST < n_tiles) {  // refill the stage tile t - 1 occupied, once every warp has left it
+            pg_mbar_wait(&b->mbar_empty[(t - 1) % NST], (unsigned)(((t - 1) / NST) & 1));
+            issue(t - 1 + NST);
+        }
+        __syncwarp();
+        pg_mbar_wait(&b->mbar_full[stg], (unsigned)((t / NST) & 1));
         if (t == 0) PG_CK(3);
-        issue(t + NST - 1, stg == 0 ? NST - 1 : stg - 1);   // refill the stage tile t - 1 occupied
-#ifdef PG_DIAG
-        if (tid == 0 && t > 0) ck_d[2] += (unsigned long long)(clock64() - tw2);
-#endif
+        const int stg_used = stg;
         const unsigned sbase = stage0 + (unsigned)stg * stage_bytes;
         stg = stg + 1 == NST ? 0 : stg + 1;
         const long long r0 = B0 + (long long)t * PGR_T;
         const int rows = (int)min((long long)PGR_T, B1 - r0);
-        if (lr >= rows) continue;
+        if (lr < rows) {                                    // (a short last tile leaves some lanes without rows)
         const long long row = r0 + lr;
-#ifdef PG_DIAG
-        const long long tc0 = clock64();
-#endif
         const int nv = (int)min(4ll, st.n - row);           // valid rows of this lane's four (>= 1 except past n)
         const unsigned cols = sbase + PGR_T * 12u;          // shared-space address of the staged columns
         double o0, o1, o2, o3;
@@ -894,18 +890,11 @@ __device__ void pg_pass_root_staged(const PgState& st, const PgBuf& bf, const Pg
                 o3 = o3 - (nv > 3 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, lr + 3, row + 3) : 0.0);
             } else { o0 = o0 - sub_c; o1 = o1 - sub_c; o2 = o2 - sub_c; o3 = o3 - sub_c; }
         }
-#ifdef PG_DIAG
-        const long long tc1 = clock64();
-#endif
         if (grp == 0) {
             __stcg(reinterpret_cast<double2*>(bf.A_dst + row), make_double2(o0, o1));
             __stcg(reinterpret_cast<double2*>(bf.A_dst + row + 2), make_double2(o2, o3));
         }
-#ifdef PG_DIAG
-        const long long tc2 = clock64();
-        if (tid == 0 && t > 0) { ck_d[0] += (unsigned long long)(tc1 - tc0); ck_d[1] += (unsigned long long)(tc2 - tc1); }
-#endif
-        if (commit_only) continue;
+        if (!commit_only) {
         double r0v = (double)yy.x - o0, r1v = (double)yy.y - o1, r2v = (double)yy.z - o2, r3v = (double)yy.w - o3;
         if (grp == 0) {
             if (nv >= 4) {
@@ -956,11 +945,11 @@ __device__ void pg_pass_root_staged(const PgState& st, const PgBuf& bf, const Pg
                 }
                 break;
         }
-#ifdef PG_DIAG
-        if (tid == 0 && t > 0) ck_d[3] += (unsigned long long)(clock64() - tc2);
-#endif
+        }   // !commit_only
+        }   // lr < rows
+        __syncwarp();
+        if (lane == 0) pg_mbar_arrive(&b->mbar_empty[stg_used]);   // this warp is done with the stage
     }
-    pg_cp_wait_pending(0);
     PG_CK(4);
 
     // ---- block results
@@ -979,6 +968,10 @@ __device__ void pg_pass_root_staged(const PgState& st, const PgBuf& bf, const Pg
         }
     }
     __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < PGR_MAXST; ++q) { pg_mbar_inval(&b->mbar_full[q]); pg_mbar_inval(&b->mbar_empty[q]); }
+    }
     if (commit_only) return;
     if (tid < 4) {
         double v = 0.0;
@@ -1555,7 +1548,7 @@ __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView&
             if (VAR == PGV_GENERIC) { if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true, false>(st, bf, sm); else pg_pass_root<false, false>(st, bf, sm); }
             else if (VAR == PGV_BERN) pg_pass_root<true, true>(st, bf, sm);
             else if (VAR == PGV_QUARTERS) pg_pass_root_quarters<false, 5>(st, bf, sm);
-            else if (VAR == PGV_STAGED) { if (st.S <= 20) pg_pass_root_staged<false, 5>(st, bf, sm); else pg_pass_root_staged<false, PGR_JW>(st, bf, sm); }
+            else if (VAR == PGV_STAGED) { if (st.S <= 20) pg_pass_root_tma<false, 5>(st, bf, sm); else pg_pass_root_tma<false, PGR_JW>(st, bf, sm); }
             else pg_pass_root<false, true>(st, bf, sm);
             break;
         case PH_MINMAX: pg_pass_minmax(st, bf, sm); break;
