@@ -612,7 +612,7 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     int status;
     const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
     f->mm_valid[0][lane] = 0; f->mm_valid[1][lane] = 0; f->sc_valid[lane] = 0;
-    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; }
+    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; f->pred_valid = 0; f->pred_ok = 0; }
     if (lane < S) {
         const int s = lane;
         f->hw[s] = 0.0;       // smc.rs:53: once per update, never reset (Q1)
@@ -1247,6 +1247,9 @@ __device__ __forceinline__ int fw_finalize(const PgState& st, const FwCx& x, int
     const int sel = fw_select(st, x, lane, Wl, &Wn0);
     const size_t fb = (size_t)t * st.maxn;
     int depth = 0, internal = 0;
+    if (lane == 0)     // early commit: did the update end with the tree predicted after round 0 (same lineage, never grown further)?
+        f->pred_ok = f->pred_valid && ((sel == 0 && f->pred_sel == 0) ||
+                                       (sel > 0 && f->pred_sel > 0 && f->hlin[sel - 1] == f->pred_lin && f->hsize[pg_six(st, cur, sel - 1)] == 3));
     if (sel == 0) { if (lane == 0) fw_write_stump(st, t); }
     else {
         const int s = sel - 1;
@@ -1391,6 +1394,46 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         const int buf = (int)(c->upd % 3ull);
         const bool single = K == 1 && st.family != PG_BERNOULLI_LOGIT && __all_sync(PG_FULL, !act || need) && st.maxn > 6;
         int nq = 0;
+        if (single && !st.tr_upd && c->k + 1 < c->batch) {
+            // Early commit: every slot now holds a copy of ONE grown particle.  Under the stale-weight
+            // rule later rounds cannot change that (their mutated particles die), so the final selection is between the
+            // stump and this tree with weights that are known now: run the selection (smc.rs:105-122) on those weights,
+            // write the predicted tree to the forest, and let the section after the update's last data pass issue the next
+            // update's root pass before it digests the results.  fw_finalize checks the prediction; a miss is drained.
+            const int P = st.P;
+            const double Gl = (c->g_stump - c->g_stump) + (f->jr_gL[f->hsjob[anc]] + f->jr_gR[f->hsjob[anc]]);
+            const bool pact = lane < P;
+            const double Wl = pact ? c->C0 + (lane == 0 ? c->g_stump : Gl) : -INFINITY;
+            const double mx = fw_max(Wl);
+            const double e = pact ? exp(Wl - mx) : 0.0;
+            const double sum = fw_sum_seq(e, P);
+            const double Wn = e / sum;
+            const double total = fw_sum_seq(pact ? Wn : 0.0, P);
+            const double chosen = fw_u7(st, x, c->upd) * total;
+            int sel = 0;
+            {
+                double cum = 0.0;
+                bool open = true;
+#pragma unroll 1
+                for (int i = 0; i + 1 < P; ++i) {
+                    cum += __shfl_sync(PG_FULL, Wn, i);
+                    if (open && cum <= chosen) sel = i + 1; else open = false;
+                }
+            }
+            if (lane == 0) {
+                const int t = c->t_cur, j = f->hsjob[anc];
+                const size_t fb = (size_t)t * st.maxn;
+                if (sel == 0) fw_write_stump(st, t);
+                else {
+                    st.f_split_var[fb] = f->jvar[j]; st.f_split_val[fb] = f->jsplit[j]; st.f_thr32[fb] = f->jthr[j]; st.f_leaf_val[fb] = pg_nan();
+                    st.f_split_var[fb + 1] = -1; st.f_split_val[fb + 1] = pg_nan(); st.f_thr32[fb + 1] = 0.0f; st.f_leaf_val[fb + 1] = f->jr_vL[j];
+                    st.f_split_var[fb + 2] = -1; st.f_split_val[fb + 2] = pg_nan(); st.f_thr32[fb + 2] = 0.0f; st.f_leaf_val[fb + 2] = f->jr_vR[j];
+                    st.f_size[t] = 3;
+                }
+                f->pred_sel = sel; f->pred_lin = anc; f->pred_valid = 1;
+            }
+            __syncwarp();
+        }
         if (single) {
             const int j = f->hsjob[anc];
             const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n_global - cL, cLl = f->jr_cLl[act ? j : 0];
@@ -1530,6 +1573,19 @@ __device__ __forceinline__ bool fw_issue_prestaged(const PgState& st, const FwCx
     return true;
 }
 
+// Early commit: the root pass of the next update, adding the tree predicted for this one (already in the forest).
+__device__ __forceinline__ bool fw_issue_predicted(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const unsigned long long U1 = c->upd + 1ull;
+    if (!(f->pred_valid && f->pre_upd == U1 && c->k + 1 < c->batch && c->error == PG_OK && st.family != PG_BERNOULLI_LOGIT)) return false;
+    const int t_sub1 = (c->next_tree_idx + c->k + 1) % st.m;
+    const int src = c->a_cur, dst = 1 - c->a_cur;
+    fw_issue(st, x, lane, PH_ROOT, f->pred_sel == 0 ? -2 : c->t_cur, t_sub1, f->pre_J, f->pre_G, 0, src | (dst << 1) | ((int)(U1 & 1ull) << 2));
+    if (lane == 0) c->n_spec += 1;
+    return true;
+}
+
 // ---- the serial block's whole-kernel control loop ------------------------------------------------------
 __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
     __shared__ PgCtrl fw_scratch[FW_DR + 1];   // helpers must not raise errors for draws that may never be consumed
@@ -1583,7 +1639,10 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
         const long long t_entry = clock64();
         const int gerr = threadIdx.x == 0 ? __ldcg(&st.ctrl->error) : PG_OK;   // a pass may have flagged an error
         if (warp == 0) {   // the next update's root pass, if its jobs are staged: issue it before anything else
-            const bool sp = phase == PH_ROOT && fw_issue_prestaged(st, x, lane);
+            // ... or, after the last data pass of an update whose outcome was predicted after round 0 (the statistics pass;
+            // with pruning the partition pass), the next update's root pass on the predicted tree
+            const bool sp = (phase == PH_ROOT && fw_issue_prestaged(st, x, lane)) ||
+                            ((phase == PH_STATS || (phase == PH_PART && st.prune)) && fw_issue_predicted(st, x, lane));
             if (lane == 0) f->spec_now = sp ? 1 : 0;
         }
         fw_reduce(st, f, phase, J, pb);   // contains a __syncthreads before its combine step
@@ -1630,6 +1689,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                         if (lane == 0) f->pf_n = 0;
                         __syncwarp();
                     }
+                    spec = f->spec_now != 0;
                     sn = fw_after_stats(st, x, lane, phase);
                     FW_TICK(1);
                     break;
@@ -1649,6 +1709,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                     }
                     if (lane == 0) { c->round += 1; f->n_mq = 0; }
                     __syncwarp();
+                    spec = f->spec_now != 0;
                     sn = SN_DRAW_ROUND;
                     break;
                 }
@@ -1665,7 +1726,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                 if (c->error != PG_OK) { sn = SN_NONE; break; }
                 if (sn == SN_NONE || sn == SN_PREP_PART) break;
                 if (sn == SN_BEGIN_UPDATE) {
-                    if (spec) {   // the guess "this update commits a stump" held: the root pass in flight is the next update's
+                    if (spec && (phase == PH_ROOT || f->pred_ok)) {   // the guess held: the root pass in flight is the next update's
                         if (lane == 0) c->a_cur = 1 - c->a_cur;
                         __syncwarp();
                         fw_start_update(st, x, lane, true);

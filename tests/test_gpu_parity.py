@@ -156,7 +156,7 @@ def test_gpu_pruned_dead_proposals_same_forest():
     """Option prune_dead_proposals: proposals of particles whose weight is provably 0 are not evaluated.
     Forest, predictions and BartInfo must still equal the oracle's, which evaluates everything."""
     from oracle import pyoracle as po
-    n, p, m, P = 3000, 6, 20, 20
+    n, p, m, P = 4000, 6, 40, 20      # 160 tree updates without a trace: speculation, early commit and pruning all active
     X, y = datagen.small(n, p, seed=11)
     cfg = cfg_for(y, m, P, p, seed=5)
     orc = po.OracleSampler(X.astype(np.float64), y, **cfg)
@@ -168,9 +168,9 @@ def test_gpu_pruned_dead_proposals_same_forest():
         dev.set_likelihood_code(0, [1.0])
         dev.set_rng_philox(5)
         dev.set_option("prune_dead_proposals", prune)
-        preds = [dev.step(t) for t in (True, True, False)]
+        preds = [dev.step(t) for t in (True, True, False, False)]
         outs[prune] = (preds, dev.counters()["bytes_contract"], dev)
-    opreds = [orc.step(t) for t in (True, True, False)]
+    opreds = [orc.step(t) for t in (True, True, False, False)]
     for prune in ("0", "1"):
         preds, _, dev = outs[prune]
         for a, b in zip(opreds, preds):
