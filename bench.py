@@ -304,7 +304,8 @@ def run_gpu(args):
                          "fused_bytes_per_launch": bytes_per_launch, "fused_gbs": fused_gbs, "fused_frac": fused_gbs / peak,
                          "note": "achieved = SURVEY.md 8(d) contract bytes (B_tree summed from device counters over the sweep's "
                                  "grows: per-slot min/max + stats + partition passes, fp64 A, no credit for cross-particle "
-                                 "sharing) / CUDA-event time of the launch.  fused_* = the bytes this implementation must move "
+                                 "sharing) / CUDA-event time of the launch; it can exceed the HBM peak because the formula charges A, y and the "
+                                 "index list once per slot while the fused root pass reads them once per tree.  fused_* = the bytes this implementation must move "
                                  "(A, y and each distinct split column read once per pass for all slots together); "
                                  "traffic = ncu dram bytes of one launch (A and y stay L2-resident, so it is below both). "
                                  "The launch is bound by latency (control sections and per-pass instruction issue), not by HBM: DESIGN.md section 4-5"},
