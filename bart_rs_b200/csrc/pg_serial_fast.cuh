@@ -612,7 +612,7 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     int status;
     const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
     f->mm_valid[0][lane] = 0; f->mm_valid[1][lane] = 0; f->sc_valid[lane] = 0;
-    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; f->pred_valid = 0; f->pred_ok = 0; }
+    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; f->pred_valid = 0; f->pred_ok = 0; f->pred_sel = 0; }
     if (lane < S) {
         const int s = lane;
         f->hw[s] = 0.0;       // smc.rs:53: once per update, never reset (Q1)
@@ -1394,46 +1394,7 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         const int buf = (int)(c->upd % 3ull);
         const bool single = K == 1 && st.family != PG_BERNOULLI_LOGIT && __all_sync(PG_FULL, !act || need) && st.maxn > 6;
         int nq = 0;
-        if (single && !st.tr_upd && c->k + 1 < c->batch) {
-            // Early commit: every slot now holds a copy of ONE grown particle.  Under the stale-weight
-            // rule later rounds cannot change that (their mutated particles die), so the final selection is between the
-            // stump and this tree with weights that are known now: run the selection (smc.rs:105-122) on those weights,
-            // write the predicted tree to the forest, and let the section after the update's last data pass issue the next
-            // update's root pass before it digests the results.  fw_finalize checks the prediction; a miss is drained.
-            const int P = st.P;
-            const double Gl = (c->g_stump - c->g_stump) + (f->jr_gL[f->hsjob[anc]] + f->jr_gR[f->hsjob[anc]]);
-            const bool pact = lane < P;
-            const double Wl = pact ? c->C0 + (lane == 0 ? c->g_stump : Gl) : -INFINITY;
-            const double mx = fw_max(Wl);
-            const double e = pact ? exp(Wl - mx) : 0.0;
-            const double sum = fw_sum_seq(e, P);
-            const double Wn = e / sum;
-            const double total = fw_sum_seq(pact ? Wn : 0.0, P);
-            const double chosen = fw_u7(st, x, c->upd) * total;
-            int sel = 0;
-            {
-                double cum = 0.0;
-                bool open = true;
-#pragma unroll 1
-                for (int i = 0; i + 1 < P; ++i) {
-                    cum += __shfl_sync(PG_FULL, Wn, i);
-                    if (open && cum <= chosen) sel = i + 1; else open = false;
-                }
-            }
-            if (lane == 0) {
-                const int t = c->t_cur, j = f->hsjob[anc];
-                const size_t fb = (size_t)t * st.maxn;
-                if (sel == 0) fw_write_stump(st, t);
-                else {
-                    st.f_split_var[fb] = f->jvar[j]; st.f_split_val[fb] = f->jsplit[j]; st.f_thr32[fb] = f->jthr[j]; st.f_leaf_val[fb] = pg_nan();
-                    st.f_split_var[fb + 1] = -1; st.f_split_val[fb + 1] = pg_nan(); st.f_thr32[fb + 1] = 0.0f; st.f_leaf_val[fb + 1] = f->jr_vL[j];
-                    st.f_split_var[fb + 2] = -1; st.f_split_val[fb + 2] = pg_nan(); st.f_thr32[fb + 2] = 0.0f; st.f_leaf_val[fb + 2] = f->jr_vR[j];
-                    st.f_size[t] = 3;
-                }
-                f->pred_sel = sel; f->pred_lin = anc; f->pred_valid = 1;
-            }
-            __syncwarp();
-        }
+        if (single && !st.tr_upd && c->k + 1 < c->batch && lane == 0) { f->pred_lin = anc; f->pred_sel = -1 - f->hsjob[anc]; }   // fw_predict, after PART is issued
         if (single) {
             const int j = f->hsjob[anc];
             const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n_global - cL, cLl = f->jr_cLl[act ? j : 0];
@@ -1571,6 +1532,53 @@ __device__ __forceinline__ bool fw_issue_prestaged(const PgState& st, const FwCx
     fw_issue(st, x, lane, PH_ROOT, -2 /* a stump */, t_sub1, f->pre_J, f->pre_G, 0, src | (dst << 1) | ((int)(U1 & 1ull) << 2));
     if (lane == 0) c->n_spec += 1;
     return true;
+}
+
+// Early commit, prediction step (runs right after the partition pass of an all-grew update has been issued, while it streams):
+__device__ __forceinline__ void fw_predict(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    if (f->pred_valid || f->pred_sel >= 0) return;          // nothing pending (pred_sel = -1 - job marks a pending prediction)
+    const int j0 = -1 - f->pred_sel;
+    __syncwarp();
+    // Early commit: every slot now holds a copy of ONE grown particle.  Under the stale-weight
+    // rule later rounds cannot change that (their mutated particles die), so the final selection is between the
+    // stump and this tree with weights that are known now: run the selection (smc.rs:105-122) on those weights,
+    // write the predicted tree to the forest, and let the section after the update's last data pass issue the next
+    // update's root pass before it digests the results.  fw_finalize checks the prediction; a miss is drained.
+    const int P = st.P;
+    const double Gl = (c->g_stump - c->g_stump) + (f->jr_gL[j0] + f->jr_gR[j0]);
+    const bool pact = lane < P;
+    const double Wl = pact ? c->C0 + (lane == 0 ? c->g_stump : Gl) : -INFINITY;
+    const double mx = fw_max(Wl);
+    const double e = pact ? exp(Wl - mx) : 0.0;
+    const double sum = fw_sum_seq(e, P);
+    const double Wn = e / sum;
+    const double total = fw_sum_seq(pact ? Wn : 0.0, P);
+    const double chosen = fw_u7(st, x, c->upd) * total;
+    int sel = 0;
+    {
+        double cum = 0.0;
+        bool open = true;
+#pragma unroll 1
+        for (int i = 0; i + 1 < P; ++i) {
+            cum += __shfl_sync(PG_FULL, Wn, i);
+            if (open && cum <= chosen) sel = i + 1; else open = false;
+        }
+    }
+    if (lane == 0) {
+        const int t = c->t_cur, j = j0;
+        const size_t fb = (size_t)t * st.maxn;
+        if (sel == 0) fw_write_stump(st, t);
+        else {
+            st.f_split_var[fb] = f->jvar[j]; st.f_split_val[fb] = f->jsplit[j]; st.f_thr32[fb] = f->jthr[j]; st.f_leaf_val[fb] = pg_nan();
+            st.f_split_var[fb + 1] = -1; st.f_split_val[fb + 1] = pg_nan(); st.f_thr32[fb + 1] = 0.0f; st.f_leaf_val[fb + 1] = f->jr_vL[j];
+            st.f_split_var[fb + 2] = -1; st.f_split_val[fb + 2] = pg_nan(); st.f_thr32[fb + 2] = 0.0f; st.f_leaf_val[fb + 2] = f->jr_vR[j];
+            st.f_size[t] = 3;
+        }
+        f->pred_sel = sel; f->pred_valid = 1;
+    }
+    __syncwarp();
 }
 
 // Early commit: the root pass of the next update, adding the tree predicted for this one (already in the forest).
@@ -1759,6 +1767,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                 if (drain) fw_await(st, x, lane);   // the speculative root pass guessed wrong: let it finish, ignore its output
                 fw_issue_ctrl(st, x, lane);
                 FW_TICK(4);
+                fw_predict(st, x, lane);            // off the critical path: the partition pass is streaming
             }
             __syncthreads();
         }
