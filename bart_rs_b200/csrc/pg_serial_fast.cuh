@@ -465,6 +465,44 @@ __device__ __forceinline__ int fw_write_jobs(const PgState& st, const FwCx& x, c
     return J;
 }
 
+// Group the first JT jobs of the cached job list (f->jseg / f->jlen) by index segment, groups in first-seen order, jobs of
+// a group in job order; writes job_order / grp_first of buffer parity pb (same result as pg_group_jobs_arrays, computed
+// by the warp from shared memory instead of one lane walking global arrays).  Returns the number of groups.
+__device__ __forceinline__ int fw_group_jobs(const PgState& st, const FwCx& x, int JT, int lane, int pb, unsigned long long* stats_bytes) {
+    PgFastSm* f = x.f;
+    const bool in = lane < JT;
+    const unsigned seg = in ? f->jseg[lane] : 0xFFFFFFF0u - (unsigned)lane, len = in ? f->jlen[lane] : 0u;
+    const unsigned m = __match_any_sync(PG_FULL, seg) & __match_any_sync(PG_FULL, len) & __ballot_sync(PG_FULL, in);
+    const int leader = in ? __ffs(m) - 1 : 31;
+    const unsigned leaders = __ballot_sync(PG_FULL, in && leader == lane);
+    const int G = __popc(leaders);
+    const int g = __popc(leaders & ((1u << leader) - 1u));              // my group: rank of my leader among the leaders
+    int offset = 0;                                                     // jobs in the groups before mine
+    {
+        unsigned rest = leaders;
+#pragma unroll 1
+        while (rest) {
+            const int l = __ffs(rest) - 1;
+            rest &= rest - 1u;
+            const int cnt = __popc(__shfl_sync(PG_FULL, m, l));
+            if (l < leader) offset += cnt;
+        }
+    }
+    const size_t jo = (size_t)pb * st.S;
+    int* gf = st.grp_first + (size_t)pb * (st.S + 1);
+    if (in) {
+        st.job_order[jo + offset + __popc(m & ((1u << lane) - 1u))] = lane;
+        if (leader == lane) gf[g] = offset;
+    }
+    if (lane == 0) gf[G] = JT;
+    // bytes a statistics pass moves for these groups: (idx 4 + A 8 + y 4) L + 4 L per job of the group
+    unsigned long long bm = (in && leader == lane) ? (16ull + 4ull * (unsigned long long)__popc(m)) * (unsigned long long)len : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bm += __shfl_xor_sync(PG_FULL, bm, o);
+    *stats_bytes = bm;
+    return G;
+}
+
 __device__ __forceinline__ int fw_unique(int var, bool live, int lane) {
     const unsigned lv = __ballot_sync(PG_FULL, live);
     const unsigned m = __match_any_sync(PG_FULL, live ? var : -1 - lane);
@@ -754,6 +792,7 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
     const int J = fw_write_jobs(st, x, jb, lane, true, pb, true, true, &G);
     // ... carrying, for round 1, the round-2 proposals of every slot (node 2: the other child) as prefetch jobs
     int Jp = 0;
+    unsigned long long grouped_bytes = 0ull;
     if (r == 1 && G == 1) {
         const int buf2 = buf;
         bool want = lane < S && f->mm_valid[1][lane] && f->d_ok[buf2][2] && f->mm_lo[1][lane] < f->mm_hi[1][lane];
@@ -774,29 +813,29 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
             const unsigned len2 = (unsigned)st.n - 0u;
             (void)len2;
             st.job_var[jo] = f->mm_var[1][lane]; st.job_thr32[jo] = thr2; st.job_seg_off[jo] = f->mm_seg[1][lane];
-            st.job_len[jo] = st.pt_len[pg_tix(st, cur, lane, 2)];
+            const unsigned len2v = st.pt_len[pg_tix(st, cur, lane, 2)];
+            st.job_len[jo] = len2v;
             st.job_slot[jo] = lane; st.job_node[jo] = 2; st.job_split[jo] = split2;
+            f->jseg[J + q] = f->mm_seg[1][lane]; f->jlen[J + q] = len2v;
             f->pf_slot[q] = lane;
             f->sc_seg[lane] = f->mm_seg[1][lane]; f->sc_var[lane] = f->mm_var[1][lane]; f->sc_thr[lane] = thr2;
         }
         __threadfence_block();
         __syncwarp();
-        if (Jp > 0 && lane == 0) {
-            const size_t jo = (size_t)pb * st.S;
-            G = pg_group_jobs_arrays(st.job_seg_off + jo, st.job_len + jo, st.job_order + jo, st.grp_first + (size_t)pb * (st.S + 1), J + Jp);
-        }
-        G = __shfl_sync(PG_FULL, G, 0);
+        if (Jp > 0) G = fw_group_jobs(st, x, J + Jp, lane, pb, &grouped_bytes);
     }
     if (lane == 0) {
         f->pf_n = Jp;
         const size_t jo = (size_t)pb * st.S;
         const int* jord = st.job_order + jo;
         const int* gf = st.grp_first + (size_t)pb * (st.S + 1);
-        unsigned long long bm = 0, bc = 0;
+        unsigned long long bm = grouped_bytes, bc = 0;
+        if (Jp == 0) {
 #pragma unroll 1
-        for (int g = 0; g < G; ++g) {
-            const unsigned long long L = st.job_len[jo + jord[gf[g]]];
-            bm += (4ull + 8ull + 4ull) * L + 4ull * L * (unsigned long long)(gf[g + 1] - gf[g]);
+            for (int g = 0; g < G; ++g) {
+                const unsigned long long L = f->jlen[jord[gf[g]]];
+                bm += (4ull + 8ull + 4ull) * L + 4ull * L * (unsigned long long)(gf[g + 1] - gf[g]);
+            }
         }
 #pragma unroll 1
         for (int j = 0; j < J; ++j) bc += 28ull * f->jlen[j];
