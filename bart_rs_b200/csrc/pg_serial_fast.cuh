@@ -1088,7 +1088,9 @@ __device__ __forceinline__ int fw_plan_partitions(const PgState& st, const FwCx&
     __syncwarp();
     if (leader) {
         st.pj_of_anc[anc] = k;
-        st.pj_anc[k] = anc; st.pj_job[k] = f->from_cache ? f->sc_job[f->jslot[j]] : j;   // where the pass left this job's per-block counts
+        const int cj = f->from_cache ? f->sc_job[f->jslot[j]] : j;   // where the pass left this job's per-block counts
+        st.pj_anc[k] = anc; st.pj_job[k] = cj;
+        f->pq_job[k] = cj; f->pq_len[k] = len; f->pq_ident[k] = f->jseg[j] == PG_SEG_IDENTITY ? 1 : 0;
         st.pj_var[k] = f->jvar[j]; st.pj_thr32[k] = f->jthr[j];
         st.pj_src_off[k] = f->jseg[j]; st.pj_len[k] = len; st.pj_cntL[k] = cntL; st.pj_dst_off[k] = (unsigned)off;
     }
@@ -1183,7 +1185,7 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
         const int lane = tid & 31, warp = tid >> 5, G = st.grid;
 #pragma unroll 1
         for (int k = warp; k < K; k += PG_WARPS) {
-            const int j = st.pj_job[k];
+            const int j = f->pq_job[k];
             unsigned carry = 0;
 #pragma unroll 1
             for (int base = 0; base < G; base += 32) {
@@ -1202,10 +1204,10 @@ __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
         unsigned long long bm = 0;
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
-            const unsigned long long L = st.pj_len[k];
-            bm += (st.pj_src_off[k] == PG_SEG_IDENTITY ? 0ull : 4ull * L) + 4ull * L + 4ull * L;
+            const unsigned long long L = f->pq_len[k];
+            bm += (f->pq_ident[k] ? 0ull : 4ull * L) + 4ull * L + 4ull * L;
         }
-        c->bytes_model += bm + 4ull * (unsigned long long)f->n_mq * (K > 0 ? (unsigned long long)st.pj_len[0] : 0ull);
+        c->bytes_model += bm + 4ull * (unsigned long long)f->n_mq * (K > 0 ? (unsigned long long)f->pq_len[0] : 0ull);
         c->n_groups = f->n_mq;          // look-ahead min/max requests riding on the partition pass
         c->phase = PH_PART; c->n_phases += 1;
     }
