@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgbart_b200.so")
+LIB_PATH = os.environ.get("PGBART_LIB_PATH") or os.path.join(_HERE, "libpgbart_b200.so")   # override: A/B runs of two builds
 
 GAUSSIAN, BERNOULLI_LOGIT, GAUSSIAN_KERNEL = 0, 1, 2
 X_F64, X_F32 = 0, 1

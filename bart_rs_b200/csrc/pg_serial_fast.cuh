@@ -650,7 +650,7 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     int status;
     const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
     f->mm_valid[0][lane] = 0; f->mm_valid[1][lane] = 0; f->sc_valid[lane] = 0;
-    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; f->pred_valid = 0; f->pred_ok = 0; f->pred_sel = 0; }
+    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; f->pred_valid = 0; f->pred_ok = 0; f->pred_sel = 0; f->sl_valid = 0; }
     if (lane < S) {
         const int s = lane;
         f->hw[s] = 0.0;       // smc.rs:53: once per update, never reset (Q1)
@@ -706,14 +706,17 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
         }
         const int ss = pg_six(st, cur, s);
         const int qh = f->hqh[ss], qt = f->hqt[ss];
+        // slots that still hold the untouched copy of the single grown particle of round 0: node / count / segment of the
+        // leaf in front of the queue come from shared memory instead of two dependent reads of the slot tables
+        const bool shallow = f->sl_valid && f->hlin[s] == f->sl_lin && f->hsize[ss] == 3 && qt == 2 && qh < 2;
         if (qh < qt) {
-            const int node = st.pt_queue[pg_tix(st, cur, s, qh)];
+            const int node = shallow ? qh + 1 : st.pt_queue[pg_tix(st, cur, s, qh)];
             f->hqh[ss] = qh + 1;
             if (tr) { tr[0] = 1; tr[1] = (double)node; tr[2] = -1; }
             const double u1 = pre ? f->d_u1[buf][r][s] : fw_cold_draw(fw_rng_view(st), c, 0, PG_D_GROW, upd, r, s, 0.0, 0.0);
             if (!(x.thr[pg_depth_of(node)] > u1)) {
                 const size_t iN = pg_tix(st, cur, s, node);
-                const unsigned cnt = st.pt_cnt[iN];
+                const unsigned cnt = shallow ? f->sl_cnt[node - 1] : st.pt_cnt[iN];
                 if (cnt == 0u) { if (tr) tr[0] = 2; }
                 else {
                     int var;
@@ -724,8 +727,9 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
                         else { var = (int)(u2 * (double)st.p); if (var > st.p - 1) var = st.p - 1; }
                     }
                     if (tr) tr[2] = (double)var;
-                    jb.live = true; jb.node = node; jb.var = var; jb.len = st.pt_len[iN];
-                    jb.seg_off = st.pt_seg_off[iN];
+                    jb.live = true; jb.node = node; jb.var = var;
+                    jb.len = shallow ? f->sl_len[node - 1] : st.pt_len[iN];
+                    jb.seg_off = shallow ? f->sl_seg[node - 1] : st.pt_seg_off[iN];
                 }
             }
         }
@@ -1439,6 +1443,10 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         if (single) {
             const int j = f->hsjob[anc];
             const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n_global - cL, cLl = f->jr_cLl[act ? j : 0];
+            if (lane == 0) {   // the two leaves every slot will propose on in rounds 1 and 2: kept at hand (fw_draw_round)
+                f->sl_lin = anc; f->sl_cnt[0] = cL; f->sl_cnt[1] = cR; f->sl_len[0] = cLl; f->sl_len[1] = (unsigned)st.n - cLl;
+                f->sl_seg[0] = off; f->sl_seg[1] = off + cLl; f->sl_valid = 1;
+            }
 #pragma unroll 1
             for (int r = 1; r <= 2; ++r) {
                 const bool want = act && f->d_ok[buf][r] && !(x.thr[1] > f->d_u1[buf][r][lane]) && (r == 1 ? cL : cR) > 0u;
