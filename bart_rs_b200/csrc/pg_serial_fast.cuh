@@ -989,7 +989,7 @@ __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, 
     }
     if (lane < J) {
         const size_t iN = pg_tix(st, cur, f->jslot[lane], f->jnode[lane]);
-        const FwVals v = fw_values(st, x, lane, st.pt_cnt[iN], st.pt_So[iN], st.pt_Sr[iN]);
+        const FwVals v = fw_values(st, x, lane, st.pt_cnt[iN], st.pt_So[iN], st.pt_Sr[iN]);   // (one round trip: L2-resident slot tables)
         f->jr_cL[lane] = v.cL;     // the partition reads the left count later
         f->jr_cLl[lane] = f->rCntL[lane];
         if (bern) {
@@ -1295,7 +1295,11 @@ __device__ __forceinline__ int fw_finalize(const PgState& st, const FwCx& x, int
     if (lane == 0)     // early commit: did the update end with the tree predicted after round 0 (same lineage, never grown further)?
         f->pred_ok = f->pred_valid && ((sel == 0 && f->pred_sel == 0) ||
                                        (sel > 0 && f->pred_sel > 0 && f->hlin[sel - 1] == f->pred_lin && f->hsize[pg_six(st, cur, sel - 1)] == 3));
-    if (sel == 0) { if (lane == 0) fw_write_stump(st, t); }
+    __syncwarp();
+    if (f->pred_ok) {              // the forest already holds this very tree (fw_predict wrote it): nothing to copy
+        if (sel != 0) { depth = 1; internal = 1; }
+    }
+    else if (sel == 0) { if (lane == 0) fw_write_stump(st, t); }
     else {
         const int s = sel - 1;
         const int sz = f->hsize[pg_six(st, cur, s)];
