@@ -1436,9 +1436,25 @@ __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemVie
         const int t = threadIdx.x;
         if (t < K && t < 32) {
             b->pp_src[t] = __ldcg(&st.pj_src_off[t]); b->pp_len[t] = __ldcg(&st.pj_len[t]); b->pp_var[t] = __ldcg(&st.pj_var[t]);
-            b->pp_thr[t] = __ldcg(&st.pj_thr32[t]); b->pp_left[t] = __ldcg(&st.pj_warp_left[(size_t)t * st.n_gwarps + PG_BID]);
+            b->pp_thr[t] = __ldcg(&st.pj_thr32[t]);
             b->pp_dst[t] = __ldcg(&st.pj_dst_off[t]); b->pp_cntL[t] = __ldcg(&st.pj_cntL[t]);
-            b->pp_exp[t] = __ldcg(&bf.part_ccnt[(size_t)PG_BID * st.S + __ldcg(&st.pj_job[t])]);
+        }
+        // this block's offset among a job's LEFT entries = the per-block left counts of the blocks before it (the pass that
+        // computed the job's statistics left them in part_ccnt): every block adds them up itself, one warp per job, instead
+        // of the control block running a 147-entry prefix per job before it can issue this pass
+        {
+            const int w = t >> 5, l = t & 31;
+            for (int k = w; k < K && k < 32; k += PG_WARPS) {
+                const int j = __ldcg(&st.pj_job[k]);
+                unsigned acc = 0u, mine = 0u;
+                for (int bq = l; bq <= PG_BID; bq += 32) {
+                    const unsigned v = __ldcg(&bf.part_ccnt[(size_t)bq * st.S + j]);
+                    if (bq < PG_BID) acc += v; else mine = v;
+                }
+                acc = __reduce_add_sync(PG_FULL, acc);
+                mine = __reduce_add_sync(PG_FULL, mine);
+                if (l == 0) { b->pp_left[k] = acc; b->pp_exp[k] = mine; }
+            }
         }
         if (t >= 64 && t - 64 < Q && t - 64 < 64) {
             const int q = t - 64;

@@ -1180,29 +1180,10 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
 __device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
-    const int K = c->n_pjobs, W = st.n_gwarps, S = st.S;
+    const int K = c->n_pjobs;
     const int tid = threadIdx.x;
-    // every segment is partitioned in block units (pg_part_ident / pg_part_seg): exclusive prefix, over pass blocks, of the
-    // per-block left counts of the pass that computed the job's statistics — one warp per job
-    {
-        const unsigned* p_ccnt = st.part_ccnt + pg_off_part_ccnt(st, (int)(c->upd & 1ull));
-        const int lane = tid & 31, warp = tid >> 5, G = st.grid;
-#pragma unroll 1
-        for (int k = warp; k < K; k += PG_WARPS) {
-            const int j = f->pq_job[k];
-            unsigned carry = 0;
-#pragma unroll 1
-            for (int base = 0; base < G; base += 32) {
-                const int bq = base + lane;
-                const unsigned v = bq < G ? __ldcg(&p_ccnt[(size_t)bq * S + j]) : 0u;
-                unsigned xx = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(PG_FULL, xx, o); if (lane >= o) xx += y; }
-                if (bq < G) st.pj_warp_left[(size_t)k * W + bq] = carry + xx - v;
-                carry += __shfl_sync(PG_FULL, xx, 31);
-            }
-        }
-    }
+    // (every segment is partitioned in block units and each pass block derives its own offset from the per-block left
+    // counts, pg_pass_part — nothing to prefix here)
     __syncthreads();
     if (tid == 0) {
         unsigned long long bm = 0;
