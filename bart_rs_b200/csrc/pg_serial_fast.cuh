@@ -767,7 +767,6 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
     }
     if (jb.live) { jb.lo = f->mm_lo[ri][lane]; jb.hi = f->mm_hi[ri][lane]; }
     fw_decide(st, x, jb);                                  // splitting.rs:39-56 (may drop the job: min >= max)
-    if (lane == 0) { unsigned long long bc = 0; (void)bc; }
     if (!__any_sync(PG_FULL, jb.live)) {
         (void)fw_write_jobs(st, x, jb, lane, true, pb, false, true, &G);
         return SN_FINISH_ROUND;

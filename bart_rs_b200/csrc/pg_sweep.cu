@@ -16,6 +16,8 @@
 
 namespace cg = cooperative_groups;
 
+extern __shared__ __align__(128) unsigned char pg_smem_raw[];   // dynamic shared memory of every kernel here (pg_smem_view)
+
 // Grid barrier with a serial section.  Block 0 is ALWAYS the serial block: its SM keeps the (large,
 // straight-line) control code in its instruction caches, which is what the section's latency is made of.
 // Other blocks arrive (release fence + counter) and wait for the generation flag; block 0 waits for the
@@ -59,7 +61,6 @@ __device__ void pg_barrier_serial(const PgState& st, const PgSmemView& smv, unsi
 template <int VAR>
 __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
     constexpr bool FAST = VAR != PGV_GENERIC;
-    extern __shared__ __align__(128) unsigned char pg_smem_raw[];
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     // sampler constants the serial section reads: staged once per launch
     for (int i = threadIdx.x; i < st.max_depth + 2 && i < 16; i += blockDim.x) sm.base->cthr[i] = st.thr_depth[i];
@@ -144,7 +145,6 @@ extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_generic(const PgState st) { pg_sweep_body<PGV_GENERIC>(st); }
 
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_phase_kernel(const PgState st) {
-    extern __shared__ __align__(128) unsigned char pg_smem_raw[];
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     if (threadIdx.x == 0) sm.base->pass_bid = (int)blockIdx.x;
     __syncthreads();
