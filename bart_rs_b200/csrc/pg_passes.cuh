@@ -119,7 +119,7 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     int n_mq, pf_n, pf_slot[32];
     unsigned long long pre_upd;                  // update whose root jobs are already staged in the global job arrays
     int pre_J, pre_G, spec_now;
-    int sl_valid, sl_lin; unsigned sl_cnt[2], sl_len[2], sl_seg[2];   // single lineage after round 0: its two leaves (mirror of the slot tables)
+    int sl_valid, sl_lin; unsigned sl_cnt[2], sl_len[2], sl_seg[2]; double sl_So[2], sl_Sr[2], sl_g[2];   // single lineage after round 0: its two leaves (mirror of the slot tables)
     int pq_job[32], pq_ident[32]; unsigned pq_len[32];   // partition jobs of the round (mirrors of pj_job / pj_src_off / pj_len)
     int pred_valid, pred_sel, pred_lin, pred_ok;  // early commit: the tree this update will commit, predicted after round 0
     int lazy_J;                                  // pruned round 0: accepted root proposals that were not evaluated (they count as grows)

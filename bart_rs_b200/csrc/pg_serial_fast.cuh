@@ -988,7 +988,12 @@ __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, 
     }
     if (lane < J) {
         const size_t iN = pg_tix(st, cur, f->jslot[lane], f->jnode[lane]);
-        const FwVals v = fw_values(st, x, lane, st.pt_cnt[iN], st.pt_So[iN], st.pt_Sr[iN]);   // (one round trip: L2-resident slot tables)
+        // node statistics: from the shared-memory mirror when the slot still holds the untouched single lineage of round 0
+        const int sj = f->jslot[lane], nj = f->jnode[lane];
+        const bool shallow = f->sl_valid && f->hlin[sj] == f->sl_lin && f->hsize[pg_six(st, cur, sj)] == 3 && (nj == 1 || nj == 2);
+        const unsigned n_cnt = shallow ? f->sl_cnt[nj - 1] : st.pt_cnt[iN];
+        const double n_So = shallow ? f->sl_So[nj - 1] : st.pt_So[iN], n_Sr = shallow ? f->sl_Sr[nj - 1] : st.pt_Sr[iN];
+        const FwVals v = fw_values(st, x, lane, n_cnt, n_So, n_Sr);
         f->jr_cL[lane] = v.cL;     // the partition reads the left count later
         f->jr_cLl[lane] = f->rCntL[lane];
         if (bern) {
@@ -1002,7 +1007,7 @@ __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, 
             const int ss = pg_six(st, cur, s);
             f->jr_vL[lane] = v.vL; f->jr_vR[lane] = v.vR; f->jr_gL[lane] = v.gL; f->jr_gR[lane] = v.gR;
             f->jr_SoL[lane] = v.SoL; f->jr_SrL[lane] = v.SrL;
-            const double G = (f->hG[ss] - st.pt_g[iN]) + (v.gL + v.gR);
+            const double G = (f->hG[ss] - (shallow ? f->sl_g[nj - 1] : st.pt_g[iN])) + (v.gL + v.gR);
             const double w = c->C0 + G;                // smc.rs:89-95
             f->hGp[s] = G;
             f->hw[s] = w;
@@ -1429,7 +1434,9 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
             const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n_global - cL, cLl = f->jr_cLl[act ? j : 0];
             if (lane == 0) {   // the two leaves every slot will propose on in rounds 1 and 2: kept at hand (fw_draw_round)
                 f->sl_lin = anc; f->sl_cnt[0] = cL; f->sl_cnt[1] = cR; f->sl_len[0] = cLl; f->sl_len[1] = (unsigned)st.n - cLl;
-                f->sl_seg[0] = off; f->sl_seg[1] = off + cLl; f->sl_valid = 1;
+                f->sl_seg[0] = off; f->sl_seg[1] = off + cLl;
+                f->sl_So[0] = f->jr_SoL[j]; f->sl_So[1] = c->T_o - f->jr_SoL[j]; f->sl_Sr[0] = f->jr_SrL[j]; f->sl_Sr[1] = c->T_r - f->jr_SrL[j];
+                f->sl_g[0] = f->jr_gL[j]; f->sl_g[1] = f->jr_gR[j]; f->sl_valid = 1;
             }
 #pragma unroll 1
             for (int r = 1; r <= 2; ++r) {
