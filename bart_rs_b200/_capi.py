@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("PGBART_LIB_PATH") or os.path.join(_HERE, "libpgbart_b
 
 GAUSSIAN, BERNOULLI_LOGIT, GAUSSIAN_KERNEL = 0, 1, 2
 X_F64, X_F32 = 0, 1
+ALLOW_FP32_ROUNDING = 0x100
 ORDER_C, ORDER_F = 0, 1
 TS_FIELDS = 12
 
@@ -23,6 +24,7 @@ EXPORTS = [
     "pgbart_set_rng_tape", "pgbart_trace_enable", "pgbart_trace_read", "pgbart_set_option", "pgbart_get_counters",
     "pgbart_timer_start", "pgbart_timer_stop", "pgbart_get_profile", "pgbart_debug_block_cycles",
     "pgbart_shard_config", "pgbart_shard_mailbox", "pgbart_shard_connect", "pgbart_predict", "pgbart_variable_inclusion",
+    "pgbart_get_spec_counters", "pgbart_host_alloc", "pgbart_host_free",
 ]
 
 
@@ -82,5 +84,8 @@ def lib():
     L.pgbart_shard_connect.argtypes = [vp, vp]
     L.pgbart_predict.argtypes = [vp, vp, i32, i32, u64, vp]
     L.pgbart_variable_inclusion.argtypes = [vp, vp]
+    L.pgbart_get_spec_counters.argtypes = [vp, vp]
+    L.pgbart_host_alloc.argtypes = [u64, C.POINTER(vp)]
+    L.pgbart_host_free.argtypes = [vp]
     _lib = L
     return L

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/pgbart.h"
 #include "pg_sweep.h"
@@ -18,7 +19,7 @@
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;   // per host thread: concurrent pgbart_create calls do not race
 
 struct Sampler {
     int device = 0;
@@ -39,6 +40,9 @@ struct Sampler {
     long long tr_u_cap = 0;
     int tr_r_cap = 0;
     PgCtrl host_ctrl{};
+    bool allow_rounding = false;     // created with PGBART_ALLOW_FP32_ROUNDING: x / y (and predict inputs) are rounded to fp32 knowingly
+    double* pin_pred = nullptr;      // pinned staging buffer of pgbart_step's device->host copy (lazily allocated, n doubles)
+    std::vector<cudaEvent_t> chunk_ev;   // one event per staged chunk of that copy
     std::vector<void*> ipc_open;     // peer mailboxes opened through CUDA IPC (observation sharding)
     long long steps_done = 0;
 };
@@ -91,6 +95,99 @@ double unrolled_mean(const double* xs, size_t n) {
     return acc / (double)n;
 }
 
+// The device stores X and y as fp32 (north_star: "fp32 data, fp64 accumulation"); the reference computes on the f64 values.
+// A value that is not exactly representable in fp32 would be silently quantised: distinct values can collapse (a column
+// like 1e9 + k becomes constant), ties and child counts change, and decisions diverge from the reference.  So f64 input is
+// checked and refused unless the caller passes PGBART_ALLOW_FP32_ROUNDING.  Returns the index of the first offending
+// element, or -1.  NaN / inf pass (they round to themselves).
+template <typename T>
+long long first_not_fp32(const T* v, size_t count) {
+    for (size_t i = 0; i < count; ++i) {
+        const double d = (double)v[i];
+        if ((double)(float)d != d && d == d) return (long long)i;
+    }
+    return -1;
+}
+
+// X (n x p, f64 or f32, C or Fortran order, host) -> column-major fp32 [p][ld] in HBM, with per-column min / max
+// (splitting.rs:43-49 at the root is a per-column constant).  Row blocks are converted by a few host threads into pinned
+// staging tiles [p][R] and copied with one 2-D async copy each, so a 10M x 100 matrix (BASELINE C4) uploads at memory
+// speed instead of p strided walks over the whole matrix.  Padding rows [n, ld) hold +inf: they compare as "not left"
+// for every threshold, so block-unit passes need no row masks on x.
+bool upload_columns(Sampler* s, const void* x, int x_dtype, int x_order, uint64_t n, uint64_t p, uint64_t ld,
+                    float* dX, float* cmin, float* cmax) {
+    const uint64_t R = 8192;                                   // rows per tile (a multiple of 32)
+    const uint64_t n_tiles = (ld + R - 1) / R;
+    unsigned T = std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 8) T = 8;
+    if (T > n_tiles) T = (unsigned)n_tiles;
+    std::vector<std::vector<float>> tmin(T, std::vector<float>(p, std::numeric_limits<float>::infinity()));
+    std::vector<std::vector<float>> tmax(T, std::vector<float>(p, -std::numeric_limits<float>::infinity()));
+    std::vector<cudaError_t> terr(T, cudaSuccess);
+    auto work = [&](unsigned t) {
+        cudaSetDevice(s->device);
+        cudaStream_t st_ = nullptr;
+        float* stage[2] = {nullptr, nullptr};
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        cudaError_t e = cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking);
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+            e = cudaHostAlloc((void**)&stage[b], (size_t)p * R * 4, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+        }
+        int buf = 0;
+        for (uint64_t tile = t; tile < n_tiles && e == cudaSuccess; tile += T, buf ^= 1) {
+            const uint64_t i0 = tile * R, i1 = std::min(i0 + R, ld), rows = i1 - i0;
+            e = cudaEventSynchronize(done[buf]);               // the copy that last used this staging tile has finished
+            if (e != cudaSuccess) break;
+            float* sg = stage[buf];
+            const uint64_t iv = std::min(i1, n);               // rows below iv are real
+            auto conv = [&](auto* src) {
+                if (x_order == PGBART_ORDER_F) {
+                    for (uint64_t j = 0; j < p; ++j) {
+                        float mn = tmin[t][j], mx = tmax[t][j];
+                        float* d = sg + j * R;
+                        const auto* c = src + (size_t)j * n;
+                        for (uint64_t i = i0; i < iv; ++i) { const float v = (float)c[i]; d[i - i0] = v; mn = std::fmin(mn, v); mx = std::fmax(mx, v); }
+                        tmin[t][j] = mn; tmax[t][j] = mx;
+                    }
+                } else {
+                    for (uint64_t i = i0; i < iv; ++i) {
+                        const auto* r = src + (size_t)i * p;
+                        for (uint64_t j = 0; j < p; ++j) sg[j * R + (i - i0)] = (float)r[j];
+                    }
+                    for (uint64_t j = 0; j < p; ++j) {
+                        float mn = tmin[t][j], mx = tmax[t][j];
+                        const float* d = sg + j * R;
+                        for (uint64_t i = 0; i < iv - std::min(iv, i0); ++i) { mn = std::fmin(mn, d[i]); mx = std::fmax(mx, d[i]); }
+                        tmin[t][j] = mn; tmax[t][j] = mx;
+                    }
+                }
+            };
+            if (iv > i0) { if (x_dtype == PGBART_X_F32) conv((const float*)x); else conv((const double*)x); }
+            for (uint64_t j = 0; j < p; ++j)
+                for (uint64_t i = std::max(iv, i0); i < i1; ++i) sg[j * R + (i - i0)] = std::numeric_limits<float>::infinity();
+            e = cudaMemcpy2DAsync(dX + i0, (size_t)ld * 4, sg, (size_t)R * 4, (size_t)rows * 4, (size_t)p, cudaMemcpyHostToDevice, st_);
+            if (e == cudaSuccess) e = cudaEventRecord(done[buf], st_);
+        }
+        if (st_) { const cudaError_t e2 = cudaStreamSynchronize(st_); if (e == cudaSuccess) e = e2; }
+        for (int b = 0; b < 2; ++b) { if (done[b]) cudaEventDestroy(done[b]); if (stage[b]) cudaFreeHost(stage[b]); }
+        if (st_) cudaStreamDestroy(st_);
+        terr[t] = e;
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& q : th) q.join();
+    for (unsigned t = 0; t < T; ++t) if (!ck(s, terr[t], "upload X")) return false;
+    for (uint64_t j = 0; j < p; ++j) {
+        float mn = std::numeric_limits<float>::infinity(), mx = -mn;
+        for (unsigned t = 0; t < T; ++t) { mn = std::fmin(mn, tmin[t][j]); mx = std::fmax(mx, tmax[t][j]); }
+        cmin[j] = mn; cmax[j] = mx;
+    }
+    return true;
+}
+
 void free_all(Sampler* s) {
     for (void* p : s->ipc_open) cudaIpcCloseMemHandle(p);
     s->ipc_open.clear();
@@ -102,6 +199,8 @@ void free_all(Sampler* s) {
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->tm0) cudaEventDestroy(s->tm0);
     if (s->tm1) cudaEventDestroy(s->tm1);
+    if (s->pin_pred) cudaFreeHost(s->pin_pred);
+    for (cudaEvent_t e : s->chunk_ev) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
 }
 
@@ -149,6 +248,37 @@ int enqueue_step(Sampler* s, int tune) {
     return 0;
 }
 
+// Predictions (f64[n], HBM) -> caller memory.  Page-locked destinations (pgbart_host_alloc, cudaHostRegister) take one
+// asynchronous copy at link speed.  Pageable destinations go through a pinned staging buffer in 2 MB chunks: chunk k is
+// copied out of the staging buffer by the host while chunk k + 1 is still on the wire (a plain pageable cudaMemcpy of
+// 8 MB cost 1.3 ms per step at BASELINE C3, more than a tenth of the sweep itself).
+bool copy_predictions(Sampler* s, double* out) {
+    const size_t n = (size_t)s->st.n;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();      // (older drivers report an unregistered pointer as an error: clear it)
+    if (pinned) return ck(s, cudaMemcpyAsync(out, s->st.A, n * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions");
+    if (!s->pin_pred && !ck(s, cudaHostAlloc((void**)&s->pin_pred, std::max<size_t>(n, 1) * 8, cudaHostAllocDefault), "cudaHostAlloc")) return false;
+    const size_t CH = (size_t)1 << 18;
+    const size_t nch = (n + CH - 1) / CH;
+    while (s->chunk_ev.size() < nch) {
+        cudaEvent_t e;
+        if (!ck(s, cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return false;
+        s->chunk_ev.push_back(e);
+    }
+    for (size_t c = 0; c < nch; ++c) {
+        const size_t off = c * CH, cnt = std::min(CH, n - off);
+        if (!ck(s, cudaMemcpyAsync(s->pin_pred + off, s->st.A + off, cnt * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions") ||
+            !ck(s, cudaEventRecord(s->chunk_ev[c], s->stream), "event")) return false;
+    }
+    for (size_t c = 0; c < nch; ++c) {
+        const size_t off = c * CH, cnt = std::min(CH, n - off);
+        if (!ck(s, cudaEventSynchronize(s->chunk_ev[c]), "copy predictions")) return false;
+        std::memcpy(out + off, s->pin_pred + off, cnt * 8);
+    }
+    return true;
+}
+
 }  // namespace
 
 struct pgbart_sampler { Sampler s; };
@@ -164,6 +294,10 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     *out = nullptr;
     auto fail = [&](const std::string& m) { g_create_error = m; return 1; };
     if (!x || !y || !cfg) return fail("null input");
+    const bool allow_rounding = (x_dtype & PGBART_ALLOW_FP32_ROUNDING) != 0;
+    x_dtype &= 0xff;
+    if (x_dtype != PGBART_X_F64 && x_dtype != PGBART_X_F32) return fail("x_dtype must be PGBART_X_F64 or PGBART_X_F32");
+    if (x_order != PGBART_ORDER_C && x_order != PGBART_ORDER_F) return fail("x_order must be PGBART_ORDER_C or PGBART_ORDER_F");
     if (n < 1 || p < 1) return fail("x must have at least one row and one column");
     if (n >= 0xFFFFFFF0ull) return fail("n must fit in 32 bits (sample indices are u32 as in the reference)");
     if (cfg->n_trees < 1) return fail("n_trees must be >= 1");
@@ -179,6 +313,23 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
             return fail("OneHotSplit is not available on the device path (SURVEY.md: out of scope; no CPU fallback)");
         return fail(std::string("Unknown split rule: '") + r + "'. Supported: 'ContinuousSplit', 'OneHotSplit'.");
     }
+    if (!allow_rounding) {
+        char msg[512];
+        long long bad = x_dtype == PGBART_X_F64 ? first_not_fp32((const double*)x, (size_t)n * p) : -1;
+        if (bad >= 0) {
+            const long long i = x_order == PGBART_ORDER_F ? bad % (long long)n : bad / (long long)p, j = x_order == PGBART_ORDER_F ? bad / (long long)n : bad % (long long)p;
+            snprintf(msg, sizeof msg, "x[%lld, %lld] = %.17g is not exactly representable in fp32: the device stores X as fp32 and would "
+                     "quantise it (split values, ties and partitions could then differ from the reference). Round the data yourself or pass "
+                     "PGBART_ALLOW_FP32_ROUNDING to accept round-to-nearest fp32 storage of x and y.", i, j, ((const double*)x)[bad]);
+            return fail(msg);
+        }
+        bad = first_not_fp32(y, (size_t)n);
+        if (bad >= 0) {
+            snprintf(msg, sizeof msg, "y[%lld] = %.17g is not exactly representable in fp32: the device stores y as fp32. Round the data "
+                     "yourself or pass PGBART_ALLOW_FP32_ROUNDING to accept round-to-nearest fp32 storage of x and y.", bad, y[bad]);
+            return fail(msg);
+        }
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {   // runtime failure, not a bad argument: status 2
@@ -191,6 +342,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     Sampler* s = &h->s;
     auto bail = [&]() { g_create_error = s->err; free_all(s); delete h; return 2; };
     s->device = device;
+    s->allow_rounding = allow_rounding;
     if (!ck(s, cudaSetDevice(device), "cudaSetDevice")) return bail();
     if (!ck(s, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "stream")) return bail();
     if (!ck(s, cudaEventCreate(&s->ev0), "event") || !ck(s, cudaEventCreate(&s->ev1), "event") ||
@@ -236,19 +388,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         std::vector<float> cmin(p), cmax(p);
         float* dX = nullptr;
         if (!dalloc(s, &dX, (size_t)st.ld * p, false)) return bail();
-        for (uint64_t j = 0; j < p; ++j) {
-            float mn = std::numeric_limits<float>::infinity(), mx = -mn;
-            for (uint64_t i = 0; i < n; ++i) {
-                const size_t src = x_order == PGBART_ORDER_F ? (size_t)j * n + i : (size_t)i * p + j;
-                const float v = x_dtype == PGBART_X_F32 ? ((const float*)x)[src] : (float)((const double*)x)[src];
-                colbuf[i] = v;
-                mn = std::fmin(mn, v); mx = std::fmax(mx, v);
-            }
-            // padding rows compare as "not left" for every threshold, so block-unit passes need no row masks on x
-            for (uint64_t i = n; i < (uint64_t)st.ld; ++i) colbuf[i] = std::numeric_limits<float>::infinity();
-            cmin[j] = mn; cmax[j] = mx;
-            if (!ck(s, cudaMemcpy(dX + (size_t)j * st.ld, colbuf.data(), (size_t)st.ld * 4, cudaMemcpyHostToDevice), "upload X")) return bail();
-        }
+        if (!upload_columns(s, x, x_dtype, x_order, n, p, (uint64_t)st.ld, dX, cmin.data(), cmax.data())) return bail();
         st.X = dX;
         float *dmin = nullptr, *dmax = nullptr, *dy = nullptr;
         if (!dalloc(s, &dmin, p, false) || !dalloc(s, &dmax, p, false) || !dalloc(s, &dy, (size_t)st.ld, false)) return bail();
@@ -337,6 +477,7 @@ int pgbart_destroy(pgbart_handle h) {
 }
 
 int pgbart_set_likelihood(pgbart_handle h, int family, const double* params, int nparams) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (family != PGBART_GAUSSIAN && family != PGBART_BERNOULLI_LOGIT && family != PGBART_GAUSSIAN_KERNEL) {
         s->err = "unknown likelihood family (device path supports Gaussian and Bernoulli-logit; no CPU fallback)";
@@ -350,28 +491,32 @@ int pgbart_set_likelihood(pgbart_handle h, int family, const double* params, int
     return 0;
 }
 
-int pgbart_step_device(pgbart_handle h, int tune) { h->s.steps_done += 1; return enqueue_step(&h->s, tune); }
+int pgbart_step_device(pgbart_handle h, int tune) { if (!h) return 1; h->s.steps_done += 1; return enqueue_step(&h->s, tune); }
 
-int pgbart_sync(pgbart_handle h) { return finish_step(&h->s); }
+int pgbart_sync(pgbart_handle h) { return h ? finish_step(&h->s) : 1; }
 
 int pgbart_step(pgbart_handle h, int tune, double* out_pred) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     s->steps_done += 1;
     int rc = enqueue_step(s, tune);
     if (rc) return rc;
-    if (out_pred && !ck(s, cudaMemcpyAsync(out_pred, s->st.A, (size_t)s->st.n * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions")) return 2;
+    if (out_pred && !copy_predictions(s, out_pred)) return 2;
     return finish_step(s);
 }
 
-const double* pgbart_predictions_device(pgbart_handle h) { return h->s.st.A; }
+const double* pgbart_predictions_device(pgbart_handle h) { return h ? h->s.st.A : nullptr; }
 
 int pgbart_get_predictions(pgbart_handle h, double* out_pred) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
-    if (!ck(s, cudaMemcpyAsync(out_pred, s->st.A, (size_t)s->st.n * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions")) return 2;
+    if (!out_pred) { s->err = "null output"; return 1; }
+    if (!copy_predictions(s, out_pred)) return 2;
     return ck(s, cudaStreamSynchronize(s->stream), "synchronize") ? 0 : 2;
 }
 
 int pgbart_get_info(pgbart_handle h, double* ll, int64_t* acc, uint8_t* depths, int* n_depths) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (!fetch_ctrl(s)) return 2;
     *ll = s->host_ctrl.info_loglik;
@@ -384,6 +529,7 @@ int pgbart_get_info(pgbart_handle h, double* ll, int64_t* acc, uint8_t* depths, 
 }
 
 int pgbart_tree_size(pgbart_handle h, uint64_t t, int* size) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (t >= (uint64_t)s->st.m) { s->err = "tree index out of range"; return 1; }
     if (!ck(s, cudaStreamSynchronize(s->stream), "synchronize")) return 2;
@@ -391,6 +537,7 @@ int pgbart_tree_size(pgbart_handle h, uint64_t t, int* size) {
 }
 
 int pgbart_get_tree(pgbart_handle h, uint64_t t, int32_t* split_var, double* split_val, double* leaf_val) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     int size = 0;
     int rc = pgbart_tree_size(h, t, &size);
@@ -403,6 +550,7 @@ int pgbart_get_tree(pgbart_handle h, uint64_t t, int32_t* split_var, double* spl
 }
 
 int pgbart_get_leaf_indices(pgbart_handle h, uint64_t t, uint32_t* out) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (t >= (uint64_t)s->st.m) { s->err = "tree index out of range"; return 1; }
     unsigned* d = nullptr;
@@ -416,6 +564,7 @@ int pgbart_get_leaf_indices(pgbart_handle h, uint64_t t, uint32_t* out) {
 }
 
 int pgbart_get_state(pgbart_handle h, uint64_t* next_tree_idx, int* tune, uint64_t* n_updates) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (!fetch_ctrl(s)) return 2;
     if (next_tree_idx) *next_tree_idx = (uint64_t)s->host_ctrl.next_tree_idx;
@@ -425,6 +574,7 @@ int pgbart_get_state(pgbart_handle h, uint64_t* next_tree_idx, int* tune, uint64
 }
 
 int pgbart_set_rng_philox(pgbart_handle h, uint64_t seed) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     s->st.rng_mode = PG_RNG_PHILOX;
     s->st.philox_key0 = (unsigned)seed;
@@ -434,6 +584,7 @@ int pgbart_set_rng_philox(pgbart_handle h, uint64_t seed) {
 
 int pgbart_set_rng_tape(pgbart_handle h, const double* slot, const double* round, const double* upd,
                         int64_t n_upd, int r_cap) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (n_upd < 1 || r_cap < 1 || !slot || !round || !upd) { s->err = "bad tape"; return 1; }
     if (!fetch_ctrl(s)) return 2;
@@ -452,10 +603,12 @@ int pgbart_set_rng_tape(pgbart_handle h, const double* slot, const double* round
 }
 
 int pgbart_trace_enable(pgbart_handle h, int64_t u_cap, int r_cap) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     for (double** p : {&s->tr_slot, &s->tr_round, &s->tr_upd}) if (*p) { cudaFree(*p); *p = nullptr; }
     s->st.tr_slot = s->st.tr_round = s->st.tr_upd = nullptr;
     if (u_cap <= 0) return 0;
+    if (r_cap < 1) { s->err = "trace_enable: r_cap must be >= 1 when u_cap > 0"; return 1; }
     const size_t S = s->st.S, P = s->st.P;
     const size_t ns = (size_t)u_cap * r_cap * S * PG_TS_FIELDS, nr = (size_t)u_cap * r_cap * (2 + 2 * S), nu = (size_t)u_cap * (4 + 2 * P);
     if (!ck(s, cudaMalloc(&s->tr_slot, ns * 8), "cudaMalloc") || !ck(s, cudaMalloc(&s->tr_round, nr * 8), "cudaMalloc") ||
@@ -475,6 +628,7 @@ int pgbart_trace_enable(pgbart_handle h, int64_t u_cap, int r_cap) {
 }
 
 int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd, int64_t* n_upd, int* overflow) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (!s->tr_slot) { s->err = "trace not enabled"; return 1; }
     if (!fetch_ctrl(s)) return 2;
@@ -490,6 +644,7 @@ int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd,
 }
 
 int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (!key || !value) { s->err = "null option"; return 1; }
     if (std::strcmp(key, "driver") == 0) {
@@ -528,6 +683,7 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
 }
 
 int pgbart_get_counters(pgbart_handle h, double* out8) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (!fetch_ctrl(s)) return 2;
     float ms = 0.0f;
@@ -543,7 +699,16 @@ int pgbart_get_counters(pgbart_handle h, double* out8) {
     return 0;
 }
 
+int pgbart_get_spec_counters(pgbart_handle h, uint64_t* out4) {
+    if (!h || !out4) return 1;
+    Sampler* s = &h->s;
+    if (!fetch_ctrl(s)) return 2;
+    out4[0] = s->host_ctrl.n_spec; out4[1] = s->host_ctrl.n_pred; out4[2] = s->host_ctrl.n_pred_miss; out4[3] = s->host_ctrl.n_drain;
+    return 0;
+}
+
 int pgbart_get_profile(pgbart_handle h, double* out32) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (!fetch_ctrl(s)) return 2;
     for (int i = 0; i < 32; ++i) out32[i] = (double)s->host_ctrl.prof[i];
@@ -556,6 +721,7 @@ int pgbart_get_profile(pgbart_handle h, double* out32) {
 }
 
 int pgbart_debug_block_cycles(pgbart_handle h, double* out, int cap) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     const int G = s->st.grid;
     std::vector<unsigned long long> tmp((size_t)G * 16);
@@ -568,6 +734,7 @@ int pgbart_debug_block_cycles(pgbart_handle h, double* out, int cap) {
 // ---- observation sharding (include/pgbart.h) ---------------------------------------------------------
 int pgbart_shard_config(pgbart_handle h, int rank, int world, uint64_t n_global, double y_mean_global,
                         const float* col_min_global, const float* col_max_global) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     PgState& st = s->st;
     if (world < 1 || world > PG_MAX_RANKS || rank < 0 || rank >= world) { s->err = "shard_config: need 0 <= rank < world <= 8"; return 1; }
@@ -591,6 +758,7 @@ int pgbart_shard_config(pgbart_handle h, int rank, int world, uint64_t n_global,
 }
 
 int pgbart_shard_mailbox(pgbart_handle h, unsigned char* handle64) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (!s->st.mail[s->st.rank]) { s->err = "shard_mailbox: call shard_config first"; return 1; }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -602,6 +770,7 @@ int pgbart_shard_mailbox(pgbart_handle h, unsigned char* handle64) {
 }
 
 int pgbart_shard_connect(pgbart_handle h, const unsigned char* handles) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     PgState& st = s->st;
     cudaSetDevice(s->device);
@@ -620,22 +789,36 @@ int pgbart_shard_connect(pgbart_handle h, const unsigned char* handles) {
 // Out-of-sample prediction (tree.rs:169-192 summed over the forest) and variable inclusion (state.rs:10, declared by
 // the reference and never filled): the "next" rows of SURVEY.md 8(f).
 int pgbart_predict(pgbart_handle h, const void* x, int x_dtype, int x_order, uint64_t n_new, double* out) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     const PgState& st = s->st;
     if (!x || !out) { s->err = "predict: null argument"; return 1; }
+    const bool allow = s->allow_rounding || (x_dtype & PGBART_ALLOW_FP32_ROUNDING) != 0;
+    x_dtype &= 0xff;
     if (x_dtype != PGBART_X_F32 && x_dtype != PGBART_X_F64) { s->err = "predict: x_dtype must be f32 or f64"; return 1; }
     if (n_new == 0) return 0;
-    cudaSetDevice(s->device);
     const uint64_t p = (uint64_t)st.p;
-    std::vector<double> col((size_t)n_new * p);
+    if (x_dtype == PGBART_X_F64 && !allow) {
+        const long long bad = first_not_fp32((const double*)x, (size_t)n_new * p);
+        if (bad >= 0) {
+            char msg[256];
+            snprintf(msg, sizeof msg, "predict: x element %lld = %.17g is not exactly representable in fp32 (the forest was trained on fp32 "
+                     "data); round it or pass PGBART_ALLOW_FP32_ROUNDING", bad, ((const double*)x)[bad]);
+            s->err = msg;
+            return 1;
+        }
+    }
+    cudaSetDevice(s->device);
+    std::vector<float> col((size_t)n_new * p);
     for (uint64_t j = 0; j < p; ++j)
         for (uint64_t i = 0; i < n_new; ++i) {
             const size_t src = x_order == PGBART_ORDER_F ? (size_t)j * n_new + i : (size_t)i * p + j;
-            col[(size_t)j * n_new + i] = x_dtype == PGBART_X_F32 ? (double)((const float*)x)[src] : ((const double*)x)[src];
+            col[(size_t)j * n_new + i] = x_dtype == PGBART_X_F32 ? ((const float*)x)[src] : (float)((const double*)x)[src];
         }
-    double *dx = nullptr, *dout = nullptr;
-    if (!ck(s, cudaMalloc(&dx, col.size() * 8), "cudaMalloc") || !ck(s, cudaMalloc(&dout, (size_t)n_new * 8), "cudaMalloc")) { if (dx) cudaFree(dx); return 2; }
-    bool ok = ck(s, cudaMemcpyAsync(dx, col.data(), col.size() * 8, cudaMemcpyHostToDevice, s->stream), "upload x")
+    float* dx = nullptr;
+    double* dout = nullptr;
+    if (!ck(s, cudaMalloc(&dx, col.size() * 4), "cudaMalloc") || !ck(s, cudaMalloc(&dout, (size_t)n_new * 8), "cudaMalloc")) { if (dx) cudaFree(dx); return 2; }
+    bool ok = ck(s, cudaMemcpyAsync(dx, col.data(), col.size() * 4, cudaMemcpyHostToDevice, s->stream), "upload x")
            && ck(s, pg_launch_predict(st, dx, (long long)n_new, (long long)n_new, dout, s->stream), "launch predict")
            && ck(s, cudaMemcpyAsync(out, dout, (size_t)n_new * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions")
            && ck(s, cudaStreamSynchronize(s->stream), "synchronize");
@@ -645,6 +828,7 @@ int pgbart_predict(pgbart_handle h, const void* x, int x_dtype, int x_order, uin
 }
 
 int pgbart_variable_inclusion(pgbart_handle h, uint32_t* out_p) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     const PgState& st = s->st;
     cudaSetDevice(s->device);
@@ -661,12 +845,29 @@ int pgbart_variable_inclusion(pgbart_handle h, uint32_t* out_p) {
     return 0;
 }
 
+// Page-locked host memory for callers that want pgbart_step's device->host copy to run at link speed straight into
+// their own buffer (the Python mirror hands such buffers out as the arrays PySampler.step returns).
+int pgbart_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return 1;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, std::max<uint64_t>(bytes, 1), cudaHostAllocPortable);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); cudaGetLastError(); return 2; }
+    return 0;
+}
+
+int pgbart_host_free(void* p) {
+    if (!p) return 0;
+    return cudaFreeHost(p) == cudaSuccess ? 0 : 2;
+}
+
 int pgbart_timer_start(pgbart_handle h) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     return ck(s, cudaEventRecord(s->tm0, s->stream), "event record") ? 0 : 2;
 }
 
 int pgbart_timer_stop(pgbart_handle h, double* elapsed_ms) {
+    if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;
     if (!ck(s, cudaEventRecord(s->tm1, s->stream), "event record")) return 2;
     if (!ck(s, cudaEventSynchronize(s->tm1), "event synchronize")) return 2;

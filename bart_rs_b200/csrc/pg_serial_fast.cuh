@@ -1278,8 +1278,11 @@ __device__ __forceinline__ int fw_finalize(const PgState& st, const FwCx& x, int
     const size_t fb = (size_t)t * st.maxn;
     int depth = 0, internal = 0;
     if (lane == 0)     // early commit: did the update end with the tree predicted after round 0 (same lineage, never grown further)?
+    {
         f->pred_ok = f->pred_valid && ((sel == 0 && f->pred_sel == 0) ||
                                        (sel > 0 && f->pred_sel > 0 && f->hlin[sel - 1] == f->pred_lin && f->hsize[pg_six(st, cur, sel - 1)] == 3));
+        if (f->pred_valid && !f->pred_ok) c->n_pred_miss += 1ull;
+    }
     __syncwarp();
     if (f->pred_ok) {              // the forest already holds this very tree (fw_predict wrote it): nothing to copy
         if (sel != 0) { depth = 1; internal = 1; }
@@ -1617,6 +1620,7 @@ __device__ __forceinline__ void fw_predict(const PgState& st, const FwCx& x, int
             st.f_size[t] = 3;
         }
         f->pred_sel = sel; f->pred_valid = 1;
+        c->n_pred += 1ull;
     }
     __syncwarp();
 }
@@ -1790,7 +1794,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
             }
             if (c->error != PG_OK) { if (lane == 0) c->phase = PH_DONE; sn = SN_NONE; __syncwarp(); }
             if (sn != SN_PREP_PART) {
-                if (spec && !spec_commit && c->phase != PH_DONE) fw_await(st, x, lane);   // drain a wrong guess (only on odd paths)
+                if (spec && !spec_commit) { fw_await(st, x, lane); if (lane == 0) c->n_drain += 1ull; }   // drain a wrong guess (odd paths, and before PH_DONE on an error)
                 if (!spec_commit) fw_issue_ctrl(st, x, lane);                              // next pass, or PH_DONE
                 if (c->phase == PH_ROOT && c->round == 0) fw_prestage(st, x, lane);        // an update just started: stage the one after it
             }
@@ -1804,7 +1808,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
             fb_prep_part(st, x);
             __syncthreads();
             if (warp == 0) {
-                if (drain) fw_await(st, x, lane);   // the speculative root pass guessed wrong: let it finish, ignore its output
+                if (drain) { fw_await(st, x, lane); if (lane == 0) c->n_drain += 1ull; }   // the speculative root pass guessed wrong: let it finish, ignore its output
                 fw_issue_ctrl(st, x, lane);
                 FW_TICK(4);
                 fw_predict(st, x, lane);            // off the critical path: the partition pass is streaming

@@ -61,6 +61,7 @@ __device__ void pg_barrier_serial(const PgState& st, const PgSmemView& smv, unsi
 template <int VAR>
 __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
     constexpr bool FAST = VAR != PGV_GENERIC;
+    if (__ldcg(&st.ctrl->poisoned)) return;      // an earlier step failed on the device: every block leaves at once
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     // sampler constants the serial section reads: staged once per launch
     for (int i = threadIdx.x; i < st.max_depth + 2 && i < 16; i += blockDim.x) sm.base->cthr[i] = st.thr_depth[i];
@@ -152,12 +153,15 @@ extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_phase_kernel(cons
 }
 
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_serial_kernel(const PgState st) {
+    if (__ldcg(&st.ctrl->poisoned)) return;
     PgTeam tm{(int)threadIdx.x, (int)blockDim.x};
     pg_serial(st, tm);
 }
 
 extern "C" __global__ void pg_prepare_step(const PgState st, int tune) {
     PgCtrl* c = st.ctrl;
+    c->poisoned = c->error != PG_OK ? 1 : 0;
+    if (c->poisoned) { c->phase = PH_DONE; return; }
     if (tune >= 0) c->tune = tune;
     c->phase = PH_BEGIN;
     c->snext = SN_NONE;
@@ -195,8 +199,9 @@ extern "C" __global__ void pg_leaf_indices_kernel(const PgState st, int t, unsig
 }
 
 // Out-of-sample prediction of the whole forest (tree.rs:169-192 per tree, summed over trees in tree order):
-// x is column-major f64 [p][ldx]; the comparison is the reference's `sample[sv] < split_val` in f64.
-extern "C" __global__ void pg_predict_kernel(const PgState st, const double* x, long long n_new, long long ldx, double* out) {
+// x is column-major fp32 [p][ldx], compared with thr32 = the smallest float >= split_val exactly as the training passes
+// do; for fp32-representable x that IS the reference's `sample[sv] < split_val` in f64 (pg_thr32).
+extern "C" __global__ void pg_predict_kernel(const PgState st, const float* x, long long n_new, long long ldx, double* out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_new; i += (long long)gridDim.x * blockDim.x) {
         double acc = 0.0;
         for (int t = 0; t < st.m; ++t) {
@@ -204,7 +209,7 @@ extern "C" __global__ void pg_predict_kernel(const PgState st, const double* x, 
             const int size = st.f_size[t];
             int node = 0, sv;
             while (node < size && (sv = st.f_split_var[fb + node]) >= 0)
-                node = 2 * node + 1 + (x[(size_t)sv * ldx + i] < st.f_split_val[fb + node] ? 0 : 1);
+                node = 2 * node + 1 + (x[(size_t)sv * ldx + i] < st.f_thr32[fb + node] ? 0 : 1);
             if (node < size) acc += st.f_leaf_val[fb + node];
         }
         out[i] = acc;
@@ -294,7 +299,7 @@ cudaError_t pg_launch_init_forest(const PgState& st, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t pg_launch_predict(const PgState& st, const double* x, long long n_new, long long ldx, double* out, cudaStream_t s) {
+cudaError_t pg_launch_predict(const PgState& st, const float* x, long long n_new, long long ldx, double* out, cudaStream_t s) {
     pg_predict_kernel<<<592, 256, 0, s>>>(st, x, n_new, ldx, out);
     return cudaGetLastError();
 }

@@ -11,4 +11,4 @@ cudaError_t pg_launch_serial(const PgState& st, cudaStream_t s);
 cudaError_t pg_launch_fill(double* p, long long n, double v, cudaStream_t s);
 cudaError_t pg_launch_init_forest(const PgState& st, cudaStream_t s);
 cudaError_t pg_launch_leaf_indices(const PgState& st, int t, unsigned* out, cudaStream_t s);
-cudaError_t pg_launch_predict(const PgState& st, const double* x, long long n_new, long long ldx, double* out, cudaStream_t s);
+cudaError_t pg_launch_predict(const PgState& st, const float* x, long long n_new, long long ldx, double* out, cudaStream_t s);

@@ -102,6 +102,9 @@ struct PgCtrl {
     unsigned long long n_phases;        // grid passes executed
     unsigned long long n_updates;       // tree updates executed
     unsigned long long n_spec;          // root passes issued speculatively (pg_serial_fast.cuh)
+    unsigned long long n_pred;          // early commit: tree updates whose outcome was predicted after round 0 (fw_predict)
+    unsigned long long n_pred_miss;     // ... of which the final selection disagreed (the root pass issued ahead was drained)
+    unsigned long long n_drain;         // speculative / predicted root passes that were awaited and discarded
     unsigned long long trace_n;         // tree updates recorded in the trace
     int trace_overflow;
     int a_cur;                      // which A buffer holds the running array of the update in progress
@@ -129,6 +132,9 @@ struct PgCtrl {
     // ---- hint for the pass blocks: number of root jobs staged ahead in the job arrays of each buffer parity
     // (written by the control block when it pre-stages the next tree update; read after a root pass to prefetch)
     int pre_J[2];
+    // ---- set by pg_prepare_step when an earlier step left a device error behind: steps queued after it must not run on
+    // the broken state (pgbart_step_device can be queued several times before pgbart_sync reports the error)
+    int poisoned;
 };
 
 struct PgState {

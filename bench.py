@@ -10,6 +10,11 @@ batch = (1.0, 1.0) (reference kernel.rs:60-126, pgbart.py:65).  Workload at N = 
 GPU) every rank runs an independent chain of the same workload with its own seed — the "chains" sharding of
 SURVEY.md §8(e): no data-path collective, weak scaling; value = sweeps of all ranks / max-over-ranks time.
 
+Every run also carries, in the same JSON line, a `sharded` block: workload C4 (n = 10M, p = 100) as ONE chain whose
+rows are split over the N GPUs (observation sharding; at N = 1 the same workload on one GPU), with
+ms per sweep, sweeps/s and rank 0's roofline figures, plus `sharded_parity_ok` from running the smallest case of
+tests/run_sharded.py against the oracle before timing.  `value` stays the chains number so it is comparable across N.
+
 One JSON line on stdout (rank 0).  Keys beyond the base contract:
   roofline      dominant (and only) hot kernel pg_sweep_persistent: achieved = SURVEY.md §8(d) algorithmic bytes of the
                 sweep (device counters) / CUDA-event time on the sampler's stream; fused_* = bytes this
@@ -54,6 +59,22 @@ def make_data(w, seed=0, rows=None):
                             bernoulli=(w["family"] == "bernoulli_logit"))
     prm = datagen.pgbart_params(y, w["m"], w["p"])
     return X, y, prm
+
+
+def config_for(name, world):
+    """The `config` object of the JSON line: both arms (this repo's and --impl reference) print the same one."""
+    w = WORKLOADS[name]
+    sharded = bool(w.get("sharded")) and world > 1
+    rows = w["n"] // world if sharded else w["n"]
+    x_mb = rows * w["p"] * 4 / 1e6
+    return {"workload": f"{name}: Friedman n={w['n']} p={w['p']} m={w['m']} P={w['P']} {w['family']}, "
+                        "batch=(1,1) so one step = one sweep",
+            "parallelism": "1 GPU" if world == 1 else (f"one chain, rows sharded over {world} GPUs, in-kernel exchange of sufficient "
+                                                         "statistics over NVLink peer memory" if sharded
+                                                         else f"{world} independent chains, one per GPU, no collective"),
+            "l2": f"inputs larger than L2 (X {x_mb:.0f} MB fp32 per GPU vs 126 MB L2); no flush" if x_mb * 1e6 > 126e6
+                  else "working set fits L2 (L2-resident by design of this config)",
+            "storage": "X, y fp32; running sum-of-trees fp64; accumulation fp64"}
 
 
 def peaks():
@@ -157,15 +178,94 @@ def run_reference(args):
         "impl": "reference", "metric": "PG sweeps/sec", "value": sweeps_per_s, "unit": "sweeps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: Friedman n={w['n']} p={w['p']} m={w['m']} P={w['P']} {w['family']}, "
-                               "batch=(1,1) so one step = one sweep",
-                   "sample": f"each step = {per_step} tree updates of the sweep, scaled to m={w['m']}"},
+        "config": config_for(args.workload, args.gpus),
         "cpu_baseline": {"value": sweeps_per_s, "unit": "sweeps/s", "cores": 1, "kind": "port",
-                         "sample": f"{done_total} tree updates in {total:.2f} s, scaled to m={w['m']}"},
+                         "sample": f"each step = {per_step} tree updates of the sweep on 1 host core (the reference is single-threaded); "
+                                   f"{done_total} tree updates in {total:.2f} s, scaled to m={w['m']}"},
         "e2e": {"value": sweeps_per_s, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def time_sweeps(smp, steps, warmup, barrier):
+    """K sweeps back to back on the sampler's stream, CUDA events around them; returns (ms_total, counters before / after)."""
+    for _ in range(warmup):
+        smp.step_device(False)
+    smp.sync()
+    c0 = smp.counters()
+    barrier()
+    smp.timer_start()
+    for _ in range(steps):
+        smp.step_device(False)
+    ms = smp.timer_stop()
+    smp.sync()
+    barrier()
+    return ms, c0, smp.counters()
+
+
+def sharded_block(args, rank, local_rank, world, barrier, peak):
+    """Workload C4 as one chain over `world` GPUs (rows sharded; world = 1: the whole workload on one GPU)."""
+    import torch
+    import torch.distributed as dist
+    from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
+    w = WORKLOADS[args.sharded_workload]
+    parity_ok = None
+    if world > 1:
+        from tests import run_sharded
+        run_sharded.QUIET = True
+        ok = run_sharded.run_case(run_sharded.CASES[0], rank, local_rank, world)
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.broadcast(flag, 0)
+        parity_ok = bool(int(flag.item()))
+    lik = DeviceLikelihood(w["family"], 1.0)
+    if world > 1:
+        from bart_rs_b200.sharded import ShardedSampler, row_range
+        lo, hi = row_range(w["n"], rank, world)
+        X, y, prm = make_data(w, rows=(lo, hi))
+        sig = torch.tensor([prm["sigma"]], dtype=torch.float64, device="cuda")
+        dist.broadcast(sig, 0)
+        st = PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, float(sig.item()), list(prm["split_prior"]),
+                            ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=0)
+        smp = ShardedSampler.init(X, y, lik, st, device=local_rank)
+    else:
+        X, y, prm = make_data(w)
+        st = PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, prm["sigma"], list(prm["split_prior"]),
+                            ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=0)
+        smp = PySampler.init(X, y, lik, st, device=local_rank)
+    rows_local = X.shape[0]
+    del X
+    steps = max(2, min(args.steps, args.sharded_steps))
+    ms, c0, c1 = time_sweeps(smp, steps, 3, barrier)
+    from bart_rs_b200.chains import job_throughput
+    _, ms_max = job_throughput(ms, steps, world, device="cuda")
+    # end to end: this rank's rows of the predictions come back to the host every step
+    smp.step(False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        smp.set_likelihood(lik)
+        smp.step(False)
+    torch.cuda.synchronize()
+    e2e_ms = 1000.0 * (time.perf_counter() - t0) / 2
+    _, e2e_ms_max = job_throughput(e2e_ms, 1, world, device="cuda")
+    smp.close()
+    bm = (c1["bytes_model"] - c0["bytes_model"]) / steps
+    bc = (c1["bytes_contract"] - c0["bytes_contract"]) / steps
+    sec = ms / 1000.0 / steps
+    return {
+        "workload": f"{args.sharded_workload}: Friedman n={w['n']} p={w['p']} m={w['m']} P={w['P']} {w['family']}, one chain",
+        "n_gpus": world, "rows_per_gpu": rows_local, "steps": steps, "scaling": "strong",
+        "parallelism": "1 GPU" if world == 1 else f"rows sharded over {world} GPUs; per-proposal sufficient statistics exchanged inside "
+                                                  "the persistent kernel through NVLink peer mailboxes, combined in rank order",
+        "ms_per_sweep": ms_max / steps, "sweeps_per_s": steps / (ms_max / 1000.0),
+        "e2e_ms_per_sweep": e2e_ms_max, "e2e_sweeps_per_s": 1000.0 / e2e_ms_max,
+        "roofline_rank0": {"algorithmic_bytes_per_launch": bc, "achieved": bc / sec / 1e9, "frac": bc / sec / 1e9 / peak,
+                           "fused_bytes_per_launch": bm, "fused_gbs": bm / sec / 1e9, "fused_frac": bm / sec / 1e9 / peak,
+                           "unit": "GB/s", "peak": peak, "note": "bytes of rank 0's own rows / its own launch time"},
+        "parity_ok": parity_ok,
+        "parity_case": None if world == 1 else "tests/run_sharded.py CASES[0] (n=5003, p=8, m=12, P=20, 2 sweeps) vs the oracle on all rows",
+    }
 
 
 def run_gpu(args):
@@ -210,22 +310,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing: inputs already in HBM, K sweeps, CUDA events on the sampler's stream
-    for _ in range(args.warmup):
-        smp.step_device(False)
-    smp.sync()
-    c0 = smp.counters()
     clocks = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         clocks.start()
-    smp.timer_start()
-    for _ in range(args.steps):
-        smp.step_device(False)
-    ms = smp.timer_stop()
-    smp.sync()
-    barrier()
+    ms, c0, c1 = time_sweeps(smp, args.steps, args.warmup, barrier)
     clk = clocks.stop() if rank == 0 else None
-    c1 = smp.counters()
     value, ms_max = job_throughput(ms, args.steps, world, device="cuda")
     if sharded:
         value /= world            # all ranks worked on the SAME sweeps
@@ -264,6 +353,12 @@ def run_gpu(args):
                   "note": "option prune_dead_proposals=1 (off by default; DESIGN.md section 4b): same forest and predictions, "
                           "dead proposals not evaluated; NOT the headline value"}
 
+    spec = smp.spec_counters()
+    smp.close()
+    shard = None
+    if not args.no_sharded and not w.get("sharded"):
+        shard = sharded_block(args, rank, local_rank, world, barrier, peaks()[0])
+
     if rank == 0:
         peak, peak_src = peaks()
         k = args.steps
@@ -288,14 +383,7 @@ def run_gpu(args):
             "metric": "PG sweeps/sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: Friedman n={w['n']} p={w['p']} m={w['m']} P={w['P']} {w['family']}, "
-                                   "batch=(1,1) so one step = one sweep",
-                       "parallelism": "1 GPU" if world == 1 else (f"one chain, rows sharded over {world} GPUs, in-kernel exchange of sufficient "
-                                                                    "statistics over NVLink peer memory" if sharded
-                                                                    else f"{world} independent chains, one per GPU, no collective"),
-                       "l2": f"inputs larger than L2 (X {X.shape[0] * w['p'] * 4 / 1e6:.0f} MB fp32 per GPU vs 126 MB L2); no flush" if X.shape[0] * w["p"] * 4 > 126e6
-                             else "working set fits L2 (L2-resident by design of this config)",
-                       "storage": "X, y fp32; running sum-of-trees fp64; accumulation fp64"},
+            "config": config_for(args.workload, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "pg_sweep_persistent_direct (one launch = one sweep = m tree updates)"
@@ -313,12 +401,14 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8 * X.shape[0],
                     "steps": e2e_steps},
             "pruned": pruned,
+            "sharded": shard,
+            "sharded_parity_ok": None if shard is None else shard["parity_ok"],
+            "speculation": spec,
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
             "grid_passes_per_step": (c1["grid_passes"] - c0["grid_passes"]) / k,
             "clocks": clk,
         }
         print(json.dumps(line), flush=True)
-    smp.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -333,6 +423,9 @@ def main():
     ap.add_argument("--ref-updates", type=int, default=40, help="tree updates per timed CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded-workload", default="C4", choices=["C4", "C3s"], help="workload of the `sharded` block")
+    ap.add_argument("--sharded-steps", type=int, default=5)
+    ap.add_argument("--no-sharded", action="store_true", help="skip the observation-sharded block")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -49,14 +49,23 @@ enum { PGBART_GAUSSIAN = 0,        /* params = {sigma}: sum -0.5((y-mu)/sigma)^2
        PGBART_GAUSSIAN_KERNEL = 2  /* no params:        sum -0.5 (mu-y)^2  (benches/particle_gibbs.rs:22-32) */ };
 
 enum { PGBART_X_F64 = 0, PGBART_X_F32 = 1 };
+/* OR into x_dtype: accept round-to-nearest fp32 storage of f64 x and y.  Without it pgbart_create (and pgbart_predict)
+ * refuse, with status 1, data that is not exactly representable in fp32: the device computes on fp32 X / y
+ * (north_star) while the reference computes on the f64 values (data.rs:31-35), and a silent quantisation could merge
+ * distinct values, change ties and child counts, and so diverge from the reference. */
+enum { PGBART_ALLOW_FP32_ROUNDING = 0x100 };
 enum { PGBART_ORDER_C = 0, PGBART_ORDER_F = 1 };
 
 /* PySampler.init (lib.rs:115-180).  x: n-by-p host matrix (f64 or f32, C or Fortran order), y: f64[n].
  * Copies both (as the reference does), stores X column-major fp32 and y fp32 in HBM, builds m stump
- * trees and predictions = mean(y) (kernel.rs:38-58).  device = CUDA ordinal. */
+ * trees and predictions = mean(y) (kernel.rs:38-58).  device = CUDA ordinal.  f64 values must be exactly
+ * representable in fp32 unless x_dtype carries PGBART_ALLOW_FP32_ROUNDING (checked before any device work). */
 int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t p, const double* y,
                   const pgbart_settings* settings, int device, pgbart_handle* out);
 int pgbart_destroy(pgbart_handle h);
+/* Page-locked host buffers for out_pred (freed by the caller; error text via pgbart_last_error(NULL)). */
+int pgbart_host_alloc(uint64_t bytes, void** out);
+int pgbart_host_free(void* p);
 const char* pgbart_last_error(pgbart_handle h);   /* h may be NULL: error of the last failed create */
 
 /* Replaces the LogpFunc pointer (lib.rs:125-126): callable before every step, e.g. with the
@@ -64,7 +73,9 @@ const char* pgbart_last_error(pgbart_handle h);   /* h may be NULL: error of the
 int pgbart_set_likelihood(pgbart_handle h, int family, const double* params, int nparams);
 
 /* PySampler.step (lib.rs:182-202): tune = 1/0, or -1 to keep the current flag (None).  Writes the
- * new sum-of-trees, f64[n], to HOST memory out_pred (device->host copy inside the call). */
+ * new sum-of-trees, f64[n], to HOST memory out_pred (device->host copy inside the call): one copy at link speed
+ * when out_pred is page-locked (pgbart_host_alloc / cudaHostRegister), a chunked copy through a pinned staging
+ * buffer otherwise. */
 int pgbart_step(pgbart_handle h, int tune, double* out_pred);
 /* Same step, result left in HBM; asynchronous until pgbart_sync. */
 int pgbart_step_device(pgbart_handle h, int tune);
@@ -110,6 +121,11 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value);
  * [6] grid blocks, [7] dynamic shared memory per block. */
 int pgbart_get_counters(pgbart_handle h, double* out8);
 
+/* Speculation / early-commit counters since creation: [0] root passes issued ahead of the decision
+ * they depend on, [1] tree updates whose outcome was predicted after round 0, [2] predictions the final selection
+ * contradicted (the pass issued ahead was drained and re-issued), [3] passes issued ahead that were awaited and discarded. */
+int pgbart_get_spec_counters(pgbart_handle h, uint64_t* out4);
+
 /* In-kernel stopwatch, SM cycles since creation: out32[0..7] pass time by phase as seen by block 0,
  * [8..15] pass end -> barrier exit (wait for the slowest block + serial section), [16..23] serial section alone,
  * [24..31] passes by phase (phases: 1 ROOT, 2 MINMAX, 3 STATS, 4 BERN, 5 PART, 6 FINAL); [32..39] serial sub-step
@@ -122,7 +138,11 @@ int pgbart_get_profile(pgbart_handle h, double* out69);
 
 /* Out-of-sample prediction: out[i] = sum over the forest's trees, in tree order, of the leaf value row i of x reaches
  * (reference TreeArrays::predict_batch_test, src/tree.rs:169-192, applied to every tree; comparison `x < split_val` in
- * f64).  x: n_new x p, dtype / order as in pgbart_create.  Under observation sharding every rank holds the whole forest. */
+ * f64).  x: n_new x p, dtype / order as in pgbart_create.  Training saw fp32 x and compared it with thr32 = the smallest
+ * float >= split_val, which for fp32-representable x IS the reference's f64 comparison; new rows are treated the same way
+ * (rounded to fp32 when the sampler was created with PGBART_ALLOW_FP32_ROUNDING, refused with status 1 otherwise if not
+ * representable), so predict(X_train) always equals the in-sample predictions.  Under observation sharding every rank
+ * holds the whole forest. */
 int pgbart_predict(pgbart_handle h, const void* x, int x_dtype, int x_order, uint64_t n_new, double* out);
 
 /* Split counts per variable over the current forest (reference BartState.variable_inclusion, src/state.rs:10 — declared

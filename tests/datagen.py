@@ -12,7 +12,7 @@ def friedman(n: int, p: int, seed: int = 0, bernoulli: bool = False):
     assert p >= 5
     rng = np.random.default_rng(seed)
     X = rng.random((n, p), dtype=np.float32)
-    x = X.astype(np.float64)
+    x = X[:, :5].astype(np.float64)          # only the five signal columns are needed in f64 (same values as widening all of X)
     f = 10 * np.sin(np.pi * x[:, 0] * x[:, 1]) + 20 * (x[:, 2] - 0.5) ** 2 + 10 * x[:, 3] + 5 * x[:, 4]
     if bernoulli:
         pr = 1.0 / (1.0 + np.exp(-(f - f.mean())))

@@ -13,30 +13,80 @@ import numpy as np
 from oracle import pyoracle as po
 
 RTOL = 1e-6
+EPS = float(np.finfo(np.float64).eps)
+
+# Largest discrepancies seen by the last assert_traces_match call, as multiples of the tolerance that was applied
+# (tests print / record them so the margin is visible in the GPU logs).
+LAST_MARGINS = {}
 
 
-def assert_traces_match(ref, got, n_upd, S, P, rtol=RTOL):
-    """ref/got: (slot, round, upd) arrays in the layout of include/pgbart.h."""
+def weight_tolerance(n: int, wmax: float) -> float:
+    """Absolute agreement to expect between two f64 evaluations of one log-likelihood of n rows.
+
+    The reference (weight.rs:26-30 -> the logp loop) and the oracle add the n per-row terms sequentially: every addition
+    rounds the partial sum, so the result carries a random-walk error of standard deviation eps * |sum| * sqrt(n) / 6.
+    The device adds per-block partial sums of sufficient statistics in a fixed tree order (smaller error) and then
+    forms C0 + G (a few ulps of |sum|).  The bound below is 24 standard deviations of the sequential sum plus 32 ulps:
+    1.2e-6 absolute on log-weights of magnitude 1.4e6 at BASELINE C3 (n = 1M), 1e-12 relative — six orders of magnitude
+    tighter than the 1e-6 relative north_star allows, because resampling decisions depend on DIFFERENCES of log-weights.
+    """
+    return (4.0 * float(np.sqrt(max(n, 1))) + 32.0) * EPS * max(abs(float(wmax)), 1.0)
+
+
+def _check_logw(got, ref, n, what):
+    """Log-weights: north_star's 1e-6 relative AND the absolute bound that follows from the summation error."""
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    live = np.isfinite(ref)
+    np.testing.assert_array_equal(np.isfinite(got), live, err_msg=what + " (finite pattern)")
+    if not live.any():
+        return 0.0
+    wtol = weight_tolerance(n, np.max(np.abs(ref[live])))
+    d = np.max(np.abs(got[live] - ref[live]))
+    assert d <= wtol, f"{what}: log-weight differs by {d:.3e} > {wtol:.3e} (n={n})"
+    np.testing.assert_allclose(got[live], ref[live], rtol=RTOL, atol=0, err_msg=what)
+    LAST_MARGINS["logw"] = max(LAST_MARGINS.get("logw", 0.0), d / wtol)
+    return wtol
+
+
+def _check_normalised(got, ref, wtol, P, what):
+    """Normalised weights exp(w - max) / sum: an absolute error d in the log-weights is a relative error <= 2 d here
+    (numerator and denominator), plus the rounding of exp / the P-term sum / the division."""
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    rt = 2.0 * wtol + 8.0 * (P + 4) * EPS
+    err = np.abs(got - ref)
+    lim = rt * np.abs(ref) + 1e-300
+    bad = err > lim
+    assert not bad.any(), f"{what}: normalised weight off by {np.max(err / lim):.2f}x the bound {rt:.3e}"
+    LAST_MARGINS["wnorm"] = max(LAST_MARGINS.get("wnorm", 0.0), float(np.max(err / lim)))
+
+
+def assert_traces_match(ref, got, n_upd, S, P, rtol=RTOL, n=None):
+    """ref/got: (slot, round, upd) arrays in the layout of include/pgbart.h; n = rows behind every log-weight."""
     rs, rr, ru = ref
     gs, gr, gu = got
+    LAST_MARGINS.clear()
+    if n is None:
+        n = 1 << 20          # callers that do not know n get the loosest bound any test here needs
     for u in range(n_upd):
         assert int(ru[u, 0]) == int(gu[u, 0]), f"update {u}: rounds {ru[u, 0]} vs {gu[u, 0]}"
         assert ru[u, 1] == gu[u, 1], f"update {u}: selected particle {ru[u, 1]} vs {gu[u, 1]}"
         assert ru[u, 2] == gu[u, 2] and ru[u, 3] == gu[u, 3], f"update {u}: tree/acceptance"
-        np.testing.assert_allclose(gu[u, 4:4 + P], ru[u, 4:4 + P], rtol=rtol, atol=0, err_msg=f"update {u} log W")
-        np.testing.assert_allclose(gu[u, 4 + P:4 + 2 * P], ru[u, 4 + P:4 + 2 * P], rtol=1e-4, atol=1e-12,
-                                   err_msg=f"update {u} normalised W")
+        wtol = _check_logw(gu[u, 4:4 + P], ru[u, 4:4 + P], n, f"update {u} log W")
+        _check_normalised(gu[u, 4 + P:4 + 2 * P], ru[u, 4 + P:4 + 2 * P], wtol, P, f"update {u} normalised W")
         for r in range(int(ru[u, 0])):
             a, b = rs[u, r], gs[u, r]
             for f, name in ((0, "status"), (1, "node"), (2, "var"), (3, "split"), (6, "cntL"), (7, "cntR"),
                             (9, "min"), (10, "max")):
                 np.testing.assert_array_equal(b[:, f], a[:, f], err_msg=f"update {u} round {r} {name}")
-            for f, name in ((4, "vL"), (5, "vR"), (8, "logw"), (11, "SoL")):
+            for f, name in ((4, "vL"), (5, "vR"), (11, "SoL")):
                 np.testing.assert_allclose(b[:, f], a[:, f], rtol=rtol, atol=1e-9, err_msg=f"update {u} round {r} {name}")
+            np.testing.assert_array_equal(np.isnan(b[:, 8]), np.isnan(a[:, 8]), err_msg=f"update {u} round {r} logw pattern")
+            grown = ~np.isnan(a[:, 8])
+            wt = _check_logw(b[grown, 8], a[grown, 8], n, f"update {u} round {r} logw") if grown.any() else weight_tolerance(n, 1.0)
             np.testing.assert_array_equal(gr[u, r, 2 + S:2 + 2 * S], rr[u, r, 2 + S:2 + 2 * S],
                                           err_msg=f"update {u} round {r} ancestors")
-            np.testing.assert_allclose(gr[u, r, 2:2 + S], rr[u, r, 2:2 + S], rtol=1e-4, atol=1e-12,
-                                       err_msg=f"update {u} round {r} normalised weights")
+            # the weight vector also carries stale entries (normalised weights of earlier rounds, Q1): same bound
+            _check_normalised(gr[u, r, 2:2 + S], rr[u, r, 2:2 + S], max(wt, wtol), S, f"update {u} round {r} normalised weights")
             assert gr[u, r, 1] == rr[u, r, 1]
 
 
@@ -97,7 +147,7 @@ def replay_parity(make_dev, X, y, cfg, family, lik_sigma, tunes, r_cap=24, rtol=
     ds, dr, du, n_upd, ovf = dev.trace_read()
     assert not ovf
     assert n_upd == orc.trace_count()
-    assert_traces_match((tr.slot, tr.round, tr.upd), (ds, dr, du), n_upd, S, P, rtol)
+    assert_traces_match((tr.slot, tr.round, tr.upd), (ds, dr, du), n_upd, S, P, rtol, n=X.shape[0])
     for a, b in zip(opreds, dpreds):
         np.testing.assert_allclose(b, a, rtol=rtol, atol=0, err_msg="predictions")
     assert_forest_matches(orc, dev, m, rtol)
@@ -105,7 +155,7 @@ def replay_parity(make_dev, X, y, cfg, family, lik_sigma, tunes, r_cap=24, rtol=
     dll, dacc, ddep = dev.info()
     assert oacc == dacc
     np.testing.assert_array_equal(ddep, odep)
-    np.testing.assert_allclose(dll, oll, rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(dll, oll, rtol=1e-5, atol=1e-12)
     return tr
 
 
@@ -130,7 +180,7 @@ def philox_parity(make_dev, X, y, cfg, family, lik_sigma, tunes, r_cap=24, rtol=
         np.testing.assert_allclose(b, a, rtol=rtol, atol=0)
     ds, dr, du, n_upd, ovf = dev.trace_read()
     assert not ovf and orc.overflowed() == 0
-    assert_traces_match((tr.slot, tr.round, tr.upd), (ds, dr, du), n_upd, S, P, rtol)
+    assert_traces_match((tr.slot, tr.round, tr.upd), (ds, dr, du), n_upd, S, P, rtol, n=X.shape[0])
     assert_forest_matches(orc, dev, m, rtol)
     return tr
 
@@ -183,7 +233,7 @@ def golden_parity(make_dev, g, rtol=RTOL):
     preds = np.stack([dev.step(t) for t in meta["tunes"]])
     ds, dr, du, n_upd, ovf = dev.trace_read()
     assert not ovf and n_upd == int(g["n_upd"])
-    assert_traces_match((g["trace_slot"], g["trace_round"], g["trace_upd"]), (ds, dr, du), n_upd, S, P, rtol)
+    assert_traces_match((g["trace_slot"], g["trace_round"], g["trace_upd"]), (ds, dr, du), n_upd, S, P, rtol, n=g["X"].shape[0])
     np.testing.assert_allclose(preds, g["preds"], rtol=rtol, atol=0, err_msg="predictions")
     gf = GoldenForest(g)
     for t in range(m):

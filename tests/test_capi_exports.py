@@ -41,7 +41,7 @@ def test_no_cpu_fallback_without_a_device():
     y = X[:, 0]
     st = PyBartSettings(4, 4, 3, 0.95, 2.0, 0.1, [1.0, 2.0, 3.0], ["ContinuousSplit"] * 3, "constant", "systematic")
     with pytest.raises(RuntimeError, match="no CUDA device"):
-        PySampler.init(X, y, DeviceLikelihood("gaussian", 1.0), st)
+        PySampler.init(X, y, DeviceLikelihood("gaussian", 1.0), st, fp32_rounding="allow")
 
 
 def test_reference_error_behaviour_of_settings_and_init():

@@ -81,6 +81,52 @@ def test_gpu_stepwise_driver_matches(case):
     parity.replay_parity(make_gpu("stepwise"), X, y, cfg, family, lik_sigma, tunes, r_cap=64)
 
 
+# ---- replay parity at the BASELINE shapes (VERDICT r01 "Next round" item 1) ------------------------------------------
+# The oracle needs 0.3 s per tree update at C3 (n = 1M, p = 50), so 20 updates of replay cost seconds; at C2 a full sweep
+# does.  Decisions bit-exact; log-weights within parity.weight_tolerance (1.2e-6 ABSOLUTE on magnitudes of 1.4e6 at C3).
+
+@pytest.mark.timeout(1500)
+def test_gpu_replay_parity_C3_headline_shape():
+    """BASELINE C3: n = 1M, p = 50, m = 200, P = 20, Gaussian — 20 tree updates (batch 0.1 of m), trace on."""
+    n, p, m, P = 1_000_000, 50, 200, 20
+    X, y = datagen.friedman(n, p, seed=0)
+    cfg = cfg_for(y, m, P, p, batch=(0.1, 0.1), seed=0)
+    tr = parity.replay_parity(make_gpu(), X, y, cfg, 0, 1.0, [True], r_cap=24)
+    print("C3 replay margins (fraction of the tolerance used):", parity.LAST_MARGINS)
+    assert np.any(tr.upd[:20, 0] > 1), "no update went past round 0: the test would not cover partitions / later rounds"
+
+
+@pytest.mark.timeout(1500)
+def test_gpu_replay_parity_C2_full_sweep():
+    """BASELINE C2: n = 100k, p = 20, m = 200, P = 20, Gaussian — one full sweep (200 tree updates), trace on."""
+    n, p, m, P = 100_000, 20, 200, 20
+    X, y = datagen.friedman(n, p, seed=0)
+    cfg = cfg_for(y, m, P, p, batch=(1.0, 1.0), seed=0)
+    parity.replay_parity(make_gpu(), X, y, cfg, 0, 1.0, [True], r_cap=24)
+    print("C2 replay margins:", parity.LAST_MARGINS)
+
+
+@pytest.mark.timeout(1500)
+def test_gpu_replay_parity_C5_shape_256_particles_bernoulli():
+    """BASELINE C5 shape at n = 100k: Bernoulli-logit, p = 50, m = 200, P = 256 — 4 tree updates, trace on."""
+    n, p, m, P = 100_000, 50, 200, 256
+    X, y = datagen.friedman(n, p, seed=0, bernoulli=True)
+    cfg = cfg_for(y, m, P, p, batch=(0.02, 0.02), seed=0)
+    parity.replay_parity(make_gpu(), X, y, cfg, 1, 1.0, [True], r_cap=16)
+    print("C5-shape replay margins:", parity.LAST_MARGINS)
+
+
+@pytest.mark.parametrize("P,family", [(64, 0), (256, 0), (100, 1)])
+def test_gpu_replay_parity_many_particles_all_grow(P, family):
+    """P > 32 where the particles really compete: alpha = 0.9999 makes every slot grow in round 0 (no stale zero weight
+    kills the grown ones, Q1), so later rounds, resampling copies and partitions run with many distinct lineages."""
+    n, p, m = 3000, 6, 4
+    X, y = datagen.small(n, p, seed=P, bernoulli=(family == 1))
+    cfg = cfg_for(y, m, P, p, alpha=0.9999, beta=1.5, max_depth=6, seed=P)
+    tr = parity.replay_parity(make_gpu(), X, y, cfg, family, 1.0, [True, True], r_cap=64)
+    assert np.any(tr.upd[:2 * m, 0] > 2)
+
+
 def test_gpu_philox_parity():
     X, y = datagen.friedman(3000, 5, seed=2)
     cfg = cfg_for(y, 12, 10, 5, seed=5)
@@ -180,11 +226,83 @@ def test_gpu_pruned_dead_proposals_same_forest():
         dll, dacc, ddep = dev.info()
         assert oacc == dacc
         np.testing.assert_array_equal(ddep, odep)
-        np.testing.assert_allclose(dll, oll, rtol=1e-4, atol=1e-12)
+        np.testing.assert_allclose(dll, oll, rtol=1e-5, atol=1e-12)
     # bit-identical between the two modes, and the pruned run really skipped work
     for a, b in zip(outs["0"][0], outs["1"][0]):
         np.testing.assert_array_equal(a, b)
     assert outs["1"][1] < 0.8 * outs["0"][1]
+
+
+# ---- the shipped default path: no trace attached, so speculation, early commit and their miss paths are live ------------
+# (every replay case enables the trace, which disables early commit; these compare the un-traced kernel with
+# the oracle through forest, predictions and BartInfo, both sides drawing from Philox by coordinates.)
+NOTRACE_CASES = [
+    # n, p, m, P, family, lik_sigma, kwargs, tunes, expect_miss
+    (4000, 6, 40, 20, 0, 1.0, dict(), [True, True, False, False], False),
+    (400, 2, 3, 4, 0, 0.01, dict(), [True] * 8, False),                                  # positive log-likelihoods
+    (2003, 3, 10, 3, 0, 1.0, dict(beta=0.3, max_depth=10), [True] * 8, True),            # grown particles survive later rounds
+    (1501, 4, 8, 4, 0, 1.0, dict(beta=0.3, max_depth=10), [True] * 6, False),
+    (5000, 8, 10, 20, 0, 0.7, dict(batch=(0.5, 0.3)), [True, True, False, False, False], False),   # batch < 1
+    (3000, 5, 12, 2, 0, 0.05, dict(beta=0.5, max_depth=9), [True] * 6, True),            # one growing particle, small sigma
+    (2500, 5, 9, 6, 1, 1.0, dict(), [True, True, False], False),                         # Bernoulli-logit
+]
+
+
+@pytest.mark.parametrize("n,p,m,P,family,lik_sigma,kw,tunes,expect_miss", NOTRACE_CASES)
+def test_gpu_default_path_without_trace_matches_oracle(n, p, m, P, family, lik_sigma, kw, tunes, expect_miss):
+    from oracle import pyoracle as po
+    X, y = datagen.small(n, p, seed=n + m, bernoulli=(family == 1))
+    cfg = cfg_for(y, m, P, p, seed=n, **kw)
+    orc = po.OracleSampler(X.astype(np.float64), y, **cfg)
+    orc.set_likelihood(family, [lik_sigma])
+    orc.set_rng(po.RNG_PHILOX, n)
+    dev = make_gpu()(X, y, cfg)
+    dev.set_likelihood_code(family, [lik_sigma])
+    dev.set_rng_philox(n)
+    for t in tunes:
+        a, b = orc.step(t), dev.step(t)
+        np.testing.assert_allclose(b, a, rtol=parity.RTOL, atol=0)
+        oll, oacc, odep = orc.info()
+        dll, dacc, ddep = dev.info()
+        assert oacc == dacc
+        np.testing.assert_array_equal(ddep, odep)
+        np.testing.assert_allclose(dll, oll, rtol=1e-5, atol=1e-12)
+    parity.assert_forest_matches(orc, dev, m)
+    sc = dev.spec_counters()
+    print("speculation counters:", sc)
+    if family == 0:
+        assert sc["issued_ahead"] > 0
+    if expect_miss:       # the misprediction path (drain, rewrite the forest entry, re-issue) really ran
+        assert sc["predictions"] > 0 and sc["mispredictions"] > 0 and sc["drained"] > 0, sc
+
+
+def test_gpu_data_that_is_not_fp32_representable():
+    """f64 X / y that fp32 cannot hold.  Strict mode refuses (tests/test_capi_args.py); with rounding accepted
+    the sampler must behave exactly like the oracle run on the ROUNDED data, and predict(X_train) must reproduce the
+    in-sample predictions (same rounding, same thr32 comparisons)."""
+    from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(12)
+    n, p, m, P = 3000, 4, 10, 8
+    X = rng.random((n, p))                                          # float64, not fp32-exact
+    X[:, 3] = 1e9 + np.arange(n)                                    # distinct in f64, 64-wide plateaus in fp32
+    y = X[:, 0] * 2 + X[:, 1] + 0.3 * rng.standard_normal(n)
+    X32, y32 = X.astype(np.float32).astype(np.float64), y.astype(np.float32).astype(np.float64)
+    cfg = cfg_for(y32, m, P, p, seed=2)
+    st = PyBartSettings(m, P, cfg["max_depth"], 0.95, 2.0, cfg["sigma"], list(cfg["split_prior"]), ["ContinuousSplit"] * p,
+                        "constant", "systematic", 1.0, 1.0, 2)
+    with pytest.raises(ValueError, match="not exactly representable in fp32"):
+        PySampler.init(X, y, DeviceLikelihood("gaussian", 1.0), st)
+    dev = PySampler.init(X, y, DeviceLikelihood("gaussian", 1.0), st, fp32_rounding="allow")
+    dev.set_rng_philox(2)
+    orc = po.OracleSampler(X32, y32, **cfg)
+    orc.set_likelihood(po.FAM_GAUSSIAN, [1.0])
+    orc.set_rng(po.RNG_PHILOX, 2)
+    for t in (True, True, False):
+        a, b = orc.step(t), dev.step(t)
+        np.testing.assert_allclose(b, a, rtol=parity.RTOL, atol=0)
+    parity.assert_forest_matches(orc, dev, m)
+    np.testing.assert_allclose(dev.predict(X), b, rtol=1e-12, atol=1e-12)      # un-rounded rows in: same leaves as training
 
 
 def _numpy_forest_predict(dev, m, Xnew):
@@ -214,11 +332,13 @@ def test_gpu_out_of_sample_predict_and_variable_inclusion():
     # on the training rows the traversal must reproduce the running sum of trees (fp32 X widened: same comparisons)
     np.testing.assert_allclose(dev.predict(X), pred, rtol=1e-12, atol=1e-12)
     rng = np.random.default_rng(4)
-    Xnew = rng.random((257, p))                       # float64, C order
-    ref = _numpy_forest_predict(dev, m, Xnew)
+    Xnew = rng.random((257, p), dtype=np.float32).astype(np.float64)      # float64 holding fp32 values, C order
+    ref = _numpy_forest_predict(dev, m, Xnew)          # the reference's f64 comparison `x < split_val`
     np.testing.assert_array_equal(dev.predict(Xnew), ref)
     np.testing.assert_array_equal(dev.predict(np.asfortranarray(Xnew)), ref)
-    np.testing.assert_array_equal(dev.predict(Xnew.astype(np.float32)), _numpy_forest_predict(dev, m, Xnew.astype(np.float32).astype(np.float64)))
+    np.testing.assert_array_equal(dev.predict(Xnew.astype(np.float32)), ref)
+    with pytest.raises(ValueError, match="not exactly representable in fp32"):     # strict sampler: no silent rounding
+        dev.predict(rng.random((5, p)))
     vi = dev.variable_inclusion()
     cnt = np.zeros(p, dtype=np.uint32)
     for t in range(m):

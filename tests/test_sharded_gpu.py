@@ -18,4 +18,4 @@ def test_two_rank_observation_sharding_matches_oracle():
            "--master-port", "29533", os.path.join(ROOT, "tests", "run_sharded.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=850)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("sharded parity OK") == 4, r.stdout[-3000:]
+    assert r.stdout.count("sharded parity OK") == 5, r.stdout[-3000:]
