@@ -364,21 +364,22 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     char ebuf[256];
     int grid = 0;
     int stage_bytes = 0;
-    const char* env_root = std::getenv("PGBART_ROOT_PASS");      // experiments: "staged" reserves the staging area and selects the staged pass
-#ifdef PGBART_WITH_STAGED
-    const bool want_stage = env_root && std::strcmp(env_root, "staged") == 0;
-#else
-    const bool want_stage = false;   // the staged root pass is compiled only with -DPGBART_WITH_STAGED (it is slower than the default)
-#endif
-    if (pg_query_grid(device, st.S, want_stage, &grid, &s->smem, &stage_bytes, ebuf, sizeof ebuf)) { s->err = ebuf; return bail(); }
+    // P <= 32: 164 KB of shared memory per block — ~145 KB of staging ring for the root pass in the pass blocks, and the L1
+    // the control block's SM keeps is still 92 KB (a 225 KB carve-out made every control section slower)
+    int smem_kb = st.P <= 32 ? 163 : 0;   // + 1 KB the system reserves per block = the 164 KB carve-out
+    if (const char* e = std::getenv("PGBART_SMEM_KB")) smem_kb = std::atoi(e);
+    if (pg_query_grid(device, st.S, smem_kb, &grid, &s->smem, &stage_bytes, ebuf, sizeof ebuf)) { s->err = ebuf; return bail(); }
     st.grid = grid;
     st.stage_bytes = stage_bytes;
-    st.root_staged = 0;
     st.prefetch_next = 0;
     st.prune = 0;
     if (const char* e = std::getenv("PGBART_PRUNE")) st.prune = std::atoi(e) != 0;
-    st.root_staged = want_stage ? 1 : 0;
-    st.root_quarters = (env_root && std::strcmp(env_root, "quarters") == 0) ? 1 : 0;
+    st.root_ring = 1;
+    st.root_tile_groups = 0;
+    st.root_stages = 0;
+    if (const char* e = std::getenv("PGBART_ROOT_PASS")) st.root_ring = std::strcmp(e, "direct") != 0;
+    if (const char* e = std::getenv("PGBART_ROOT_TILE_GROUPS")) st.root_tile_groups = std::atoi(e);
+    if (const char* e = std::getenv("PGBART_ROOT_STAGES")) st.root_stages = std::atoi(e);
     if (const char* e = std::getenv("PGBART_PREFETCH_NEXT")) st.prefetch_next = std::atoi(e) != 0;
     st.n_gwarps = grid * PG_WARPS;
 
@@ -654,15 +655,16 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
         return 1;
     }
     if (std::strcmp(key, "root_pass") == 0) {
-        if (std::strcmp(value, "staged") == 0) {
-            if (s->st.stage_bytes < 64 * 1024) { s->err = "the staged root pass needs its staging area: create the sampler with PGBART_ROOT_PASS=staged"; return 1; }
-            s->st.root_staged = 1; return 0;
+        if (std::strcmp(value, "ring") == 0 || std::strcmp(value, "staged") == 0) {
+            if (s->st.stage_bytes <= 0) { s->err = "the ring root pass needs a staging area (PGBART_SMEM_KB, n_particles <= 32)"; return 1; }
+            s->st.root_ring = 1; return 0;
         }
-        if (std::strcmp(value, "direct") == 0) { s->st.root_staged = 0; s->st.root_quarters = 0; return 0; }
-        if (std::strcmp(value, "quarters") == 0) { s->st.root_staged = 0; s->st.root_quarters = 1; return 0; }
-        s->err = "root_pass must be 'staged' or 'direct'";
+        if (std::strcmp(value, "direct") == 0) { s->st.root_ring = 0; return 0; }
+        s->err = "root_pass must be 'ring' or 'direct'";
         return 1;
     }
+    if (std::strcmp(key, "root_tile_groups") == 0) { s->st.root_tile_groups = std::atoi(value); return 0; }
+    if (std::strcmp(key, "root_stages") == 0) { s->st.root_stages = std::atoi(value); return 0; }
     if (std::strcmp(key, "prune_dead_proposals") == 0) { s->st.prune = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "prefetch_next") == 0) { s->st.prefetch_next = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "pool_factor") == 0) {

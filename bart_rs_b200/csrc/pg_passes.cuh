@@ -25,11 +25,11 @@
 #include "pg_serial.h"
 
 #define PG_TREE_SM 63      // tree nodes staged in shared memory (depth <= 5); larger trees read global
-#define PGR_T 512          // staged root pass: rows per tile
-#define PGR_MAXST 8        //   stages of the ring (as many as the staging area holds, at least 3)
+#define PGR_RG 128         // ring root pass: rows per row group (32 lanes x 4 consecutive rows)
+#define PGR_MAXG 8         //   row groups per tile at most (1024 rows: 4 KB per column copy)
+#define PGR_MAXST 4        //   stages of the ring at most
 #define PGR_MAXU 40        //   distinct columns per tile (S <= 31 job columns + tree columns)
 #define PGR_JW 8           //   jobs per warp: 4 job groups x 8 >= S
-#define PGR_KP 6           //   staged arrays per thread whose source pointers live in registers
 #define PG_FULL 0xFFFFFFFFu
 
 // Index of this block among the PASS blocks (st.grid of them).  In the persistent kernel block 0 is the serial
@@ -130,18 +130,18 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
 struct PgSmem {
     PgTreeSm tadd, tsub;
     double tot[PG_WARPS][4];
-    PgFastSm fast;
     double cthr[16];       // depth-prior thresholds (staged once per kernel)
     int cstaged;           // split prior / column min-max are staged in the dynamic area
     int pass_bid;          // this block's index among the pass blocks (-1: serial-only block)
     int is_last;
-    // ---- staged root pass (pg_pass_root_tma): bulk-copy ring in the staging area behind the dynamic arrays
-    unsigned long long mbar_full[PGR_MAXST], mbar_empty[PGR_MAXST];   // per stage: tile landed / every warp done with it
+    // ---- ring root pass (pg_pass_root_ring): bulk-copy ring in the staging area behind the dynamic arrays
+    unsigned long long mbar_full[PGR_MAXST];   // per stage: the tile's bytes have landed
+    unsigned r_done[PGR_MAXST];            // per stage: warps that have finished with the tile it holds (the last one refills it)
     int r_ucol[PGR_MAXU];                  // distinct columns staged per tile
     int r_jslot[32];                       // job -> staged column
     short r_add_slot[PG_TREE_SM], r_sub_slot[PG_TREE_SM];   // tree node -> staged column, -1 = gather from global
     int r_U;
-    unsigned long long r_src[3 + PGR_MAXU];   // per staged array (A rows 0-255, A rows 256-511, y, columns...): address of tile row 0 at r0 = 0
+    unsigned long long r_src[2 + PGR_MAXU];   // per staged array (A, y, columns...): global address of the array's row 0
     double r_acc[4][32][2];                // [row quarter][job]: sum A, sum y-A over LEFT rows
     unsigned r_cnt[4][32];
     unsigned p_scan[2][PG_WARPS];          // block-unit identity partition: warp totals of a chunk, double-buffered
@@ -156,29 +156,31 @@ struct PgSmem {
 
 #define FW_MAXP 512   // split prior / column min-max staged in shared memory up to this many columns
 
-// dynamic shared memory layout after PgSmem (all sized by S):
-//   int   jvar[S]; float jthr[S]; int jorder[S]; int grp[S+1]; double jvL[S]; double jvR[S];
-//   double accA[PG_WARPS][S]; double accB[PG_WARPS][S]; unsigned accC[PG_WARPS][S];
-//   unsigned mmin[S]; unsigned mmax[S];
-__host__ __device__ inline size_t pg_smem_bytes(int S) {
-    size_t b = sizeof(PgSmem);
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)S * (4 + 4 + 4) + (size_t)(S + 1) * 4;
-    b = (b + 15) & ~(size_t)15;
+// Dynamic shared memory of every kernel: [PgSmem][pass arrays sized by S][union area].  The union area holds, in the
+// control block (block 0 of the P <= 32 persistent kernels), its kernel-lifetime state PgFastSm and the staged split prior
+// / column min-max; in the pass blocks, which never touch that state, the same bytes are the staging ring of the root pass.
+//   pass arrays: double jvL[S], jvR[S]; double accA[PG_WARPS][S], accB[PG_WARPS][S]; unsigned accC[PG_WARPS][S];
+//                unsigned mmin[2S], mmax[2S]; int jvar[S]; float jthr[S]; int jorder[S]; int grp[S+1]
+__host__ __device__ inline size_t pg_smem_pass_bytes(int S) {
+    size_t b = (sizeof(PgSmem) + 15) & ~(size_t)15;
     b += (size_t)S * 16;                       // jvL, jvR
     b += (size_t)PG_WARPS * S * (8 + 8 + 4);   // accA, accB, accC
     b += (size_t)S * 16;                       // mmin, mmax (2S each)
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)FW_MAXP * (8 + 4 + 4);        // cprior, cmin, cmax
-    return ((b + 127) & ~(size_t)127) + 128;   // the staging area starts 128-byte aligned behind this
+    b += (size_t)S * (4 + 4 + 4) + (size_t)(S + 1) * 4;
+    return ((b + 127) & ~(size_t)127) + 128;   // the union area starts 128-byte aligned behind this
 }
+__host__ __device__ inline size_t pg_smem_ctrl_bytes() {   // the control block's part of the union area
+    return ((sizeof(PgFastSm) + 15) & ~(size_t)15) + (size_t)FW_MAXP * (8 + 4 + 4);
+}
+__host__ __device__ inline size_t pg_smem_bytes(int S) { return pg_smem_pass_bytes(S) + pg_smem_ctrl_bytes(); }   // without a ring
 
 struct PgSmemView {
     PgSmem* base;
     int* jvar; float* jthr; int* jorder; int* grp; double* jvL; double* jvR;
     double* accA; double* accB; unsigned* accC; unsigned* mmin; unsigned* mmax;
-    double* cprior; float* cmin; float* cmax;
-    unsigned char* stage;      // staging area (st.stage_bytes), 128-byte aligned
+    PgFastSm* fast;            // control block only
+    double* cprior; float* cmin; float* cmax;   // control block only
+    unsigned char* stage;      // pass blocks only: staging ring (st.stage_bytes), 128-byte aligned; aliases fast / cprior / ...
 };
 
 __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
@@ -196,11 +198,12 @@ __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
     v.jthr = reinterpret_cast<float*>(raw + off); off += (size_t)S * 4;
     v.jorder = reinterpret_cast<int*>(raw + off); off += (size_t)S * 4;
     v.grp = reinterpret_cast<int*>(raw + off); off += (size_t)(S + 1) * 4;
-    off = (off + 15) & ~(size_t)15;
-    v.cprior = reinterpret_cast<double*>(raw + off); off += (size_t)FW_MAXP * 8;
-    v.cmin = reinterpret_cast<float*>(raw + off); off += (size_t)FW_MAXP * 4;
-    v.cmax = reinterpret_cast<float*>(raw + off); off += (size_t)FW_MAXP * 4;
     v.stage = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw + off) + 127) & ~(uintptr_t)127);
+    unsigned char* u = v.stage;
+    v.fast = reinterpret_cast<PgFastSm*>(u); u += (sizeof(PgFastSm) + 15) & ~(size_t)15;
+    v.cprior = reinterpret_cast<double*>(u); u += (size_t)FW_MAXP * 8;
+    v.cmin = reinterpret_cast<float*>(u); u += (size_t)FW_MAXP * 4;
+    v.cmax = reinterpret_cast<float*>(u);
     return v;
 }
 
@@ -463,195 +466,22 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
 }
 
 // =============================================================================
-// PH_ROOT / PH_FINAL, quarter/group variant (P <= 32 persistent kernel, default)
+// PH_ROOT / PH_FINAL, ring variant (P <= 32 persistent kernels; root_pass = "ring")
 // =============================================================================
-// Same arithmetic as pg_pass_root on a different work split.  The block's rows (pg_block_range) are cut into four
-// contiguous quarters; warp w = (quarter w / 4, job group w % 4) streams its quarter 128 rows at a time (4 consecutive
-// rows per lane, float4 loads) and accumulates ITS jobs (every fourth one) in per-lane registers for the whole pass:
-// no cross-lane reduction and no shared memory inside the loop, one reduction at the end.  The split columns of the
-// next 128 rows are loaded before the current ones are consumed (register double buffer), so every warp always has
-// ~2.5 KB in flight.  A and y come from L2 (they are re-read every tree update and stay resident).  Each of the four
-// groups of a quarter re-derives A -> "others" for its rows (a dozen instructions); only group 0 writes A back and keeps
-// the totals.  Fixed summation order => bit-reproducible.  Emits per-BLOCK results (part_tot, part_sum, part_ccnt).
-template <bool BERN, int JW>
-__device__ void pg_pass_root_quarters(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
-    PgCtrl* c = st.ctrl;
-    PgSmem* b = sm.base;
-    const bool is_root = __ldcg(&c->phase) == PH_ROOT;
-    const int J = is_root ? __ldcg(&c->n_jobs) : 0;
-    const int t_add = __ldcg(&c->t_add), t_sub = is_root ? __ldcg(&c->t_sub) : -1;
-    const int S = st.S;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int qd = warp >> 2, grp = warp & 3;
-
-    pg_stage_tree(st, t_add, b->tadd);
-    pg_stage_tree(st, t_sub, b->tsub);
-    for (int j = tid; j < J; j += blockDim.x) { sm.jvar[j] = __ldcg(&bf.job_var[j]); sm.jthr[j] = __ldcg(&bf.job_thr32[j]); }
-    __syncthreads();
-    const bool add_nontrivial = t_add >= 0 && b->tadd.size > 1;
-    const bool sub_nontrivial = t_sub >= 0 && b->tsub.size > 1;
-    const double add_c = t_add == -2 ? st.init_leaf : ((t_add >= 0 && !add_nontrivial) ? b->tadd.leaf_val[0] : 0.0);
-    const double sub_c = (t_sub >= 0 && !sub_nontrivial) ? b->tsub.leaf_val[0] : 0.0;
-    const bool do_add = t_add >= 0 || t_add == -2, do_sub = t_sub >= 0;
-    const bool commit_only = J == 0 && t_sub < 0;      // PH_FINAL
-
-    long long B0, B1;
-    pg_block_range(st.n, PG_BID, st.grid, &B0, &B1);
-    unsigned long long qb, qe;
-    pg_warp_range((unsigned long long)(B1 - B0), qd, 4, 128, &qb, &qe);     // quarters in units of one warp-iteration
-    const long long Q0 = B0 + (long long)qb, Q1 = B0 + (long long)qe;
-    const long long n = st.n;
-    const size_t ld = (size_t)st.ld;
-
-    // my jobs: group g takes jobs j with (j + 1) % 4 == g, so group 0 (which also writes A and keeps the totals) gets the fewest
-    const int jfirst = (grp + 3) & 3;
-    const int myJ = J > jfirst ? min((J - jfirst + 3) / 4, JW) : 0;
-    const float* colp[JW];
-    float jthr[JW];
-    double accA[JW], accB[JW];
-    unsigned accC[JW];
-#pragma unroll
-    for (int q = 0; q < JW; ++q) {
-        const int j = jfirst + 4 * q;
-        const bool lv = q < myJ;
-        colp[q] = st.X + (size_t)(lv ? sm.jvar[j] : 0) * ld + Q0 + 4 * lane;
-        jthr[q] = lv ? sm.jthr[j] : -INFINITY;
-        accA[q] = 0.0; accB[q] = 0.0; accC[q] = 0u;
-    }
-    double tot_o = 0.0, tot_r = 0.0, tot_rr = 0.0, tot_ll = 0.0;
-    const float4 finf = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-
-    float4 xc[JW], xn[JW];
-    double2 ac01 = make_double2(0.0, 0.0), ac23 = make_double2(0.0, 0.0), an01, an23;
-    float4 yc = make_float4(0.f, 0.f, 0.f, 0.f), yn;
-    {
-        const long long row0 = Q0 + 4 * lane;
-        const bool in0 = row0 < Q1;
-#pragma unroll
-        for (int q = 0; q < JW; ++q) xc[q] = (q < myJ && in0) ? pg_ld_x4(colp[q]) : finf;
-        if (in0) { ac01 = pg_ld_a2(bf.A_src + row0); ac23 = pg_ld_a2(bf.A_src + row0 + 2); yc = __ldg(reinterpret_cast<const float4*>(st.y + row0)); }
-    }
-#pragma unroll 1
-    for (long long base = Q0; base < Q1; base += 128) {
-        const long long row = base + 4 * lane;
-        const bool in = row < Q1;
-        const bool in_next = row + 128 < Q1;
-        // the next iteration's inputs: in flight while this one is consumed
-#pragma unroll
-        for (int q = 0; q < JW; ++q) xn[q] = (q < myJ && in_next) ? pg_ld_x4(colp[q] + (base - Q0) + 128) : finf;
-        an01 = make_double2(0.0, 0.0); an23 = make_double2(0.0, 0.0); yn = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in_next) { an01 = pg_ld_a2(bf.A_src + row + 128); an23 = pg_ld_a2(bf.A_src + row + 130); yn = __ldg(reinterpret_cast<const float4*>(st.y + row + 128)); }
-        double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
-        float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in) {
-            yy = yc;
-            o0 = ac01.x; o1 = ac01.y; o2 = ac23.x; o3 = ac23.y;
-            const int nv = (int)min(4ll, n - row);
-            // kernel.rs:99-102 then :84-87, each a separately rounded f64 operation
-            if (do_add) {
-                if (add_nontrivial) {
-                    o0 = o0 + (nv > 0 ? pg_tree_eval(st, t_add, b->tadd, row + 0) : 0.0);
-                    o1 = o1 + (nv > 1 ? pg_tree_eval(st, t_add, b->tadd, row + 1) : 0.0);
-                    o2 = o2 + (nv > 2 ? pg_tree_eval(st, t_add, b->tadd, row + 2) : 0.0);
-                    o3 = o3 + (nv > 3 ? pg_tree_eval(st, t_add, b->tadd, row + 3) : 0.0);
-                } else { o0 = o0 + add_c; o1 = o1 + add_c; o2 = o2 + add_c; o3 = o3 + add_c; }
-            }
-            if (do_sub) {
-                if (sub_nontrivial) {
-                    o0 = o0 - (nv > 0 ? pg_tree_eval(st, t_sub, b->tsub, row + 0) : 0.0);
-                    o1 = o1 - (nv > 1 ? pg_tree_eval(st, t_sub, b->tsub, row + 1) : 0.0);
-                    o2 = o2 - (nv > 2 ? pg_tree_eval(st, t_sub, b->tsub, row + 2) : 0.0);
-                    o3 = o3 - (nv > 3 ? pg_tree_eval(st, t_sub, b->tsub, row + 3) : 0.0);
-                } else { o0 = o0 - sub_c; o1 = o1 - sub_c; o2 = o2 - sub_c; o3 = o3 - sub_c; }
-            }
-            if (grp == 0) {
-                __stcg(reinterpret_cast<double2*>(bf.A_dst + row), make_double2(o0, o1));
-                __stcg(reinterpret_cast<double2*>(bf.A_dst + row + 2), make_double2(o2, o3));
-            }
-            if (nv < 4) {                                   // the lane that straddles n (padding rows: x = +inf already)
-                if (nv < 2) { o1 = 0.0; yy.y = 0.f; }
-                if (nv < 3) { o2 = 0.0; yy.z = 0.f; }
-                o3 = 0.0; yy.w = 0.f;
-                if (nv < 1) { o0 = 0.0; yy.x = 0.f; }
-            }
-        }
-        if (!commit_only) {
-            const double r0v = (double)yy.x - o0, r1v = (double)yy.y - o1, r2v = (double)yy.z - o2, r3v = (double)yy.w - o3;
-            if (grp == 0) {                                 // rows past the range / past n contribute exact zeros
-                tot_o += o0; tot_o += o1; tot_o += o2; tot_o += o3;
-                tot_r += r0v; tot_r += r1v; tot_r += r2v; tot_r += r3v;
-                tot_rr += r0v * r0v; tot_rr += r1v * r1v; tot_rr += r2v * r2v; tot_rr += r3v * r3v;
-                if (BERN && in) {
-                    const int nv = (int)min(4ll, n - row);
-                    const double ov[4] = {o0, o1, o2, o3};
-                    const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (e < nv) { const double mu = ov[e] + st.init_leaf; tot_ll += (double)yv[e] * mu - pg_softplus(mu); }
-                }
-            }
-            // smc.rs:201-217 for this warp's slots of round 1; +inf never compares LEFT
-#pragma unroll
-            for (int q = 0; q < JW; ++q) {
-                pg_acc_left(accA[q], accB[q], accC[q], xc[q].x, jthr[q], o0, r0v);
-                pg_acc_left(accA[q], accB[q], accC[q], xc[q].y, jthr[q], o1, r1v);
-                pg_acc_left(accA[q], accB[q], accC[q], xc[q].z, jthr[q], o2, r2v);
-                pg_acc_left(accA[q], accB[q], accC[q], xc[q].w, jthr[q], o3, r3v);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < JW; ++q) xc[q] = xn[q];
-        ac01 = an01; ac23 = an23; yc = yn;
-    }
-
-    // ---- block results
-    if (!commit_only) {
-#pragma unroll
-        for (int q = 0; q < JW; ++q) {
-            if (q < myJ) {                                  // warp-uniform
-                const double a = pg_warp_sum(accA[q]), bb = pg_warp_sum(accB[q]);
-                const unsigned cc = __reduce_add_sync(PG_FULL, accC[q]);
-                if (lane == 0) { const int j = jfirst + 4 * q; b->r_acc[qd][j][0] = a; b->r_acc[qd][j][1] = bb; b->r_cnt[qd][j] = cc; }
-            }
-        }
-        if (grp == 0) {
-            tot_o = pg_warp_sum(tot_o); tot_r = pg_warp_sum(tot_r); tot_rr = pg_warp_sum(tot_rr); tot_ll = pg_warp_sum(tot_ll);
-            if (lane == 0) { b->tot[qd][0] = tot_o; b->tot[qd][1] = tot_r; b->tot[qd][2] = tot_rr; b->tot[qd][3] = tot_ll; }
-        }
-    }
-    __syncthreads();
-    if (commit_only) return;
-    if (tid < 4) {
-        double v = 0.0;
-        for (int q = 0; q < 4; ++q) v += b->tot[q][tid];
-        bf.part_tot[(size_t)PG_BID * 4 + tid] = v;
-    }
-    for (int j = tid; j < J; j += blockDim.x) {
-        double a = 0.0, bb = 0.0;
-        unsigned cc = 0u;
-        for (int q = 0; q < 4; ++q) { a += b->r_acc[q][j][0]; bb += b->r_acc[q][j][1]; cc += b->r_cnt[q][j]; }
-        bf.part_sum[((size_t)PG_BID * S + j) * 2 + 0] = a;
-        bf.part_sum[((size_t)PG_BID * S + j) * 2 + 1] = bb;
-        bf.part_ccnt[(size_t)PG_BID * S + j] = cc;
-    }
-}
-
-// =============================================================================
-// PH_ROOT / PH_FINAL, staged variant (P <= 32 persistent kernel; -DPGBART_WITH_STAGED, root_pass = "staged")
-// =============================================================================
-// The direct pass is latency / issue bound: each warp walks its rows through dependent global loads with loads only
-// one job group ahead.  Here the loads are decoupled from the arithmetic: a ring of tiles is kept in flight with bulk
-// asynchronous copies into shared memory (cp.async.bulk, completion on an mbarrier, evict-first for X); a tile = PGR_T
-// rows of A, y and every DISTINCT column the pass needs (the slots' split variables plus the split variables of the trees
-// being committed / opened, so tree evaluation reads shared memory too).  Warp w = (row quarter w / 4, job group
-// w % 4): a lane owns 4 consecutive rows of its quarter and accumulates its group's jobs in registers across ALL tiles of
-// the block, so the cross-lane reduction happens once per pass.  Every warp issues the copies of "its" arrays (one lane,
-// 1-2 bulk copies per tile) and the warps synchronise only through the per-stage "landed" / "done" mbarriers.  Fixed
-// summation order => bit-reproducible.  Emits per-BLOCK results only (part_tot, part_sum, part_ccnt).
-// Measured: parity-green, 15.1 ms per sweep at C3 against 13.9 for the direct pass (an earlier
-// version that copied with cp.async from all threads and synchronised the block per tile: 16.5).  Its arithmetic is lean
-// (26 K warp-instructions per SM per pass in the job loop); it waits for tiles — 17 bulk copies of 2 KB per tile do not
-// reach the rate a few large copies would.  Kept selectable for the next round (TMA gather4 tiles).
+// The direct pass is latency bound: a block owns only ~6.8 K rows at BASELINE C3, so each warp runs two iterations of
+// five dependent load -> reduce phases and the pass takes 24 us where the bytes need 12.  Here the loads are decoupled
+// from the arithmetic: the block's rows are cut into tiles of G row groups (128 rows each, G <= 8) and a ring of tiles
+// is kept in flight with bulk asynchronous copies (cp.async.bulk -> UBLKCP, completion on an mbarrier, evict-first for
+// X): per tile ONE copy per array — A (8 B/row), y, and every DISTINCT column the pass needs (the slots' split variables
+// plus the split variables of the trees being committed / opened, so tree evaluation reads shared memory too) — 4 KB per
+// column at G = 8, because the copy engine accepts one copy per ~90 cycles and 2 KB copies cannot feed an SM its share of
+// HBM bandwidth (the first staged version, 512-row tiles, lost to the direct pass for that reason).
+// Warp w = (row quarter w / 4, job group w % 4): the tile's row groups are dealt round-robin to the quarters (rotating
+// with the tile index so that every quarter gets the odd group in turn); a lane owns 4 consecutive rows of a row group
+// and accumulates its job group's jobs in registers across ALL tiles of the block, so the cross-lane reduction happens
+// once per pass.  There is no producer warp and no block barrier in the loop: the warp that finishes a tile LAST
+// (shared-memory counter) refills the stage with the tile NST ahead, its lanes issuing the copies of one array each.
+// Fixed summation order => bit-reproducible.  Emits per-BLOCK results only (part_tot, part_sum, part_ccnt).
 __device__ __forceinline__ unsigned pg_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned long long pg_policy_evict_first() {
     unsigned long long pol;
@@ -703,21 +533,23 @@ __device__ __forceinline__ void pg_bulk_g2s_hint_u32(unsigned dst, const void* s
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(pg_smem_u32(bar)), "l"(pol) : "memory");
 }
 
-// tree value of a row whose columns are (mostly) staged: tile-local row `lr`, global row `row`
+// tree value of a row whose columns are (mostly) staged: tile-local row `lr` (stride `T` rows per staged column), global row `row`
 __device__ __forceinline__ double pg_tree_eval_staged(const PgState& st, int t, const PgTreeSm& tr, const short* slot,
-                                                       unsigned cols_u32, int lr, long long row) {
+                                                       unsigned cols_u32, int T, int lr, long long row) {
     if (tr.from_global) return pg_tree_eval(st, t, tr, row);
     int node = 0, sv;
     while ((sv = tr.split_var[node]) >= 0) {
         const int sl = slot[node];
-        const float x = sl >= 0 ? pg_lds_f1(cols_u32 + (unsigned)(sl * PGR_T + lr) * 4u) : __ldg(&st.X[(size_t)sv * st.ld + row]);
+        const float x = sl >= 0 ? pg_lds_f1(cols_u32 + (unsigned)(sl * T + lr) * 4u) : __ldg(&st.X[(size_t)sv * st.ld + row]);
         node = 2 * node + 1 + (x < tr.thr32[node] ? 0 : 1);
     }
     return tr.leaf_val[node];
 }
 
+// Returns false (block-uniformly, before touching anything) when the staging area cannot hold two tiles of one row group
+// for this pass's distinct columns: the caller then runs the direct pass.
 template <bool BERN, int JW>
-__device__ void pg_pass_root_tma(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+__device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     PgSmem* b = sm.base;
     const bool is_root = __ldcg(&c->phase) == PH_ROOT;
@@ -726,24 +558,11 @@ __device__ void pg_pass_root_tma(const PgState& st, const PgBuf& bf, const PgSme
     const int S = st.S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qd = warp >> 2, grp = warp & 3;
-#ifdef PG_DIAG
-    long long ck_t = clock64();
-    unsigned long long* ck_d = st.diag_blocks + (size_t)st.grid * 8 + (size_t)PG_BID * 8;
-#define PG_CK(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); ck_d[i] += (unsigned long long)(now_ - ck_t); ck_t = now_; } } while (0)
-#else
-#define PG_CK(i) do { } while (0)
-#endif
 
     pg_stage_tree(st, t_add, b->tadd);
     pg_stage_tree(st, t_sub, b->tsub);
     for (int j = tid; j < J; j += blockDim.x) { sm.jvar[j] = __ldcg(&bf.job_var[j]); sm.jthr[j] = __ldcg(&bf.job_thr32[j]); }
-    if (tid == 0) {
-#pragma unroll
-        for (int q = 0; q < PGR_MAXST; ++q) { pg_mbar_init(&b->mbar_full[q], PG_WARPS); pg_mbar_init(&b->mbar_empty[q], PG_WARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
-    PG_CK(0);
     // ---- the distinct columns of this pass (warp 0)
     if (warp == 0) {
         const bool live = lane < J;
@@ -756,7 +575,7 @@ __device__ void pg_pass_root_tma(const PgState& st, const PgBuf& bf, const PgSme
         const int slot = __shfl_sync(PG_FULL, slot_l, live ? (__ffs(same) - 1) : 0);
         if (live) b->r_jslot[lane] = slot;
         int U = __popc(leadm);
-        const int ucap = min(PGR_MAXU, (st.stage_bytes / 3 - PGR_T * 12) / (PGR_T * 4));   // at least three stages must fit
+        const int ucap = min(PGR_MAXU, (st.stage_bytes / (2 * PGR_RG) - 12) / 4);   // two tiles of one row group must fit
         __syncwarp();
 #pragma unroll 1
         for (int which = 0; which < 2; ++which) {
@@ -776,11 +595,30 @@ __device__ void pg_pass_root_tma(const PgState& st, const PgBuf& bf, const PgSme
                 __syncwarp();
             }
         }
-        if (lane == 0) b->r_U = U;
+        if (lane == 0) b->r_U = U <= ucap ? U : -1;          // more job columns than the staging area holds: direct pass
     }
     __syncthreads();
-    PG_CK(1);
     const int U = b->r_U;
+    if (U < 0) { __syncthreads(); return false; }
+    const size_t ld = (size_t)st.ld;
+    const int n_arr = 2 + U;
+    // ---- ring geometry: G row groups per tile, NST stages
+    const unsigned bpg = (unsigned)PGR_RG * (12u + 4u * (unsigned)U);            // bytes of one row group of every staged array
+    int G = (int)((unsigned)st.stage_bytes / (2u * bpg));
+    if (st.root_tile_groups > 0 && G > st.root_tile_groups) G = st.root_tile_groups;
+    if (G > PGR_MAXG) G = PGR_MAXG;
+    const int T = G * PGR_RG;
+    const unsigned stage_bytes = (unsigned)G * bpg;
+    int NST = (int)((unsigned)st.stage_bytes / stage_bytes);
+    if (NST > PGR_MAXST) NST = PGR_MAXST;
+    if (st.root_stages >= 2 && NST > st.root_stages) NST = st.root_stages;
+    if (tid < PGR_MAXST) { pg_mbar_init(&b->mbar_full[tid], 1); b->r_done[tid] = 0u; }
+    for (int a = tid; a < n_arr; a += blockDim.x)
+        b->r_src[a] = a == 0 ? (unsigned long long)bf.A_src : a == 1 ? (unsigned long long)st.y
+                                                                    : (unsigned long long)(st.X + (size_t)b->r_ucol[a - 2] * ld);
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
     const bool add_nontrivial = t_add >= 0 && b->tadd.size > 1;
     const bool sub_nontrivial = t_sub >= 0 && b->tsub.size > 1;
     const double add_c = t_add == -2 ? st.init_leaf : ((t_add >= 0 && !add_nontrivial) ? b->tadd.leaf_val[0] : 0.0);
@@ -790,46 +628,32 @@ __device__ void pg_pass_root_tma(const PgState& st, const PgBuf& bf, const PgSme
 
     long long B0, B1;
     pg_block_range(st.n, PG_BID, st.grid, &B0, &B1);
-    const int n_tiles = (int)((B1 - B0 + PGR_T - 1) / PGR_T);
-    const unsigned stage_bytes = (unsigned)PGR_T * (12u + 4u * (unsigned)U);
-    const int NST = min(PGR_MAXST, (int)((unsigned)st.stage_bytes / stage_bytes));
-    const size_t ld = (size_t)st.ld;
+    const int n_tiles = (int)((B1 - B0 + T - 1) / T);
     const unsigned long long pol = pg_policy_evict_first();
     const unsigned stage0 = pg_smem_u32(sm.stage);
-    // staged arrays a = 0: A (4096 B of a full tile), 1: y (2048 B), 2 + u: column u (2048 B each).  Warp w issues the bulk
-    // copies of arrays w, w + 16, w + 32 (one lane, a couple of instructions per tile) and every warp arrives once per stage
-    // on the "landed" barrier with the bytes it asked for; a warp arrives on the "done" barrier of a stage when it has
-    // consumed it, and refills a stage only after all 16 have.  No block-wide barrier inside the loop: warps drift apart
-    // by up to NST - 1 tiles.
-    const int n_arr = 2 + U;
-    for (int a = tid; a < n_arr; a += blockDim.x)
-        b->r_src[a] = a == 0 ? (unsigned long long)bf.A_src : a == 1 ? (unsigned long long)st.y
-                                                                    : (unsigned long long)(st.X + (size_t)b->r_ucol[a - 2] * ld);
-    __syncthreads();
-    auto issue = [&](int t) {                                // lane 0 of every warp
+    // One tile = one bulk copy per staged array: a = 0: A (8 B per row), 1: y, 2 + u: column u.  Issued by ONE warp (whichever
+    // finished the stage's previous tile last), lane a taking arrays a, a + 32: lane 0 first posts the byte count.
+    auto issue = [&](int t) {
         const int s_ = t % NST;
-        const long long r0 = B0 + (long long)t * PGR_T;
-        const unsigned rows = (unsigned)min((long long)PGR_T, B1 - r0);
+        const long long r0 = B0 + (long long)t * T;
+        const unsigned rows = (unsigned)min((long long)T, B1 - r0);
         const unsigned sbase = stage0 + (unsigned)s_ * stage_bytes;
-        unsigned bytes = 0;
+        // generic-proxy accesses this thread has observed (A written by the previous pass through the command's release /
+        // acquire chain; the other warps' reads of the stage through the r_done count) are ordered before its bulk copies
+        asm volatile("fence.proxy.async;" ::: "memory");
+        if (lane == 0) pg_mbar_expect_tx(&b->mbar_full[s_], rows * (12u + 4u * (unsigned)U));
+        __syncwarp();
 #pragma unroll 1
-        for (int a = warp; a < n_arr; a += PG_WARPS) bytes += rows * (a == 0 ? 8u : 4u);
-        if (bytes) pg_mbar_expect_tx(&b->mbar_full[s_], bytes); else pg_mbar_arrive(&b->mbar_full[s_]);
-#pragma unroll 1
-        for (int a = warp; a < n_arr; a += PG_WARPS) {
+        for (int a = lane; a < n_arr; a += 32) {
             const unsigned es = a == 0 ? 8u : 4u;
-            const unsigned dst = sbase + (a == 0 ? 0u : a == 1 ? PGR_T * 8u : PGR_T * 12u + (unsigned)(a - 2) * (PGR_T * 4u));
+            const unsigned dst = sbase + (a == 0 ? 0u : a == 1 ? (unsigned)T * 8u : (unsigned)T * 12u + (unsigned)(a - 2) * ((unsigned)T * 4u));
             const char* src = reinterpret_cast<const char*>(b->r_src[a]) + r0 * es;
             if (a < 2) pg_bulk_g2s_u32(dst, src, rows * es, &b->mbar_full[s_]);
             else pg_bulk_g2s_hint_u32(dst, src, rows * es, &b->mbar_full[s_], pol);
         }
     };
-    if (lane == 0) {
-        asm volatile("fence.proxy.async;" ::: "memory");    // A was written with ordinary stores by the previous pass
+    if (warp == 0)
         for (int t = 0; t < NST && t < n_tiles; ++t) issue(t);
-    }
-    __syncwarp();
-    PG_CK(2);
 
     // my jobs: group g takes jobs j with (j + 1) % 4 == g, so group 0 (which also writes A and keeps the totals) gets the fewest
     const int jfirst = (grp + 3) & 3;
@@ -842,118 +666,119 @@ __device__ void pg_pass_root_tma(const PgState& st, const PgBuf& bf, const PgSme
     for (int q = 0; q < JW; ++q) {
         const int j = jfirst + 4 * q;
         const bool lv = j < J;
-        coff[q] = lv ? (unsigned)b->r_jslot[j] * (PGR_T * 4u) : 0u;
+        coff[q] = lv ? (unsigned)b->r_jslot[j] * ((unsigned)T * 4u) : 0u;
         jthr[q] = lv ? sm.jthr[j] : 0.0f;
         accA[q] = 0.0; accB[q] = 0.0; accC[q] = 0u;
     }
     double tot_o = 0.0, tot_r = 0.0, tot_rr = 0.0, tot_ll = 0.0;
-    const int lr = qd * 128 + lane * 4;     // tile-local first row of this lane
     int stg = 0;
 
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
-        if (lane == 0 && t >= 1 && t - 1 + NST < n_tiles) {  // refill the stage tile t - 1 occupied, once every warp has left it
-            pg_mbar_wait(&b->mbar_empty[(t - 1) % NST], (unsigned)(((t - 1) / NST) & 1));
-            issue(t - 1 + NST);
-        }
-        __syncwarp();
         pg_mbar_wait(&b->mbar_full[stg], (unsigned)((t / NST) & 1));
-        if (t == 0) PG_CK(3);
-        const int stg_used = stg;
         const unsigned sbase = stage0 + (unsigned)stg * stage_bytes;
-        stg = stg + 1 == NST ? 0 : stg + 1;
-        const long long r0 = B0 + (long long)t * PGR_T;
-        const int rows = (int)min((long long)PGR_T, B1 - r0);
-        if (lr < rows) {                                    // (a short last tile leaves some lanes without rows)
-        const long long row = r0 + lr;
-        const int nv = (int)min(4ll, st.n - row);           // valid rows of this lane's four (>= 1 except past n)
-        const unsigned cols = sbase + PGR_T * 12u;          // shared-space address of the staged columns
-        double o0, o1, o2, o3;
-        float4 yy;
-        {
-            const double2 a01 = pg_lds_d2(sbase + (unsigned)lr * 8u);
-            const double2 a23 = pg_lds_d2(sbase + (unsigned)lr * 8u + 16u);
-            yy = pg_lds_f4(sbase + PGR_T * 8u + (unsigned)lr * 4u);
-            o0 = a01.x; o1 = a01.y; o2 = a23.x; o3 = a23.y;
-        }
-        // kernel.rs:99-102 then :84-87, each a separately rounded f64 operation
-        if (do_add) {
-            if (add_nontrivial) {
-                o0 = o0 + (nv > 0 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, lr + 0, row + 0) : 0.0);
-                o1 = o1 + (nv > 1 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, lr + 1, row + 1) : 0.0);
-                o2 = o2 + (nv > 2 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, lr + 2, row + 2) : 0.0);
-                o3 = o3 + (nv > 3 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, lr + 3, row + 3) : 0.0);
-            } else { o0 = o0 + add_c; o1 = o1 + add_c; o2 = o2 + add_c; o3 = o3 + add_c; }
-        }
-        if (do_sub) {
-            if (sub_nontrivial) {
-                o0 = o0 - (nv > 0 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, lr + 0, row + 0) : 0.0);
-                o1 = o1 - (nv > 1 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, lr + 1, row + 1) : 0.0);
-                o2 = o2 - (nv > 2 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, lr + 2, row + 2) : 0.0);
-                o3 = o3 - (nv > 3 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, lr + 3, row + 3) : 0.0);
-            } else { o0 = o0 - sub_c; o1 = o1 - sub_c; o2 = o2 - sub_c; o3 = o3 - sub_c; }
-        }
-        if (grp == 0) {
-            __stcg(reinterpret_cast<double2*>(bf.A_dst + row), make_double2(o0, o1));
-            __stcg(reinterpret_cast<double2*>(bf.A_dst + row + 2), make_double2(o2, o3));
-        }
-        if (!commit_only) {
-        double r0v = (double)yy.x - o0, r1v = (double)yy.y - o1, r2v = (double)yy.z - o2, r3v = (double)yy.w - o3;
-        if (grp == 0) {
-            if (nv >= 4) {
-                tot_o += o0; tot_o += o1; tot_o += o2; tot_o += o3;
-                tot_r += r0v; tot_r += r1v; tot_r += r2v; tot_r += r3v;
-                tot_rr += r0v * r0v; tot_rr += r1v * r1v; tot_rr += r2v * r2v; tot_rr += r3v * r3v;
-                if (BERN) {
-                    const double m0 = o0 + st.init_leaf, m1 = o1 + st.init_leaf, m2 = o2 + st.init_leaf, m3 = o3 + st.init_leaf;
-                    tot_ll += (double)yy.x * m0 - pg_softplus(m0); tot_ll += (double)yy.y * m1 - pg_softplus(m1);
-                    tot_ll += (double)yy.z * m2 - pg_softplus(m2); tot_ll += (double)yy.w * m3 - pg_softplus(m3);
-                }
-            } else {                                        // the lane that straddles n: rows row .. row + nv - 1 are real
-                const double ov[4] = {o0, o1, o2, o3}, rv[4] = {r0v, r1v, r2v, r3v};
-                const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
+        const long long r0 = B0 + (long long)t * T;
+        const int rows = (int)min((long long)T, B1 - r0);
+        const unsigned cols = sbase + (unsigned)T * 12u;          // shared-space address of the staged columns
+        // this warp's row groups of the tile: g = (qd + t) mod 4, + 4, ...  (the odd group of a tile visits every quarter in turn)
 #pragma unroll 1
-                for (int e = 0; e < nv; ++e) {
-                    tot_o += ov[e]; tot_r += rv[e]; tot_rr += rv[e] * rv[e];
-                    if (BERN) { const double mu = ov[e] + st.init_leaf; tot_ll += (double)yv[e] * mu - pg_softplus(mu); }
+        for (int g = (qd + t) & 3; g < G; g += 4) {
+            const int lr = g * PGR_RG + lane * 4;               // tile-local first row of this lane
+            if (lr >= rows) continue;                           // (a short last tile leaves some lanes without rows)
+            const long long row = r0 + lr;
+            const int nv = (int)min(4ll, st.n - row);           // valid rows of this lane's four (>= 1 except past n)
+            double o0, o1, o2, o3;
+            float4 yy;
+            {
+                const double2 a01 = pg_lds_d2(sbase + (unsigned)lr * 8u);
+                const double2 a23 = pg_lds_d2(sbase + (unsigned)lr * 8u + 16u);
+                yy = pg_lds_f4(sbase + (unsigned)T * 8u + (unsigned)lr * 4u);
+                o0 = a01.x; o1 = a01.y; o2 = a23.x; o3 = a23.y;
+            }
+            // kernel.rs:99-102 then :84-87, each a separately rounded f64 operation
+            if (do_add) {
+                if (add_nontrivial) {
+                    o0 = o0 + (nv > 0 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, T, lr + 0, row + 0) : 0.0);
+                    o1 = o1 + (nv > 1 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, T, lr + 1, row + 1) : 0.0);
+                    o2 = o2 + (nv > 2 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, T, lr + 2, row + 2) : 0.0);
+                    o3 = o3 + (nv > 3 ? pg_tree_eval_staged(st, t_add, b->tadd, b->r_add_slot, cols, T, lr + 3, row + 3) : 0.0);
+                } else { o0 = o0 + add_c; o1 = o1 + add_c; o2 = o2 + add_c; o3 = o3 + add_c; }
+            }
+            if (do_sub) {
+                if (sub_nontrivial) {
+                    o0 = o0 - (nv > 0 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, T, lr + 0, row + 0) : 0.0);
+                    o1 = o1 - (nv > 1 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, T, lr + 1, row + 1) : 0.0);
+                    o2 = o2 - (nv > 2 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, T, lr + 2, row + 2) : 0.0);
+                    o3 = o3 - (nv > 3 ? pg_tree_eval_staged(st, t_sub, b->tsub, b->r_sub_slot, cols, T, lr + 3, row + 3) : 0.0);
+                } else { o0 = o0 - sub_c; o1 = o1 - sub_c; o2 = o2 - sub_c; o3 = o3 - sub_c; }
+            }
+            if (grp == 0) {
+                __stcg(reinterpret_cast<double2*>(bf.A_dst + row), make_double2(o0, o1));
+                __stcg(reinterpret_cast<double2*>(bf.A_dst + row + 2), make_double2(o2, o3));
+            }
+            if (commit_only) continue;
+            const double r0v = (double)yy.x - o0, r1v = (double)yy.y - o1, r2v = (double)yy.z - o2, r3v = (double)yy.w - o3;
+            if (grp == 0) {
+                if (nv >= 4) {
+                    tot_o += o0; tot_o += o1; tot_o += o2; tot_o += o3;
+                    tot_r += r0v; tot_r += r1v; tot_r += r2v; tot_r += r3v;
+                    tot_rr += r0v * r0v; tot_rr += r1v * r1v; tot_rr += r2v * r2v; tot_rr += r3v * r3v;
+                    if (BERN) {
+                        const double m0 = o0 + st.init_leaf, m1 = o1 + st.init_leaf, m2 = o2 + st.init_leaf, m3 = o3 + st.init_leaf;
+                        tot_ll += (double)yy.x * m0 - pg_softplus(m0); tot_ll += (double)yy.y * m1 - pg_softplus(m1);
+                        tot_ll += (double)yy.z * m2 - pg_softplus(m2); tot_ll += (double)yy.w * m3 - pg_softplus(m3);
+                    }
+                } else {                                        // the lane that straddles n: rows row .. row + nv - 1 are real
+                    const double ov[4] = {o0, o1, o2, o3}, rv[4] = {r0v, r1v, r2v, r3v};
+                    const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll 1
+                    for (int e = 0; e < nv; ++e) {
+                        tot_o += ov[e]; tot_r += rv[e]; tot_rr += rv[e] * rv[e];
+                        if (BERN) { const double mu = ov[e] + st.init_leaf; tot_ll += (double)yv[e] * mu - pg_softplus(mu); }
+                    }
                 }
             }
-        }
-        // smc.rs:201-217 for this warp's slots of round 1 (padding rows hold x = +inf: never LEFT).  Dispatch on the
-        // warp-uniform job count so that the unrolled bodies carry no per-job branches.
-        const unsigned xb = sbase + PGR_T * 12u + (unsigned)lr * 4u;
-        auto jobs = [&](auto njc) {
-            constexpr int NJ = decltype(njc)::value;
+            // smc.rs:201-217 for this warp's slots of round 1 (padding rows hold x = +inf: never LEFT).  Dispatch on the
+            // warp-uniform job count so that the unrolled bodies carry no per-job branches.
+            const unsigned xb = cols + (unsigned)lr * 4u;
+            auto jobs = [&](auto njc) {
+                constexpr int NJ = decltype(njc)::value;
 #pragma unroll
-            for (int q = 0; q < NJ; ++q) {
-                const float4 xv = pg_lds_f4(xb + coff[q]);
-                pg_acc_left(accA[q], accB[q], accC[q], xv.x, jthr[q], o0, r0v);
-                pg_acc_left(accA[q], accB[q], accC[q], xv.y, jthr[q], o1, r1v);
-                pg_acc_left(accA[q], accB[q], accC[q], xv.z, jthr[q], o2, r2v);
-                pg_acc_left(accA[q], accB[q], accC[q], xv.w, jthr[q], o3, r3v);
-            }
-        };
-        switch (myJ) {
-            case 0: break;
-            case 1: jobs(std::integral_constant<int, 1>{}); break;
-            case 2: jobs(std::integral_constant<int, 2>{}); break;
-            case 3: jobs(std::integral_constant<int, 3>{}); break;
-            case 4: jobs(std::integral_constant<int, 4>{}); break;
-            case 5: jobs(std::integral_constant<int, 5>{}); break;
-            default:
-                if constexpr (JW > 5) {
-                    if (myJ == 6) jobs(std::integral_constant<int, 6>{});
-                    else if (myJ == 7) jobs(std::integral_constant<int, 7>{});
-                    else jobs(std::integral_constant<int, JW>{});
+                for (int q = 0; q < NJ; ++q) {
+                    const float4 xv = pg_lds_f4(xb + coff[q]);
+                    pg_acc_left(accA[q], accB[q], accC[q], xv.x, jthr[q], o0, r0v);
+                    pg_acc_left(accA[q], accB[q], accC[q], xv.y, jthr[q], o1, r1v);
+                    pg_acc_left(accA[q], accB[q], accC[q], xv.z, jthr[q], o2, r2v);
+                    pg_acc_left(accA[q], accB[q], accC[q], xv.w, jthr[q], o3, r3v);
                 }
-                break;
+            };
+            switch (myJ) {
+                case 0: break;
+                case 1: jobs(std::integral_constant<int, 1>{}); break;
+                case 2: jobs(std::integral_constant<int, 2>{}); break;
+                case 3: jobs(std::integral_constant<int, 3>{}); break;
+                case 4: jobs(std::integral_constant<int, 4>{}); break;
+                case 5: jobs(std::integral_constant<int, 5>{}); break;
+                default:
+                    if constexpr (JW > 5) {
+                        if (myJ == 6) jobs(std::integral_constant<int, 6>{});
+                        else if (myJ == 7) jobs(std::integral_constant<int, 7>{});
+                        else jobs(std::integral_constant<int, JW>{});
+                    }
+                    break;
+            }
         }
-        }   // !commit_only
-        }   // lr < rows
+        // done with this tile: the last warp to say so refills the stage with the tile NST ahead
         __syncwarp();
-        if (lane == 0) pg_mbar_arrive(&b->mbar_empty[stg_used]);   // this warp is done with the stage
+        unsigned last = 0u;
+        if (lane == 0) {
+            __threadfence_block();                              // this warp's reads of the stage are done before the count moves
+            last = ((atomicAdd(&b->r_done[stg], 1u) + 1u) % (unsigned)PG_WARPS) == 0u ? 1u : 0u;
+        }
+        last = __shfl_sync(PG_FULL, last, 0);
+        if (last && t + NST < n_tiles) issue(t + NST);
+        stg = stg + 1 == NST ? 0 : stg + 1;
     }
-    PG_CK(4);
 
     // ---- block results
     if (!commit_only) {
@@ -971,11 +796,8 @@ __device__ void pg_pass_root_tma(const PgState& st, const PgBuf& bf, const PgSme
         }
     }
     __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int q = 0; q < PGR_MAXST; ++q) { pg_mbar_inval(&b->mbar_full[q]); pg_mbar_inval(&b->mbar_empty[q]); }
-    }
-    if (commit_only) return;
+    if (tid < PGR_MAXST) pg_mbar_inval(&b->mbar_full[tid]);
+    if (commit_only) return true;
     if (tid < 4) {
         double v = 0.0;
         for (int q = 0; q < 4; ++q) v += b->tot[q][tid];
@@ -989,7 +811,7 @@ __device__ void pg_pass_root_tma(const PgState& st, const PgBuf& bf, const PgSme
         bf.part_sum[((size_t)PG_BID * S + j) * 2 + 1] = bb;
         bf.part_ccnt[(size_t)PG_BID * S + j] = cc;
     }
-    PG_CK(5);
+    return true;
 }
 
 // =============================================================================
@@ -1552,10 +1374,9 @@ __device__ __forceinline__ void pg_prefetch_next_root(const PgState& st, int fla
 // one variant never disturb another (the kernels are monoliths: control block + every pass inlined):
 //   PGV_GENERIC   warp-range passes, both likelihood families at run time: generic control code (P > 32), stepwise driver
 //   PGV_DIRECT    P <= 32, Gaussian families: block-unit scheme, root pass = register loads over warp sub-ranges
-//   PGV_QUARTERS  P <= 32, Gaussian families, S <= 20: block-unit scheme, quarter/group root pass (default)
-//   PGV_STAGED    P <= 32, Gaussian families: block-unit scheme, async-copy ring root pass (needs the staging area)
-//   PGV_BERN      P <= 32, Bernoulli-logit: block-unit scheme, direct root pass with the stump log-likelihood
-enum { PGV_GENERIC = 0, PGV_DIRECT = 1, PGV_QUARTERS = 2, PGV_STAGED = 3, PGV_BERN = 4 };
+//   PGV_RING      P <= 32, Gaussian families: block-unit scheme, root pass = bulk-copy ring in shared memory (default)
+//   PGV_BERN      P <= 32, Bernoulli-logit: block-unit scheme, ring root pass with the stump log-likelihood
+enum { PGV_GENERIC = 0, PGV_DIRECT = 1, PGV_RING = 3, PGV_BERN = 4 };
 
 template <int VAR>
 __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView& sm, int phase) {
@@ -1565,9 +1386,11 @@ __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView&
         case PH_ROOT:
         case PH_FINAL:
             if (VAR == PGV_GENERIC) { if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true, false>(st, bf, sm); else pg_pass_root<false, false>(st, bf, sm); }
-            else if (VAR == PGV_BERN) pg_pass_root<true, true>(st, bf, sm);
-            else if (VAR == PGV_QUARTERS) pg_pass_root_quarters<false, 5>(st, bf, sm);
-            else if (VAR == PGV_STAGED) { if (st.S <= 20) pg_pass_root_tma<false, 5>(st, bf, sm); else pg_pass_root_tma<false, PGR_JW>(st, bf, sm); }
+            else if (VAR == PGV_BERN) { if (!st.root_ring || !pg_pass_root_ring<true, PGR_JW>(st, bf, sm)) pg_pass_root<true, true>(st, bf, sm); }
+            else if (VAR == PGV_RING) {
+                const bool done = st.S <= 20 ? pg_pass_root_ring<false, 5>(st, bf, sm) : pg_pass_root_ring<false, PGR_JW>(st, bf, sm);
+                if (!done) pg_pass_root<false, true>(st, bf, sm);      // more distinct columns than the staging area holds
+            }
             else pg_pass_root<false, true>(st, bf, sm);
             break;
         case PH_MINMAX: pg_pass_minmax(st, bf, sm); break;

@@ -1641,7 +1641,7 @@ __device__ __forceinline__ bool fw_issue_predicted(const PgState& st, const FwCx
 // ---- the serial block's whole-kernel control loop ------------------------------------------------------
 __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
     __shared__ PgCtrl fw_scratch[FW_DR + 1];   // helpers must not raise errors for draws that may never be consumed
-    PgFastSm* f = &sm.base->fast;
+    PgFastSm* f = sm.fast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FwCx x;
     x.f = f;

@@ -66,7 +66,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
     // sampler constants the serial section reads: staged once per launch
     for (int i = threadIdx.x; i < st.max_depth + 2 && i < 16; i += blockDim.x) sm.base->cthr[i] = st.thr_depth[i];
     if (threadIdx.x == 0) { sm.base->cstaged = (st.p <= FW_MAXP && st.max_depth + 2 <= 16) ? 1 : 0; sm.base->pass_bid = (int)blockIdx.x - 1; }
-    if (st.p <= FW_MAXP)
+    if (st.p <= FW_MAXP && FAST && blockIdx.x == 0)     // control block only: in the pass blocks these bytes are the staging ring
         for (int i = threadIdx.x; i < st.p; i += blockDim.x) {
             sm.cprior[i] = st.prior ? st.prior[i] : 0.0;
             sm.cmin[i] = st.col_min[i];
@@ -137,12 +137,9 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
 }
 
 // P <= 32: latency-organised control block, one kernel per pass variant; P > 32: generic team serial section.
-extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent(const PgState st) { pg_sweep_body<PGV_QUARTERS>(st); }
+extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_ring(const PgState st) { pg_sweep_body<PGV_RING>(st); }
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_direct(const PgState st) { pg_sweep_body<PGV_DIRECT>(st); }
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_bern(const PgState st) { pg_sweep_body<PGV_BERN>(st); }
-#ifdef PGBART_WITH_STAGED
-extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_staged(const PgState st) { pg_sweep_body<PGV_STAGED>(st); }
-#endif
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_generic(const PgState st) { pg_sweep_body<PGV_GENERIC>(st); }
 
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_phase_kernel(const PgState st) {
@@ -220,16 +217,13 @@ extern "C" __global__ void pg_predict_kernel(const PgState st, const float* x, l
 // launchers
 // ---------------------------------------------------------------------------
 
-int pg_query_grid(int device, int S, bool want_stage, int* grid_out, size_t* smem_out, int* stage_out, char* err, size_t errlen) {
+int pg_query_grid(int device, int S, int smem_kb, int* grid_out, size_t* smem_out, int* stage_out, char* err, size_t errlen) {
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return 1; }
-    // dynamic shared memory = the pass arrays + a staging area (bulk-copy ring of the staged root pass) that takes
-    // whatever one block per SM can have
-    const void* kernels[] = {(const void*)pg_sweep_persistent, (const void*)pg_sweep_persistent_direct, (const void*)pg_sweep_persistent_bern,
-#ifdef PGBART_WITH_STAGED
-                             (const void*)pg_sweep_persistent_staged,
-#endif
+    // dynamic shared memory = the pass arrays + the union area (pg_smem_view): control state in block 0, staging ring of
+    // the root pass in the pass blocks.  smem_kb = total to ask for (P <= 32; 0 = no ring, just what the control state needs).
+    const void* kernels[] = {(const void*)pg_sweep_persistent_ring, (const void*)pg_sweep_persistent_direct, (const void*)pg_sweep_persistent_bern,
                              (const void*)pg_sweep_persistent_generic, (const void*)pg_phase_kernel};
     size_t static_smem = 0;
     for (const void* k : kernels) {
@@ -238,18 +232,20 @@ int pg_query_grid(int device, int S, bool want_stage, int* grid_out, size_t* sme
         if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncGetAttributes: %s", cudaGetErrorString(e)); return 1; }
         if (fa.sharedSizeBytes > static_smem) static_smem = fa.sharedSizeBytes;
     }
-    const size_t base = pg_smem_bytes(S);
+    const size_t pass = pg_smem_pass_bytes(S), ctrl = pg_smem_ctrl_bytes();
     const size_t optin = prop.sharedMemPerBlockOptin;
-    if (base + static_smem + (want_stage ? 16 * 1024 : 0) > optin) { snprintf(err, errlen, "shared memory: %zu B needed, %zu B available", base + static_smem + (want_stage ? 16 * 1024 : 0), optin); return 1; }
-    // (only when the staged root pass is requested: a large carve-out leaves the control block almost no L1)
-    const size_t stage = want_stage ? ((optin - static_smem - base - 1024) / 1024) * 1024 : 0;
-    const size_t smem = base + stage;
+    if (pass + ctrl + static_smem > optin) { snprintf(err, errlen, "shared memory: %zu B needed, %zu B available", pass + ctrl + static_smem, optin); return 1; }
+    size_t want = (size_t)smem_kb * 1024;
+    if (want + static_smem > optin) want = optin - static_smem;
+    size_t stage = want > pass + 1024 ? ((want - pass) / 1024) * 1024 : 0;
+    if (stage < ctrl) stage = 0;                         // no room for a useful ring: the union area only holds the control state
+    const size_t smem = pass + (stage > ctrl ? stage : ctrl);
     for (const void* k : kernels) {
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { snprintf(err, errlen, "shared memory request %zu B: %s", smem, cudaGetErrorString(e)); return 1; }
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_sweep_persistent, PG_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_sweep_persistent_ring, PG_THREADS, smem);
     if (e != cudaSuccess || per_sm < 1) { snprintf(err, errlen, "occupancy query failed: %s", cudaGetErrorString(e)); return 1; }
     if (per_sm > 1) per_sm = 1;   // one 512-thread block per SM: 148 partials per pass for the serial reduce
     if (!prop.cooperativeLaunch) { snprintf(err, errlen, "device lacks cooperative launch"); return 1; }
@@ -270,10 +266,7 @@ cudaError_t pg_launch_persistent(const PgState& st, size_t smem, cudaStream_t s)
     void* fn = (void*)pg_sweep_persistent_generic;
     if (st.P <= 32) {
         if (st.family == PG_BERNOULLI_LOGIT) fn = (void*)pg_sweep_persistent_bern;
-#ifdef PGBART_WITH_STAGED
-        else if (st.root_staged) fn = (void*)pg_sweep_persistent_staged;
-#endif
-        else if (st.root_quarters && st.S <= 20) fn = (void*)pg_sweep_persistent;
+        else if (st.root_ring && st.stage_bytes > 0) fn = (void*)pg_sweep_persistent_ring;
         else fn = (void*)pg_sweep_persistent_direct;
     }
     return cudaLaunchCooperativeKernel(fn, dim3(st.grid + 1), dim3(PG_THREADS), args, smem, s);   // + the serial block

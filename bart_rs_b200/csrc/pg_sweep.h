@@ -3,7 +3,7 @@
 #include <cuda_runtime.h>
 #include "pg_types.h"
 
-int pg_query_grid(int device, int S, bool want_stage, int* grid_out, size_t* smem_out, int* stage_out, char* err, size_t errlen);
+int pg_query_grid(int device, int S, int smem_kb, int* grid_out, size_t* smem_out, int* stage_out, char* err, size_t errlen);
 cudaError_t pg_launch_prepare(const PgState& st, int tune, cudaStream_t s);
 cudaError_t pg_launch_persistent(const PgState& st, size_t smem, cudaStream_t s);
 cudaError_t pg_launch_phase(const PgState& st, size_t smem, cudaStream_t s);

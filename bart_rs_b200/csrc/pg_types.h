@@ -150,8 +150,9 @@ struct PgState {
     double* mail[PG_MAX_RANKS];  // mail[r] = rank r's mailbox (peer memory for r != rank)
     int prune;                   // option prune_dead_proposals: do not evaluate proposals whose particle provably gets weight 0
     int prefetch_next;           // pass blocks prefetch the next update's root columns into L2 after a root pass
-    int root_quarters;           // P <= 32 persistent kernel: 1 = quarter/group root pass (pg_pass_root_quarters)
-    int root_staged;             // P <= 32 persistent kernel: 1 = staged root pass (pg_pass_root_staged), 0 = warp-range loads
+    int root_ring;               // P <= 32 persistent kernels: 1 = ring root pass (pg_pass_root_ring, default), 0 = direct register loads
+    int root_tile_groups;        // ring root pass: cap on the row groups (128 rows) per tile, 0 = as many as fit (<= 8)
+    int root_stages;             // ring root pass: cap on the stages of the ring, 0 = as many as fit (<= 4)
     // data
     const float* X;
     const float* y;
