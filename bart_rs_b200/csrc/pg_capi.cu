@@ -374,10 +374,11 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     st.prefetch_next = 0;
     st.prune = 0;
     if (const char* e = std::getenv("PGBART_PRUNE")) st.prune = std::atoi(e) != 0;
-    st.root_ring = 1;
+    st.root_ring = 2;
     st.root_tile_groups = 0;
     st.root_stages = 0;
-    if (const char* e = std::getenv("PGBART_ROOT_PASS")) st.root_ring = std::strcmp(e, "direct") != 0;
+    st.root_dbg = 0;
+    if (const char* e = std::getenv("PGBART_ROOT_PASS")) st.root_ring = std::strcmp(e, "direct") == 0 ? 0 : std::strcmp(e, "ring") == 0 ? 1 : 2;
     if (const char* e = std::getenv("PGBART_ROOT_TILE_GROUPS")) st.root_tile_groups = std::atoi(e);
     if (const char* e = std::getenv("PGBART_ROOT_STAGES")) st.root_stages = std::atoi(e);
     if (const char* e = std::getenv("PGBART_PREFETCH_NEXT")) st.prefetch_next = std::atoi(e) != 0;
@@ -660,11 +661,13 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
             s->st.root_ring = 1; return 0;
         }
         if (std::strcmp(value, "direct") == 0) { s->st.root_ring = 0; return 0; }
-        s->err = "root_pass must be 'ring' or 'direct'";
+        if (std::strcmp(value, "auto") == 0) { s->st.root_ring = 2; return 0; }
+        s->err = "root_pass must be 'ring', 'direct' or 'auto'";
         return 1;
     }
     if (std::strcmp(key, "root_tile_groups") == 0) { s->st.root_tile_groups = std::atoi(value); return 0; }
     if (std::strcmp(key, "root_stages") == 0) { s->st.root_stages = std::atoi(value); return 0; }
+    if (std::strcmp(key, "root_dbg") == 0) { s->st.root_dbg = std::atoi(value); return 0; }
     if (std::strcmp(key, "prune_dead_proposals") == 0) { s->st.prune = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "prefetch_next") == 0) { s->st.prefetch_next = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "pool_factor") == 0) {

@@ -27,7 +27,7 @@
 #define PG_TREE_SM 63      // tree nodes staged in shared memory (depth <= 5); larger trees read global
 #define PGR_RG 128         // ring root pass: rows per row group (32 lanes x 4 consecutive rows)
 #define PGR_MAXG 8         //   row groups per tile at most (1024 rows: 4 KB per column copy)
-#define PGR_MAXST 4        //   stages of the ring at most
+#define PGR_MAXST 8        //   stages of the ring at most
 #define PGR_MAXU 40        //   distinct columns per tile (S <= 31 job columns + tree columns)
 #define PGR_JW 8           //   jobs per warp: 4 job groups x 8 >= S
 #define PG_FULL 0xFFFFFFFFu
@@ -479,8 +479,14 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
 // Warp w = (row quarter w / 4, job group w % 4): the tile's row groups are dealt round-robin to the quarters (rotating
 // with the tile index so that every quarter gets the odd group in turn); a lane owns 4 consecutive rows of a row group
 // and accumulates its job group's jobs in registers across ALL tiles of the block, so the cross-lane reduction happens
-// once per pass.  There is no producer warp and no block barrier in the loop: the warp that finishes a tile LAST
-// (shared-memory counter) refills the stage with the tile NST ahead, its lanes issuing the copies of one array each.
+// once per pass.  There is no producer warp and no block barrier in the loop.  Lane 0 of warp w issues the copies of
+// arrays w, w + 16, w + 32 (measured, tools/microbench_bulk.cu: one thread sustains a bulk copy per ~300-570 cycles whatever
+// its size, so an SM needs several issuing threads to reach its share of HBM bandwidth with copies of a few KB; 147 blocks
+// x 16 issuers x 2 KB copies stream at 6.9 TB/s).  A warp that has finished tile t counts itself out of the tile's stage
+// and then refills the stage of tile t - 1 — free once all 16 warps have counted out of it, which they normally have by
+// then — with tile t - 1 + NST: warps may drift apart by a tile, and NST - 1 tiles are in flight ahead of the consumers.
+// (A first version let the LAST warp out of a tile issue all of the next tile's copies: that warp fell 1.2 us behind per
+// tile, became the last one out again, and the pass took 31 us against 24 for the direct pass.)
 // Fixed summation order => bit-reproducible.  Emits per-BLOCK results only (part_tot, part_sum, part_ccnt).
 __device__ __forceinline__ unsigned pg_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned long long pg_policy_evict_first() {
@@ -602,17 +608,19 @@ __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSm
     if (U < 0) { __syncthreads(); return false; }
     const size_t ld = (size_t)st.ld;
     const int n_arr = 2 + U;
-    // ---- ring geometry: G row groups per tile, NST stages
+    // ---- ring geometry: G row groups per tile, NST stages.  G = 4 (one row group per row quarter per tile: the quarters stay
+    // balanced) when three such stages fit, else 2 or 1; at least two stages or the direct pass takes over.
     const unsigned bpg = (unsigned)PGR_RG * (12u + 4u * (unsigned)U);            // bytes of one row group of every staged array
-    int G = (int)((unsigned)st.stage_bytes / (2u * bpg));
-    if (st.root_tile_groups > 0 && G > st.root_tile_groups) G = st.root_tile_groups;
-    if (G > PGR_MAXG) G = PGR_MAXG;
+    int G = 4;
+    while (G > 1 && (unsigned)st.stage_bytes < 3u * (unsigned)G * bpg) G >>= 1;
+    if (st.root_tile_groups > 0) G = min(st.root_tile_groups, PGR_MAXG);
+    while (G > 1 && (unsigned)st.stage_bytes < 2u * (unsigned)G * bpg) G >>= 1;
     const int T = G * PGR_RG;
     const unsigned stage_bytes = (unsigned)G * bpg;
     int NST = (int)((unsigned)st.stage_bytes / stage_bytes);
     if (NST > PGR_MAXST) NST = PGR_MAXST;
     if (st.root_stages >= 2 && NST > st.root_stages) NST = st.root_stages;
-    if (tid < PGR_MAXST) { pg_mbar_init(&b->mbar_full[tid], 1); b->r_done[tid] = 0u; }
+    if (tid < PGR_MAXST) { pg_mbar_init(&b->mbar_full[tid], PG_WARPS); b->r_done[tid] = 0u; }
     for (int a = tid; a < n_arr; a += blockDim.x)
         b->r_src[a] = a == 0 ? (unsigned long long)bf.A_src : a == 1 ? (unsigned long long)st.y
                                                                     : (unsigned long long)(st.X + (size_t)b->r_ucol[a - 2] * ld);
@@ -631,20 +639,19 @@ __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSm
     const int n_tiles = (int)((B1 - B0 + T - 1) / T);
     const unsigned long long pol = pg_policy_evict_first();
     const unsigned stage0 = pg_smem_u32(sm.stage);
-    // One tile = one bulk copy per staged array: a = 0: A (8 B per row), 1: y, 2 + u: column u.  Issued by ONE warp (whichever
-    // finished the stage's previous tile last), lane a taking arrays a, a + 32: lane 0 first posts the byte count.
-    auto issue = [&](int t) {
+    // One tile = one bulk copy per staged array: a = 0: A (8 B per row), 1: y, 2 + u: column u.  Lane 0 of warp w issues
+    // arrays w, w + 16, w + 32 and arrives once per tile on the stage's "landed" barrier with the bytes it asked for.
+    auto issue = [&](int t) {                                // lane 0 of every warp
         const int s_ = t % NST;
         const long long r0 = B0 + (long long)t * T;
         const unsigned rows = (unsigned)min((long long)T, B1 - r0);
         const unsigned sbase = stage0 + (unsigned)s_ * stage_bytes;
-        // generic-proxy accesses this thread has observed (A written by the previous pass through the command's release /
-        // acquire chain; the other warps' reads of the stage through the r_done count) are ordered before its bulk copies
-        asm volatile("fence.proxy.async;" ::: "memory");
-        if (lane == 0) pg_mbar_expect_tx(&b->mbar_full[s_], rows * (12u + 4u * (unsigned)U));
-        __syncwarp();
+        unsigned bytes = 0;
 #pragma unroll 1
-        for (int a = lane; a < n_arr; a += 32) {
+        for (int a = warp; a < n_arr; a += PG_WARPS) bytes += rows * (a == 0 ? 8u : 4u);
+        if (bytes) pg_mbar_expect_tx(&b->mbar_full[s_], bytes); else pg_mbar_arrive(&b->mbar_full[s_]);
+#pragma unroll 1
+        for (int a = warp; a < n_arr; a += PG_WARPS) {
             const unsigned es = a == 0 ? 8u : 4u;
             const unsigned dst = sbase + (a == 0 ? 0u : a == 1 ? (unsigned)T * 8u : (unsigned)T * 12u + (unsigned)(a - 2) * ((unsigned)T * 4u));
             const char* src = reinterpret_cast<const char*>(b->r_src[a]) + r0 * es;
@@ -652,8 +659,13 @@ __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSm
             else pg_bulk_g2s_hint_u32(dst, src, rows * es, &b->mbar_full[s_], pol);
         }
     };
-    if (warp == 0)
+    if (lane == 0) {
+        // generic-proxy writes this thread has observed (A, written by the previous pass, through the command's release /
+        // acquire chain) are ordered before its bulk copies
+        asm volatile("fence.proxy.async;" ::: "memory");
         for (int t = 0; t < NST && t < n_tiles; ++t) issue(t);
+    }
+    __syncwarp();
 
     // my jobs: group g takes jobs j with (j + 1) % 4 == g, so group 0 (which also writes A and keeps the totals) gets the fewest
     const int jfirst = (grp + 3) & 3;
@@ -685,6 +697,7 @@ __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSm
         for (int g = (qd + t) & 3; g < G; g += 4) {
             const int lr = g * PGR_RG + lane * 4;               // tile-local first row of this lane
             if (lr >= rows) continue;                           // (a short last tile leaves some lanes without rows)
+            if (st.root_dbg & 4) continue;
             const long long row = r0 + lr;
             const int nv = (int)min(4ll, st.n - row);           // valid rows of this lane's four (>= 1 except past n)
             double o0, o1, o2, o3;
@@ -716,7 +729,7 @@ __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSm
                 __stcg(reinterpret_cast<double2*>(bf.A_dst + row), make_double2(o0, o1));
                 __stcg(reinterpret_cast<double2*>(bf.A_dst + row + 2), make_double2(o2, o3));
             }
-            if (commit_only) continue;
+            if (commit_only || (st.root_dbg & 2)) continue;
             const double r0v = (double)yy.x - o0, r1v = (double)yy.y - o1, r2v = (double)yy.z - o2, r3v = (double)yy.w - o3;
             if (grp == 0) {
                 if (nv >= 4) {
@@ -768,15 +781,22 @@ __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSm
                     break;
             }
         }
-        // done with this tile: the last warp to say so refills the stage with the tile NST ahead
+        // done with this tile: count this warp out of its stage, then refill the stage tile t - 1 occupied (free once all
+        // warps have counted out of it) with this warp's arrays of tile t - 1 + NST
         __syncwarp();
-        unsigned last = 0u;
         if (lane == 0) {
             __threadfence_block();                              // this warp's reads of the stage are done before the count moves
-            last = ((atomicAdd(&b->r_done[stg], 1u) + 1u) % (unsigned)PG_WARPS) == 0u ? 1u : 0u;
+            atomicAdd(&b->r_done[stg], 1u);
+            if (t >= 1 && t - 1 + NST < n_tiles) {
+                const int sp = stg == 0 ? NST - 1 : stg - 1;
+                const unsigned want = (unsigned)PG_WARPS * (unsigned)((t - 1) / NST + 1);
+                unsigned spins = 0;
+                while (*(volatile unsigned*)&b->r_done[sp] < want) { if (++spins > (1u << 26)) __trap(); }
+                if (!(st.root_dbg & 1)) asm volatile("fence.proxy.async;" ::: "memory");   // the other warps' reads of that stage precede the copies into it
+                issue(t - 1 + NST);
+            }
         }
-        last = __shfl_sync(PG_FULL, last, 0);
-        if (last && t + NST < n_tiles) issue(t + NST);
+        __syncwarp();
         stg = stg + 1 == NST ? 0 : stg + 1;
     }
 
@@ -1378,6 +1398,13 @@ __device__ __forceinline__ void pg_prefetch_next_root(const PgState& st, int fla
 //   PGV_BERN      P <= 32, Bernoulli-logit: block-unit scheme, ring root pass with the stump log-likelihood
 enum { PGV_GENERIC = 0, PGV_DIRECT = 1, PGV_RING = 3, PGV_BERN = 4 };
 
+// Ring root pass: always when asked for (root_ring = 1); by default (2) only while a block's rows fit the ring a few tiles
+// deep, where every copy of the pass is in flight at once — measured 8.3 us against 11.4 for the direct pass at n = 100k,
+// but 34 us against 24 at n = 1M, where the refills are paced by the consumers.
+__host__ __device__ inline bool pg_use_ring(const PgState& st) {
+    return st.stage_bytes > 0 && (st.root_ring == 1 || (st.root_ring == 2 && st.n <= (long long)st.grid * 2048));
+}
+
 template <int VAR>
 __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView& sm, int phase) {
     const PgBuf bf = pg_make_buf(st, __ldcg(&st.ctrl->flags));
@@ -1386,7 +1413,7 @@ __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView&
         case PH_ROOT:
         case PH_FINAL:
             if (VAR == PGV_GENERIC) { if (st.family == PG_BERNOULLI_LOGIT) pg_pass_root<true, false>(st, bf, sm); else pg_pass_root<false, false>(st, bf, sm); }
-            else if (VAR == PGV_BERN) { if (!st.root_ring || !pg_pass_root_ring<true, PGR_JW>(st, bf, sm)) pg_pass_root<true, true>(st, bf, sm); }
+            else if (VAR == PGV_BERN) { if (!pg_use_ring(st) || !pg_pass_root_ring<true, PGR_JW>(st, bf, sm)) pg_pass_root<true, true>(st, bf, sm); }
             else if (VAR == PGV_RING) {
                 const bool done = st.S <= 20 ? pg_pass_root_ring<false, 5>(st, bf, sm) : pg_pass_root_ring<false, PGR_JW>(st, bf, sm);
                 if (!done) pg_pass_root<false, true>(st, bf, sm);      // more distinct columns than the staging area holds

@@ -684,6 +684,7 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
 }
 
 __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, int lane, int phase);
+__device__ __forceinline__ void fw_issue_part(const PgState& st, const FwCx& x, int lane);
 
 // rounds >= 1: pop the next expandable node of every slot, depth-prior test, split variable (smc.rs:61-86 front half)
 __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, int lane) {
@@ -1175,31 +1176,9 @@ __device__ __forceinline__ int fw_finish_round(const PgState& st, const FwCx& x,
     if (lane == 0) { c->acc_update += n_mut; c->cur = dst; c->n_pjobs = K; c->any_queue = any_queue; f->n_mq = 0; }
     __syncwarp();
     if (c->error != PG_OK) return SN_NONE;
-    if (K > 0) return SN_PREP_PART;
+    if (K > 0) { fw_issue_part(st, x, lane); return SN_PART_ISSUED; }
     if (any_queue) { if (lane == 0) c->round += 1; __syncwarp(); return SN_DRAW_ROUND; }
     return SN_FINALIZE;
-}
-
-// block-wide: the partition jobs' block offsets
-__device__ __forceinline__ void fb_prep_part(const PgState& st, const FwCx& x) {
-    PgCtrl* c = x.c;
-    PgFastSm* f = x.f;
-    const int K = c->n_pjobs;
-    const int tid = threadIdx.x;
-    // (every segment is partitioned in block units and each pass block derives its own offset from the per-block left
-    // counts, pg_pass_part — nothing to prefix here)
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long bm = 0;
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-            const unsigned long long L = f->pq_len[k];
-            bm += (f->pq_ident[k] ? 0ull : 4ull * L) + 4ull * L + 4ull * L;
-        }
-        c->bytes_model += bm + 4ull * (unsigned long long)f->n_mq * (K > 0 ? (unsigned long long)f->pq_len[0] : 0ull);
-        c->n_groups = f->n_mq;          // look-ahead min/max requests riding on the partition pass
-        c->phase = PH_PART; c->n_phases += 1;
-    }
 }
 
 // end of a tree update: diagnostics, counters, next update or the step's final pass (kernel.rs:104-117)
@@ -1388,10 +1367,53 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         if (lane == 0) fw_write_stump(st, c->t_cur);
         return fw_end_update(st, x, lane, 0, 0, Wn);
     }
-    // ---- survivors that grew: write the slot tables of ALL slots (copies of their ancestors) into half `cur`
+    // ---- survivors that grew.  The partition pass needs only the partition jobs and the look-ahead requests, so those are
+    // prepared first and the pass is issued BEFORE the slot tables of all slots (copies of their ancestors) are written
+    // into half `cur`: the table writes run while the pass streams.
     unsigned off, cntL;
     int node;
     const int K = fw_plan_partitions(st, x, lane, anc, need, &off, &cntL, &node);
+    if (lane == 0) { c->n_pjobs = K; c->any_queue = 1; }
+    // ---- look-ahead (DESIGN.md §4): when every slot is a copy of ONE grown particle, the proposals of rounds 1 and 2
+    // are known now — slot s will try node 1 with (u1, var)(round 1, s) and node 2 with (u1, var)(round 2, s), whatever
+    // the resampling does in between.  Let the partition pass compute the min/max those proposals need.
+    const int buf = (int)(c->upd % 3ull);
+    const bool single = K == 1 && st.family != PG_BERNOULLI_LOGIT && __all_sync(PG_FULL, !act || need) && st.maxn > 6;
+    {
+        int nq = 0;
+        if (single && !st.tr_upd && c->k + 1 < c->batch && lane == 0) { f->pred_lin = anc; f->pred_sel = -1 - f->hsjob[anc]; }   // fw_predict, after PART is issued
+        if (single) {
+            const int j = f->hsjob[anc];
+            const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n_global - cL, cLl = f->jr_cLl[act ? j : 0];
+#pragma unroll 1
+            for (int r = 1; r <= 2; ++r) {
+                const bool want = act && f->d_ok[buf][r] && !(x.thr[1] > f->d_u1[buf][r][lane]) && (r == 1 ? cL : cR) > 0u;
+                const unsigned m = __ballot_sync(PG_FULL, want);
+                const int q = nq + __popc(m & ((1u << lane) - 1u));
+                if (want && q < 32) {
+                    st.mq_pj[q] = 0; st.mq_side[q] = r - 1; st.mq_var[q] = f->d_var[buf][r][lane];
+                    f->rq_r[q] = r; f->rq_s[q] = lane; f->rq_seg[q] = r == 1 ? off : off + cLl;
+                }
+                nq += __popc(m);
+            }
+            if (nq > 32) nq = 32;
+        }
+        if (lane == 0) f->n_mq = nq;
+    }
+    __syncwarp();
+    if (c->error != PG_OK) return SN_NONE;
+    fw_issue_part(st, x, lane);          // K >= 1 here; after PH_PART the general rounds continue
+    // ---- the slot tables, while the partition pass streams
+    if (single) {
+        const int j = f->hsjob[anc];
+        const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n_global - cL, cLl = f->jr_cLl[act ? j : 0];
+        if (lane == 0) {   // the two leaves every slot will propose on in rounds 1 and 2: kept at hand (fw_draw_round)
+            f->sl_lin = anc; f->sl_cnt[0] = cL; f->sl_cnt[1] = cR; f->sl_len[0] = cLl; f->sl_len[1] = (unsigned)st.n - cLl;
+            f->sl_seg[0] = off; f->sl_seg[1] = off + cLl;
+            f->sl_So[0] = f->jr_SoL[j]; f->sl_So[1] = c->T_o - f->jr_SoL[j]; f->sl_Sr[0] = f->jr_SrL[j]; f->sl_Sr[1] = c->T_r - f->jr_SrL[j];
+            f->sl_g[0] = f->jr_gL[j]; f->sl_g[1] = f->jr_gR[j]; f->sl_valid = 1;
+        }
+    }
     if (act) {
         const int ss = pg_six(st, cur, lane);
         const size_t i0 = pg_tix(st, cur, lane, 0);
@@ -1423,42 +1445,8 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
             f->hG[ss] = c->g_stump;
         }
     }
-    if (lane == 0) { c->n_pjobs = K; c->any_queue = 1; }
-    // ---- look-ahead (DESIGN.md §4): when every slot is a copy of ONE grown particle, the proposals of rounds 1 and 2
-    // are known now — slot s will try node 1 with (u1, var)(round 1, s) and node 2 with (u1, var)(round 2, s), whatever
-    // the resampling does in between.  Let the partition pass compute the min/max those proposals need.
-    {
-        const int buf = (int)(c->upd % 3ull);
-        const bool single = K == 1 && st.family != PG_BERNOULLI_LOGIT && __all_sync(PG_FULL, !act || need) && st.maxn > 6;
-        int nq = 0;
-        if (single && !st.tr_upd && c->k + 1 < c->batch && lane == 0) { f->pred_lin = anc; f->pred_sel = -1 - f->hsjob[anc]; }   // fw_predict, after PART is issued
-        if (single) {
-            const int j = f->hsjob[anc];
-            const unsigned cL = f->jr_cL[act ? j : 0], cR = (unsigned)st.n_global - cL, cLl = f->jr_cLl[act ? j : 0];
-            if (lane == 0) {   // the two leaves every slot will propose on in rounds 1 and 2: kept at hand (fw_draw_round)
-                f->sl_lin = anc; f->sl_cnt[0] = cL; f->sl_cnt[1] = cR; f->sl_len[0] = cLl; f->sl_len[1] = (unsigned)st.n - cLl;
-                f->sl_seg[0] = off; f->sl_seg[1] = off + cLl;
-                f->sl_So[0] = f->jr_SoL[j]; f->sl_So[1] = c->T_o - f->jr_SoL[j]; f->sl_Sr[0] = f->jr_SrL[j]; f->sl_Sr[1] = c->T_r - f->jr_SrL[j];
-                f->sl_g[0] = f->jr_gL[j]; f->sl_g[1] = f->jr_gR[j]; f->sl_valid = 1;
-            }
-#pragma unroll 1
-            for (int r = 1; r <= 2; ++r) {
-                const bool want = act && f->d_ok[buf][r] && !(x.thr[1] > f->d_u1[buf][r][lane]) && (r == 1 ? cL : cR) > 0u;
-                const unsigned m = __ballot_sync(PG_FULL, want);
-                const int q = nq + __popc(m & ((1u << lane) - 1u));
-                if (want && q < 32) {
-                    st.mq_pj[q] = 0; st.mq_side[q] = r - 1; st.mq_var[q] = f->d_var[buf][r][lane];
-                    f->rq_r[q] = r; f->rq_s[q] = lane; f->rq_seg[q] = r == 1 ? off : off + cLl;
-                }
-                nq += __popc(m);
-            }
-            if (nq > 32) nq = 32;
-        }
-        if (lane == 0) f->n_mq = nq;
-    }
     __syncwarp();
-    if (c->error != PG_OK) return SN_NONE;
-    return SN_PREP_PART;     // K >= 1 here; after PH_PART the general rounds continue
+    return SN_PART_ISSUED;
 }
 
 // ---- commands to the pass blocks ---------------------------------------------------------------------
@@ -1506,6 +1494,33 @@ __device__ __forceinline__ void fw_issue_ctrl(const PgState& st, const FwCx& x, 
 __device__ __forceinline__ void fw_await(const PgState& st, const FwCx& x, int lane) {
     if (lane == 0) pg_spin_until(&st.ctrl->bar_count, x.f->issued * (gridDim.x - 1u), st.ctrl);
     __syncwarp();
+}
+
+// Issue the partition pass of the round (bytes accounting, then the command).  A root pass issued ahead on a guess that
+// this very round refuted is drained first: the partition pass reuses the pass blocks.
+__device__ __forceinline__ void fw_issue_part(const PgState& st, const FwCx& x, int lane) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    __syncwarp();
+    if (f->spec_now) {
+        fw_await(st, x, lane);
+        if (lane == 0) { c->n_drain += 1ull; f->spec_now = 0; }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        const int K = c->n_pjobs;
+        unsigned long long bm = 0;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const unsigned long long L = f->pq_len[k];
+            bm += (f->pq_ident[k] ? 0ull : 4ull * L) + 4ull * L + 4ull * L;
+        }
+        c->bytes_model += bm + 4ull * (unsigned long long)f->n_mq * (K > 0 ? (unsigned long long)f->pq_len[0] : 0ull);
+        c->n_groups = f->n_mq;          // look-ahead min/max requests riding on the partition pass
+        c->phase = PH_PART; c->n_phases += 1;
+    }
+    __syncwarp();
+    fw_issue_ctrl(st, x, lane);
 }
 
 // Speculation: the root pass of update U+1 only needs (i) U+1's root proposals, which are
@@ -1776,7 +1791,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
 #pragma unroll 1
             for (int it = 0; it < (1 << 20); ++it) {
                 if (c->error != PG_OK) { sn = SN_NONE; break; }
-                if (sn == SN_NONE || sn == SN_PREP_PART) break;
+                if (sn == SN_NONE || sn == SN_PART_ISSUED) break;
                 if (sn == SN_BEGIN_UPDATE) {
                     if (spec && (phase == PH_ROOT || f->pred_ok)) {   // the guess held: the root pass in flight is the next update's
                         if (lane == 0) c->a_cur = 1 - c->a_cur;
@@ -1793,28 +1808,17 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                 else { if (lane == 0) c->error = PG_ERR_INTERNAL; sn = SN_NONE; }
             }
             if (c->error != PG_OK) { if (lane == 0) c->phase = PH_DONE; sn = SN_NONE; __syncwarp(); }
-            if (sn != SN_PREP_PART) {
-                if (spec && !spec_commit) { fw_await(st, x, lane); if (lane == 0) c->n_drain += 1ull; }   // drain a wrong guess (odd paths, and before PH_DONE on an error)
+            if (sn == SN_PART_ISSUED) {
+                FW_TICK(4);
+                fw_predict(st, x, lane);            // off the critical path: the partition pass is streaming
+            } else {
+                if (spec && !spec_commit && f->spec_now) { fw_await(st, x, lane); if (lane == 0) c->n_drain += 1ull; }   // drain a wrong guess (odd paths, and before PH_DONE on an error)
                 if (!spec_commit) fw_issue_ctrl(st, x, lane);                              // next pass, or PH_DONE
                 if (c->phase == PH_ROOT && c->round == 0) fw_prestage(st, x, lane);        // an update just started: stage the one after it
             }
-            if (lane == 0) { f->sn = sn; f->quit = c->phase == PH_DONE ? 1 : 0; f->scan[PG_THREADS] = spec && !spec_commit ? 1u : 0u; }
+            if (lane == 0) { f->sn = sn; f->quit = c->phase == PH_DONE ? 1 : 0; }
         }
         __syncthreads();
-        if (f->sn == SN_PREP_PART) {   // survivors grew: partition offsets (block-wide), then the PART pass
-            tq = clock64();
-            const bool drain = f->scan[PG_THREADS] != 0u;
-            __syncthreads();
-            fb_prep_part(st, x);
-            __syncthreads();
-            if (warp == 0) {
-                if (drain) { fw_await(st, x, lane); if (lane == 0) c->n_drain += 1ull; }   // the speculative root pass guessed wrong: let it finish, ignore its output
-                fw_issue_ctrl(st, x, lane);
-                FW_TICK(4);
-                fw_predict(st, x, lane);            // off the critical path: the partition pass is streaming
-            }
-            __syncthreads();
-        }
         if (threadIdx.x == 0) {
             const unsigned long long d = (unsigned long long)(clock64() - t_entry);
             c->prof_ser[phase & 7] += d;

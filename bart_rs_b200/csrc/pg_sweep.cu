@@ -266,7 +266,7 @@ cudaError_t pg_launch_persistent(const PgState& st, size_t smem, cudaStream_t s)
     void* fn = (void*)pg_sweep_persistent_generic;
     if (st.P <= 32) {
         if (st.family == PG_BERNOULLI_LOGIT) fn = (void*)pg_sweep_persistent_bern;
-        else if (st.root_ring && st.stage_bytes > 0) fn = (void*)pg_sweep_persistent_ring;
+        else if (pg_use_ring(st)) fn = (void*)pg_sweep_persistent_ring;
         else fn = (void*)pg_sweep_persistent_direct;
     }
     return cudaLaunchCooperativeKernel(fn, dim3(st.grid + 1), dim3(PG_THREADS), args, smem, s);   // + the serial block

@@ -150,9 +150,11 @@ struct PgState {
     double* mail[PG_MAX_RANKS];  // mail[r] = rank r's mailbox (peer memory for r != rank)
     int prune;                   // option prune_dead_proposals: do not evaluate proposals whose particle provably gets weight 0
     int prefetch_next;           // pass blocks prefetch the next update's root columns into L2 after a root pass
-    int root_ring;               // P <= 32 persistent kernels: 1 = ring root pass (pg_pass_root_ring, default), 0 = direct register loads
+    int root_ring;               // P <= 32 persistent kernels: 0 = direct root pass (register loads), 1 = ring root pass (pg_pass_root_ring),
+                                 // 2 = ring when a pass block holds at most 2048 rows, else direct (default)
     int root_tile_groups;        // ring root pass: cap on the row groups (128 rows) per tile, 0 = as many as fit (<= 8)
-    int root_stages;             // ring root pass: cap on the stages of the ring, 0 = as many as fit (<= 4)
+    int root_stages;             // ring root pass: cap on the stages of the ring, 0 = as many as fit
+    int root_dbg;                // ring root pass, timing experiments only (results are wrong): 1 no proxy fence in the loop, 2 no job loop, 4 no row work at all
     // data
     const float* X;
     const float* y;

@@ -17,16 +17,14 @@ st = PyBartSettings(w["m"], w["P"], prm["max_depth"], 0.95, 2.0, prm["sigma"], l
                     ["ContinuousSplit"] * w["p"], "constant", "systematic", 1.0, 1.0, seed=0)
 CONFIGS = [
     dict(name="direct", smem=163, root="direct"),
-    dict(name="ring 163KB auto", smem=163, root="ring"),
-    dict(name="ring 163KB G8 NST2", smem=163, root="ring", groups=8, stages=2),
-    dict(name="ring 163KB G5 NST3", smem=163, root="ring", groups=5, stages=3),
-    dict(name="ring 163KB G4 NST4", smem=163, root="ring", groups=4, stages=4),
-    dict(name="ring 195KB auto", smem=195, root="ring"),
-    dict(name="ring 195KB G6 NST3", smem=195, root="ring", groups=6, stages=3),
-    dict(name="ring 227KB auto", smem=227, root="ring"),
-    dict(name="ring 227KB G7 NST3", smem=227, root="ring", groups=7, stages=3),
-    dict(name="ring 131KB auto", smem=131, root="ring"),
-    dict(name="direct 99KB", smem=99, root="direct"),
+    dict(name="ring G4", smem=163, root="ring"),
+    dict(name="ring G4 nofence", smem=163, root="ring", dbg=1),
+    dict(name="ring G4 nojobs", smem=163, root="ring", dbg=2),
+    dict(name="ring G4 norowwork", smem=163, root="ring", dbg=4),
+    dict(name="ring G4 norowwork nofence", smem=163, root="ring", dbg=5),
+    dict(name="ring G8 NST2 norowwork nofence", smem=163, root="ring", groups=8, dbg=5),
+    dict(name="ring G2 norowwork nofence", smem=163, root="ring", groups=2, dbg=5),
+    dict(name="ring 227KB G8 nofence", smem=227, root="ring", groups=8, dbg=1),
 ]
 ghz = 1.965
 ref = None
@@ -36,6 +34,7 @@ for cfg in CONFIGS:
     s.set_option("root_pass", cfg["root"])
     s.set_option("root_tile_groups", str(cfg.get("groups", 0)))
     s.set_option("root_stages", str(cfg.get("stages", 0)))
+    s.set_option("root_dbg", str(cfg.get("dbg", 0)))
     for _ in range(3):
         s.step_device(False)
     s.sync()
