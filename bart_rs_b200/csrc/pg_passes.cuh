@@ -107,10 +107,13 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     unsigned long long d_upd[3];                 // which tree update each buffer holds
     volatile unsigned long long d_flag[3][FW_DR + 1];   // per helper warp: token (= update + 1) when its part is written
     int sn;
-    // control loop of the serial block: the pass that is in flight
+    // control loop of the serial block: the passes in flight (at most two: the pass in progress and a root pass issued ahead)
     unsigned issued;                             // commands issued so far (= value of bar_gen)
-    int out_phase, out_J, out_pb;                // phase / job count / buffer parity of the outstanding pass
+    unsigned cur_gen;                            // generation of the pass whose completion the current section digests
+    int out_phase[2], out_J[2], out_pb[2];       // by generation parity: phase / job count / buffer parity of an issued pass
     int quit;
+    int stat_spec;                               // profiling: a root pass was in flight ahead during this section
+    int pred_tried;                              // early commit: the predicted root pass of this update has been issued once
     // look-ahead caches of the update in progress (rounds 1 and 2), indexed [round-1][slot]
     int mm_valid[2][32]; unsigned mm_seg[2][32]; int mm_var[2][32]; float mm_lo[2][32], mm_hi[2][32];
     int sc_valid[32]; unsigned sc_seg[32]; int sc_var[32]; float sc_thr[32]; unsigned sc_cnt[32], sc_cntL[32]; double sc_So[32], sc_Sr[32];
@@ -128,6 +131,7 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
 };
 
 struct PgSmem {
+    PgCmd cmd;             // the command of the pass being executed (pg_fetch_cmd)
     PgTreeSm tadd, tsub;
     double tot[PG_WARPS][4];
     double cthr[16];       // depth-prior thresholds (staged once per kernel)
@@ -205,6 +209,11 @@ __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
     v.cmin = reinterpret_cast<float*>(u); u += (size_t)FW_MAXP * 4;
     v.cmax = reinterpret_cast<float*>(u);
     return v;
+}
+
+// Copy a 16-int pass command from global memory into this block's shared memory; the caller synchronises the block.
+__device__ __forceinline__ void pg_fetch_cmd(const int* src, PgSmem* b) {
+    if (threadIdx.x < 16) reinterpret_cast<int*>(&b->cmd)[threadIdx.x] = __ldcg(&src[threadIdx.x]);
 }
 
 // ---- loads ------------------------------------------------------------------
@@ -331,9 +340,9 @@ __device__ __forceinline__ void pg_acc_left(double& a, double& b, unsigned& c, f
 // warps; otherwise every global warp owns one pg_warp_range (generic control code, stepwise driver).
 template <bool BERN, bool BLOCKR>
 __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
-    PgCtrl* c = st.ctrl;
-    const int J = __ldcg(&c->n_jobs) * (__ldcg(&c->phase) == PH_ROOT ? 1 : 0);
-    const int t_add = __ldcg(&c->t_add), t_sub = __ldcg(&c->phase) == PH_ROOT ? __ldcg(&c->t_sub) : -1;
+    const PgCmd& cm = sm.base->cmd;
+    const int J = cm.n_jobs * (cm.phase == PH_ROOT ? 1 : 0);
+    const int t_add = cm.t_add, t_sub = cm.phase == PH_ROOT ? cm.t_sub : -1;
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
@@ -556,11 +565,11 @@ __device__ __forceinline__ double pg_tree_eval_staged(const PgState& st, int t, 
 // for this pass's distinct columns: the caller then runs the direct pass.
 template <bool BERN, int JW>
 __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
-    PgCtrl* c = st.ctrl;
     PgSmem* b = sm.base;
-    const bool is_root = __ldcg(&c->phase) == PH_ROOT;
-    const int J = is_root ? __ldcg(&c->n_jobs) : 0;
-    const int t_add = __ldcg(&c->t_add), t_sub = is_root ? __ldcg(&c->t_sub) : -1;
+    const PgCmd& cm = sm.base->cmd;
+    const bool is_root = cm.phase == PH_ROOT;
+    const int J = is_root ? cm.n_jobs : 0;
+    const int t_add = cm.t_add, t_sub = is_root ? cm.t_sub : -1;
     const int S = st.S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qd = warp >> 2, grp = warp & 3;
@@ -838,8 +847,7 @@ __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSm
 // PH_MINMAX — splitting.rs:43-49 over index segments
 // =============================================================================
 __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
-    PgCtrl* c = st.ctrl;
-    const int J = __ldcg(&c->n_jobs);
+    const int J = sm.base->cmd.n_jobs;
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
@@ -879,8 +887,7 @@ __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemV
 // (A = left-child sum, B = right-child sum); identity segments allowed.
 template <int MODE>
 __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
-    PgCtrl* c = st.ctrl;
-    const int J = __ldcg(&c->n_jobs), G = __ldcg(&c->n_groups);
+    const int J = sm.base->cmd.n_jobs, G = sm.base->cmd.n_groups;
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
@@ -970,8 +977,7 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
 // thread at once: 8 index loads in flight, then the gathers of A, y and up to four jobs' columns for all 8 entries
 // together — three memory round trips per 4096 entries instead of three per 128 per warp.  Emits per-block results.
 __device__ void pg_pass_seg_block(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
-    PgCtrl* c = st.ctrl;
-    const int J = __ldcg(&c->n_jobs), G = __ldcg(&c->n_groups);
+    const int J = sm.base->cmd.n_jobs, G = sm.base->cmd.n_groups;
     const int S = st.S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pg_stage_jobs(st, bf, sm, J, G, false);
@@ -1264,8 +1270,8 @@ __device__ void pg_part_seg(const PgState& st, const PgBuf& bf, const PgSmemView
 template <bool FASTP>
 __device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
-    const int K = __ldcg(&c->n_pjobs);
-    const int Q = __ldcg(&c->n_groups);     // look-ahead min/max requests riding on this pass (0 in the generic control code)
+    const int K = sm.base->cmd.n_pjobs;
+    const int Q = sm.base->cmd.n_groups;     // look-ahead min/max requests riding on this pass (0 in the generic control code)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -1407,7 +1413,7 @@ __host__ __device__ inline bool pg_use_ring(const PgState& st) {
 
 template <int VAR>
 __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView& sm, int phase) {
-    const PgBuf bf = pg_make_buf(st, __ldcg(&st.ctrl->flags));
+    const PgBuf bf = pg_make_buf(st, sm.base->cmd.flags);
     constexpr bool FASTP = VAR != PGV_GENERIC;
     switch (phase) {
         case PH_ROOT:

@@ -64,7 +64,8 @@ __device__ void fw_load_state(const PgState& st, PgFastSm* f) {
     }
     if (threadIdx.x < 3) f->d_upd[threadIdx.x] = ~0ull;
     if (threadIdx.x < 3 * (FW_DR + 1)) f->d_flag[threadIdx.x / (FW_DR + 1)][threadIdx.x % (FW_DR + 1)] = 0ull;
-    if (threadIdx.x == 0) { f->issued = 0u; f->out_phase = PH_BEGIN; f->out_J = 0; f->out_pb = 0; f->quit = 0; f->pre_upd = ~0ull; f->spec_now = 0; f->lazy_J = 0; }
+    if (threadIdx.x == 0) { f->issued = 0u; f->cur_gen = 0u; f->out_phase[0] = f->out_phase[1] = PH_BEGIN; f->out_J[0] = f->out_J[1] = 0; f->out_pb[0] = f->out_pb[1] = 0;
+                            f->quit = 0; f->pre_upd = ~0ull; f->spec_now = 0; f->stat_spec = 0; f->pred_tried = 0; f->lazy_J = 0; }
 }
 
 __device__ void fw_store_state(const PgState& st, PgFastSm* f) {
@@ -650,7 +651,7 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     int status;
     const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
     f->mm_valid[0][lane] = 0; f->mm_valid[1][lane] = 0; f->sc_valid[lane] = 0;
-    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; f->pred_valid = 0; f->pred_ok = 0; f->pred_sel = 0; f->sl_valid = 0; }
+    if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; f->pred_valid = 0; f->pred_ok = 0; f->pred_sel = 0; f->pred_tried = 0; f->sl_valid = 0; }
     if (lane < S) {
         const int s = lane;
         f->hw[s] = 0.0;       // smc.rs:53: once per update, never reset (Q1)
@@ -1455,23 +1456,27 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
 __device__ __forceinline__ void fw_issue(const PgState& st, const FwCx& x, int lane, int phase, int t_add, int t_sub,
                                          int n_jobs, int n_groups, int n_pjobs, int flags) {
     PgFastSm* f = x.f;
+    const unsigned g = f->issued + 1u;                       // this command's generation; its buffer: the one generation g - 2 used
     if (lane < 16) {
         int v = reinterpret_cast<const int*>(&f->lc)[lane];
         if (lane == 0) v = phase; else if (lane == 4) v = t_add; else if (lane == 5) v = t_sub; else if (lane == 7) v = n_jobs;
         else if (lane == 8) v = n_groups; else if (lane == 9) v = n_pjobs; else if (lane == 15) v = flags;
-        reinterpret_cast<int*>(st.ctrl)[lane] = v;
+        st.ctrl->cmd[g & 1u][lane] = v;
     }
 #ifdef PG_DIAG
     if (lane == 0) { st.ctrl->dbg[1] = 0ull; st.ctrl->dbg[2] = 0ull; st.ctrl->dbg[3] = 0ull; st.ctrl->dbg[0] = pg_globaltimer(); }
 #endif
     __syncwarp();                                            // the lanes' stores are ordered before lane 0's release store
     if (lane == 0) {
-        f->issued += 1u;
-        f->out_phase = phase; f->out_J = n_jobs; f->out_pb = (flags >> 2) & 1;
-        pg_st_release(&st.ctrl->bar_gen, f->issued);
+        f->issued = g;
+        f->out_phase[g & 1u] = phase; f->out_J[g & 1u] = n_jobs; f->out_pb[g & 1u] = (flags >> 2) & 1;
+        pg_st_release(&st.ctrl->bar_gen, g);
     }
     __syncwarp();
 }
+
+// passes of one generation parity completed when generation g has: 147 x (generations <= g of g's parity)
+__device__ __forceinline__ unsigned fw_cnt_target(unsigned g) { return ((g + 1u) >> 1) * (gridDim.x - 1u); }
 
 // Issue the pass the control block asks for (c->phase), on the buffers of the update in progress.
 __device__ __forceinline__ void fw_issue_ctrl(const PgState& st, const FwCx& x, int lane) {
@@ -1486,13 +1491,17 @@ __device__ __forceinline__ void fw_issue_ctrl(const PgState& st, const FwCx& x, 
     const int nj = phase == PH_STATS ? c->n_jobs + x.f->pf_n : c->n_jobs;
     fw_issue(st, x, lane, phase, c->t_add, phase == PH_ROOT ? c->t_sub : -1, nj, c->n_groups, c->n_pjobs,
              src | (dst << 1) | (pb << 2));
-    if (phase == PH_PART && lane == 0) x.f->out_J = x.f->n_mq;   // what the next section reduces: the look-ahead min/max
+    if (phase == PH_PART && lane == 0) x.f->out_J[x.f->issued & 1u] = x.f->n_mq;   // what the next section reduces: the look-ahead min/max
     __syncwarp();
 }
 
-// wait until the outstanding pass has completed on every pass block
+// wait until every pass issued so far has completed on every pass block
 __device__ __forceinline__ void fw_await(const PgState& st, const FwCx& x, int lane) {
-    if (lane == 0) pg_spin_until(&st.ctrl->bar_count, x.f->issued * (gridDim.x - 1u), st.ctrl);
+    if (lane == 0) {
+        const unsigned g = x.f->issued;
+        if (g >= 2u) pg_spin_until(&st.ctrl->cnt[(g - 1u) & 1u][0], fw_cnt_target(g - 1u), st.ctrl);
+        if (g >= 1u) pg_spin_until(&st.ctrl->cnt[g & 1u][0], fw_cnt_target(g), st.ctrl);
+    }
     __syncwarp();
 }
 
@@ -1645,11 +1654,11 @@ __device__ __forceinline__ bool fw_issue_predicted(const PgState& st, const FwCx
     PgCtrl* c = x.c;
     PgFastSm* f = x.f;
     const unsigned long long U1 = c->upd + 1ull;
-    if (!(f->pred_valid && f->pre_upd == U1 && c->k + 1 < c->batch && c->error == PG_OK && st.family != PG_BERNOULLI_LOGIT)) return false;
+    if (!(f->pred_valid && !f->pred_tried && f->pre_upd == U1 && c->k + 1 < c->batch && c->error == PG_OK && st.family != PG_BERNOULLI_LOGIT)) return false;
     const int t_sub1 = (c->next_tree_idx + c->k + 1) % st.m;
     const int src = c->a_cur, dst = 1 - c->a_cur;
     fw_issue(st, x, lane, PH_ROOT, f->pred_sel == 0 ? -2 : c->t_cur, t_sub1, f->pre_J, f->pre_G, 0, src | (dst << 1) | ((int)(U1 & 1ull) << 2));
-    if (lane == 0) c->n_spec += 1;
+    if (lane == 0) { c->n_spec += 1; f->pred_tried = 1; }     // once per update: a drained guess is not repeated
     return true;
 }
 
@@ -1685,8 +1694,10 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
         // ---- (A) the outstanding pass (if any) completes
         if (!first && threadIdx.x == 0) {
             const long long tw = clock64();
-            pg_spin_until(&st.ctrl->bar_count, f->issued * (gridDim.x - 1u), st.ctrl);
-            const int ph = f->out_phase;
+            const unsigned g = f->issued - (f->spec_now ? 1u : 0u);   // the OLDEST outstanding pass: a root pass issued ahead queues behind it
+            pg_spin_until(&st.ctrl->cnt[g & 1u][0], fw_cnt_target(g), st.ctrl);
+            f->cur_gen = g;
+            const int ph = f->out_phase[g & 1u];
             c->prof3[ph == PH_ROOT ? 4 : ph == PH_STATS ? 5 : ph == PH_PART ? 6 : 7] += (unsigned long long)(clock64() - tw);
 #ifdef PG_DIAG
             const int cls = ph == PH_ROOT ? 0 : ph == PH_STATS ? 1 : ph == PH_PART ? 2 : -1;
@@ -1699,18 +1710,23 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
 #endif
         }
         __syncthreads();
-        const int phase = first ? PH_BEGIN : f->out_phase;
-        const int J = first ? 0 : f->out_J;
-        const int pb = first ? 0 : f->out_pb;
+        const int phase = first ? PH_BEGIN : f->out_phase[f->cur_gen & 1u];
+        const int J = first ? 0 : f->out_J[f->cur_gen & 1u];
+        const int pb = first ? 0 : f->out_pb[f->cur_gen & 1u];
         first = false;
         const long long t_entry = clock64();
         const int gerr = threadIdx.x == 0 ? __ldcg(&st.ctrl->error) : PG_OK;   // a pass may have flagged an error
-        if (warp == 0) {   // the next update's root pass, if its jobs are staged: issue it before anything else
-            // ... or, after the last data pass of an update whose outcome was predicted after round 0 (the statistics pass;
-            // with pruning the partition pass), the next update's root pass on the predicted tree
-            const bool sp = (phase == PH_ROOT && fw_issue_prestaged(st, x, lane)) ||
-                            ((phase == PH_STATS || (phase == PH_PART && st.prune)) && fw_issue_predicted(st, x, lane));
-            if (lane == 0) f->spec_now = sp ? 1 : 0;
+        if (warp == 0) {
+            // A root pass for the NEXT update is normally in flight already, issued ahead at the end of the previous section
+            // (it queues behind the pass that just completed, so the pass blocks never idle between the two).  If it could
+            // not be issued then (draws / staged jobs not ready), issue it now before anything else: after a root pass the
+            // next update's root pass on a stump; after the last data pass of an update whose outcome was predicted after
+            // round 0 (the statistics pass; with pruning the partition pass) the next root pass on the predicted tree.
+            bool sp = f->spec_now != 0;
+            if (!sp) sp = (phase == PH_ROOT && fw_issue_prestaged(st, x, lane)) ||
+                          ((phase == PH_STATS || (phase == PH_PART && st.prune)) && fw_issue_predicted(st, x, lane));
+            __syncwarp();
+            if (lane == 0) { f->spec_now = sp ? 1 : 0; f->stat_spec = sp ? 1 : 0; }
         }
         fw_reduce(st, f, phase, J, pb);   // contains a __syncthreads before its combine step
         if (st.world > 1 && warp == 0) fw_exchange(st, f, phase, J, lane);
@@ -1793,8 +1809,10 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                 if (c->error != PG_OK) { sn = SN_NONE; break; }
                 if (sn == SN_NONE || sn == SN_PART_ISSUED) break;
                 if (sn == SN_BEGIN_UPDATE) {
-                    if (spec && (phase == PH_ROOT || f->pred_ok)) {   // the guess held: the root pass in flight is the next update's
-                        if (lane == 0) c->a_cur = 1 - c->a_cur;
+                    __syncwarp();
+                    if (spec && f->spec_now && (phase == PH_ROOT || f->pred_ok)) {   // the guess held: the root pass in flight is the next update's
+                        __syncwarp();
+                        if (lane == 0) { c->a_cur = 1 - c->a_cur; f->spec_now = 0; }   // adopted: no longer "ahead"
                         __syncwarp();
                         fw_start_update(st, x, lane, true);
                         spec_commit = true;
@@ -1812,9 +1830,25 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                 FW_TICK(4);
                 fw_predict(st, x, lane);            // off the critical path: the partition pass is streaming
             } else {
-                if (spec && !spec_commit && f->spec_now) { fw_await(st, x, lane); if (lane == 0) c->n_drain += 1ull; }   // drain a wrong guess (odd paths, and before PH_DONE on an error)
+                __syncwarp();
+                if (f->spec_now && !spec_commit) {      // drain a wrong guess (odd paths, and before PH_DONE on an error)
+                    fw_await(st, x, lane);
+                    if (lane == 0) { c->n_drain += 1ull; f->spec_now = 0; }
+                    __syncwarp();
+                }
                 if (!spec_commit) fw_issue_ctrl(st, x, lane);                              // next pass, or PH_DONE
-                if (c->phase == PH_ROOT && c->round == 0) fw_prestage(st, x, lane);        // an update just started: stage the one after it
+                // ---- issue AHEAD: the pass blocks find the next root pass queued behind the pass they are running
+                if (c->phase == PH_ROOT && c->round == 0) {
+                    // an update just started (its root pass was issued, or adopted): stage the jobs of the update after it and,
+                    // if this one is expected to end as a stump (some slot proposes nothing: Q1), issue that update's root pass
+                    fw_prestage(st, x, lane);
+                    if (!f->spec_now && fw_issue_prestaged(st, x, lane)) { if (lane == 0) f->spec_now = 1; }
+                } else if (c->phase == PH_STATS && !f->spec_now) {
+                    // early commit: the statistics pass just issued is normally the update's last data pass and the outcome was
+                    // predicted after round 0: the next update's root pass on the predicted tree goes right behind it
+                    if (fw_issue_predicted(st, x, lane)) { if (lane == 0) f->spec_now = 1; }
+                }
+                __syncwarp();
             }
             if (lane == 0) { f->sn = sn; f->quit = c->phase == PH_DONE ? 1 : 0; }
         }
@@ -1822,7 +1856,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
         if (threadIdx.x == 0) {
             const unsigned long long d = (unsigned long long)(clock64() - t_entry);
             c->prof_ser[phase & 7] += d;
-            if (phase == PH_ROOT) { const int q = f->spec_now ? 0 : 2; c->prof3[q] += d; c->prof3[q + 1] += 1ull; }
+            if (phase == PH_ROOT) { const int q = f->stat_spec ? 0 : 2; c->prof3[q] += d; c->prof3[q + 1] += 1ull; }
         }
         if (f->quit) break;
     }

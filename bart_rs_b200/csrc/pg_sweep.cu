@@ -83,17 +83,22 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
         unsigned gen = 0;
         long long t_idle = clock64();
         for (;;) {
-            if (threadIdx.x == 0) {
-                pg_spin_until(&c->bar_gen, gen + 1u, c);
+            const unsigned g = gen + 1u;                         // the command this block executes next
+            if (threadIdx.x < 32) {
+                if (threadIdx.x == 0) {
+                    pg_spin_until(&c->bar_gen, g, c);
 #ifdef PG_DIAG
-                atomicMax(&c->dbg[1], pg_globaltimer());
+                    atomicMax(&c->dbg[1], pg_globaltimer());
 #endif
+                }
+                __syncwarp();
+                pg_fetch_cmd(c->cmd[g & 1u], sm.base);
             }
             __syncthreads();
-            const int phase = __ldcg(&c->phase);
+            const int phase = sm.base->cmd.phase;
             if (phase == PH_DONE) break;
             const long long t0 = clock64();
-            const int flags = __ldcg(&c->flags);
+            const int flags = sm.base->cmd.flags;
             pg_run_pass<VAR>(st, sm, phase);
             __syncthreads();
             const long long t1 = clock64();
@@ -103,7 +108,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
                 st.diag_blocks[(size_t)(blockIdx.x - 1) * 8 + (phase & 7)] += (unsigned long long)(t1 - t0);
                 atomicMax(&c->dbg[2], pg_globaltimer());
 #endif
-                pg_red_release_add(&c->bar_count, 1u);
+                pg_red_release_add(&c->cnt[g & 1u][0], 1u);
             }
             if (phase == PH_ROOT && st.prefetch_next) pg_prefetch_next_root(st, flags);
             if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // stopwatch kept by the last pass block
@@ -112,15 +117,17 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
                 c->prof[24 + (phase & 7)] += 1ull;
             }
             t_idle = t1;
-            gen += 1u;
+            gen = g;
         }
         return;
     }
     unsigned gen = 0;
     pg_barrier_serial<FAST>(st, sm, gen, PH_BEGIN, 0);   // serial section of PH_BEGIN prepares the first pass
     for (;;) {
-        const int phase = __ldcg(&st.ctrl->phase);
-        const int J = __ldcg(&st.ctrl->n_jobs);
+        pg_fetch_cmd(reinterpret_cast<const int*>(st.ctrl), sm.base);   // the generic control code publishes in PgCtrl itself
+        __syncthreads();
+        const int phase = sm.base->cmd.phase;
+        const int J = sm.base->cmd.n_jobs;
         if (phase == PH_DONE) break;
         const long long t0 = clock64();
         if (blockIdx.x != 0) pg_run_pass<PGV_GENERIC>(st, sm, phase);   // block 0 = serial block: streams nothing
@@ -145,8 +152,9 @@ extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_sweep_persistent_
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_phase_kernel(const PgState st) {
     const PgSmemView sm = pg_smem_view(pg_smem_raw, st.S);
     if (threadIdx.x == 0) sm.base->pass_bid = (int)blockIdx.x;
+    pg_fetch_cmd(reinterpret_cast<const int*>(st.ctrl), sm.base);
     __syncthreads();
-    pg_run_pass<PGV_GENERIC>(st, sm, __ldcg(&st.ctrl->phase));
+    pg_run_pass<PGV_GENERIC>(st, sm, sm.base->cmd.phase);
 }
 
 extern "C" __global__ void __launch_bounds__(PG_THREADS, 1) pg_serial_kernel(const PgState st) {
@@ -164,6 +172,8 @@ extern "C" __global__ void pg_prepare_step(const PgState st, int tune) {
     c->snext = SN_NONE;
     c->bar_count = 0u;
     c->bar_gen = 0u;
+    c->cnt[0][0] = 0u;
+    c->cnt[1][0] = 0u;
 }
 
 extern "C" __global__ void pg_fill_f64(double* p, long long n, double v) {

@@ -63,6 +63,13 @@ enum PgError : int {
 // mailbox of one rank: [2 parities][PG_MAX_RANKS senders][PG_MAIL_DOUBLES] doubles, then [2][PG_MAX_RANKS] u64 flags
 #define PG_MAIL_BYTES ((size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES * 8 + (size_t)2 * PG_MAX_RANKS * 8)
 
+// A pass command: what a grid pass needs to know, = the first 16 ints of PgCtrl.  The P <= 32 control block publishes
+// commands into PgCtrl.cmd[generation & 1] (two may be outstanding: the pass in progress and a root pass issued ahead);
+// every pass block copies the command it is about to execute into its shared memory (PgSmem.cmd) and the passes read it there.
+struct PgCmd {
+    int phase, k, batch, t_cur, t_add, t_sub, round, n_jobs, n_groups, n_pjobs, cur, error, snext, max_size, t_add_internal, flags;
+};
+
 struct PgCtrl {
     // ---- state machine (written by the serial section, read by all CTAs after the barrier)
     int phase;
@@ -135,6 +142,11 @@ struct PgCtrl {
     // ---- set by pg_prepare_step when an earlier step left a device error behind: steps queued after it must not run on
     // the broken state (pgbart_step_device can be queued several times before pgbart_sync reports the error)
     int poisoned;
+    int pad_cmd[29];
+    // ---- P <= 32 persistent kernels: command buffers by generation parity, and completion counters by generation parity
+    // (zeroed with bar_gen by pg_prepare_step); counter q holds 147 x (generations of parity q completed)
+    int cmd[2][16];
+    unsigned int cnt[2][32];
 };
 
 struct PgState {

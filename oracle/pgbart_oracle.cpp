@@ -144,11 +144,33 @@ struct TapeView {
     }
 };
 
-// One object, three modes: sequential xoshiro (optionally recording a typed
-// tape), coordinate-addressed Philox, or replay of a supplied tape.
+// One object, four modes: sequential xoshiro (optionally recording a typed
+// tape), coordinate-addressed Philox, replay of a supplied tape, or a FLAT
+// sequential log: the words a reference run consumed, in consumption order —
+// raw generator outputs (u64, stored in the bit pattern of a double) for every
+// uniform / range draw, and the VALUE of every standard normal (the ziggurat of
+// rand_distr is not restated here; the reference-side dumper of INTEGRATION.md
+// section 1b logs normals at their call sites and mutes the raw words they
+// consume).  FLAT converts raw words exactly like SEQ and still records the typed
+// tape, so a log taken from the real Rust sampler drives oracle AND device.
 struct Draws {
-    enum Mode { SEQ = 0, PHILOX = 1, REPLAY = 2 } mode = SEQ;
+    enum Mode { SEQ = 0, PHILOX = 1, REPLAY = 2, FLAT = 3 } mode = SEQ;
     Xoshiro256pp seq;
+    const double* flat = nullptr;   // FLAT: the log being consumed
+    size_t flat_n = 0, flat_pos = 0;
+    double* flat_out = nullptr;     // SEQ: optional flat log being written (tests the FLAT path without a Rust toolchain)
+    size_t flat_cap = 0, flat_w = 0;
+
+    uint64_t raw_word() {           // next raw generator output: the sequential generator, or the log
+        if (mode == FLAT) {
+            if (flat_pos >= flat_n) { error = true; return 0; }
+            uint64_t b; std::memcpy(&b, &flat[flat_pos++], 8);
+            return b;
+        }
+        const uint64_t b = seq.next();
+        if (flat_out) { if (flat_w < flat_cap) std::memcpy(&flat_out[flat_w], &b, 8); flat_w++; }
+        return b;
+    }
     uint32_t key[2] = {0, 0};
     TapeView tape;  // SEQ: written if non-null; REPLAY: read
     bool error = false;
@@ -191,7 +213,7 @@ struct Draws {
         double v;
         if (mode == REPLAY) return replay(k, c);
         if (mode == PHILOX) { double ub; philox_pair(k, c, 0, v, ub); return v; }
-        v = bits53(seq.next());
+        v = bits53(raw_word());
         record(k, c, v);
         return v;
     }
@@ -211,14 +233,14 @@ struct Draws {
             if (mode == PHILOX) { double ub; philox_pair(D_SPLIT, c, attempt, u, ub); }
             else {
                 // value in [1,2) from the top 52 bits, minus 1
-                const uint64_t bits = (seq.next() >> 12) | 0x3ff0000000000000ULL;
+                const uint64_t bits = (raw_word() >> 12) | 0x3ff0000000000000ULL;
                 double v12; std::memcpy(&v12, &bits, 8);
                 u = v12 - 1.0;
             }
             const double r = u * scale + lo;
-            if (r < hi) { if (mode == SEQ) record(D_SPLIT, c, u); return r; }
+            if (r < hi) { if (mode == SEQ || mode == FLAT) record(D_SPLIT, c, u); return r; }
         }
-        if (mode == SEQ) record(D_SPLIT, c, 0.0);
+        if (mode == SEQ || mode == FLAT) record(D_SPLIT, c, 0.0);
         return lo;
     }
 
@@ -226,10 +248,19 @@ struct Draws {
     double normal(DrawKind k, const DrawCtx& c) {
         if (mode == REPLAY) return replay(k, c);
         double ua, ub;
+        if (mode == FLAT) {             // the normal itself was logged
+            if (flat_pos >= flat_n) { error = true; return 0.0; }
+            const double z = flat[flat_pos++];
+            record(k, c, z);
+            return z;
+        }
         if (mode == PHILOX) philox_pair(k, c, 0, ua, ub);
         else { ua = bits53(seq.next()); ub = bits53(seq.next()); }
         const double z = box_muller(ua, ub);
-        if (mode == SEQ) record(k, c, z);
+        if (mode == SEQ) {
+            record(k, c, z);
+            if (flat_out) { if (flat_w < flat_cap) flat_out[flat_w] = z; flat_w++; }
+        }
         return z;
     }
 };
@@ -852,6 +883,22 @@ int orc_attach_tape(void* h, double* slot, double* round, double* upd, int64_t n
     s->draws.tape.base_upd = s->upd_counter;
     s->draws.tape.overflow = false;
     return 0;
+}
+
+// FLAT mode input (mode 3 of orc_set_rng) / SEQ mode output: see struct Draws.
+int orc_attach_flat(void* h, const double* log, uint64_t n) {
+    auto* s = (orc::Sampler*)h;
+    s->draws.flat = log; s->draws.flat_n = (size_t)n; s->draws.flat_pos = 0;
+    return 0;
+}
+int orc_record_flat(void* h, double* out, uint64_t cap) {
+    auto* s = (orc::Sampler*)h;
+    s->draws.flat_out = out; s->draws.flat_cap = (size_t)cap; s->draws.flat_w = 0;
+    return 0;
+}
+uint64_t orc_flat_count(void* h) {
+    auto* s = (orc::Sampler*)h;
+    return s->draws.mode == orc::Draws::FLAT ? (uint64_t)s->draws.flat_pos : (uint64_t)s->draws.flat_w;
 }
 
 int orc_attach_trace(void* h, double* slot, double* round, double* upd, int64_t u_cap, int r_cap) {

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libpgbart_oracle.so")
 
 FAM_GAUSSIAN, FAM_BERNOULLI_LOGIT, FAM_GAUSSIAN_KERNEL = 0, 1, 2
-RNG_SEQ, RNG_PHILOX, RNG_REPLAY = 0, 1, 2
+RNG_SEQ, RNG_PHILOX, RNG_REPLAY, RNG_FLAT = 0, 1, 2, 3
 TS_FIELDS = 12
 
 
@@ -56,6 +56,10 @@ def lib():
         L.orc_set_rng.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
         L.orc_attach_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
         L.orc_attach_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        L.orc_attach_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_record_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_flat_count.restype = C.c_uint64
+        L.orc_flat_count.argtypes = [C.c_void_p]
         L.orc_trace_count.restype = C.c_int64
         L.orc_trace_count.argtypes = [C.c_void_p]
         L.orc_overflowed.argtypes = [C.c_void_p]
@@ -162,6 +166,20 @@ class OracleSampler:
     def attach_trace(self, tr: TraceBuffers):
         self._keep.append(tr)
         lib().orc_attach_trace(self._h, _ptr(tr.slot), _ptr(tr.round), _ptr(tr.upd), tr.u_cap, tr.r_cap)
+
+    def attach_flat(self, log: np.ndarray):
+        """RNG_FLAT: consume a sequential log (raw u64 words in float64 bit patterns, normals by value)."""
+        log = np.ascontiguousarray(log, dtype=np.float64)
+        self._keep.append(log)
+        lib().orc_attach_flat(self._h, _ptr(log), log.size)
+
+    def record_flat(self, out: np.ndarray):
+        """RNG_SEQ: also write the sequential log RNG_FLAT consumes."""
+        self._keep.append(out)
+        lib().orc_record_flat(self._h, _ptr(out), out.size)
+
+    def flat_count(self):
+        return lib().orc_flat_count(self._h)
 
     def trace_count(self):
         return lib().orc_trace_count(self._h)
