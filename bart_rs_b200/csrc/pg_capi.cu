@@ -378,6 +378,8 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     st.root_tile_groups = 0;
     st.root_stages = 0;
     st.root_dbg = 0;
+    st.issue_ahead = 1;
+    if (const char* e = std::getenv("PGBART_ISSUE_AHEAD")) st.issue_ahead = std::atoi(e) != 0;
     if (const char* e = std::getenv("PGBART_ROOT_PASS")) st.root_ring = std::strcmp(e, "direct") == 0 ? 0 : std::strcmp(e, "ring") == 0 ? 1 : 2;
     if (const char* e = std::getenv("PGBART_ROOT_TILE_GROUPS")) st.root_tile_groups = std::atoi(e);
     if (const char* e = std::getenv("PGBART_ROOT_STAGES")) st.root_stages = std::atoi(e);
@@ -668,6 +670,7 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
     if (std::strcmp(key, "root_tile_groups") == 0) { s->st.root_tile_groups = std::atoi(value); return 0; }
     if (std::strcmp(key, "root_stages") == 0) { s->st.root_stages = std::atoi(value); return 0; }
     if (std::strcmp(key, "root_dbg") == 0) { s->st.root_dbg = std::atoi(value); return 0; }
+    if (std::strcmp(key, "issue_ahead") == 0) { s->st.issue_ahead = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "prune_dead_proposals") == 0) { s->st.prune = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "prefetch_next") == 0) { s->st.prefetch_next = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "pool_factor") == 0) {

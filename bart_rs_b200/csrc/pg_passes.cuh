@@ -163,11 +163,11 @@ struct PgSmem {
 // Dynamic shared memory of every kernel: [PgSmem][pass arrays sized by S][union area].  The union area holds, in the
 // control block (block 0 of the P <= 32 persistent kernels), its kernel-lifetime state PgFastSm and the staged split prior
 // / column min-max; in the pass blocks, which never touch that state, the same bytes are the staging ring of the root pass.
-//   pass arrays: double jvL[S], jvR[S]; double accA[PG_WARPS][S], accB[PG_WARPS][S]; unsigned accC[PG_WARPS][S];
+//   pass arrays: double jvL[S], jvR[S], jexp[4][S] (exp(+-vL), exp(+-vR): Bernoulli pass); double accA[PG_WARPS][S], accB[PG_WARPS][S]; unsigned accC[PG_WARPS][S];
 //                unsigned mmin[2S], mmax[2S]; int jvar[S]; float jthr[S]; int jorder[S]; int grp[S+1]
 __host__ __device__ inline size_t pg_smem_pass_bytes(int S) {
     size_t b = (sizeof(PgSmem) + 15) & ~(size_t)15;
-    b += (size_t)S * 16;                       // jvL, jvR
+    b += (size_t)S * 48;                       // jvL, jvR, jexp[4]
     b += (size_t)PG_WARPS * S * (8 + 8 + 4);   // accA, accB, accC
     b += (size_t)S * 16;                       // mmin, mmax (2S each)
     b += (size_t)S * (4 + 4 + 4) + (size_t)(S + 1) * 4;
@@ -180,7 +180,7 @@ __host__ __device__ inline size_t pg_smem_bytes(int S) { return pg_smem_pass_byt
 
 struct PgSmemView {
     PgSmem* base;
-    int* jvar; float* jthr; int* jorder; int* grp; double* jvL; double* jvR;
+    int* jvar; float* jthr; int* jorder; int* grp; double* jvL; double* jvR; double* jexp;
     double* accA; double* accB; unsigned* accC; unsigned* mmin; unsigned* mmax;
     PgFastSm* fast;            // control block only
     double* cprior; float* cmin; float* cmax;   // control block only
@@ -193,6 +193,7 @@ __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
     size_t off = (sizeof(PgSmem) + 15) & ~(size_t)15;
     v.jvL = reinterpret_cast<double*>(raw + off); off += (size_t)S * 8;
     v.jvR = reinterpret_cast<double*>(raw + off); off += (size_t)S * 8;
+    v.jexp = reinterpret_cast<double*>(raw + off); off += (size_t)S * 32;
     v.accA = reinterpret_cast<double*>(raw + off); off += (size_t)PG_WARPS * S * 8;
     v.accB = reinterpret_cast<double*>(raw + off); off += (size_t)PG_WARPS * S * 8;
     v.accC = reinterpret_cast<unsigned*>(raw + off); off += (size_t)PG_WARPS * S * 4;
@@ -292,7 +293,11 @@ __device__ __forceinline__ void pg_stage_jobs(const PgState& st, const PgBuf& bf
         sm.jvar[j] = __ldcg(&bf.job_var[j]);
         sm.jthr[j] = __ldcg(&bf.job_thr32[j]);
         sm.jorder[j] = __ldcg(&bf.job_order[j]);
-        if (with_values) { sm.jvL[j] = __ldcg(&bf.job_vL[j]); sm.jvR[j] = __ldcg(&bf.job_vR[j]); }
+        if (with_values) {
+            const double vL = __ldcg(&bf.job_vL[j]), vR = __ldcg(&bf.job_vR[j]);
+            sm.jvL[j] = vL; sm.jvR[j] = vR;
+            sm.jexp[4 * j + 0] = exp(vL); sm.jexp[4 * j + 1] = exp(-vL); sm.jexp[4 * j + 2] = exp(vR); sm.jexp[4 * j + 3] = exp(-vR);
+        }
     }
     for (int g = threadIdx.x; g <= G; g += blockDim.x) sm.grp[g] = __ldcg(&bf.grp_first[g]);
 }
@@ -921,6 +926,13 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
                 yv[k] = valid[k] ? __ldg(&st.y[idx[k]]) : 0.0f;
                 r[k] = valid[k] ? (double)yv[k] - o[k] : 0.0;
             }
+            // Bernoulli: exp(+-o) once per row, shared by every job of the group (pg_bern_term)
+            double eo[R], emo[R];
+            bool wide[R];
+            if (MODE == 1) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) { wide[k] = !(fabs(o[k]) < 300.0); eo[k] = wide[k] ? 0.0 : exp(o[k]); emo[k] = wide[k] ? 0.0 : exp(-o[k]); }
+            }
             for (int jb = jb0; jb < jb1; jb += 4) {
                 double va[4], vb[4];
                 int cn[4];
@@ -943,8 +955,8 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
                             b = fma(m, r[k], b);
                             cc += left ? 1 : 0;
                         } else if (ok) {
-                            const double mu = o[k] + (left ? sm.jvL[j] : sm.jvR[j]);
-                            const double f = (double)yv[k] * mu - pg_softplus(mu);
+                            const double* je = sm.jexp + 4 * j + (left ? 0 : 2);
+                            const double f = pg_bern_term((double)yv[k], o[k], left ? sm.jvL[j] : sm.jvR[j], eo[k], emo[k], je[0], je[1], wide[k]);
                             if (left) a += f; else b += f;
                         }
                     }

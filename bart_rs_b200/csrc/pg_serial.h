@@ -36,6 +36,21 @@ enum PgSerialNext : int { SN_NONE = 0, SN_BEGIN_UPDATE, SN_DRAW_ROUND, SN_FINISH
 #define PG_FOR(i, N) for (int i = tm.rank; i < (N); i += tm.size)
 #define PG_SINGLE if (tm.rank == 0)
 
+// The order-sensitive loops of the reference (normalisation, cumulative weights, resampling, selection) stay sequential
+// in one thread, but over a copy of the weights in the team's scratch memory (shared memory on the device), and everything
+// elementwise around them runs on the whole team: with 255 slots a single thread walking global arrays needed ~1 ms per
+// tree update (BASELINE C5), the staged version a few microseconds.
+#define PG_SCR_N 512      // slots / particles the scratch arrays hold; larger samplers work on the global arrays directly
+#if defined(__CUDA_ARCH__)
+#define PG_SCRATCH(type, name, count) __shared__ type name[count]
+PG_HD void pg_team_add(int* p, int v) { atomicAdd(p, v); }
+PG_HD void pg_team_max(int* p, int v) { atomicMax(p, v); }
+#else
+#define PG_SCRATCH(type, name, count) type name[count]
+PG_HD void pg_team_add(int* p, int v) { *p += v; }
+PG_HD void pg_team_max(int* p, int v) { if (v > *p) *p = v; }
+#endif
+
 PG_HD double pg_nan() {
     union { unsigned long long u; double d; } c;
     c.u = 0x7ff8000000000000ull;
@@ -89,6 +104,35 @@ PG_HD double pg_reduce_blocks(const double* base, int grid, size_t stride, size_
 }
 
 PG_HD double pg_softplus(double mu) { return fmax(mu, 0.0) + log1p(exp(-fabs(mu))); }
+
+// log(1 + t) for 0 <= t <= ~1 (t = exp(-|mu|) in the Bernoulli pass).  u = 1 + t carries its rounding error c
+// separately; u in (1, 2] is halved above sqrt 2 so that s = (u - 1) / (u + 1) stays within +-0.1716, and
+// log u = 2 atanh s = 2 s (1 + s^2/3 + ... + s^22/23).  Measured against long double over 2e7 arguments: <= 2.5 ulp,
+// <= 1.2e-16 absolute (the quantity that matters: the result is added to max(mu, 0)).
+PG_HD double pg_log1p_unit(double t) {
+    const double u = 1.0 + t;
+    const double c = t - (u - 1.0);
+    const bool hi = u > 1.4142135623730951;
+    const double v = hi ? 0.5 * u : u;
+    const double s = (v - 1.0) / (v + 1.0);
+    const double z = s * s;
+    double p = 1.0 / 23.0;
+    p = fma(p, z, 1.0 / 21.0); p = fma(p, z, 1.0 / 19.0); p = fma(p, z, 1.0 / 17.0); p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0); p = fma(p, z, 1.0 / 11.0); p = fma(p, z, 1.0 / 9.0); p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0); p = fma(p, z, 1.0 / 3.0);
+    const double r = fma(2.0 * s * z, p, 2.0 * s);
+    return (hi ? 0.6931471805599453 : 0.0) + (r + c / u);
+}
+
+// y mu - softplus(mu) for mu = o + v when exp(+-o) (per row) and exp(+-v) (per job and child) are already known:
+// exp(-|mu|) = mu >= 0 ? exp(-o) exp(-v) : exp(o) exp(v), so a row-job costs two multiplications and one log1p instead
+// of an exp and a log1p.  `wide` rows (|o| beyond the range where exp(+-o) is safely finite) take the direct formula.
+PG_HD double pg_bern_term(double y, double o, double v, double eo, double emo, double ev, double emv, bool wide) {
+    const double mu = o + v;
+    if (wide) return y * mu - pg_softplus(mu);
+    const double t = mu >= 0.0 ? emo * emv : eo * ev;
+    return y * mu - (fmax(mu, 0.0) + pg_log1p_unit(t));
+}
 
 // ---------------------------------------------------------------------------
 
@@ -520,36 +564,61 @@ PG_HDN inline void pg_s_finish_round(const PgState& st, const PgTeam& tm) {
     PgCtrl* c = st.ctrl;
     const int S = st.S;
     const int src = c->cur, dst = 1 - c->cur;
+    PG_SCRATCH(double, s_w, PG_SCR_N);
+    PG_SCRATCH(int, s_anc, PG_SCR_N);
+    PG_SCRATCH(double, s_red, 2);
+    PG_SCRATCH(int, s_ired, 2);
+    const bool staged = S <= PG_SCR_N;
+    double* w = staged ? s_w : st.w;
+    int* anc = staged ? s_anc : st.anc;
+    PG_SINGLE { s_ired[0] = 0; s_ired[1] = 1; }
+    if (staged) { PG_FOR(s, S) w[s] = st.w[s]; }
+    tm.sync();
+    {   // mutated slots and the largest slot tree: integer partial results, order-free
+        int nm = 0, mz = 1;
+        PG_FOR(s, S) { nm += st.mutated[s]; const int z = st.pt_size[pg_six(st, src, s)]; mz = z > mz ? z : mz; }
+        pg_team_add(&s_ired[0], nm);
+        pg_team_max(&s_ired[1], mz);
+    }
+    // smc.rs:257-268.  w[] keeps last round's normalised values for slots that did not mutate.
     PG_SINGLE {
-        int n_mut = 0;
-        for (int s = 0; s < S; ++s) n_mut += st.mutated[s];
-        c->acc_update += n_mut;
-        // smc.rs:257-268.  w[] keeps last round's normalised values for slots that did not mutate.
         double mx = -INFINITY;
-        for (int s = 0; s < S; ++s) mx = fmax(mx, st.w[s]);
-        for (int s = 0; s < S; ++s) st.w[s] = exp(st.w[s] - mx);
+        for (int s = 0; s < S; ++s) mx = fmax(mx, w[s]);
+        s_red[0] = mx;
+    }
+    tm.sync();
+    { const double mx = s_red[0]; PG_FOR(s, S) w[s] = exp(w[s] - mx); }
+    tm.sync();
+    PG_SINGLE {
         double sum = 0.0;
-        for (int s = 0; s < S; ++s) sum += st.w[s];
-        for (int s = 0; s < S; ++s) st.w[s] /= sum;
+        for (int s = 0; s < S; ++s) sum += w[s];      // sequential, in slot order, like the reference's iter().sum()
+        s_red[1] = sum;
+    }
+    tm.sync();
+    { const double sum = s_red[1]; PG_FOR(s, S) w[s] /= sum; }
+    tm.sync();
+    PG_SINGLE {
+        const int n_mut = s_ired[0];
+        c->acc_update += n_mut;
         // resampling.rs:24-44
         const double u6 = pg_uniform(st, PG_D_RESAMPLE, c->upd, c->round, 0);
         int cidx = 0;
         double cum = 0.0;
         for (int i = 0; i < S; ++i) {
             const double target = ((double)i + u6) / (double)S;
-            while (cum < target && cidx < S) { cum += st.w[cidx]; cidx += 1; }
-            st.anc[i] = cidx == 0 ? 0 : cidx - 1;
+            while (cum < target && cidx < S) { cum += w[cidx]; cidx += 1; }
+            anc[i] = cidx == 0 ? 0 : cidx - 1;
         }
-        if (st.tr_round) {
-            if ((long long)c->trace_n < st.tr_u_cap && c->round < st.tr_r_cap) {
-                double* tr = st.tr_round + ((size_t)c->trace_n * st.tr_r_cap + c->round) * (size_t)(2 + 2 * S);
-                tr[0] = 1; tr[1] = (double)n_mut;
-                for (int s = 0; s < S; ++s) { tr[2 + s] = st.w[s]; tr[2 + S + s] = (double)st.anc[s]; }
-            } else c->trace_overflow = 1;
-        }
-        int mxs = 1;
-        for (int s = 0; s < S; ++s) { const int z = st.pt_size[pg_six(st, src, s)]; mxs = z > mxs ? z : mxs; }
-        c->max_size = mxs;
+        c->max_size = s_ired[1];
+    }
+    tm.sync();
+    if (staged) { PG_FOR(s, S) { st.w[s] = w[s]; st.anc[s] = anc[s]; } }
+    if (st.tr_round) {
+        if ((long long)c->trace_n < st.tr_u_cap && c->round < st.tr_r_cap) {
+            double* tr = st.tr_round + ((size_t)c->trace_n * st.tr_r_cap + c->round) * (size_t)(2 + 2 * S);
+            PG_SINGLE { tr[0] = 1; tr[1] = (double)s_ired[0]; }
+            PG_FOR(s, S) { tr[2 + s] = w[s]; tr[2 + S + s] = (double)anc[s]; }
+        } else { PG_SINGLE { c->trace_overflow = 1; } }
     }
     tm.sync();
     // smc.rs:99-102: slot i becomes a copy of slot anc[i] (tree, queue, per-node tables).
@@ -573,26 +642,39 @@ PG_HDN inline void pg_s_finish_round(const PgState& st, const PgTeam& tm) {
         st.pj_of_anc[i] = -1;
     }
     tm.sync();
+    {   // does any slot still have queued nodes / did any surviving ancestor grow?  (order-free: the whole team looks)
+        PG_SINGLE { s_ired[0] = 0; s_ired[1] = 0; }
+        tm.sync();
+        int aq = 0, am = 0;
+        PG_FOR(i, S) {
+            const int ts = pg_six(st, dst, i);
+            if (st.pt_qhead[ts] < st.pt_qtail[ts]) aq = 1;
+            if (st.mutated[st.anc[i]]) am = 1;
+        }
+        pg_team_max(&s_ired[0], aq);
+        pg_team_max(&s_ired[1], am);
+        tm.sync();
+    }
     PG_SINGLE {
         c->cur = dst;
         // Survivors that grew this round need their children's index lists: one stable partition per
-        // distinct surviving ancestor (particles that died are never materialised).
+        // distinct surviving ancestor (particles that died are never materialised), in order of first appearance.
         int K = 0;
-        int any_queue = 0;
-        for (int i = 0; i < S; ++i) {
-            const int a = st.anc[i];
-            const int ts = pg_six(st, dst, i);
-            if (st.pt_qhead[ts] < st.pt_qtail[ts]) any_queue = 1;
-            if (!st.mutated[a] || st.pj_of_anc[a] >= 0) continue;
-            const int j = st.slot_job[a];
-            st.pj_of_anc[a] = K;
-            st.pj_anc[K] = a; st.pj_job[K] = j; st.pj_var[K] = st.job_var[j]; st.pj_thr32[K] = st.job_thr32[j];
-            st.pj_src_off[K] = st.job_seg_off[j]; st.pj_len[K] = st.job_len[j];
-            st.pj_cntL[K] = (unsigned int)st.red_cnt[j];
-            if (c->pool_top + st.job_len[j] > st.pool_cap) { c->error = PG_ERR_POOL; }
-            st.pj_dst_off[K] = (unsigned int)c->pool_top;
-            c->pool_top += st.job_len[j];
-            ++K;
+        const int any_queue = s_ired[0];
+        if (s_ired[1]) {
+            for (int i = 0; i < S; ++i) {
+                const int a = st.anc[i];
+                if (!st.mutated[a] || st.pj_of_anc[a] >= 0) continue;
+                const int j = st.slot_job[a];
+                st.pj_of_anc[a] = K;
+                st.pj_anc[K] = a; st.pj_job[K] = j; st.pj_var[K] = st.job_var[j]; st.pj_thr32[K] = st.job_thr32[j];
+                st.pj_src_off[K] = st.job_seg_off[j]; st.pj_len[K] = st.job_len[j];
+                st.pj_cntL[K] = (unsigned int)st.red_cnt[j];
+                if (c->pool_top + st.job_len[j] > st.pool_cap) { c->error = PG_ERR_POOL; }
+                st.pj_dst_off[K] = (unsigned int)c->pool_top;
+                c->pool_top += st.job_len[j];
+                ++K;
+            }
         }
         c->n_pjobs = K;
         c->any_queue = any_queue;
@@ -661,16 +743,30 @@ PG_HDN inline void pg_s_after_part(const PgState& st, const PgTeam& tm) {
 PG_HDN inline void pg_s_finalize(const PgState& st, const PgTeam& tm) {
     PgCtrl* c = st.ctrl;
     const int P = st.P, S = st.S, cur = c->cur, t = c->t_cur;
+    PG_SCRATCH(double, s_W, 2 * PG_SCR_N);
+    PG_SCRATCH(double, s_fr, 2);
+    const bool staged = P <= PG_SCR_N;
+    double* W = staged ? s_W : st.Wfinal;       // [0,P) log-likelihoods, [P,2P) normalised
+    PG_SINGLE { W[0] = c->C0 + c->g_stump; }   // the reference particle is a fresh stump (Q2)
+    PG_FOR(s_, S) W[1 + s_] = c->C0 + st.pt_G[pg_six(st, cur, s_)];
+    tm.sync();
     PG_SINGLE {
-        double* W = st.Wfinal;       // [0,P) log-likelihoods, [P,2P) normalised
-        W[0] = c->C0 + c->g_stump;   // the reference particle is a fresh stump (Q2)
-        for (int s = 0; s < S; ++s) W[1 + s] = c->C0 + st.pt_G[pg_six(st, cur, s)];
         double mx = -INFINITY;
         for (int i = 0; i < P; ++i) mx = fmax(mx, W[i]);
-        for (int i = 0; i < P; ++i) W[P + i] = exp(W[i] - mx);
+        s_fr[0] = mx;
+    }
+    tm.sync();
+    { const double mx = s_fr[0]; PG_FOR(i, P) W[P + i] = exp(W[i] - mx); }
+    tm.sync();
+    PG_SINGLE {
         double sum = 0.0;
-        for (int i = 0; i < P; ++i) sum += W[P + i];
-        for (int i = 0; i < P; ++i) W[P + i] /= sum;
+        for (int i = 0; i < P; ++i) sum += W[P + i];      // sequential, in particle order (smc.rs:257-268)
+        s_fr[1] = sum;
+    }
+    tm.sync();
+    { const double sum = s_fr[1]; PG_FOR(i, P) W[P + i] /= sum; }
+    tm.sync();
+    PG_SINGLE {
         // rand WeightedIndex: cumulative weights without the last, uniform in [0,total), count of cum <= chosen
         double total = 0.0;
         for (int i = 0; i < P; ++i) total += W[P + i];
@@ -686,13 +782,14 @@ PG_HDN inline void pg_s_finalize(const PgState& st, const PgTeam& tm) {
         c->any_queue = sel;   // reused as "selected particle" for the copy below
         c->info_loglik += W[P + 0];
         c->info_acc += c->acc_update;
-        if (st.tr_upd) {
-            if ((long long)c->trace_n < st.tr_u_cap) {
-                double* tr = st.tr_upd + (size_t)c->trace_n * (size_t)(4 + 2 * P);
-                tr[0] = (double)(c->round + 1); tr[1] = (double)sel; tr[2] = (double)t; tr[3] = (double)c->acc_update;
-                for (int i = 0; i < 2 * P; ++i) tr[4 + i] = W[i];
-            } else c->trace_overflow = 1;
-        }
+    }
+    if (st.tr_upd) {
+        tm.sync();
+        if ((long long)c->trace_n < st.tr_u_cap) {
+            double* tr = st.tr_upd + (size_t)c->trace_n * (size_t)(4 + 2 * P);
+            PG_SINGLE { tr[0] = (double)(c->round + 1); tr[1] = (double)c->any_queue; tr[2] = (double)t; tr[3] = (double)c->acc_update; }
+            PG_FOR(i, 2 * P) tr[4 + i] = W[i];
+        } else { PG_SINGLE { c->trace_overflow = 1; } }
     }
     tm.sync();
     const int sel = c->any_queue;

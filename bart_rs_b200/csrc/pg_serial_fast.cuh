@@ -1842,8 +1842,8 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                     // an update just started (its root pass was issued, or adopted): stage the jobs of the update after it and,
                     // if this one is expected to end as a stump (some slot proposes nothing: Q1), issue that update's root pass
                     fw_prestage(st, x, lane);
-                    if (!f->spec_now && fw_issue_prestaged(st, x, lane)) { if (lane == 0) f->spec_now = 1; }
-                } else if (c->phase == PH_STATS && !f->spec_now) {
+                    if (st.issue_ahead && !f->spec_now && fw_issue_prestaged(st, x, lane)) { if (lane == 0) f->spec_now = 1; }
+                } else if (st.issue_ahead && c->phase == PH_STATS && !f->spec_now) {
                     // early commit: the statistics pass just issued is normally the update's last data pass and the outcome was
                     // predicted after round 0: the next update's root pass on the predicted tree goes right behind it
                     if (fw_issue_predicted(st, x, lane)) { if (lane == 0) f->spec_now = 1; }

@@ -166,6 +166,7 @@ struct PgState {
                                  // 2 = ring when a pass block holds at most 2048 rows, else direct (default)
     int root_tile_groups;        // ring root pass: cap on the row groups (128 rows) per tile, 0 = as many as fit (<= 8)
     int root_stages;             // ring root pass: cap on the stages of the ring, 0 = as many as fit
+    int issue_ahead;             // P <= 32 control block: 1 (default) = the next update's root pass is issued right behind the pass in progress
     int root_dbg;                // ring root pass, timing experiments only (results are wrong): 1 no proxy fence in the loop, 2 no job loop, 4 no row work at all
     // data
     const float* X;

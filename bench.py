@@ -362,6 +362,13 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = peaks()
         k = args.steps
+        # which persistent kernel ran (pg_launch_persistent, csrc/pg_sweep.cu): one per pass variant
+        if w["P"] > 32:
+            kernel_name = "pg_sweep_persistent_generic"
+        elif w["family"] == "bernoulli_logit":
+            kernel_name = "pg_sweep_persistent_bern"
+        else:
+            kernel_name = "pg_sweep_persistent_ring" if X.shape[0] <= c1["grid_blocks"] * 2048 else "pg_sweep_persistent_direct"
         bytes_per_launch = (c1["bytes_model"] - c0["bytes_model"]) / k
         contract_per_launch = (c1["bytes_contract"] - c0["bytes_contract"]) / k
         fused_gbs = bytes_per_launch / (ms / 1000.0 / k) / 1e9
@@ -386,7 +393,7 @@ def run_gpu(args):
             "config": config_for(args.workload, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": "pg_sweep_persistent_direct (one launch = one sweep = m tree updates)"
+                         "kernel": kernel_name + " (one launch = one sweep = m tree updates)"
                                    + (f"; rank 0 of {world}: bytes of its own rows, per-GPU figure" if sharded else ""),
                          "algorithmic_bytes_per_launch": contract_per_launch,
                          "fused_bytes_per_launch": bytes_per_launch, "fused_gbs": fused_gbs, "fused_frac": fused_gbs / peak,

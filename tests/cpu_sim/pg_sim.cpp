@@ -141,8 +141,10 @@ void pass_seg(const PgState& st, int mode) {
                     if (mode == 0) {
                         if (left) { a += o; bb += yv - o; cc += 1; wc += 1; }
                     } else {
-                        const double mu = o + (left ? st.job_vL[j] : st.job_vR[j]);
-                        const double f = yv * mu - pg_softplus(mu);
+                        // the device pass's arithmetic (pg_bern_term): exp(+-o) per row, exp(+-v) per job and child
+                        const double v = left ? st.job_vL[j] : st.job_vR[j];
+                        const bool wide = !(std::fabs(o) < 300.0);
+                        const double f = pg_bern_term(yv, o, v, wide ? 0.0 : std::exp(o), wide ? 0.0 : std::exp(-o), std::exp(v), std::exp(-v), wide);
                         if (left) a += f; else bb += f;
                     }
                 }
