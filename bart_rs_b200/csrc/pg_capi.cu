@@ -421,6 +421,14 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         if (!ck(s, cudaMemcpy(dt, thr.data(), thr.size() * 8, cudaMemcpyHostToDevice), "upload thr")) return bail();
         st.thr_depth = dt;
     }
+    {
+        double tbl[2 * PG_LOGT_K];
+        pg_log_table_fill(tbl);
+        double* dt = nullptr;
+        if (!dalloc(s, &dt, 2 * PG_LOGT_K, false)) return bail();
+        if (!ck(s, cudaMemcpy(dt, tbl, sizeof tbl, cudaMemcpyHostToDevice), "upload log table")) return bail();
+        st.log_tbl = dt;
+    }
     // ---- state arrays
     const size_t S = (size_t)st.S, MN = (size_t)st.maxn, M = (size_t)st.m, G = (size_t)st.grid, W = (size_t)st.n_gwarps;
     bool ok = dalloc(s, &st.A, (size_t)st.ld) && dalloc(s, &st.A2, (size_t)st.ld)

@@ -163,11 +163,11 @@ struct PgSmem {
 // Dynamic shared memory of every kernel: [PgSmem][pass arrays sized by S][union area].  The union area holds, in the
 // control block (block 0 of the P <= 32 persistent kernels), its kernel-lifetime state PgFastSm and the staged split prior
 // / column min-max; in the pass blocks, which never touch that state, the same bytes are the staging ring of the root pass.
-//   pass arrays: double jvL[S], jvR[S], jexp[4][S] (exp(+-vL), exp(+-vR): Bernoulli pass); double accA[PG_WARPS][S], accB[PG_WARPS][S]; unsigned accC[PG_WARPS][S];
+//   pass arrays: double jvL[S], jvR[S], jexp[2][S] (exp(vL), exp(vR): Bernoulli pass); double accA[PG_WARPS][S], accB[PG_WARPS][S]; unsigned accC[PG_WARPS][S];
 //                unsigned mmin[2S], mmax[2S]; int jvar[S]; float jthr[S]; int jorder[S]; int grp[S+1]
 __host__ __device__ inline size_t pg_smem_pass_bytes(int S) {
     size_t b = (sizeof(PgSmem) + 15) & ~(size_t)15;
-    b += (size_t)S * 48;                       // jvL, jvR, jexp[4]
+    b += (size_t)S * 32;                       // jvL, jvR, jexp[2]
     b += (size_t)PG_WARPS * S * (8 + 8 + 4);   // accA, accB, accC
     b += (size_t)S * 16;                       // mmin, mmax (2S each)
     b += (size_t)S * (4 + 4 + 4) + (size_t)(S + 1) * 4;
@@ -193,7 +193,7 @@ __device__ __forceinline__ PgSmemView pg_smem_view(unsigned char* raw, int S) {
     size_t off = (sizeof(PgSmem) + 15) & ~(size_t)15;
     v.jvL = reinterpret_cast<double*>(raw + off); off += (size_t)S * 8;
     v.jvR = reinterpret_cast<double*>(raw + off); off += (size_t)S * 8;
-    v.jexp = reinterpret_cast<double*>(raw + off); off += (size_t)S * 32;
+    v.jexp = reinterpret_cast<double*>(raw + off); off += (size_t)S * 16;
     v.accA = reinterpret_cast<double*>(raw + off); off += (size_t)PG_WARPS * S * 8;
     v.accB = reinterpret_cast<double*>(raw + off); off += (size_t)PG_WARPS * S * 8;
     v.accC = reinterpret_cast<unsigned*>(raw + off); off += (size_t)PG_WARPS * S * 4;
@@ -296,7 +296,7 @@ __device__ __forceinline__ void pg_stage_jobs(const PgState& st, const PgBuf& bf
         if (with_values) {
             const double vL = __ldcg(&bf.job_vL[j]), vR = __ldcg(&bf.job_vR[j]);
             sm.jvL[j] = vL; sm.jvR[j] = vR;
-            sm.jexp[4 * j + 0] = exp(vL); sm.jexp[4 * j + 1] = exp(-vL); sm.jexp[4 * j + 2] = exp(vR); sm.jexp[4 * j + 3] = exp(-vR);
+            sm.jexp[2 * j + 0] = pg_bern_exp(vL); sm.jexp[2 * j + 1] = pg_bern_exp(vR);
         }
     }
     for (int g = threadIdx.x; g <= G; g += blockDim.x) sm.grp[g] = __ldcg(&bf.grp_first[g]);
@@ -898,6 +898,14 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
     const int gw = PG_BID * PG_WARPS + warp;
     pg_stage_jobs(st, bf, sm, J, G, MODE == 1);
     pg_zero_acc(sm, S);
+    // Bernoulli: the logarithm table, PG_LOGT_REP copies, in the union area (idle outside the root pass)
+    double* ltab = reinterpret_cast<double*>(sm.stage);
+    if (MODE == 1)
+        for (int i = threadIdx.x; i < PG_LOGT_K * PG_LOGT_REP; i += blockDim.x) {
+            const int k = i / PG_LOGT_REP;
+            ltab[2 * i + 0] = __ldg(&st.log_tbl[2 * k + 0]);
+            ltab[2 * i + 1] = __ldg(&st.log_tbl[2 * k + 1]);
+        }
     __syncthreads();
     const size_t ld = (size_t)st.ld;
     constexpr int R = 4;   // entries per lane per iteration
@@ -926,12 +934,11 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
                 yv[k] = valid[k] ? __ldg(&st.y[idx[k]]) : 0.0f;
                 r[k] = valid[k] ? (double)yv[k] - o[k] : 0.0;
             }
-            // Bernoulli: exp(+-o) once per row, shared by every job of the group (pg_bern_term)
-            double eo[R], emo[R];
-            bool wide[R];
+            // Bernoulli: exp(o) once per row, shared by every job of the group (pg_bern_term)
+            double eo[R];
             if (MODE == 1) {
 #pragma unroll
-                for (int k = 0; k < R; ++k) { wide[k] = !(fabs(o[k]) < 300.0); eo[k] = wide[k] ? 0.0 : exp(o[k]); emo[k] = wide[k] ? 0.0 : exp(-o[k]); }
+                for (int k = 0; k < R; ++k) eo[k] = pg_bern_exp(o[k]);
             }
             for (int jb = jb0; jb < jb1; jb += 4) {
                 double va[4], vb[4];
@@ -944,6 +951,8 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
                     const float thr = sm.jthr[j];
                     double a = 0.0, b = 0.0;
                     int cc = 0;
+                    double vL = 0.0, vR = 0.0, evL = 1.0, evR = 1.0;
+                    if (MODE == 1) { vL = sm.jvL[j]; vR = sm.jvR[j]; evL = sm.jexp[2 * j]; evR = sm.jexp[2 * j + 1]; }
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
                         const bool ok = live && valid[k];
@@ -954,10 +963,11 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
                             a = fma(m, o[k], a);
                             b = fma(m, r[k], b);
                             cc += left ? 1 : 0;
-                        } else if (ok) {
-                            const double* je = sm.jexp + 4 * j + (left ? 0 : 2);
-                            const double f = pg_bern_term((double)yv[k], o[k], left ? sm.jvL[j] : sm.jvR[j], eo[k], emo[k], je[0], je[1], wide[k]);
-                            if (left) a += f; else b += f;
+                        } else {
+                            // invalid rows / dead job slots carry o = y = 0 (a finite term) and get mask 0 on both sides
+                            const double f = pg_bern_term<PG_LOGT_REP>((double)yv[k], o[k], left ? vL : vR, eo[k], left ? evL : evR, ltab, lane & (PG_LOGT_REP - 1));
+                            a = fma(left ? 1.0 : 0.0, f, a);
+                            b = fma((ok && !left) ? 1.0 : 0.0, f, b);
                         }
                     }
                     va[q] = a; vb[q] = b; cn[q] = cc;

@@ -20,6 +20,7 @@
 #include "pg_types.h"
 #include "pg_rng.h"
 #include <math.h>
+#include <string.h>
 
 struct PgTeam {
     int rank, size;
@@ -45,11 +46,20 @@ enum PgSerialNext : int { SN_NONE = 0, SN_BEGIN_UPDATE, SN_DRAW_ROUND, SN_FINISH
 #define PG_SCRATCH(type, name, count) __shared__ type name[count]
 PG_HD void pg_team_add(int* p, int v) { atomicAdd(p, v); }
 PG_HD void pg_team_max(int* p, int v) { atomicMax(p, v); }
+PG_HD void pg_team_add64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 #else
 #define PG_SCRATCH(type, name, count) type name[count]
 PG_HD void pg_team_add(int* p, int v) { *p += v; }
 PG_HD void pg_team_max(int* p, int v) { if (v > *p) *p = v; }
+PG_HD void pg_team_add64(unsigned long long* p, unsigned long long v) { *p += v; }
 #endif
+// Number of set flags before position i (flags in scratch memory): the ordered compaction of a few hundred entries is
+// done by every member summing its own prefix from shared memory, a microsecond, instead of one thread walking global arrays.
+PG_HD int pg_flags_before(const int* flag, int i) {
+    int n = 0;
+    for (int q = 0; q < i; ++q) n += flag[q];
+    return n;
+}
 
 PG_HD double pg_nan() {
     union { unsigned long long u; double d; } c;
@@ -105,33 +115,49 @@ PG_HD double pg_reduce_blocks(const double* base, int grid, size_t stride, size_
 
 PG_HD double pg_softplus(double mu) { return fmax(mu, 0.0) + log1p(exp(-fabs(mu))); }
 
-// log(1 + t) for 0 <= t <= ~1 (t = exp(-|mu|) in the Bernoulli pass).  u = 1 + t carries its rounding error c
-// separately; u in (1, 2] is halved above sqrt 2 so that s = (u - 1) / (u + 1) stays within +-0.1716, and
-// log u = 2 atanh s = 2 s (1 + s^2/3 + ... + s^22/23).  Measured against long double over 2e7 arguments: <= 2.5 ulp,
-// <= 1.2e-16 absolute (the quantity that matters: the result is added to max(mu, 0)).
-PG_HD double pg_log1p_unit(double t) {
-    const double u = 1.0 + t;
-    const double c = t - (u - 1.0);
-    const bool hi = u > 1.4142135623730951;
-    const double v = hi ? 0.5 * u : u;
-    const double s = (v - 1.0) / (v + 1.0);
-    const double z = s * s;
-    double p = 1.0 / 23.0;
-    p = fma(p, z, 1.0 / 21.0); p = fma(p, z, 1.0 / 19.0); p = fma(p, z, 1.0 / 17.0); p = fma(p, z, 1.0 / 15.0);
-    p = fma(p, z, 1.0 / 13.0); p = fma(p, z, 1.0 / 11.0); p = fma(p, z, 1.0 / 9.0); p = fma(p, z, 1.0 / 7.0);
-    p = fma(p, z, 1.0 / 5.0); p = fma(p, z, 1.0 / 3.0);
-    const double r = fma(2.0 * s * z, p, 2.0 * s);
-    return (hi ? 0.6931471805599453 : 0.0) + (r + c / u);
+// ---- log(u) for finite u >= 1: table + polynomial (Bernoulli pass) -------------------------------------------------
+// u = m 2^e with m in [1, 2).  Entry k (the top 6 mantissa bits of m) holds (inv_k, -log inv_k) with inv_k ~ 1 / (1 + (k +
+// 0.5) / 64) rounded to 12 fractional bits, so r = fma(m, inv_k, -1) is rounded once and |r| <= 0.0081;
+// log u = e ln 2 - log inv_k + log1p(r), log1p(r) = r - r^2/2 + ... + r^7/7 (truncation <= r^8/8 = 2.3e-18).  Against long
+// double over 1e7 arguments: <= 1.1e-16 absolute for u in [1, 2], <= 1.3 ulp beyond.  Nine FMAs, no division, no exp.
+// tbl: entry k of copy `rep` at tbl[(k * REP + rep) * 2]
+template <int REP>
+PG_HD double pg_log_ge1(double u, const double* tbl, int rep) {
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(u);
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(u));
+    const double2 t = *reinterpret_cast<const double2*>(tbl + (size_t)((((hi >> 14) & (PG_LOGT_K - 1)) * REP + rep) * 2));
+    const double inv = t.x, lc = t.y;
+#else
+    unsigned long long bits;
+    memcpy(&bits, &u, 8);
+    const int hi = (int)(bits >> 32);
+    const unsigned long long mb = (bits & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
+    double m;
+    memcpy(&m, &mb, 8);
+    const double* t = tbl + (size_t)((((hi >> 14) & (PG_LOGT_K - 1)) * REP + rep) * 2);
+    const double inv = t[0], lc = t[1];
+#endif
+    const double e = (double)((hi >> 20) - 1023);
+    const double r = fma(m, inv, -1.0);
+    double p = 1.0 / 7.0;
+    p = fma(p, r, -1.0 / 6.0); p = fma(p, r, 0.2); p = fma(p, r, -0.25); p = fma(p, r, 1.0 / 3.0); p = fma(p, r, -0.5);
+    p = fma(p, r, 1.0);
+    return fma(p, r, fma(e, 0.6931471805599453, lc));
 }
 
-// y mu - softplus(mu) for mu = o + v when exp(+-o) (per row) and exp(+-v) (per job and child) are already known:
-// exp(-|mu|) = mu >= 0 ? exp(-o) exp(-v) : exp(o) exp(v), so a row-job costs two multiplications and one log1p instead
-// of an exp and a log1p.  `wide` rows (|o| beyond the range where exp(+-o) is safely finite) take the direct formula.
-PG_HD double pg_bern_term(double y, double o, double v, double eo, double emo, double ev, double emv, bool wide) {
+// exp(o) of a row / exp(v) of a leaf value for pg_bern_term; +inf marks "outside the range where the product form is
+// safe" and sends the term to the direct formula
+PG_HD double pg_bern_exp(double z) { return fabs(z) < 300.0 ? exp(z) : INFINITY; }
+
+// y mu - softplus(mu) for mu = o + v with eo = pg_bern_exp(o) (once per row) and ev = pg_bern_exp(v) (once per job and
+// child): softplus(mu) = log(1 + exp(o) exp(v)), one FMA and one table logarithm instead of an exp and a log1p per row-job.
+template <int REP>
+PG_HD double pg_bern_term(double y, double o, double v, double eo, double ev, const double* tbl, int rep) {
     const double mu = o + v;
-    if (wide) return y * mu - pg_softplus(mu);
-    const double t = mu >= 0.0 ? emo * emv : eo * ev;
-    return y * mu - (fmax(mu, 0.0) + pg_log1p_unit(t));
+    const double u = fma(eo, ev, 1.0);
+    if (!(u < 1e300)) return y * mu - pg_softplus(mu);
+    return y * mu - pg_log_ge1<REP>(u, tbl, rep);
 }
 
 // ---------------------------------------------------------------------------
@@ -311,18 +337,39 @@ PG_HDN inline void pg_s_draw_round(const PgState& st, const PgTeam& tm) {
         st.pend_var[s] = var;
     }
     tm.sync();
-    PG_SINGLE {
-        int J = 0;
-        for (int s = 0; s < st.S; ++s) {
-            if (st.pend_node[s] < 0) continue;
-            const int node = st.pend_node[s];
-            const size_t iN = pg_tix(st, cur, s, node);
-            st.job_slot[J] = s; st.job_node[J] = node; st.job_var[J] = st.pend_var[s];
-            st.job_seg_off[J] = st.pt_seg_off[iN]; st.job_len[J] = st.pt_cnt[iN];
-            st.slot_job[s] = J;
-            ++J;
+    PG_SCRATCH(int, s_flag, PG_SCR_N);
+    PG_SCRATCH(int, s_var, PG_SCR_N);
+    PG_SCRATCH(int, s_cnt, 2);
+    const bool staged = st.S <= PG_SCR_N;
+    if (staged) {
+        // jobs in slot order: each proposing slot finds its job number from the flags before it
+        PG_FOR(s, st.S) s_flag[s] = st.pend_node[s] >= 0 ? 1 : 0;
+        tm.sync();
+        PG_FOR(s, st.S) {
+            const int J = pg_flags_before(s_flag, s);
+            if (s_flag[s]) {
+                const int node = st.pend_node[s];
+                const size_t iN = pg_tix(st, cur, s, node);
+                st.job_slot[J] = s; st.job_node[J] = node; st.job_var[J] = st.pend_var[s];
+                st.job_seg_off[J] = st.pt_seg_off[iN]; st.job_len[J] = st.pt_cnt[iN];
+                st.slot_job[s] = J;
+            }
+            if (s == st.S - 1) c->n_jobs = J + s_flag[s];
         }
-        c->n_jobs = J;
+    } else {
+        PG_SINGLE {
+            int J = 0;
+            for (int s = 0; s < st.S; ++s) {
+                if (st.pend_node[s] < 0) continue;
+                const int node = st.pend_node[s];
+                const size_t iN = pg_tix(st, cur, s, node);
+                st.job_slot[J] = s; st.job_node[J] = node; st.job_var[J] = st.pend_var[s];
+                st.job_seg_off[J] = st.pt_seg_off[iN]; st.job_len[J] = st.pt_cnt[iN];
+                st.slot_job[s] = J;
+                ++J;
+            }
+            c->n_jobs = J;
+        }
     }
     tm.sync();
     const int J = c->n_jobs;
@@ -334,12 +381,49 @@ PG_HDN inline void pg_s_draw_round(const PgState& st, const PgTeam& tm) {
             pg_decide_split(st, j);
         }
         tm.sync();
+        // Dropped jobs (constant column) are rare: the team counts them and the distinct split variables; only when a
+        // job was dropped does one thread compact the list.  All round-1 jobs share the root's identity segment: one group.
+        int fast_cols = -1;
+        if (staged) {
+            PG_SINGLE { s_cnt[0] = 0; s_cnt[1] = 0; }
+            PG_FOR(j, J) s_var[j] = st.job_node[j] >= 0 ? st.job_var[j] : -1;
+            tm.sync();
+            {
+                int dropped = 0, uniq = 0;
+                PG_FOR(j, J) {
+                    const int v = s_var[j];
+                    if (v < 0) { dropped += 1; continue; }
+                    // position of job j when the jobs are ordered by split variable (stable): consecutive jobs of the
+                    // segment passes then read the same column (one group: every round-1 job is on the root's rows)
+                    int before = 0, same_before = 0;
+                    for (int q = 0; q < J; ++q) {
+                        const int vq = s_var[q];
+                        before += (vq < v) ? 1 : 0;
+                        same_before += (vq == v && q < j) ? 1 : 0;
+                    }
+                    if (same_before == 0) uniq += 1;
+                    st.job_order[before + same_before] = j;
+                }
+                pg_team_add(&s_cnt[0], dropped);
+                pg_team_add(&s_cnt[1], uniq);
+            }
+            tm.sync();
+            if (s_cnt[0] == 0) fast_cols = s_cnt[1];
+        }
         PG_SINGLE {
             const int J0 = c->n_jobs;
-            pg_compact_jobs_single(st);
-            pg_group_jobs_single(st);
+            int ucols;
+            if (fast_cols >= 0) {
+                st.grp_first[0] = 0; st.grp_first[J0 > 0 ? 1 : 0] = J0;
+                c->n_groups = J0 > 0 ? 1 : 0;
+                ucols = fast_cols;
+            } else {
+                pg_compact_jobs_single(st);
+                pg_group_jobs_single(st);
+                ucols = pg_count_unique_vars(st);
+            }
             const unsigned long long n = (unsigned long long)st.n;
-            const int cols = pg_count_unique_vars(st) + pg_tree_internal_nodes(st, c->t_add)
+            const int cols = ucols + pg_tree_internal_nodes(st, c->t_add)
                            + pg_tree_internal_nodes(st, c->t_sub);
             c->bytes_model += n * (8 + 8 + 4) + 4ull * n * (unsigned long long)cols;
             c->bytes_contract += 20ull * n + 4ull * n * (unsigned long long)J0 + 16ull * n * (unsigned long long)c->n_jobs;
@@ -515,16 +599,25 @@ PG_HDN inline void pg_s_after_stats(const PgState& st, const PgTeam& tm, bool ro
         }
     }
     tm.sync();
+    PG_SCRATCH(unsigned long long, s_bytes, 1);
+    if (bern && J > 0) {
+        PG_SINGLE { s_bytes[0] = 0ull; }
+        tm.sync();
+        unsigned long long bc = 0;
+        PG_FOR(j, J) bc += 12ull * st.job_len[j];
+        pg_team_add64(&s_bytes[0], bc);
+        tm.sync();
+    }
     PG_SINGLE {
         if (bern && J > 0) {
-            unsigned long long bm = 0, bc = 0;
+            unsigned long long bm = 0;
+            const unsigned long long bc = s_bytes[0];
             for (int g = 0; g < c->n_groups; ++g) {
                 const int j0 = st.job_order[st.grp_first[g]];
                 const unsigned long long L = st.job_len[j0];
                 const unsigned long long fixed = st.job_seg_off[j0] == PG_SEG_IDENTITY ? 12ull : 16ull;
                 bm += fixed * L + 4ull * L * (unsigned long long)(st.grp_first[g + 1] - st.grp_first[g]);
             }
-            for (int j = 0; j < J; ++j) bc += 12ull * st.job_len[j];
             c->bytes_model += bm; c->bytes_contract += bc;
             c->phase = PH_BERN;
             c->n_phases += 1;
@@ -835,19 +928,30 @@ PG_HDN inline void pg_s_finalize(const PgState& st, const PgTeam& tm) {
     }
 }
 
+// Stopwatch of the sub-steps (device builds; read through pgbart_get_profile as serial_sub_*; slot 0 = after_bern here).
+#if defined(__CUDA_ARCH__)
+#define PG_SUB_T0() pg_sub_t0 = clock64()
+#define PG_SUB_T1(i) do { tm.sync(); PG_SINGLE { c->prof2[(i)] += (unsigned long long)(clock64() - pg_sub_t0); c->prof2[8 + (i)] += 1ull; } } while (0)
+#else
+#define PG_SUB_T0() (void)pg_sub_t0
+#define PG_SUB_T1(i) (void)0
+#endif
+
 // Entry point: called by one team after the grid pass `ctrl->phase` has completed (its partial
 // results are visible).  Runs serial sub-steps until another grid pass is needed or the step is done.
 PG_HDN inline void pg_serial(const PgState& st, const PgTeam& tm) {
     PgCtrl* c = st.ctrl;
+    long long pg_sub_t0 = 0;
     tm.sync();
     const int phase = c->phase;
     tm.sync();
+    PG_SUB_T0();
     switch (phase) {
         case PH_BEGIN: pg_s_begin_step(st, tm); break;
-        case PH_ROOT: pg_s_after_stats(st, tm, true); break;
-        case PH_MINMAX: pg_s_after_minmax(st, tm); break;
-        case PH_STATS: pg_s_after_stats(st, tm, false); break;
-        case PH_BERN: pg_s_after_bern(st, tm); break;
+        case PH_ROOT: pg_s_after_stats(st, tm, true); PG_SUB_T1(1); break;
+        case PH_MINMAX: pg_s_after_minmax(st, tm); PG_SUB_T1(2); break;
+        case PH_STATS: pg_s_after_stats(st, tm, false); PG_SUB_T1(1); break;
+        case PH_BERN: pg_s_after_bern(st, tm); PG_SUB_T1(0); break;
         case PH_PART: pg_s_after_part(st, tm); break;
         case PH_FINAL:
             PG_SINGLE {
@@ -868,12 +972,13 @@ PG_HDN inline void pg_serial(const PgState& st, const PgTeam& tm) {
         tm.sync();
         if (err != PG_OK) { PG_SINGLE { c->phase = PH_DONE; c->snext = SN_NONE; } break; }
         if (sn == SN_NONE) break;
+        PG_SUB_T0();
         switch (sn) {
-            case SN_BEGIN_UPDATE: pg_s_begin_update(st, tm); break;
-            case SN_DRAW_ROUND: pg_s_draw_round(st, tm); break;
-            case SN_FINISH_ROUND: pg_s_finish_round(st, tm); break;
-            case SN_PREP_PART: pg_s_prep_part(st, tm); break;
-            case SN_FINALIZE: pg_s_finalize(st, tm); break;
+            case SN_BEGIN_UPDATE: pg_s_begin_update(st, tm); PG_SUB_T1(6); break;
+            case SN_DRAW_ROUND: pg_s_draw_round(st, tm); PG_SUB_T1(7); break;
+            case SN_FINISH_ROUND: pg_s_finish_round(st, tm); PG_SUB_T1(3); break;
+            case SN_PREP_PART: pg_s_prep_part(st, tm); PG_SUB_T1(4); break;
+            case SN_FINALIZE: pg_s_finalize(st, tm); PG_SUB_T1(5); break;
             default: PG_SINGLE { c->error = PG_ERR_INTERNAL; } break;
         }
     }

@@ -134,6 +134,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
         __syncthreads();
         const long long t1 = clock64();
         pg_barrier_serial<FAST>(st, sm, gen, phase, J);
+        if (blockIdx.x != 0 && threadIdx.x == 0) st.diag_blocks[(size_t)(blockIdx.x - 1) * 8 + (phase & 7)] += (unsigned long long)(t1 - t0);
         if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // stopwatch kept by a block that never runs the serial section
             PgCtrl* c = st.ctrl;
             c->prof[phase & 7] += (unsigned long long)(t1 - t0);

@@ -149,6 +149,20 @@ struct PgCtrl {
     unsigned int cnt[2][32];
 };
 
+// Logarithm table of the Bernoulli pass (pg_log_ge1, pg_serial.h); filled on the host.
+#include <math.h>
+#define PG_LOGT_K 64
+#define PG_LOGT_REP 8   // shared-memory copies on the device: the 8 lanes of a quarter warp read 8 different 16-byte entries
+                        // (lane & 7 picks the copy), so the lookup never has a bank conflict
+inline void pg_log_table_fill(double* tbl /* [PG_LOGT_K][2] */) {
+    for (int k = 0; k < PG_LOGT_K; ++k) {
+        const long double c = 1.0L + ((long double)k + 0.5L) / (long double)PG_LOGT_K;
+        const double inv = (double)floorl(4096.0L / c + 0.5L) / 4096.0;
+        tbl[2 * k + 0] = inv;
+        tbl[2 * k + 1] = (double)(-logl((long double)inv));
+    }
+}
+
 struct PgState {
     // dimensions
     long long n, ld;
@@ -177,6 +191,7 @@ struct PgState {
     const float* col_max;
     const double* prior;         // split prior used as raw weights (Q3); null = uniform integer draw
     double prior_total;
+    const double* log_tbl;       // [PG_LOGT_K][2] (inv_k, -log inv_k): logarithm table of the Bernoulli pass (pg_log_ge1)
     const double* thr_depth;     // [max_depth+2] 1 - alpha (1+d)^-beta (host pow, smc.rs:143)
     double leaf_sigma, m_f, init_leaf, y_mean;
     double batch_tune, batch_post;

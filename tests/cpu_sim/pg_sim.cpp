@@ -141,10 +141,9 @@ void pass_seg(const PgState& st, int mode) {
                     if (mode == 0) {
                         if (left) { a += o; bb += yv - o; cc += 1; wc += 1; }
                     } else {
-                        // the device pass's arithmetic (pg_bern_term): exp(+-o) per row, exp(+-v) per job and child
+                        // the device pass's arithmetic (pg_bern_term): exp(o) per row, exp(v) per job and child
                         const double v = left ? st.job_vL[j] : st.job_vR[j];
-                        const bool wide = !(std::fabs(o) < 300.0);
-                        const double f = pg_bern_term(yv, o, v, wide ? 0.0 : std::exp(o), wide ? 0.0 : std::exp(-o), std::exp(v), std::exp(-v), wide);
+                        const double f = pg_bern_term<1>(yv, o, v, pg_bern_exp(o), pg_bern_exp(v), st.log_tbl, 0);
                         if (left) a += f; else bb += f;
                     }
                 }
@@ -233,6 +232,9 @@ void* pgsim_create(const double* x_f, uint64_t n, uint64_t p, const double* y, c
     double* thr = halloc<double>(s, (size_t)st.max_depth + 2);
     for (int d = 0; d < st.max_depth + 2; ++d) thr[d] = 1.0 - (cfg->alpha * std::pow(1.0 + (double)d, -cfg->beta));
     st.thr_depth = thr;
+    double* ltb = halloc<double>(s, 2 * PG_LOGT_K);
+    pg_log_table_fill(ltb);
+    st.log_tbl = ltb;
     const size_t S = st.S, MN = st.maxn, M = st.m, G = st.grid, W = st.n_gwarps;
     st.A = halloc<double>(s, (size_t)st.ld); st.A2 = halloc<double>(s, (size_t)st.ld);
     st.f_split_var = halloc<int>(s, M * MN); st.f_thr32 = halloc<float>(s, M * MN); st.f_split_val = halloc<double>(s, M * MN);
@@ -376,4 +378,15 @@ void pgsim_warp_range(uint64_t L, int gw, int W, int gran, uint64_t* b, uint64_t
     *b = bb; *e = ee;
 }
 
+// y mu - softplus(mu) through the product's table logarithm (pg_bern_term), elementwise: accuracy test
+void pgsim_bern_terms(const double* y, const double* o, const double* v, double* out, long long n) {
+    double tbl[2 * PG_LOGT_K];
+    pg_log_table_fill(tbl);
+    for (long long i = 0; i < n; ++i) out[i] = pg_bern_term<1>(y[i], o[i], v[i], pg_bern_exp(o[i]), pg_bern_exp(v[i]), tbl, 0);
+}
+void pgsim_log_ge1(const double* u, double* out, long long n) {
+    double tbl[2 * PG_LOGT_K];
+    pg_log_table_fill(tbl);
+    for (long long i = 0; i < n; ++i) out[i] = pg_log_ge1<1>(u[i], tbl, 0);
+}
 }  // extern "C"

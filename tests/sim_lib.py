@@ -54,6 +54,8 @@ def lib():
         L.pgsim_f2key.argtypes = [C.c_float]
         L.pgsim_key2f.restype = C.c_float
         L.pgsim_key2f.argtypes = [C.c_uint32]
+        L.pgsim_bern_terms.argtypes = [vp, vp, vp, vp, C.c_int64]
+        L.pgsim_log_ge1.argtypes = [vp, vp, C.c_int64]
         L.pgsim_warp_range.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib

@@ -36,6 +36,8 @@ CASES = [
     (40, 2, 3, 4, 0, 0.01, dict(), [True, True, True], 2),                                      # positive log-liks (tiny sigma)
     (33, 2, 4, 6, 0, 1.0, dict(), [True], 5),                                                   # more warps than rows/4
     (1, 2, 3, 4, 0, 1.0, dict(), [True], 1),                                                    # single row: min>=max rejects
+    (150, 4, 3, 40, 1, 1.0, dict(alpha=0.9999, beta=1.5, max_depth=6), [True], 2),              # P > 32, Bernoulli, every slot grows
+    (130, 3, 3, 70, 0, 1.0, dict(), [True, False], 3),                                          # P > 32, default prior (stale zero weights)
 ]
 
 

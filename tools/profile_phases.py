@@ -67,7 +67,7 @@ for n in ("root", "stats", "part"):
               f"longest pass body {d['longest_body_cycles'] / cnt / ghz / 1e3:.2f} us")
 bc = s.block_cycles()
 if bc.any():
-    for ph, n in ((1, "root"), (3, "stats"), (5, "part")):
+    for ph, n in ((1, "root"), (3, "stats"), (4, "bern"), (5, "part")):
         v = bc[:, ph] / ghz / 1e3
         order = np.argsort(v)
         print(f"per-block total {n} body time (us): min {v.min():.0f} median {np.median(v):.0f} max {v.max():.0f}; slowest blocks {order[-6:].tolist()} "
