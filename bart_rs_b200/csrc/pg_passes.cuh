@@ -886,26 +886,16 @@ __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemV
 }
 
 // =============================================================================
-// PH_STATS / PH_BERN — over index segments (gather); jobs sharing a segment share idx/A/y loads
+// PH_STATS — over index segments (gather); jobs sharing a segment share idx/A/y loads
 // =============================================================================
-// MODE 0: statistics (LEFT count, sum A, sum y-A).  MODE 1: Bernoulli child log-likelihoods
-// (A = left-child sum, B = right-child sum); identity segments allowed.
-template <int MODE>
+// LEFT count, sum A, sum y-A per job; identity segments allowed.
 __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     const int J = sm.base->cmd.n_jobs, G = sm.base->cmd.n_groups;
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
-    pg_stage_jobs(st, bf, sm, J, G, MODE == 1);
+    pg_stage_jobs(st, bf, sm, J, G, false);
     pg_zero_acc(sm, S);
-    // Bernoulli: the logarithm table, PG_LOGT_REP copies, in the union area (idle outside the root pass)
-    double* ltab = reinterpret_cast<double*>(sm.stage);
-    if (MODE == 1)
-        for (int i = threadIdx.x; i < PG_LOGT_K * PG_LOGT_REP; i += blockDim.x) {
-            const int k = i / PG_LOGT_REP;
-            ltab[2 * i + 0] = __ldg(&st.log_tbl[2 * k + 0]);
-            ltab[2 * i + 1] = __ldg(&st.log_tbl[2 * k + 1]);
-        }
     __syncthreads();
     const size_t ld = (size_t)st.ld;
     constexpr int R = 4;   // entries per lane per iteration
@@ -920,7 +910,6 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
         for (unsigned long long base = beg; base < end; base += 32 * R) {
             unsigned idx[R];
             double o[R], r[R];
-            float yv[R];
             bool valid[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) {
@@ -931,14 +920,7 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 o[k] = valid[k] ? __ldcg(&bf.A_src[idx[k]]) : 0.0;
-                yv[k] = valid[k] ? __ldg(&st.y[idx[k]]) : 0.0f;
-                r[k] = valid[k] ? (double)yv[k] - o[k] : 0.0;
-            }
-            // Bernoulli: exp(o) once per row, shared by every job of the group (pg_bern_term)
-            double eo[R];
-            if (MODE == 1) {
-#pragma unroll
-                for (int k = 0; k < R; ++k) eo[k] = pg_bern_exp(o[k]);
+                r[k] = valid[k] ? (double)__ldg(&st.y[idx[k]]) - o[k] : 0.0;
             }
             for (int jb = jb0; jb < jb1; jb += 4) {
                 double va[4], vb[4];
@@ -951,30 +933,21 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
                     const float thr = sm.jthr[j];
                     double a = 0.0, b = 0.0;
                     int cc = 0;
-                    double vL = 0.0, vR = 0.0, evL = 1.0, evR = 1.0;
-                    if (MODE == 1) { vL = sm.jvL[j]; vR = sm.jvR[j]; evL = sm.jexp[2 * j]; evR = sm.jexp[2 * j + 1]; }
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
                         const bool ok = live && valid[k];
                         const float x = ok ? __ldg(&col[idx[k]]) : 0.0f;
                         const bool left = ok && (x < thr);
-                        if (MODE == 0) {
-                            const double m = left ? 1.0 : 0.0;      // exact 0/1 mask (see pg_acc_left)
-                            a = fma(m, o[k], a);
-                            b = fma(m, r[k], b);
-                            cc += left ? 1 : 0;
-                        } else {
-                            // invalid rows / dead job slots carry o = y = 0 (a finite term) and get mask 0 on both sides
-                            const double f = pg_bern_term<PG_LOGT_REP>((double)yv[k], o[k], left ? vL : vR, eo[k], left ? evL : evR, ltab, lane & (PG_LOGT_REP - 1));
-                            a = fma(left ? 1.0 : 0.0, f, a);
-                            b = fma((ok && !left) ? 1.0 : 0.0, f, b);
-                        }
+                        const double m = left ? 1.0 : 0.0;      // exact 0/1 mask (see pg_acc_left)
+                        a = fma(m, o[k], a);
+                        b = fma(m, r[k], b);
+                        cc += left ? 1 : 0;
                     }
                     va[q] = a; vb[q] = b; cn[q] = cc;
                 }
                 const double ta = pg_xreduce4(va[0], va[1], va[2], va[3], lane);
                 const double tb = pg_xreduce4(vb[0], vb[1], vb[2], vb[3], lane);
-                const int tc = MODE == 0 ? pg_xreduce4(cn[0], cn[1], cn[2], cn[3], lane) : 0;
+                const int tc = pg_xreduce4(cn[0], cn[1], cn[2], cn[3], lane);
                 const int q = pg_xreduce4_job(lane);
                 if (lane < 4 && jb + q < jb1) {
                     const int j = sm.jorder[jb + q];
@@ -986,7 +959,158 @@ __device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView
         }
     }
     __syncthreads();
-    pg_flush_acc(st, bf, sm, J, MODE == 0, MODE == 1);
+    pg_flush_acc(st, bf, sm, J, true, false);
+}
+
+// =============================================================================
+// PH_BERN — Bernoulli-logit child log-likelihoods over index segments (weight.rs:26-30 via smc.rs:89-95)
+// =============================================================================
+// Per job: A = sum over the LEFT rows of y mu - softplus(mu) with mu = o + vL, B = the same over the RIGHT rows with vR.
+// This pass is arithmetic bound (BASELINE C5: 255 jobs x 1M rows = 2.6e8 softplus evaluations per tree update), so the
+// row-job is made as short as the formula allows: exp(o) once per row, exp(v) once per job and child, softplus(mu) =
+// log(1 + exp(o) exp(v)) through the table logarithm of pg_serial.h read from shared memory without bank conflicts — 17
+// f64 operations, no exp, no division — and kept free of branches inside the 4 rows x 4 jobs block so that sixteen
+// independent dependency chains are in flight per lane: whether any row of the chunk or the job's leaf values are out
+// of the product form's range is decided once per chunk / job, warp-uniformly, and such chunks take the direct formula.
+__device__ __forceinline__ double pg_log_ge1_sm(double u, unsigned tab_addr) {       // pg_log_ge1 with the table in shared memory
+    const int hi = __double2hiint(u);
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(u));
+    const double2 t = pg_lds_d2(tab_addr + (unsigned)(((hi >> 14) & (PG_LOGT_K - 1)) * (PG_LOGT_REP * 16)));
+    const double e = (double)((hi >> 20) - 1023);
+    const double r = fma(m, t.x, -1.0);
+    double p = 1.0 / 7.0;
+    p = fma(p, r, -1.0 / 6.0); p = fma(p, r, 0.2); p = fma(p, r, -0.25); p = fma(p, r, 1.0 / 3.0); p = fma(p, r, -0.5);
+    p = fma(p, r, 1.0);
+    return fma(p, r, fma(e, 0.6931471805599453, t.y));
+}
+
+// One block of NQ jobs x 4 rows per lane.  FULL: all 128 rows of the chunk exist and all NQ = 4 jobs are live, so the hot
+// path carries no validity logic at all (the rows past a warp's range and the last, partial job group take FULL = false).
+template <bool FULL>
+__device__ __forceinline__ void pg_bern_block(const PgState& st, const PgSmemView& sm, const unsigned (&idx)[4], const double (&o)[4],
+                                              const double (&yd)[4], const double (&eo)[4], unsigned vmask, bool rows_wide,
+                                              int jb, int jb1, int j0, unsigned tab_addr, int lane, int warp) {
+    constexpr int R = 4;
+    const size_t ld = (size_t)st.ld;
+    const int S = st.S;
+    int jq[4];
+    float x[4][R];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const bool live = FULL || jb + q < jb1;
+        jq[q] = live ? sm.jorder[jb + q] : j0;
+        const float* col = st.X + (size_t)sm.jvar[jq[q]] * ld;
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[q][k] = __ldg(&col[idx[k]]);      // rows past the end read row 0 (idx = 0) and are masked below
+    }
+    double va[4], vb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = jq[q];
+        const bool live = FULL || jb + q < jb1;
+        const float thr = sm.jthr[j];
+        const double vL = sm.jvL[j], vR = sm.jvR[j], evL = sm.jexp[2 * j], evR = sm.jexp[2 * j + 1];
+        double a = 0.0, b = 0.0;
+        if (!(rows_wide || !(evL < INFINITY) || !(evR < INFINITY))) {          // warp-uniform
+            double sall = 0.0;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const bool left = x[q][k] < thr;                                   // a NaN in X goes RIGHT, as in the reference
+                const double mu = o[k] + (left ? vL : vR);
+                double f = yd[k] * mu - pg_log_ge1_sm(fma(eo[k], left ? evL : evR, 1.0), tab_addr);
+                if (!FULL) f = (live && ((vmask >> k) & 1u)) ? f : 0.0;
+                a = fma(left ? 1.0 : 0.0, f, a);
+                sall += f;
+            }
+            b = sall - a;      // four terms per lane: the subtraction costs an ulp of a number of order 1
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < R; ++k) {
+                if (!(live && ((vmask >> k) & 1u))) continue;
+                const bool left = x[q][k] < thr;
+                const double mu = o[k] + (left ? vL : vR);
+                const double f = yd[k] * mu - pg_softplus(mu);
+                if (left) a += f; else b += f;
+            }
+        }
+        va[q] = a; vb[q] = b;
+    }
+    const double ta = pg_xreduce4(va[0], va[1], va[2], va[3], lane);
+    const double tb = pg_xreduce4(vb[0], vb[1], vb[2], vb[3], lane);
+    const int q = pg_xreduce4_job(lane);
+    if (lane < 4 && (FULL || jb + q < jb1)) {
+        const int j = sm.jorder[jb + q];
+        sm.accA[warp * S + j] += ta;
+        sm.accB[warp * S + j] += tb;
+    }
+}
+
+__device__ void pg_pass_bern(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+    const int J = sm.base->cmd.n_jobs, G = sm.base->cmd.n_groups;
+    const int S = st.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pg_stage_jobs(st, bf, sm, J, G, true);
+    pg_zero_acc(sm, S);
+    // the logarithm table, PG_LOGT_REP copies, in the union area (idle outside the root pass)
+    double* ltab = reinterpret_cast<double*>(sm.stage);
+    for (int i = threadIdx.x; i < PG_LOGT_K * PG_LOGT_REP; i += blockDim.x) {
+        const int k = i / PG_LOGT_REP;
+        ltab[2 * i + 0] = __ldg(&st.log_tbl[2 * k + 0]);
+        ltab[2 * i + 1] = __ldg(&st.log_tbl[2 * k + 1]);
+    }
+    __syncthreads();
+    const unsigned tab_addr = pg_smem_u32(ltab) + (unsigned)((lane & (PG_LOGT_REP - 1)) * 16);
+    constexpr int R = 4;   // entries per lane per chunk
+    // Work units: (chunk of 128 segment entries) x (slice of the group's jobs), dealt round-robin to the block's warps.
+    // A block takes whole chunks (ceil(chunks / grid) of them), so only the segment's last chunk is partial, and slicing
+    // the jobs keeps the warps level when a block has few chunks per warp (BASELINE C5: 54 chunks x 8 slices of 32 jobs =
+    // 27 units per warp; one row range per warp would leave each warp a quarter-filled fourth chunk).
+    for (int g = 0; g < G; ++g) {
+        const int jb0 = sm.grp[g], jb1 = sm.grp[g + 1];
+        const int j0 = sm.jorder[jb0];
+        const unsigned off = __ldcg(&bf.job_seg_off[j0]);
+        const bool ident = off == PG_SEG_IDENTITY;
+        const unsigned long long L = __ldcg(&bf.job_len[j0]);
+        const unsigned long long chunks = (L + 32ull * R - 1) / (32ull * R);
+        const unsigned long long cper = (chunks + (unsigned long long)st.grid - 1) / (unsigned long long)st.grid;
+        unsigned long long c0 = (unsigned long long)PG_BID * cper, c1 = c0 + cper;
+        if (c0 > chunks) c0 = chunks;
+        if (c1 > chunks) c1 = chunks;
+        const int slice = (jb1 - jb0 >= 64) ? 32 : 8;                       // jobs per slice, a multiple of 4
+        const int nsl = (jb1 - jb0 + slice - 1) / slice;
+        const unsigned long long units = (c1 - c0) * (unsigned long long)nsl;
+        for (unsigned long long u = (unsigned long long)warp; u < units; u += PG_WARPS) {
+            const unsigned long long base = (c0 + u / (unsigned long long)nsl) * (32ull * R);
+            const int sj0 = jb0 + (int)(u % (unsigned long long)nsl) * slice;
+            const int sj1 = sj0 + slice < jb1 ? sj0 + slice : jb1;
+            const unsigned rem = (unsigned)(L - base < 32ull * R ? L - base : 32ull * R);
+            unsigned idx[R];
+            double o[R], yd[R], eo[R];
+            unsigned vmask = 0u;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const unsigned e = (unsigned)lane + 32u * k;
+                const bool valid = e < rem;
+                vmask |= valid ? (1u << k) : 0u;
+                idx[k] = valid ? (ident ? (unsigned)(base + e) : __ldcg(&st.pool[(size_t)off + base + e])) : 0u;
+            }
+            bool rows_wide = false;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                o[k] = __ldcg(&bf.A_src[idx[k]]);
+                yd[k] = (double)__ldg(&st.y[idx[k]]);
+                eo[k] = pg_bern_exp(o[k]);
+                rows_wide |= !(eo[k] < INFINITY);
+            }
+            rows_wide = __any_sync(PG_FULL, rows_wide);
+            int jb = sj0;
+            if (rem == 32u * R)
+                for (; jb + 4 <= sj1; jb += 4) pg_bern_block<true>(st, sm, idx, o, yd, eo, vmask, rows_wide, jb, sj1, j0, tab_addr, lane, warp);
+            for (; jb < sj1; jb += 4) pg_bern_block<false>(st, sm, idx, o, yd, eo, vmask, rows_wide, jb, sj1, j0, tab_addr, lane, warp);
+        }
+    }
+    __syncthreads();
+    pg_flush_acc(st, bf, sm, J, false, true);
 }
 
 // =============================================================================
@@ -1449,8 +1573,8 @@ __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView&
             else pg_pass_root<false, true>(st, bf, sm);
             break;
         case PH_MINMAX: pg_pass_minmax(st, bf, sm); break;
-        case PH_STATS: if (FASTP && VAR != PGV_BERN) pg_pass_seg_block(st, bf, sm); else pg_pass_seg<0>(st, bf, sm); break;
-        case PH_BERN: if (VAR == PGV_GENERIC || VAR == PGV_BERN) pg_pass_seg<1>(st, bf, sm); break;
+        case PH_STATS: if (FASTP && VAR != PGV_BERN) pg_pass_seg_block(st, bf, sm); else pg_pass_seg(st, bf, sm); break;
+        case PH_BERN: if (VAR == PGV_GENERIC || VAR == PGV_BERN) pg_pass_bern(st, bf, sm); break;
         case PH_PART: pg_pass_part<FASTP>(st, bf, sm); break;
         default: break;
     }
