@@ -45,6 +45,7 @@ struct Sampler {
     std::vector<cudaEvent_t> chunk_ev;   // one event per staged chunk of that copy
     std::vector<void*> ipc_open;     // peer mailboxes opened through CUDA IPC (observation sharding)
     long long steps_done = 0;
+    bool any_onehot = false;         // some split_rules entry is OneHotSplit: the step runs on the generic control code
 };
 
 const char* pg_error_text(int code) {
@@ -309,9 +310,33 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         const char* r = cfg->split_rules ? cfg->split_rules[i] : nullptr;
         if (!r) return fail("null split rule");
         if (std::strcmp(r, "ContinuousSplit") == 0) continue;
-        if (std::strcmp(r, "OneHotSplit") == 0)
-            return fail("OneHotSplit is not available on the device path (SURVEY.md: out of scope; no CPU fallback)");
+        if (std::strcmp(r, "OneHotSplit") == 0) continue;
         return fail(std::string("Unknown split rule: '") + r + "'. Supported: 'ContinuousSplit', 'OneHotSplit'.");
+    }
+    // OneHotSplit columns (lib.rs:134-144 pads the rule list with ContinuousSplit): integer codes spanning < 64 values
+    std::vector<unsigned char> onehot((size_t)p, 0);
+    std::vector<int> col_imin((size_t)p, 0);
+    std::vector<unsigned long long> col_bits((size_t)p, 0ull);
+    bool any_onehot = false;
+    for (uint64_t j = 0; j < cfg->n_split_rules && j < p; ++j) {
+        if (std::strcmp(cfg->split_rules[j], "OneHotSplit") != 0) continue;
+        onehot[j] = 1; any_onehot = true;
+        auto at = [&](uint64_t i) -> double {
+            const size_t k = x_order == PGBART_ORDER_F ? (size_t)j * n + i : (size_t)i * p + j;
+            return x_dtype == PGBART_X_F64 ? ((const double*)x)[k] : (double)((const float*)x)[k];
+        };
+        int lo = INT32_MAX, hi = INT32_MIN;
+        for (uint64_t i = 0; i < n; ++i) {
+            const double v = at(i);
+            if (!(std::fabs(v) < 16777216.0)) return fail("OneHotSplit column " + std::to_string(j) + ": values must be finite and below 2^24 in magnitude");
+            const int c = (int)v;      // Rust `as i32`: truncation toward zero (splitting.rs:131)
+            lo = c < lo ? c : lo; hi = c > hi ? c : hi;
+        }
+        if ((long long)hi - (long long)lo >= 64)
+            return fail("OneHotSplit column " + std::to_string(j) + ": integer codes span " + std::to_string((long long)hi - lo + 1) +
+                        " values; at most 64 consecutive codes per column are supported");
+        col_imin[j] = lo;
+        for (uint64_t i = 0; i < n; ++i) col_bits[j] |= 1ull << ((int)at(i) - lo);
     }
     if (!allow_rounding) {
         char msg[512];
@@ -379,6 +404,8 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     st.root_stages = 0;
     st.root_dbg = 0;
     st.issue_ahead = 1;
+    st.pg_correct = 0;
+    st.generic = (st.P > 32 || any_onehot) ? 1 : 0;
     if (const char* e = std::getenv("PGBART_ISSUE_AHEAD")) st.issue_ahead = std::atoi(e) != 0;
     if (const char* e = std::getenv("PGBART_ROOT_PASS")) st.root_ring = std::strcmp(e, "direct") == 0 ? 0 : std::strcmp(e, "ring") == 0 ? 1 : 2;
     if (const char* e = std::getenv("PGBART_ROOT_TILE_GROUPS")) st.root_tile_groups = std::atoi(e);
@@ -429,6 +456,16 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         if (!ck(s, cudaMemcpy(dt, tbl, sizeof tbl, cudaMemcpyHostToDevice), "upload log table")) return bail();
         st.log_tbl = dt;
     }
+    s->any_onehot = any_onehot;
+    if (any_onehot) {
+        unsigned char* d_oh = nullptr; int* d_im = nullptr; unsigned long long* d_cb = nullptr;
+        if (!dalloc(s, &d_oh, (size_t)p, false) || !dalloc(s, &d_im, (size_t)p, false) || !dalloc(s, &d_cb, (size_t)p, false) ||
+            !dalloc(s, &st.job_bits, (size_t)st.S)) return bail();
+        if (!ck(s, cudaMemcpy(d_oh, onehot.data(), (size_t)p, cudaMemcpyHostToDevice), "upload split rules") ||
+            !ck(s, cudaMemcpy(d_im, col_imin.data(), (size_t)p * 4, cudaMemcpyHostToDevice), "upload code minima") ||
+            !ck(s, cudaMemcpy(d_cb, col_bits.data(), (size_t)p * 8, cudaMemcpyHostToDevice), "upload code masks")) return bail();
+        st.onehot = d_oh; st.col_imin = d_im; st.col_bits = d_cb;
+    }
     // ---- state arrays
     const size_t S = (size_t)st.S, MN = (size_t)st.maxn, M = (size_t)st.m, G = (size_t)st.grid, W = (size_t)st.n_gwarps;
     bool ok = dalloc(s, &st.A, (size_t)st.ld) && dalloc(s, &st.A2, (size_t)st.ld)
@@ -450,7 +487,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         && dalloc(s, &st.pj_src_off, S) && dalloc(s, &st.pj_len, S) && dalloc(s, &st.pj_dst_off, S) && dalloc(s, &st.pj_cntL, S)
         && dalloc(s, &st.pj_warp_left, S * W) && dalloc(s, &st.pj_of_anc, S) && dalloc(s, &st.scan_tmp, PG_THREADS + 1)
         && dalloc(s, &st.part_sum, 2 * G * S * 2) && dalloc(s, &st.part_cnt, 2 * W * S) && dalloc(s, &st.part_ccnt, 2 * G * S)
-        && dalloc(s, &st.part_tot, 2 * G * 4) && dalloc(s, &st.part_mm, G * 2 * S * 2) && dalloc(s, &st.mq_pj, 2 * S) && dalloc(s, &st.mq_side, 2 * S) && dalloc(s, &st.mq_var, 2 * S) && dalloc(s, &st.part_ll, G * S * 2) && dalloc(s, &st.diag_blocks, G * 16)
+        && dalloc(s, &st.part_tot, 2 * G * 4) && dalloc(s, &st.part_mm, G * 2 * S * 2) && dalloc(s, &st.mq_pj, 2 * S) && dalloc(s, &st.mq_side, 2 * S) && dalloc(s, &st.mq_var, 2 * S) && dalloc(s, &st.part_ll, G * S * 2) && dalloc(s, &st.diag_blocks, G * 16) && dalloc(s, &st.part_old, G)
         && dalloc(s, &st.info_depths, M) && dalloc(s, &st.ctrl, 1);
     if (!ok) return bail();
     {
@@ -665,6 +702,19 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
         s->err = "driver must be 'persistent' or 'stepwise'";
         return 1;
     }
+    if (std::strcmp(key, "weight_mode") == 0) {
+        // "reference" = the reference's stale-weight rule and fresh-stump reference particle (Q1, Q2; default);
+        // "pg_correct" = log-weights carried with the particles and the tree being replaced as the conditional reference particle
+        if (s->steps_done != 0) { s->err = "weight_mode must be set before the first step"; return 1; }
+        if (s->st.world > 1) { s->err = "weight_mode pg_correct is not available with observation sharding"; return 1; }
+        if (std::strcmp(value, "reference") == 0) { s->st.pg_correct = 0; s->st.generic = (s->st.P > 32 || s->any_onehot) ? 1 : 0; return 0; }
+        if (std::strcmp(value, "pg_correct") == 0) {
+            if (s->st.S > 512) { s->err = "weight_mode pg_correct supports at most 513 particles"; return 1; }
+            s->st.pg_correct = 1; s->st.generic = 1; return 0;
+        }
+        s->err = "weight_mode must be 'reference' or 'pg_correct'";
+        return 1;
+    }
     if (std::strcmp(key, "root_pass") == 0) {
         if (std::strcmp(value, "ring") == 0 || std::strcmp(value, "staged") == 0) {
             if (s->st.stage_bytes <= 0) { s->err = "the ring root pass needs a staging area (PGBART_SMEM_KB, n_particles <= 32)"; return 1; }
@@ -728,7 +778,7 @@ int pgbart_get_profile(pgbart_handle h, double* out32) {
     Sampler* s = &h->s;
     if (!fetch_ctrl(s)) return 2;
     for (int i = 0; i < 32; ++i) out32[i] = (double)s->host_ctrl.prof[i];
-    if (s->st.P <= 32 && !s->stepwise) for (int i = 0; i < 8; ++i) out32[16 + i] = (double)s->host_ctrl.prof_ser[i];
+    if (!s->st.generic && !s->stepwise) for (int i = 0; i < 8; ++i) out32[16 + i] = (double)s->host_ctrl.prof_ser[i];
     for (int i = 0; i < 16; ++i) out32[32 + i] = (double)s->host_ctrl.prof2[i];
     out32[48] = (double)s->host_ctrl.n_spec;
     for (int i = 0; i < 16; ++i) out32[49 + i] = (double)s->host_ctrl.prof3[i];
@@ -754,7 +804,7 @@ int pgbart_shard_config(pgbart_handle h, int rank, int world, uint64_t n_global,
     Sampler* s = &h->s;
     PgState& st = s->st;
     if (world < 1 || world > PG_MAX_RANKS || rank < 0 || rank >= world) { s->err = "shard_config: need 0 <= rank < world <= 8"; return 1; }
-    if (st.P > 32) { s->err = "observation sharding is implemented for n_particles <= 32"; return 1; }
+    if (st.generic) { s->err = "observation sharding is implemented for n_particles <= 32 in the reference weight mode with ContinuousSplit columns"; return 1; }
     if (s->stepwise) { s->err = "observation sharding needs the persistent driver"; return 1; }
     if (s->steps_done != 0) { s->err = "shard_config must precede the first step"; return 1; }
     cudaSetDevice(s->device);

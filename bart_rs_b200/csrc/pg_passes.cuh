@@ -371,7 +371,7 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
     } else pg_warp_range((unsigned long long)st.n, gw, st.n_gwarps, 4, &beg, &end);
     const long long n = st.n;
     const size_t ld = (size_t)st.ld;
-    double tot_o = 0.0, tot_r = 0.0, tot_rr = 0.0, tot_ll = 0.0;
+    double tot_o = 0.0, tot_r = 0.0, tot_rr = 0.0, tot_ll = 0.0, tot_old = 0.0;
 
     for (unsigned long long base = beg; base < end; base += 256) {
         const long long r0 = (long long)base + 4 * lane, r1 = r0 + 128;
@@ -401,6 +401,16 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
             for (int q = 0; q < 8; ++q) {
                 const double v = add_nontrivial ? (valid[q] ? pg_tree_eval(st, t_add, sm.base->tadd, (q < 4 ? r0 : r1 - 4) + q) : 0.0) : add_c;
                 o[q] = o[q] + v;
+            }
+        }
+        if (!BLOCKR && st.pg_correct && cm.phase == PH_ROOT) {
+            // weight_mode pg_correct: o is the current sum of ALL trees here; its log-likelihood is the weight of the
+            // conditional reference particle (the tree being replaced)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (!valid[q]) continue;
+                if (BERN) tot_old += (double)yv[q] * o[q] - pg_softplus(o[q]);
+                else { const double d = (double)yv[q] - o[q]; tot_old += d * d; }
             }
         }
         if (t_sub >= 0) {
@@ -475,6 +485,17 @@ __device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemVie
         double v = 0.0;
         for (int w = 0; w < PG_WARPS; ++w) v += sm.base->tot[w][threadIdx.x];
         bf.part_tot[(size_t)PG_BID * 4 + threadIdx.x] = v;
+    }
+    if (!BLOCKR && st.pg_correct && cm.phase == PH_ROOT) {
+        __syncthreads();
+        tot_old = pg_warp_sum(tot_old);
+        if (lane == 0) sm.base->tot[warp][0] = tot_old;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double v = 0.0;
+            for (int w = 0; w < PG_WARPS; ++w) v += sm.base->tot[w][0];
+            st.part_old[PG_BID] = v;
+        }
     }
     pg_flush_acc(st, bf, sm, J, true, false, !BLOCKR);
 }
@@ -856,7 +877,12 @@ __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemV
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = PG_BID * PG_WARPS + warp;
-    for (int j = threadIdx.x; j < J; j += blockDim.x) { sm.mmin[j] = 0xFFFFFFFFu; sm.mmax[j] = 0u; sm.jvar[j] = __ldcg(&bf.job_var[j]); }
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        const int var = __ldcg(&bf.job_var[j]);
+        sm.jvar[j] = var;
+        const bool oh = st.onehot && st.onehot[var];
+        sm.mmin[j] = oh ? 0u : 0xFFFFFFFFu; sm.mmax[j] = 0u;
+    }
     __syncthreads();
     const size_t ld = (size_t)st.ld;
     for (int j = 0; j < J; ++j) {
@@ -865,6 +891,21 @@ __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemV
         const float* col = st.X + (size_t)sm.jvar[j] * ld;
         unsigned long long beg, end;
         pg_warp_range(L, gw, st.n_gwarps, 1, &beg, &end);
+        if (st.onehot && st.onehot[sm.jvar[j]]) {
+            // OneHotSplit column (splitting.rs:79-90): which integer codes occur in the node — a 64-bit presence mask,
+            // its low / high words in the slots the min / max keys use
+            const int imin = st.col_imin[sm.jvar[j]];
+            unsigned lo = 0u, hi = 0u;
+            for (unsigned long long e = beg + lane; e < end; e += 32) {
+                const unsigned idx = __ldcg(&st.pool[(size_t)off + e]);
+                const int b = (int)__ldg(&col[idx]) - imin;      // `as i32` truncates toward zero, like the conversion
+                if (b < 32) lo |= 1u << b; else hi |= 1u << (b - 32);
+            }
+            lo = __reduce_or_sync(PG_FULL, lo);
+            hi = __reduce_or_sync(PG_FULL, hi);
+            if (lane == 0) { atomicOr(&sm.mmin[j], lo); atomicOr(&sm.mmax[j], hi); }
+            continue;
+        }
         float mn = INFINITY, mx = -INFINITY;
         bool any = false;
         for (unsigned long long e = beg + lane; e < end; e += 32) {

@@ -215,8 +215,27 @@ PG_HD void pg_decide_split(const PgState& st, int j) {
     PgCtrl* c = st.ctrl;
     const int s = st.job_slot[j];
     const int node = st.job_node[j];
-    const float lo = st.job_lo[j], hi = st.job_hi[j];
     double* tr = pg_trace_slot(st, c->round, s);
+    if (st.onehot && st.onehot[st.job_var[j]]) {
+        // splitting.rs:127-137 -> :79-90: one of the node's distinct integer codes, uniformly (taken in ascending order;
+        // the reference's HashSet order is process-random, Q7); random_range(0..k) = floor of the f64 range draw on [0, k)
+        const unsigned long long bits = st.job_bits[j];
+        const int imin = st.col_imin[st.job_var[j]];
+        int nu = 0, first = -1, last = -1;
+        for (int b = 0; b < 64; ++b) if ((bits >> b) & 1ull) { nu += 1; if (first < 0) first = b; last = b; }
+        if (tr) { tr[9] = (double)(imin + first); tr[10] = (double)(imin + last); }
+        if (nu <= 1) { if (tr) tr[0] = 3; st.job_node[j] = -1; return; }     // splitting.rs:85-87
+        if (2 * node + 2 >= st.maxn) { c->error = PG_ERR_DEPTH; st.job_node[j] = -1; return; }
+        int k = (int)pg_split_draw(st, c->upd, c->round, s, 0.0, (double)nu);
+        if (k > nu - 1) k = nu - 1;
+        int code = imin;
+        for (int b = 0, seen = 0; b < 64; ++b) if ((bits >> b) & 1ull) { if (seen == k) { code = imin + b; break; } seen += 1; }
+        st.job_split[j] = (double)code;
+        st.job_thr32[j] = (float)code;            // |code| < 2^24 (checked at creation): exact, and x < (float)code <=> (double)x < code
+        if (tr) tr[3] = (double)code;
+        return;
+    }
+    const float lo = st.job_lo[j], hi = st.job_hi[j];
     if (tr) { tr[9] = (double)lo; tr[10] = (double)hi; }
     if (lo >= hi) {                 // splitting.rs:51-53
         if (tr) tr[0] = 3;
@@ -246,6 +265,7 @@ PG_HDN inline void pg_compact_jobs_single(const PgState& st) {
             st.job_thr32[J] = st.job_thr32[j]; st.job_split[J] = st.job_split[j];
             st.job_seg_off[J] = st.job_seg_off[j]; st.job_len[J] = st.job_len[j];
             st.job_lo[J] = st.job_lo[j]; st.job_hi[J] = st.job_hi[j];
+            if (st.onehot) st.job_bits[J] = st.job_bits[j];
         }
         st.slot_job[st.job_slot[J]] = J;
         ++J;
@@ -378,6 +398,7 @@ PG_HDN inline void pg_s_draw_round(const PgState& st, const PgTeam& tm) {
         PG_FOR(j, J) {
             st.job_lo[j] = st.col_min[st.job_var[j]];
             st.job_hi[j] = st.col_max[st.job_var[j]];
+            if (st.onehot) st.job_bits[j] = st.col_bits[st.job_var[j]];
             pg_decide_split(st, j);
         }
         tm.sync();
@@ -466,6 +487,13 @@ PG_HDN inline void pg_s_after_minmax(const PgState& st, const PgTeam& tm) {
         }
         st.job_lo[j] = pg_key2f(kmin);
         st.job_hi[j] = pg_key2f(kmax);
+        if (st.onehot && st.onehot[st.job_var[j]]) {       // the pass wrote the low / high words of the presence mask instead
+            unsigned long long bits = 0ull;
+            for (int b = 0; b < st.grid; ++b)
+                bits |= (unsigned long long)st.part_mm[((size_t)b * 2 * st.S + j) * 2 + 0]
+                      | ((unsigned long long)st.part_mm[((size_t)b * 2 * st.S + j) * 2 + 1] << 32);
+            st.job_bits[j] = bits;
+        }
         pg_decide_split(st, j);
     }
     tm.sync();
@@ -572,11 +600,21 @@ PG_HDN inline void pg_s_after_stats(const PgState& st, const PgTeam& tm, bool ro
                 c->g_stump = c->T_ll0;
             }
         }
+        if (st.pg_correct) {
+            // conditional reference particle: the log-likelihood of the current predictions (all trees, the old one included)
+            PG_SINGLE {
+                const double t_old = pg_reduce_blocks(st.part_old, st.grid, 1, 0);
+                if (st.family == PG_GAUSSIAN) c->ll_old = -(double)st.n * (log(st.lik_sigma) + 0.5 * log(6.283185307179586476925286766559)) - 0.5 * t_old / (st.lik_sigma * st.lik_sigma);
+                else if (st.family == PG_GAUSSIAN_KERNEL) c->ll_old = -0.5 * t_old;
+                else c->ll_old = t_old;
+            }
+        }
         tm.sync();
         PG_FOR(s, st.S) {
             const size_t i0 = pg_tix(st, cur, s, 0);
             st.pt_So[i0] = c->T_o; st.pt_Sr[i0] = c->T_r; st.pt_g[i0] = c->g_stump;
             st.pt_G[pg_six(st, cur, s)] = c->g_stump;
+            if (st.pg_correct) st.w[s] = c->C0 + c->g_stump;      // every slot starts as a stump: its log-likelihood, not 0.0 (Q1)
         }
         tm.sync();
     }
@@ -664,8 +702,9 @@ PG_HDN inline void pg_s_finish_round(const PgState& st, const PgTeam& tm) {
     const bool staged = S <= PG_SCR_N;
     double* w = staged ? s_w : st.w;
     int* anc = staged ? s_anc : st.anc;
+    PG_SCRATCH(double, s_lw, PG_SCR_N);        // weight_mode pg_correct: the slots' log-likelihoods, permuted with the ancestors below
     PG_SINGLE { s_ired[0] = 0; s_ired[1] = 1; }
-    if (staged) { PG_FOR(s, S) w[s] = st.w[s]; }
+    if (staged) { PG_FOR(s, S) { w[s] = st.w[s]; s_lw[s] = st.w[s]; } }
     tm.sync();
     {   // mutated slots and the largest slot tree: integer partial results, order-free
         int nm = 0, mz = 1;
@@ -705,7 +744,9 @@ PG_HDN inline void pg_s_finish_round(const PgState& st, const PgTeam& tm) {
         c->max_size = s_ired[1];
     }
     tm.sync();
-    if (staged) { PG_FOR(s, S) { st.w[s] = w[s]; st.anc[s] = anc[s]; } }
+    // Reference (Q1): the normalised weights stay in w[] and meet next round's fresh log-likelihoods.  pg_correct: slot s
+    // continues with the log-likelihood of the particle it now holds.
+    if (staged) { PG_FOR(s, S) { st.w[s] = st.pg_correct ? s_lw[anc[s]] : w[s]; st.anc[s] = anc[s]; } }
     if (st.tr_round) {
         if ((long long)c->trace_n < st.tr_u_cap && c->round < st.tr_r_cap) {
             double* tr = st.tr_round + ((size_t)c->trace_n * st.tr_r_cap + c->round) * (size_t)(2 + 2 * S);
@@ -840,7 +881,7 @@ PG_HDN inline void pg_s_finalize(const PgState& st, const PgTeam& tm) {
     PG_SCRATCH(double, s_fr, 2);
     const bool staged = P <= PG_SCR_N;
     double* W = staged ? s_W : st.Wfinal;       // [0,P) log-likelihoods, [P,2P) normalised
-    PG_SINGLE { W[0] = c->C0 + c->g_stump; }   // the reference particle is a fresh stump (Q2)
+    PG_SINGLE { W[0] = st.pg_correct ? c->ll_old : c->C0 + c->g_stump; }   // the reference particle is a fresh stump (Q2); pg_correct: the tree being replaced
     PG_FOR(s_, S) W[1 + s_] = c->C0 + st.pt_G[pg_six(st, cur, s_)];
     tm.sync();
     PG_SINGLE {
@@ -887,7 +928,9 @@ PG_HDN inline void pg_s_finalize(const PgState& st, const PgTeam& tm) {
     tm.sync();
     const int sel = c->any_queue;
     const size_t fb = (size_t)t * st.maxn;
-    if (sel == 0) {
+    if (sel == 0 && st.pg_correct) {
+        // conditional SMC kept the tree being replaced: the forest entry stays as it is
+    } else if (sel == 0) {
         PG_SINGLE {
             st.f_split_var[fb] = -1; st.f_split_val[fb] = pg_nan(); st.f_thr32[fb] = 0.0f; st.f_leaf_val[fb] = st.init_leaf;
             st.f_size[t] = 1;

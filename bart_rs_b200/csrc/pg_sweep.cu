@@ -275,7 +275,7 @@ cudaError_t pg_launch_prepare(const PgState& st, int tune, cudaStream_t s) {
 cudaError_t pg_launch_persistent(const PgState& st, size_t smem, cudaStream_t s) {
     void* args[] = {(void*)&st};
     void* fn = (void*)pg_sweep_persistent_generic;
-    if (st.P <= 32) {
+    if (!st.generic) {
         if (st.family == PG_BERNOULLI_LOGIT) fn = (void*)pg_sweep_persistent_bern;
         else if (pg_use_ring(st)) fn = (void*)pg_sweep_persistent_ring;
         else fn = (void*)pg_sweep_persistent_direct;

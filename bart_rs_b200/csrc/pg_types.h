@@ -97,6 +97,7 @@ struct PgCtrl {
     double C0;                      // particle-independent part of the log-likelihood
     double Cconst, inv_s2;          // per step: -n (log sigma + 0.5 log 2 pi) and 1/sigma^2 (Gaussian), else 0 and 1
     double g_stump;
+    double ll_old;                  // weight_mode pg_correct: log-likelihood of the current predictions (= of the tree being replaced)
     int acc_update;                 // accepted grows in this update
     int any_queue;
     // ---- BartInfo (state.rs:16-20) of the current step
@@ -180,6 +181,9 @@ struct PgState {
                                  // 2 = ring when a pass block holds at most 2048 rows, else direct (default)
     int root_tile_groups;        // ring root pass: cap on the row groups (128 rows) per tile, 0 = as many as fit (<= 8)
     int root_stages;             // ring root pass: cap on the stages of the ring, 0 = as many as fit
+    int pg_correct;              // SURVEY.md 8(f4) weight mode (NOT the reference's behaviour, off by default): slot log-weights are kept as
+                                 // log-likelihoods and permuted with the ancestors, particle 0 is the tree being replaced (conditional SMC)
+    int generic;                 // 1 = the generic control code (pg_serial.h) runs the step: P > 32, pg_correct, or a OneHotSplit column
     int issue_ahead;             // P <= 32 control block: 1 (default) = the next update's root pass is issued right behind the pass in progress
     int root_dbg;                // ring root pass, timing experiments only (results are wrong): 1 no proxy fence in the loop, 2 no job loop, 4 no row work at all
     // data
@@ -191,6 +195,13 @@ struct PgState {
     const float* col_max;
     const double* prior;         // split prior used as raw weights (Q3); null = uniform integer draw
     double prior_total;
+    // ---- OneHotSplit columns (splitting.rs:72-104; generic control code only).  The reference casts the node's values to i32,
+    // collects the distinct codes and picks one uniformly (its partition still tests x < code: SURVEY.md Q7).  Here a
+    // column's codes must span fewer than 64 consecutive integers, so a node's distinct codes are a 64-bit presence mask.
+    const unsigned char* onehot; // [p] 1 = OneHotSplit, or null when every column is ContinuousSplit
+    const int* col_imin;         // [p] smallest code of the column (bit 0 of the masks)
+    const unsigned long long* col_bits;   // [p] presence mask over all rows (the root's candidates)
+    unsigned long long* job_bits;         // [S] presence mask of each job's node
     const double* log_tbl;       // [PG_LOGT_K][2] (inv_k, -log inv_k): logarithm table of the Bernoulli pass (pg_log_ge1)
     const double* thr_depth;     // [max_depth+2] 1 - alpha (1+d)^-beta (host pow, smc.rs:143)
     double leaf_sigma, m_f, init_leaf, y_mean;
@@ -232,6 +243,7 @@ struct PgState {
     unsigned int* part_mm;       // [grid][2S][2] ordered-uint keys of min / max (2S: the partition pass may carry look-ahead requests)
     int* mq_pj; int* mq_side; int* mq_var;   // [2S] look-ahead min/max requests of the partition pass: (partition job, child side, column)
     double* part_ll;             // [grid][S][2]  Bernoulli: log-likelihood of the left / right child
+    double* part_old;            // [grid] per-block sum behind ll_old (root pass, pg_correct only)
     unsigned long long* diag_blocks;   // [grid][8] per pass block, by phase: cycles spent in pass bodies (-DPG_DIAG only)
     // segment pool
     unsigned int* pool; unsigned long long pool_cap;

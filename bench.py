@@ -137,10 +137,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bounded_updates(w, updates, budget_s=15.0):
+    """Tree updates of the CPU sample, cut so that the sample stays near `budget_s` seconds: the oracle (like the
+    reference) costs about 1.8e-8 s (Gaussian) / 3.5e-8 s (Bernoulli) per row per growing particle per tree update."""
+    per = w["n"] * max(w["P"] - 1, 1) * (3.5e-8 if w["family"] == "bernoulli_logit" else 1.8e-8)
+    return int(min(max(updates, 1), max(2, int(budget_s / per))))
+
+
 def oracle_sample(X, y, prm, w, updates, seed=0, warm=2):
     """Time `updates` tree updates of the CPU oracle on the workload (single core, like the reference)."""
     from oracle import pyoracle as po
     m = w["m"]
+    updates = bounded_updates(w, updates)
+    warm = min(warm, updates)
     frac = max(updates, 1) / m
     o = po.OracleSampler(X.astype(np.float64), y, n_trees=m, n_particles=w["P"], max_depth=prm["max_depth"],
                          alpha=0.95, beta=2.0, sigma=prm["sigma"], split_prior=prm["split_prior"],
@@ -165,7 +174,7 @@ def run_reference(args):
         return
     w = WORKLOADS[args.workload]
     X, y, prm = make_data(w)
-    per_step = max(1, int(args.ref_updates))
+    per_step = bounded_updates(w, max(1, int(args.ref_updates)))
     times, done_total = [], 0
     for i in range(args.warmup + args.steps):
         done, dt = oracle_sample(X, y, prm, w, per_step, seed=i, warm=1)

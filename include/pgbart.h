@@ -26,8 +26,11 @@ typedef struct pgbart_sampler* pgbart_handle;
 
 /* PyBartSettings (lib.rs:35-104), field for field.  response_rule / resampling_rule are accepted
  * and ignored exactly as the reference ignores them (always Gaussian leaf rule, systematic
- * resampling; lib.rs:47-48,166).  split_rules: only "ContinuousSplit" is executed on the device;
- * an unknown name is an error as in lib.rs:129-132, "OneHotSplit" is rejected (out of scope). */
+ * resampling; lib.rs:47-48,166).  split_rules: "ContinuousSplit" or "OneHotSplit" per column, padded with
+ * ContinuousSplit (lib.rs:134-144); an unknown name is an error as in lib.rs:129-132.  A OneHotSplit column
+ * (splitting.rs:72-104) must hold integer codes spanning fewer than 64 consecutive values; its split value is one of
+ * the node's distinct codes, uniformly, and the partition tests x < code as in the reference (particle.rs:128).  A
+ * sampler with a OneHotSplit column runs on the generic control code (slower than the n_particles <= 32 path). */
 typedef struct pgbart_settings {
     uint64_t n_trees;
     uint64_t n_particles;          /* includes the reference stump (smc.rs:42-52) */
@@ -110,6 +113,10 @@ int pgbart_trace_enable(pgbart_handle h, int64_t u_cap, int r_cap);
 int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd, int64_t* n_upd, int* overflow);
 
 /* Options: "driver" = "persistent" (default) | "stepwise"; "pool_factor" = integer >= 1;
+ * "weight_mode" = "reference" (default: the reference's arithmetic, smc.rs:53,89-102 — slot weights are normalised in
+ * place and meet next round's log-likelihoods, the reference particle is a fresh stump) | "pg_correct" (NOT the
+ * reference's behaviour: every slot keeps the log-likelihood of the particle it holds, permuted with the ancestors, and
+ * particle 0 is the tree being replaced — conditional SMC; runs on the generic control code; set before the first step);
  * "root_pass" = "direct" (default: register loads over warp sub-ranges of the block's rows) | "quarters" (row quarter x job
  * group, per-lane accumulators) | "staged" (async-copy ring in shared memory; only in -DPGBART_WITH_STAGED builds);
  * "prefetch_next" = 0 | 1 (L2 prefetch of the next tree update's root columns after a root pass). */

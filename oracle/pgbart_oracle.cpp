@@ -470,6 +470,13 @@ struct BartConfig {  // config.rs:4-18
     double alpha = 0.95, beta = 2.0, sigma = 1.0;
     std::vector<double> splitting_probs;  // empty = None
     double batch_tune = 0.1, batch_post = 0.1;
+    // SURVEY.md 8(f4) modes (NOT the reference's behaviour; each has its device counterpart and its own parity tests):
+    //   pg_correct: per-slot log-weights are kept as log-likelihoods, normalised into a copy, and permuted with the
+    //               ancestors (instead of the stale-weight rule Q1, smc.rs:53,89-102); particle 0 is the tree being
+    //               replaced, with nothing to expand (conditional SMC; instead of the fresh stump of smc.rs:42-50, Q2).
+    bool pg_correct = false;
+    // split_rules[j] == OneHotSplit (splitting.rs:72-104 through SplitRules::sample_split_value :127-137)
+    std::vector<uint8_t> onehot;
 };
 
 struct BartInfo {  // state.rs:16-20
@@ -628,6 +635,25 @@ struct Sampler {
         if (tr) tr[2] = (double)split_var;
         const double* col = x.data() + split_var * n;
 
+        if (split_var < cfg.onehot.size() && cfg.onehot[split_var]) {
+            // splitting.rs:127-137 casts the node's values to i32, :79-90 collects the distinct ones and picks one
+            // uniformly.  The reference iterates a HashSet (process-random order, Q7); here the distinct codes are taken
+            // in ascending order, which has the same distribution.  random_range(0..len) for usize is restated as
+            // floor of the f64 range draw on [0, len), like the uniform variable draw above.  The partition and the
+            // leaf statistics below use `v < split_val` for every rule (particle.rs:128, smc.rs:208: Q7).
+            std::vector<int32_t> codes(len);
+            for (size_t i = 0; i < len; ++i) {
+                const double v = col[node_samples[i]];
+                codes[i] = std::isnan(v) ? 0 : (v >= 2147483647.0 ? INT32_MAX : (v <= -2147483648.0 ? INT32_MIN : (int32_t)v));  // Rust `as i32`
+            }
+            std::sort(codes.begin(), codes.end());
+            codes.erase(std::unique(codes.begin(), codes.end()), codes.end());
+            if (tr) { tr[9] = (double)codes.front(); tr[10] = (double)codes.back(); }
+            if (codes.size() <= 1) { if (tr) tr[0] = 3; return false; }
+            const size_t k = std::min<size_t>((size_t)draws.range(c, 0.0, (double)codes.size()), codes.size() - 1);
+            return finish_proposal(particle, node_idx, others, c, split_var, (double)codes[k], out, tr);
+        }
+
         // splitting.rs:39-56
         double mn = col[node_samples[0]], mx = mn;
         for (size_t i = 1; i < len; ++i) {
@@ -638,7 +664,15 @@ struct Sampler {
         if (tr) { tr[9] = mn; tr[10] = mx; }
         if (mn >= mx) { if (tr) tr[0] = 3; return false; }
         const double split_val = draws.range(c, mn, mx);
+        return finish_proposal(particle, node_idx, others, c, split_var, split_val, out, tr);
+    }
 
+    // smc.rs:189-240 propose_leaf_values + the Accept arm of propose_mutation
+    bool finish_proposal(const Particle& particle, size_t node_idx, const double* others, const DrawCtx& c,
+                         size_t split_var, double split_val, TreeProposal& out, double* tr) {
+        const uint32_t* node_samples = particle.sample_map.data.data() + particle.sample_map.node_start[node_idx];
+        const size_t len = particle.sample_map.node_len[node_idx];
+        const double* col = x.data() + split_var * n;
         // smc.rs:197-217
         double l_sum = 0.0, r_sum = 0.0;
         size_t l_n = 0, r_n = 0;
@@ -669,7 +703,7 @@ struct Sampler {
 
     // smc.rs:26-130
     bool smc_step(const std::vector<double>& others, TreeArrays& out_tree, double& info_loglik,
-                  size_t& info_acc, size_t tree_idx) {
+                  size_t& info_acc, size_t tree_idx, const TreeArrays* old_tree = nullptr) {
         const size_t P = cfg.n_particles;
         const size_t S = P - 1;
         const double init_leaf = (n ? unrolled_sum(y.data(), n) / (double)n : 0.0) / (double)cfg.n_trees;  // smc.rs:40
@@ -677,10 +711,16 @@ struct Sampler {
         std::vector<Particle> particles;
         particles.reserve(P);
         for (size_t i = 0; i < P; ++i) particles.push_back(Particle::fresh(init_leaf, n, cfg.max_depth, i == 0));
+        if (cfg.pg_correct && old_tree) particles[0].tree = std::make_shared<TreeArrays>(*old_tree);   // conditional SMC (not the reference: Q2)
 
         std::vector<double> inner_weights(S, 0.0);  // smc.rs:53 (never reset: Q1)
         size_t acceptance_count = 0;
         std::vector<double> predictions_buf(n, 0.0);
+        std::vector<double> slot_logw;              // pg_correct: log-likelihood of each slot's particle, permuted with the ancestors
+        if (cfg.pg_correct) {
+            for (size_t r = 0; r < n; ++r) predictions_buf[r] = init_leaf + others[r];
+            slot_logw.assign(S, wf.log_weight(predictions_buf.data()));
+        }
         std::vector<size_t> ancestors(S);
         std::vector<Particle> scratch;
         std::vector<char> mutated(S, 0);
@@ -725,10 +765,12 @@ struct Sampler {
                 particle.tree->predict_training_into(predictions_buf.data());
                 for (size_t r = 0; r < n; ++r) predictions_buf[r] += others[r];
                 inner_weights[i] = wf.log_weight(predictions_buf.data());
+                if (cfg.pg_correct) slot_logw[i] = inner_weights[i];
                 c.slot = (int)i;
                 double* tr = ts(c);
                 if (tr) tr[8] = inner_weights[i];
             }
+            if (cfg.pg_correct) inner_weights = slot_logw;    // every slot enters with its particle's log-likelihood
             normalize_weights_inplace(inner_weights.data(), S);
 
             c.slot = 0;
@@ -740,6 +782,11 @@ struct Sampler {
                 for (size_t i = 0; i < S; ++i) { tr[2 + i] = inner_weights[i]; tr[2 + S + i] = (double)ancestors[i]; }
             } else if (trace.round) trace.overflow = true;
 
+            if (cfg.pg_correct) {
+                std::vector<double> lw(S);
+                for (size_t i = 0; i < S; ++i) lw[i] = slot_logw[ancestors[i]];
+                slot_logw.swap(lw);
+            }
             scratch.clear();
             for (size_t i = 0; i < S; ++i) scratch.push_back(particles[1 + ancestors[i]]);  // clone (copies CSR data)
             particles.resize(1);
@@ -793,7 +840,7 @@ struct Sampler {
 
             TreeArrays new_tree;
             double ll = 0.0; size_t acc = 0;
-            if (!smc_step(residuals_buf, new_tree, ll, acc, tree_idx)) {
+            if (!smc_step(residuals_buf, new_tree, ll, acc, tree_idx, &forest[tree_idx])) {
                 if (error.empty()) error = "RNG tape exhausted or inconsistent";
                 return false;
             }
@@ -851,6 +898,14 @@ void* orc_create(const double* x_f, uint64_t n, uint64_t p, const double* y, con
 }
 
 void orc_destroy(void* h) { delete (orc::Sampler*)h; }
+
+// SURVEY.md 8(f4) modes, set before the first step: pg_correct (0/1), onehot[p] flags (may be NULL)
+int orc_set_modes(void* h, int pg_correct, const uint8_t* onehot) {
+    auto* s = (orc::Sampler*)h;
+    s->cfg.pg_correct = pg_correct != 0;
+    if (onehot) s->cfg.onehot.assign(onehot, onehot + s->p); else s->cfg.onehot.clear();
+    return 0;
+}
 
 int orc_set_likelihood(void* h, int family, const double* params, int nparams) {
     auto* s = (orc::Sampler*)h;

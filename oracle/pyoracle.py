@@ -53,6 +53,7 @@ def lib():
         L.orc_create.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(_Settings)]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_likelihood.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_set_modes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_set_rng.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
         L.orc_attach_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
         L.orc_attach_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
@@ -127,7 +128,7 @@ class OracleSampler:
     """CPU oracle with the PySampler-shaped surface (init/step)."""
 
     def __init__(self, x, y, *, n_trees, n_particles, max_depth, alpha, beta, sigma, split_prior=(),
-                 batch_tune=0.1, batch_post=0.1, seed=0):
+                 batch_tune=0.1, batch_post=0.1, seed=0, pg_correct=False, onehot=None):
         L = lib()
         x = np.asarray(x, dtype=np.float64)
         self.n, self.p = x.shape
@@ -140,6 +141,10 @@ class OracleSampler:
         self.n_trees, self.n_particles = n_trees, n_particles
         self._h = L.orc_create(_ptr(self._x), self.n, self.p, _ptr(self._y), C.byref(st))
         self._keep = []
+        if pg_correct or onehot is not None:      # SURVEY.md 8(f4) modes (not the reference's behaviour)
+            oh = None if onehot is None else np.ascontiguousarray(np.asarray(onehot, dtype=np.uint8))
+            assert oh is None or oh.size == self.p
+            L.orc_set_modes(self._h, int(bool(pg_correct)), None if oh is None else _ptr(oh))
 
     def close(self):
         if self._h:

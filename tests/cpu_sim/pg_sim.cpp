@@ -62,7 +62,7 @@ void pass_root(const PgState& st) {
     const int t_add = c->t_add, t_sub = is_root ? c->t_sub : -1;
     const int S = st.S;
     for (int b = 0; b < st.grid; ++b) {
-        double tot[4] = {0, 0, 0, 0};
+        double tot[4] = {0, 0, 0, 0}, tot_old = 0.0;
         std::vector<double> so(J, 0.0), sr(J, 0.0);
         std::vector<unsigned> cc(J, 0u);
         for (int w = 0; w < PG_WARPS; ++w) {
@@ -73,6 +73,10 @@ void pass_root(const PgState& st) {
             for (unsigned long long row = beg; row < end; ++row) {
                 double o = st.A[row];
                 if (t_add >= 0) o = o + tree_eval(st, t_add, (long long)row);
+                if (st.pg_correct && is_root) {     // log-likelihood of the current predictions (conditional reference particle)
+                    if (st.family == PG_BERNOULLI_LOGIT) tot_old += (double)st.y[row] * o - pg_softplus(o);
+                    else { const double d = (double)st.y[row] - o; tot_old += d * d; }
+                }
                 if (t_sub >= 0) o = o - tree_eval(st, t_sub, (long long)row);
                 st.A[row] = o;
                 if (!is_root) continue;
@@ -88,6 +92,7 @@ void pass_root(const PgState& st) {
             for (int j = 0; j < J; ++j) st.part_cnt[(size_t)gw * S + j] = wc[j];
         }
         for (int q = 0; q < 4; ++q) st.part_tot[(size_t)b * 4 + q] = tot[q];
+        if (st.pg_correct && is_root) st.part_old[b] = tot_old;
         for (int j = 0; j < J; ++j) {
             st.part_sum[((size_t)b * S + j) * 2 + 0] = so[j];
             st.part_sum[((size_t)b * S + j) * 2 + 1] = sr[j];
@@ -104,6 +109,18 @@ void pass_minmax(const PgState& st) {
             uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
             const unsigned off = st.job_seg_off[j];
             const unsigned long long L = st.job_len[j];
+            if (st.onehot && st.onehot[st.job_var[j]]) {     // presence mask of the node's integer codes (low / high words)
+                unsigned long long bits = 0ull;
+                for (int w = 0; w < PG_WARPS; ++w) {
+                    unsigned long long beg, end;
+                    pg_warp_range(L, b * PG_WARPS + w, st.n_gwarps, 1, &beg, &end);
+                    for (unsigned long long e = beg; e < end; ++e)
+                        bits |= 1ull << ((int)st.X[(size_t)st.job_var[j] * st.ld + st.pool[(size_t)off + e]] - st.col_imin[st.job_var[j]]);
+                }
+                st.part_mm[((size_t)b * 2 * S + j) * 2 + 0] = (unsigned)(bits & 0xFFFFFFFFull);
+                st.part_mm[((size_t)b * 2 * S + j) * 2 + 1] = (unsigned)(bits >> 32);
+                continue;
+            }
             for (int w = 0; w < PG_WARPS; ++w) {
                 unsigned long long beg, end;
                 pg_warp_range(L, b * PG_WARPS + w, st.n_gwarps, 1, &beg, &end);
@@ -220,6 +237,21 @@ void* pgsim_create(const double* x_f, uint64_t n, uint64_t p, const double* y, c
         cmin[j] = mn; cmax[j] = mx;
     }
     st.X = X; st.col_min = cmin; st.col_max = cmax;
+    {   // OneHotSplit columns (same preparation as pgbart_create)
+        unsigned char* oh = halloc<unsigned char>(s, p);
+        int* imin = halloc<int>(s, p);
+        unsigned long long* cb = halloc<unsigned long long>(s, p);
+        bool any = false;
+        for (uint64_t j = 0; j < cfg->n_split_rules && j < p; ++j) {
+            if (!cfg->split_rules || std::strcmp(cfg->split_rules[j], "OneHotSplit") != 0) continue;
+            oh[j] = 1; any = true;
+            int lo = INT32_MAX;
+            for (uint64_t i = 0; i < n; ++i) { const int c = (int)X[j * st.ld + i]; lo = c < lo ? c : lo; }
+            imin[j] = lo;
+            for (uint64_t i = 0; i < n; ++i) cb[j] |= 1ull << ((int)X[j * st.ld + i] - lo);
+        }
+        if (any) { st.onehot = oh; st.col_imin = imin; st.col_bits = cb; st.job_bits = halloc<unsigned long long>(s, (size_t)st.S); }
+    }
     float* yy = halloc<float>(s, (size_t)st.ld);
     for (uint64_t i = 0; i < n; ++i) yy[i] = (float)y[i];
     st.y = yy;
@@ -257,7 +289,7 @@ void* pgsim_create(const double* x_f, uint64_t n, uint64_t p, const double* y, c
     st.pj_cntL = halloc<unsigned>(s, S); st.pj_warp_left = halloc<unsigned>(s, S * W); st.pj_of_anc = halloc<int>(s, S);
     st.scan_tmp = halloc<unsigned>(s, PG_THREADS + 1);
     st.part_sum = halloc<double>(s, G * S * 2); st.part_cnt = halloc<unsigned>(s, W * S); st.part_ccnt = halloc<unsigned>(s, G * S);
-    st.part_tot = halloc<double>(s, G * 4); st.part_mm = halloc<unsigned>(s, G * 2 * S * 2); st.mq_pj = halloc<int>(s, 2 * S); st.mq_side = halloc<int>(s, 2 * S); st.mq_var = halloc<int>(s, 2 * S); st.part_ll = halloc<double>(s, G * S * 2);
+    st.part_tot = halloc<double>(s, G * 4); st.part_mm = halloc<unsigned>(s, G * 2 * S * 2); st.mq_pj = halloc<int>(s, 2 * S); st.mq_side = halloc<int>(s, 2 * S); st.mq_var = halloc<int>(s, 2 * S); st.part_ll = halloc<double>(s, G * S * 2); st.part_old = halloc<double>(s, G);
     st.info_depths = halloc<unsigned char>(s, M);
     st.ctrl = halloc<PgCtrl>(s, 1);
     st.pool_cap = (unsigned long long)std::max<size_t>(2 * S, (size_t)st.max_depth + 2) * n;
@@ -284,6 +316,13 @@ int pgsim_set_likelihood(void* h, int family, const double* params, int nparams)
     Sim* s = (Sim*)h;
     s->st.family = family;
     if (family == PG_GAUSSIAN && nparams >= 1) s->st.lik_sigma = params[0];
+    return 0;
+}
+
+// SURVEY.md 8(f4) weight mode (pgbart_set_option "weight_mode")
+int pgsim_set_pg_correct(void* h, int on) {
+    Sim* s = (Sim*)h;
+    s->st.pg_correct = on != 0;
     return 0;
 }
 

@@ -36,6 +36,7 @@ def lib():
         L.pgsim_last_error.restype = C.c_char_p
         L.pgsim_last_error.argtypes = [vp]
         L.pgsim_set_likelihood.argtypes = [vp, C.c_int, vp, C.c_int]
+        L.pgsim_set_pg_correct.argtypes = [vp, C.c_int]
         L.pgsim_set_rng_philox.argtypes = [vp, C.c_uint64]
         L.pgsim_set_rng_tape.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int]
         L.pgsim_trace_attach.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int]
@@ -69,7 +70,7 @@ class SimSampler:
     """Same method names as bart_rs_b200.PySampler's test-facing surface."""
 
     def __init__(self, x, y, *, n_trees, n_particles, max_depth, alpha, beta, sigma, split_prior=(), batch_tune=0.1,
-                 batch_post=0.1, seed=0, grid=3):
+                 batch_post=0.1, seed=0, grid=3, pg_correct=False, onehot=None):
         L = lib()
         self._L = L
         xf = np.asfortranarray(np.asarray(x, dtype=np.float64))
@@ -77,11 +78,15 @@ class SimSampler:
         self.n, self.p = xf.shape
         self.n_trees, self.n_particles = n_trees, n_particles
         prior = np.ascontiguousarray(np.asarray(split_prior, dtype=np.float64))
+        names = [b"OneHotSplit" if (onehot is not None and onehot[j]) else b"ContinuousSplit" for j in range(self.p)]
+        rules = (C.c_char_p * self.p)(*names)
         st = _capi.Settings(n_trees, n_particles, max_depth, alpha, beta, sigma,
-                            prior.ctypes.data_as(C.POINTER(C.c_double)), prior.size, None, 0, b"", b"",
+                            prior.ctypes.data_as(C.POINTER(C.c_double)), prior.size, rules, self.p, b"", b"",
                             batch_tune, batch_post, seed)
         self._h = L.pgsim_create(_p(xf), self.n, self.p, _p(y), C.byref(st), grid)
-        self._keep = []
+        self._keep = [rules]
+        if pg_correct:
+            L.pgsim_set_pg_correct(self._h, 1)
 
     def set_likelihood_code(self, family, params=()):
         a = np.ascontiguousarray(np.asarray(params, dtype=np.float64))

@@ -19,11 +19,15 @@ class GpuAdapter:
 
     def __init__(self, X, y, cfg, driver):
         from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
+        oh = cfg.get("onehot")
+        rules = ["OneHotSplit" if (oh is not None and oh[j]) else "ContinuousSplit" for j in range(X.shape[1])]
         st = PyBartSettings(cfg["n_trees"], cfg["n_particles"], cfg["max_depth"], cfg["alpha"], cfg["beta"], cfg["sigma"],
-                            list(cfg["split_prior"]), ["ContinuousSplit"] * X.shape[1], "constant", "systematic",
+                            list(cfg["split_prior"]), rules, "constant", "systematic",
                             cfg["batch_tune"], cfg["batch_post"], cfg.get("seed", 0))
         self.s = PySampler.init(np.asfortranarray(X.astype(np.float64)), y, DeviceLikelihood("gaussian", 1.0), st)
         self.s.set_option("driver", driver)
+        if cfg.get("pg_correct"):
+            self.s.set_option("weight_mode", "pg_correct")
         self._DL = DeviceLikelihood
 
     def set_likelihood_code(self, family, params=()):
@@ -348,3 +352,45 @@ def test_gpu_out_of_sample_predict_and_variable_inclusion():
                 cnt[v] += 1
     np.testing.assert_array_equal(vi, cnt)
     assert vi.sum() > 0
+
+
+# ---- modes beyond the reference's live behaviour, each against its own oracle mode -------------------
+
+@pytest.mark.parametrize("n,p,m,P,family,driver", [(3000, 6, 6, 12, 0, "persistent"), (2500, 5, 5, 8, 1, "persistent"),
+                                                   (2000, 4, 4, 48, 0, "persistent"), (1200, 4, 4, 6, 0, "stepwise")])
+def test_gpu_pg_correct_mode(n, p, m, P, family, driver):
+    """weight_mode pg_correct (log-weights carried with the particles, the tree being replaced as conditional reference
+    particle) on the generic control code: decisions bit-exact and values within tolerance against the oracle's same mode."""
+    X, y = datagen.small(n, p, seed=n + P, bernoulli=(family == 1))
+    cfg = cfg_for(y, m, P, p, seed=n, beta=1.2, max_depth=9)
+    cfg["pg_correct"] = True
+    tr = parity.replay_parity(make_gpu(driver), X, y, cfg, family, 1.0, [True, True], r_cap=128)
+    assert np.any(tr.upd[:2 * m, 0] > 3)
+
+
+@pytest.mark.parametrize("P,pg_correct", [(10, False), (8, True), (40, True)])
+def test_gpu_onehot_columns(P, pg_correct):
+    """OneHotSplit columns (splitting.rs:72-104): split value = one of the node's distinct integer codes (presence-mask
+    pass below the root), partition by x < code like the reference (Q7)."""
+    from tests.test_sim_parity import _categorical
+    n, p, m = 4000, 6, 6
+    X, y = _categorical(n, p, seed=P, cats=(0, 1, 3))
+    cfg = cfg_for(y, m, P, p, seed=P, beta=0.8, max_depth=9)
+    cfg["onehot"] = [1, 1, 1, 0, 0, 0]
+    if pg_correct:
+        cfg["pg_correct"] = True
+    tr = parity.replay_parity(make_gpu(), X, y, cfg, 0, 1.0, [True, True], r_cap=128)
+    st = tr.slot[:2 * m]
+    oh = (st[..., 0] == 4) & (st[..., 2] <= 2)
+    assert oh.any()
+    if pg_correct:
+        assert (oh & (st[..., 1] > 0)).any()
+
+
+def test_gpu_onehot_rejects_wide_code_range():
+    from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
+    X = np.stack([np.arange(200, dtype=np.float64), np.linspace(0, 1, 200)], axis=1).astype(np.float32).astype(np.float64)
+    y = X[:, 1].copy()
+    st = PyBartSettings(4, 4, 4, 0.95, 2.0, 0.1, [1.0, 1.0], ["OneHotSplit", "ContinuousSplit"], "constant", "systematic", 1.0, 1.0, 0)
+    with pytest.raises(ValueError, match="at most 64 consecutive codes"):
+        PySampler.init(np.asfortranarray(X), y, DeviceLikelihood("gaussian", 1.0), st)

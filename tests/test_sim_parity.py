@@ -100,3 +100,54 @@ def test_helpers_thr32_keys_ranges():
             prev = e.value
             cover += e.value - b.value
         assert cover == Lh and prev == Lh
+
+
+# ---- modes beyond the reference's live behaviour, each against its own oracle mode -------------------
+
+def _categorical(n, p, seed, cats=(0, 1, 2)):
+    """Columns 0 .. len(cats)-1 hold integer codes (column j: cats[j] + 2 distinct values, shifted by j - 1), the rest U[0, 1)."""
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, p), dtype=np.float32)
+    for j, extra in enumerate(cats):
+        X[:, j] = (rng.integers(0, 2 + extra, n) + (j - 1)).astype(np.float32)
+    y = (X[:, 0] * 1.5 - (X[:, 1] > 0) + np.sin(3 * X[:, -1]) + 0.3 * rng.standard_normal(n)).astype(np.float32).astype(np.float64)
+    return X, y
+
+
+PG_CORRECT_CASES = [
+    (200, 4, 6, 8, 0, 1.0, dict(), [True, True]),
+    (150, 3, 5, 4, 1, 1.0, dict(beta=1.0, max_depth=8), [True, True]),
+    (120, 3, 4, 40, 0, 0.5, dict(), [True]),                    # P > 32
+    (90, 3, 4, 3, 2, 1.0, dict(beta=0.7, max_depth=9), [True, True, True]),
+]
+
+
+@pytest.mark.parametrize("n,p,m,P,family,lik_sigma,kw,tunes", PG_CORRECT_CASES)
+def test_sim_pg_correct_mode(n, p, m, P, family, lik_sigma, kw, tunes):
+    """weight_mode pg_correct: log-weights carried with the particles, the tree being replaced as reference particle.
+    Unlike the reference mode (Q1) trees grow past one split and the old tree can be kept."""
+    X, y = datagen.small(n, p, seed=n + P, bernoulli=(family == 1))
+    cfg = cfg_for(y, m, P, p, seed=n, **kw)
+    cfg["pg_correct"] = True
+    tr = parity.replay_parity(make_sim(2), X, y, cfg, family, lik_sigma, tunes, r_cap=96)
+    U = len(tunes) * m
+    assert np.any(tr.upd[:U, 0] > 3), "no tree update ran more than three rounds: the mode did not take effect"
+
+
+@pytest.mark.parametrize("P,pg_correct", [(6, False), (5, True), (40, True)])
+def test_sim_onehot_columns(P, pg_correct):
+    """OneHotSplit columns (splitting.rs:72-104): the split value is one of the node's distinct integer codes; the
+    partition still tests x < code (Q7).  With pg_correct trees get deep enough for non-root nodes to draw codes."""
+    n, p, m = 240, 5, 5
+    X, y = _categorical(n, p, seed=P)
+    cfg = cfg_for(y, m, P, p, seed=P, beta=0.8, max_depth=9)
+    cfg["onehot"] = [1, 1, 1, 0, 0]
+    if pg_correct:
+        cfg["pg_correct"] = True
+    tr = parity.replay_parity(make_sim(3), X, y, cfg, 0, 1.0, [True, True], r_cap=96)
+    st = tr.slot[:2 * m]
+    onehot_accepts = (st[..., 0] == 4) & (st[..., 2] <= 2)
+    assert onehot_accepts.any()
+    assert np.all(st[..., 3][onehot_accepts] == np.round(st[..., 3][onehot_accepts]))      # split values are integer codes
+    if pg_correct:
+        assert (onehot_accepts & (st[..., 1] > 0)).any(), "no OneHot split below the root: the presence-mask pass was not exercised"
