@@ -55,7 +55,9 @@ enum PgError : int {
 #define PG_SEG_IDENTITY 0xFFFFFFFFu  // node's samples are 0..n (root): no index list is read
 #define PG_SEG_NONE 0xFFFFFFFEu      // children not materialised yet
 #define PG_TS_FIELDS 12
+#ifndef PG_THREADS
 #define PG_THREADS 512
+#endif
 #define PG_WARPS (PG_THREADS / 32)
 
 #define PG_MAX_RANKS 8

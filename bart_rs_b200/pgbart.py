@@ -177,6 +177,10 @@ class PGBART:
     sigma = 1 is assumed and a warning is raised.  sigma_source: optional zero-argument callable returning the current
     sigma; astep() calls it before every step (what update_shared_arrays does in the reference, pgbart.py:190).  Without
     it the caller must keep `self.likelihood.sigma` current.
+    split_rules: "ContinuousSplit" / "OneHotSplit" per column (reference pgbart.py:146-152 -> splitting.rs); a OneHotSplit
+    column holds integer codes spanning fewer than 64 values and runs the sampler on the generic control code.
+    weight_mode: "reference" (default: the reference's arithmetic, stale-weight rule and fresh-stump reference particle
+    included) | "pg_correct" (conditional SMC with log-weights carried by the particles; not the reference's behaviour).
     fp32_rounding: "warn" (default) | "allow" | "error" — the device stores X and Y as fp32; float64 data that is not
     fp32-representable is rounded with a warning (or silently / refused).
     """
@@ -189,7 +193,8 @@ class PGBART:
                  split_prior: Optional[Sequence[float]] = None, split_rules: Optional[Sequence[str]] = None,
                  response: str = "constant", num_particles: int = 10, batch: Tuple[float, float] = (0.1, 0.1),
                  likelihood: Optional[DeviceLikelihood] = None, device: int = 0, seed: int = 0,
-                 sigma_source: Optional[Callable[[], float]] = None, fp32_rounding: str = "warn"):
+                 sigma_source: Optional[Callable[[], float]] = None, fp32_rounding: str = "warn",
+                 weight_mode: str = "reference"):
         self.X = np.asarray(X)
         self.Y = np.asarray(Y, dtype=np.float64)
         self.m = int(m)
@@ -231,6 +236,8 @@ class PGBART:
             response_rule=response, resampling_rule="systematic", batch_tune=batch[0], batch_post=batch[1], seed=seed)
         self.pg_bart = PySampler.init(x=np.asfortranarray(self.X), y=self.Y, model=self.likelihood, settings=settings,
                                       device=device, fp32_rounding="error" if fp32_rounding == "error" else "allow")
+        if weight_mode != "reference":      # "pg_correct": NOT the reference's sampler (include/pgbart.h, option weight_mode)
+            self.pg_bart.set_option("weight_mode", weight_mode)
         self.tune = True
 
     def astep(self, _=None):
