@@ -872,6 +872,7 @@ __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSm
 // =============================================================================
 // PH_MINMAX — splitting.rs:43-49 over index segments
 // =============================================================================
+template <bool ONEHOT>   // ONEHOT: the generic kernels, where OneHotSplit columns ask for a presence mask instead of min / max
 __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     const int J = sm.base->cmd.n_jobs;
     const int S = st.S;
@@ -880,7 +881,7 @@ __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemV
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
         const int var = __ldcg(&bf.job_var[j]);
         sm.jvar[j] = var;
-        const bool oh = st.onehot && st.onehot[var];
+        const bool oh = ONEHOT && st.onehot && st.onehot[var];
         sm.mmin[j] = oh ? 0u : 0xFFFFFFFFu; sm.mmax[j] = 0u;
     }
     __syncthreads();
@@ -891,7 +892,7 @@ __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemV
         const float* col = st.X + (size_t)sm.jvar[j] * ld;
         unsigned long long beg, end;
         pg_warp_range(L, gw, st.n_gwarps, 1, &beg, &end);
-        if (st.onehot && st.onehot[sm.jvar[j]]) {
+        if (ONEHOT && st.onehot && st.onehot[sm.jvar[j]]) {
             // OneHotSplit column (splitting.rs:79-90): which integer codes occur in the node — a 64-bit presence mask,
             // its low / high words in the slots the min / max keys use
             const int imin = st.col_imin[sm.jvar[j]];
@@ -1613,7 +1614,7 @@ __device__ __forceinline__ void pg_run_pass(const PgState& st, const PgSmemView&
             }
             else pg_pass_root<false, true>(st, bf, sm);
             break;
-        case PH_MINMAX: pg_pass_minmax(st, bf, sm); break;
+        case PH_MINMAX: pg_pass_minmax<VAR == PGV_GENERIC>(st, bf, sm); break;
         case PH_STATS: if (FASTP && VAR != PGV_BERN) pg_pass_seg_block(st, bf, sm); else pg_pass_seg(st, bf, sm); break;
         case PH_BERN: if (VAR == PGV_GENERIC || VAR == PGV_BERN) pg_pass_bern(st, bf, sm); break;
         case PH_PART: pg_pass_part<FASTP>(st, bf, sm); break;

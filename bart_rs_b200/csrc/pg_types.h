@@ -99,7 +99,6 @@ struct PgCtrl {
     double C0;                      // particle-independent part of the log-likelihood
     double Cconst, inv_s2;          // per step: -n (log sigma + 0.5 log 2 pi) and 1/sigma^2 (Gaussian), else 0 and 1
     double g_stump;
-    double ll_old;                  // weight_mode pg_correct: log-likelihood of the current predictions (= of the tree being replaced)
     int acc_update;                 // accepted grows in this update
     int any_queue;
     // ---- BartInfo (state.rs:16-20) of the current step
@@ -145,7 +144,8 @@ struct PgCtrl {
     // ---- set by pg_prepare_step when an earlier step left a device error behind: steps queued after it must not run on
     // the broken state (pgbart_step_device can be queued several times before pgbart_sync reports the error)
     int poisoned;
-    int pad_cmd[29];
+    int pad_cmd[27];
+    double ll_old;                  // weight_mode pg_correct: log-likelihood of the current predictions (= of the tree being replaced)
     // ---- P <= 32 persistent kernels: command buffers by generation parity, and completion counters by generation parity
     // (zeroed with bar_gen by pg_prepare_step); counter q holds 147 x (generations of parity q completed)
     int cmd[2][16];
