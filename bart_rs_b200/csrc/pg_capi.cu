@@ -786,6 +786,17 @@ int pgbart_get_profile(pgbart_handle h, double* out32) {
     return 0;
 }
 
+int pgbart_debug_state(pgbart_handle h, double* out8) {
+    if (!h || !out8) return 1;
+    Sampler* s = &h->s;
+    // no error check on purpose: this is what one reads AFTER a step failed (the copy itself fails if the context is lost)
+    if (cudaMemcpy(&s->host_ctrl, s->st.ctrl, sizeof(PgCtrl), cudaMemcpyDeviceToHost) != cudaSuccess) { s->err = "device state is not readable (context lost)"; return 2; }
+    const PgCtrl& c = s->host_ctrl;
+    out8[0] = c.phase; out8[1] = c.k; out8[2] = c.round; out8[3] = (double)c.upd; out8[4] = (double)c.xseq;
+    out8[5] = (double)c.n_phases; out8[6] = c.error; out8[7] = c.t_cur;
+    return 0;
+}
+
 int pgbart_debug_block_cycles(pgbart_handle h, double* out, int cap) {
     if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;

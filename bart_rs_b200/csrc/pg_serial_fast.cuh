@@ -225,7 +225,9 @@ __device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, in
         const long long t0 = clock64();
         while (fw_ld_acquire_sys(&my_flags[par * PG_MAX_RANKS + lane]) < seq) {
             __nanosleep(100);
-            if (clock64() - t0 > 40000000000ll) { f->lc.error = PG_ERR_WATCHDOG; break; }   // a lost peer becomes an error
+            // a lost peer becomes an error — after half the time the pass blocks' own watchdog allows (pg_spin_until), so that
+            // every rank leaves its kernel in an orderly way and the host can still read where each one stood
+            if (clock64() - t0 > 20000000000ll) { f->lc.error = PG_ERR_WATCHDOG; break; }
         }
     }
     __syncwarp();                                            // the acquiring lanes' loads are ordered before every lane's reads below

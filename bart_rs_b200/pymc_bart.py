@@ -350,6 +350,14 @@ class PySampler:
         self._check(self._L.pgbart_variable_inclusion(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def debug_state(self) -> dict:
+        """Where the device state machine stands (readable after a step that failed gracefully; include/pgbart.h)."""
+        out = np.zeros(8)
+        rc = self._L.pgbart_debug_state(self._h, out.ctypes.data_as(C.c_void_p))
+        if rc:
+            return {"unreadable": True}
+        return dict(zip(["phase", "k", "round", "upd", "xseq", "grid_passes", "error", "t_cur"], out.tolist()))
+
     def block_cycles(self) -> np.ndarray:
         """[pass block][phase] cycles spent in pass bodies (only filled by -DPG_DIAG builds)."""
         g = int(self.counters()["grid_blocks"])

@@ -69,6 +69,11 @@ class ShardedSampler(PySampler):
         dist.all_gather_object(handles, handle.tobytes(), group=group)
         blob = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
         self._check(L.pgbart_shard_connect(self._h, blob.ctypes.data_as(C.c_void_p)))
-        dist.barrier(group=group)          # every mailbox is mapped everywhere before the first step
+        # Every mailbox must be mapped everywhere before the first step, and the ranks' HOSTS must leave together: the
+        # control blocks wait for each other inside the kernel (with a watchdog), while mapping seven peers' memory can
+        # take a rank many seconds longer than another.  dist.barrier() on NCCL only orders streams, so gather an object
+        # instead (that blocks the host on every backend).
+        done = [None] * world
+        dist.all_gather_object(done, rank, group=group)
         self.rank, self.world, self.n_global = rank, world, n_global
         return self

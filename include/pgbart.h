@@ -175,6 +175,10 @@ int pgbart_shard_connect(pgbart_handle h, const unsigned char* handles);
 /* Diagnostics (-DPG_DIAG builds): out[b*8 + phase] = SM cycles pass block b has spent in pass bodies of that phase;
  * out[G*8 + b*8 + i] = cycles between checkpoints i of the staged root pass (G = pass blocks; cap >= 16 G). */
 int pgbart_debug_block_cycles(pgbart_handle h, double* out, int cap);
+/* Where the device state machine stands (after a step, or after a step that failed gracefully — e.g. an exchange that timed
+ * out in an observation-sharded run): out8 = phase, tree update in the batch, round, tree updates since creation,
+ * exchanges between ranks since creation, grid passes since creation, device error code, tree being updated. */
+int pgbart_debug_state(pgbart_handle h, double* out8);
 
 /* CUDA-event stopwatch on the sampler's own stream (the stream the sweep kernels are launched on):
  * start records an event, stop records a second one, synchronises and returns the milliseconds between. */
