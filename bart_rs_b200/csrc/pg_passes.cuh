@@ -1652,7 +1652,7 @@ __device__ __forceinline__ void pg_spin_until(const unsigned* p, unsigned target
     while (pg_ld_relaxed(p) < target) {
         __nanosleep(ns);
         if (ns < 160) ns <<= 1;
-        if (clock64() - t0 > 40000000000ll) {   // ~20 s at 2 GHz: a lost block becomes an error, not a hang
+        if (clock64() - t0 > 80000000000ll) {   // ~40 s at 2 GHz (twice the exchange time-out of a sharded run): a lost block becomes an error, not a hang
             c->error = PG_ERR_WATCHDOG;
             __threadfence();
             __trap();

@@ -227,7 +227,7 @@ __device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, in
             __nanosleep(100);
             // a lost peer becomes an error — after half the time the pass blocks' own watchdog allows (pg_spin_until), so that
             // every rank leaves its kernel in an orderly way and the host can still read where each one stood
-            if (clock64() - t0 > 20000000000ll) { f->lc.error = PG_ERR_WATCHDOG; break; }
+            if (clock64() - t0 > 40000000000ll) { f->lc.error = PG_ERR_WATCHDOG; break; }
         }
     }
     __syncwarp();                                            // the acquiring lanes' loads are ordered before every lane's reads below
@@ -237,11 +237,17 @@ __device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, in
         const int i = lane + 32 * q;
         if (i >= n_val) continue;
         const volatile double* col = box + i;
-        double acc = sums ? 0.0 : col[0];
-        if (sums) { for (int r = 0; r < W; ++r) acc += col[(size_t)r * PG_MAIL_DOUBLES]; }
-        else {
+        double v[PG_MAX_RANKS];                              // every rank's contribution requested at once, combined in rank order
+#pragma unroll
+        for (int r = 0; r < PG_MAX_RANKS; ++r) v[r] = r < W ? col[(size_t)r * PG_MAIL_DOUBLES] : 0.0;
+        double acc = sums ? 0.0 : v[0];
+        if (sums) {
+#pragma unroll
+            for (int r = 0; r < PG_MAX_RANKS; ++r) if (r < W) acc += v[r];
+        } else {
             const int k = (i - 4) % 3;
-            for (int r = 1; r < W; ++r) { const double v = col[(size_t)r * PG_MAIL_DOUBLES]; acc = k == 0 ? fmin(acc, v) : fmax(acc, v); }
+#pragma unroll
+            for (int r = 1; r < PG_MAX_RANKS; ++r) if (r < W) acc = k == 0 ? fmin(acc, v[r]) : fmax(acc, v[r]);
         }
         if (i < 4) { if (phase == PH_ROOT) f->tot[i] = acc; }
         else {
