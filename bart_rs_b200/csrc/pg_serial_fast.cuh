@@ -175,17 +175,20 @@ __device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int 
 // ---- stage A': observation sharding — exchange the reduced values between the ranks' control blocks ------------
 // Every rank holds a contiguous block of rows and runs the identical control code on identical draws; the only
 // data-dependent inputs of that code are the values fw_reduce produces.  Each rank writes its values into every peer's
-// mailbox (plain stores into peer memory over NVLink, then a system-scope release of a sequence flag), waits for the
-// peers' flags, and combines all ranks' contributions IN RANK ORDER, so every rank computes bit-identical totals and
-// takes bit-identical decisions; no host round trip, no collective launch.  Mailbox slots alternate with the parity of
-// the sequence number: a rank can be at most one exchange ahead of a peer that still reads the previous slot.
-__device__ __forceinline__ void fw_st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// mailbox (stores into peer memory over NVLink), waits until every peer's values have arrived in its own, and combines all
+// ranks' contributions IN RANK ORDER, so every rank computes bit-identical totals and takes bit-identical decisions; no
+// host round trip, no collective launch.
+// Flag-in-data: a value travels as two 8-byte words (low half | seq << 32, high half | seq << 32), each written by one
+// store, which the hardware performs as a unit; the receiver polls the words themselves until both carry the sequence
+// number of this exchange.  No release fence on the sender (a system-scope release waits for the acknowledgement of every
+// earlier store to the peers: one more NVLink round trip per exchange) and no separate flag.  Mailbox slots alternate with
+// the parity of the sequence number: a rank can be at most one exchange ahead of a peer that still reads the previous
+// slot, and a stale word carries seq - 2.
+__device__ __forceinline__ void fw_st_mail(unsigned long long* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ unsigned long long fw_ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void fw_ld_mail(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, int lane) {
     const int W = st.world, me = st.rank;
@@ -195,59 +198,54 @@ __device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, in
     // payload: [0..3] root totals, then per job three values
     const int n_val = 4 + 3 * J;
     const unsigned long long seq = f->lc.xseq + 1ull;
+    const unsigned long long tag = (seq & 0xFFFFFFFFull) << 32;
     const int par = (int)(seq & 1ull);
-    double mine[4];                                          // this lane's values: indices lane, lane + 32, ...
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {                            // this lane's values: indices lane, lane + 32, ...
         const int i = lane + 32 * q;
+        if (i >= n_val) break;
         double v = 0.0;
         if (i < 4) v = phase == PH_ROOT ? f->tot[i] : 0.0;
-        else if (i < n_val) {
+        else {
             const int j = (i - 4) / 3, k = (i - 4) % 3;
             if (phase == PH_BERN) v = k == 0 ? f->rllL[j] : k == 1 ? f->rllR[j] : 0.0;
             else if (sums) v = k == 0 ? f->rSo[j] : k == 1 ? f->rSr[j] : (double)f->rCnt[j];
             else v = k == 0 ? (double)f->rMin[j] : k == 1 ? (double)f->rMax[j] : 0.0;      // ordered keys: exact in a double
         }
-        mine[q] = v;
-    }
-    for (int r = 0; r < W; ++r) {                            // my slot in every rank's mailbox (my own included)
-        double* dst = st.mail[r] + ((size_t)par * PG_MAX_RANKS + me) * PG_MAIL_DOUBLES;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+        const unsigned long long w0 = (bits & 0xFFFFFFFFull) | tag, w1 = (bits >> 32) | tag;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n_val) dst[i] = mine[q]; }
+        for (int r = 0; r < PG_MAX_RANKS; ++r)               // my slot in every rank's mailbox (my own included)
+            if (r < W) fw_st_mail(reinterpret_cast<unsigned long long*>(st.mail[r]) + (((size_t)par * PG_MAX_RANKS + me) * PG_MAIL_DOUBLES + i) * 2, w0, w1);
     }
-    __syncwarp();                                            // every lane's payload stores are ordered before the release stores below
-    unsigned long long* my_flags = reinterpret_cast<unsigned long long*>(st.mail[me] + (size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES);
-    if (lane < W && lane != me) {
-        unsigned long long* peer_flags = reinterpret_cast<unsigned long long*>(st.mail[lane] + (size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES);
-        fw_st_release_sys(&peer_flags[par * PG_MAX_RANKS + me], seq);
-    }
-    if (lane < W && lane != me) {
-        const long long t0 = clock64();
-        while (fw_ld_acquire_sys(&my_flags[par * PG_MAX_RANKS + lane]) < seq) {
-            __nanosleep(100);
-            // a lost peer becomes an error — after half the time the pass blocks' own watchdog allows (pg_spin_until), so that
-            // every rank leaves its kernel in an orderly way and the host can still read where each one stood
-            if (clock64() - t0 > 40000000000ll) { f->lc.error = PG_ERR_WATCHDOG; break; }
-        }
-    }
-    __syncwarp();                                            // the acquiring lanes' loads are ordered before every lane's reads below
-    const double* box = st.mail[me] + (size_t)par * PG_MAX_RANKS * PG_MAIL_DOUBLES;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    const unsigned long long* box = reinterpret_cast<const unsigned long long*>(st.mail[me]) + (size_t)par * PG_MAX_RANKS * PG_MAIL_DOUBLES * 2;
+    const long long t0 = clock64();
+    bool lost = false;
+#pragma unroll 1
+    for (int q = 0; q < 4 && !lost; ++q) {
         const int i = lane + 32 * q;
-        if (i >= n_val) continue;
-        const volatile double* col = box + i;
-        double v[PG_MAX_RANKS];                              // every rank's contribution requested at once, combined in rank order
+        if (i >= n_val) break;
+        unsigned long long a[PG_MAX_RANKS], b[PG_MAX_RANKS];
+        for (;;) {                                           // every rank's words requested at once, until all carry this exchange's tag
+            bool ok = true;
 #pragma unroll
-        for (int r = 0; r < PG_MAX_RANKS; ++r) v[r] = r < W ? col[(size_t)r * PG_MAIL_DOUBLES] : 0.0;
-        double acc = sums ? 0.0 : v[0];
-        if (sums) {
+            for (int r = 0; r < PG_MAX_RANKS; ++r)
+                if (r < W) fw_ld_mail(box + ((size_t)r * PG_MAIL_DOUBLES + i) * 2, a[r], b[r]);
 #pragma unroll
-            for (int r = 0; r < PG_MAX_RANKS; ++r) if (r < W) acc += v[r];
-        } else {
-            const int k = (i - 4) % 3;
+            for (int r = 0; r < PG_MAX_RANKS; ++r)
+                if (r < W) ok = ok && (a[r] >> 32) == (tag >> 32) && (b[r] >> 32) == (tag >> 32);
+            if (ok) break;
+            if (clock64() - t0 > 40000000000ll) { lost = true; break; }   // a lost peer becomes an error (half the pass blocks' watchdog)
+            __nanosleep(40);
+        }
+        if (lost) break;
+        double acc = 0.0;
 #pragma unroll
-            for (int r = 1; r < PG_MAX_RANKS; ++r) if (r < W) acc = k == 0 ? fmin(acc, v[r]) : fmax(acc, v[r]);
+        for (int r = 0; r < PG_MAX_RANKS; ++r) {             // combined in rank order
+            if (r >= W) continue;
+            const double v = __longlong_as_double((long long)((a[r] & 0xFFFFFFFFull) | (b[r] << 32)));
+            if (sums) acc += v;
+            else { const int k = (i - 4) % 3; acc = r == 0 ? v : (k == 0 ? fmin(acc, v) : fmax(acc, v)); }
         }
         if (i < 4) { if (phase == PH_ROOT) f->tot[i] = acc; }
         else {
@@ -257,6 +255,7 @@ __device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, in
             else { if (k == 0) f->rMin[j] = (unsigned)acc; else if (k == 1) f->rMax[j] = (unsigned)acc; }
         }
     }
+    if (__any_sync(PG_FULL, lost) && lane == 0) f->lc.error = PG_ERR_WATCHDOG;
     if (lane == 0) f->lc.xseq = seq;
     __syncwarp();
 }

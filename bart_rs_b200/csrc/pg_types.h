@@ -62,8 +62,9 @@ enum PgError : int {
 
 #define PG_MAX_RANKS 8
 #define PG_MAIL_DOUBLES 128                    // payload of one exchange
-// mailbox of one rank: [2 parities][PG_MAX_RANKS senders][PG_MAIL_DOUBLES] doubles, then [2][PG_MAX_RANKS] u64 flags
-#define PG_MAIL_BYTES ((size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES * 8 + (size_t)2 * PG_MAX_RANKS * 8)
+// mailbox of one rank: [2 parities][PG_MAX_RANKS senders][PG_MAIL_DOUBLES] entries of 16 bytes — the two halves of a double,
+// each in an 8-byte word that carries the exchange's sequence number in its upper half (flag-in-data: fw_exchange)
+#define PG_MAIL_BYTES ((size_t)2 * PG_MAX_RANKS * PG_MAIL_DOUBLES * 16)
 
 // A pass command: what a grid pass needs to know, = the first 16 ints of PgCtrl.  The P <= 32 control block publishes
 // commands into PgCtrl.cmd[generation & 1] (two may be outstanding: the pass in progress and a root pass issued ahead);
