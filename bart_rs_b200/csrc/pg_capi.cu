@@ -253,20 +253,31 @@ int enqueue_step(Sampler* s, int tune) {
 // asynchronous copy at link speed.  Pageable destinations go through a pinned staging buffer in 2 MB chunks: chunk k is
 // copied out of the staging buffer by the host while chunk k + 1 is still on the wire (a plain pageable cudaMemcpy of
 // 8 MB cost 1.3 ms per step at BASELINE C3, more than a tenth of the sweep itself).
+// The pinned staging buffer and the per-chunk events of the pageable path.  Created on first use — or ahead of time
+// (option "prewarm_host"): an observation-sharded sampler must not allocate inside a step, because its peers' kernels
+// are already waiting for this rank's by then.
+constexpr size_t PRED_CHUNK = (size_t)1 << 18;
+bool prepare_staging(Sampler* s) {
+    const size_t n = (size_t)s->st.n;
+    if (!s->pin_pred && !ck(s, cudaHostAlloc((void**)&s->pin_pred, std::max<size_t>(n, 1) * 8, cudaHostAllocDefault), "cudaHostAlloc")) return false;
+    const size_t nch = (n + PRED_CHUNK - 1) / PRED_CHUNK;
+    while (s->chunk_ev.size() < nch) {
+        cudaEvent_t e;
+        if (!ck(s, cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return false;
+        s->chunk_ev.push_back(e);
+    }
+    return true;
+}
+
 bool copy_predictions(Sampler* s, double* out) {
     const size_t n = (size_t)s->st.n;
     cudaPointerAttributes at;
     const bool pinned = cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost;
     if (!pinned) cudaGetLastError();      // (older drivers report an unregistered pointer as an error: clear it)
     if (pinned) return ck(s, cudaMemcpyAsync(out, s->st.A, n * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions");
-    if (!s->pin_pred && !ck(s, cudaHostAlloc((void**)&s->pin_pred, std::max<size_t>(n, 1) * 8, cudaHostAllocDefault), "cudaHostAlloc")) return false;
-    const size_t CH = (size_t)1 << 18;
+    const size_t CH = PRED_CHUNK;
     const size_t nch = (n + CH - 1) / CH;
-    while (s->chunk_ev.size() < nch) {
-        cudaEvent_t e;
-        if (!ck(s, cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return false;
-        s->chunk_ev.push_back(e);
-    }
+    if (!prepare_staging(s)) return false;
     for (size_t c = 0; c < nch; ++c) {
         const size_t off = c * CH, cnt = std::min(CH, n - off);
         if (!ck(s, cudaMemcpyAsync(s->pin_pred + off, s->st.A + off, cnt * 8, cudaMemcpyDeviceToHost, s->stream), "copy predictions") ||
@@ -702,6 +713,7 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
         s->err = "driver must be 'persistent' or 'stepwise'";
         return 1;
     }
+    if (std::strcmp(key, "prewarm_host") == 0) { return prepare_staging(s) ? 0 : 2; }
     if (std::strcmp(key, "weight_mode") == 0) {
         // "reference" = the reference's stale-weight rule and fresh-stump reference particle (Q1, Q2; default);
         // "pg_correct" = log-weights carried with the particles and the tree being replaced as the conditional reference particle

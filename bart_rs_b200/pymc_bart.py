@@ -126,6 +126,15 @@ class _PinnedPool:
         weakref.finalize(arr, self._give, ptr)
         return arr
 
+    def prewarm(self, k: int) -> None:
+        """Pin k blocks now (observation-sharded samplers: nothing may be allocated inside a step)."""
+        self.warm = True
+        while len(self.free) + self.lent < min(k, self.cap):
+            ptr = self._alloc()
+            if ptr is None:
+                break
+            self.free.append(ptr)
+
     def _alloc(self):
         p = C.c_void_p()
         if self.L.pgbart_host_alloc(self.n * 8, C.byref(p)) != 0 or not p.value:

@@ -69,6 +69,10 @@ class ShardedSampler(PySampler):
         dist.all_gather_object(handles, handle.tobytes(), group=group)
         blob = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
         self._check(L.pgbart_shard_connect(self._h, blob.ctypes.data_as(C.c_void_p)))
+        # Nothing may be allocated or page-locked inside a step: a rank that stalls on the host while its peers' kernels
+        # already wait for it in the exchange runs into their watchdog.  Pin the output blocks and the staging buffer now.
+        self._pool.prewarm(4)
+        self.set_option("prewarm_host", "1")
         # Every mailbox must be mapped everywhere before the first step, and the ranks' HOSTS must leave together: the
         # control blocks wait for each other inside the kernel (with a watchdog), while mapping seven peers' memory can
         # take a rank many seconds longer than another.  dist.barrier() on NCCL only orders streams, so gather an object

@@ -249,13 +249,16 @@ def sharded_block(args, rank, local_rank, world, barrier, peak):
     from bart_rs_b200.chains import job_throughput
     _, ms_max = job_throughput(ms, steps, world, device="cuda")
     # end to end: this rank's rows of the predictions come back to the host every step
-    smp.step(False)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(2):
-        smp.set_likelihood(lik)
+    try:
         smp.step(False)
-    torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            smp.set_likelihood(lik)
+            smp.step(False)
+        torch.cuda.synchronize()
+    except RuntimeError as e:
+        raise RuntimeError(f"{e}; rank {rank} device state {smp.debug_state()}") from None
     e2e_ms = 1000.0 * (time.perf_counter() - t0) / 2
     _, e2e_ms_max = job_throughput(e2e_ms, 1, world, device="cuda")
     smp.close()
@@ -366,7 +369,12 @@ def run_gpu(args):
     smp.close()
     shard = None
     if not args.no_sharded and not w.get("sharded"):
-        shard = sharded_block(args, rank, local_rank, world, barrier, peaks()[0])
+        try:
+            shard = sharded_block(args, rank, local_rank, world, barrier, peaks()[0])
+        except RuntimeError as e:
+            # a device-side failure of the sharded run (e.g. an exchange that timed out) is reported by every rank in an
+            # orderly way (pgbart_step returns the error): the headline line is still printed, with the error in the block
+            shard = {"workload": WORKLOADS[args.sharded_workload]["n"], "n_gpus": world, "error": str(e)[:300]}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -418,7 +426,7 @@ def run_gpu(args):
                     "steps": e2e_steps},
             "pruned": pruned,
             "sharded": shard,
-            "sharded_parity_ok": None if shard is None else shard["parity_ok"],
+            "sharded_parity_ok": None if shard is None else shard.get("parity_ok"),
             "speculation": spec,
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
             "grid_passes_per_step": (c1["grid_passes"] - c0["grid_passes"]) / k,

@@ -119,7 +119,9 @@ int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd,
  * particle 0 is the tree being replaced — conditional SMC; runs on the generic control code; set before the first step);
  * "root_pass" = "direct" (default: register loads over warp sub-ranges of the block's rows) | "quarters" (row quarter x job
  * group, per-lane accumulators) | "staged" (async-copy ring in shared memory; only in -DPGBART_WITH_STAGED builds);
- * "prefetch_next" = 0 | 1 (L2 prefetch of the next tree update's root columns after a root pass). */
+ * "prefetch_next" = 0 | 1 (L2 prefetch of the next tree update's root columns after a root pass);
+ * "prewarm_host" = 1: create now the page-locked staging buffer that pgbart_step uses for pageable out_pred (observation-
+ * sharded samplers call it before their first step: nothing may be allocated while the peers' kernels wait for this rank). */
 int pgbart_set_option(pgbart_handle h, const char* key, const char* value);
 
 /* Counters since creation: [0] compulsory bytes of this implementation's passes, [1] bytes by the
