@@ -415,6 +415,8 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     st.root_stages = 0;
     st.root_dbg = 0;
     st.issue_ahead = 1;
+    st.early_stats = 1;
+    if (const char* e = std::getenv("PGBART_EARLY_STATS")) st.early_stats = std::atoi(e) != 0;
     st.pg_correct = 0;
     st.generic = (st.P > 32 || any_onehot) ? 1 : 0;
     if (const char* e = std::getenv("PGBART_ISSUE_AHEAD")) st.issue_ahead = std::atoi(e) != 0;
@@ -498,7 +500,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         && dalloc(s, &st.pj_src_off, S) && dalloc(s, &st.pj_len, S) && dalloc(s, &st.pj_dst_off, S) && dalloc(s, &st.pj_cntL, S)
         && dalloc(s, &st.pj_warp_left, S * W) && dalloc(s, &st.pj_of_anc, S) && dalloc(s, &st.scan_tmp, PG_THREADS + 1)
         && dalloc(s, &st.part_sum, 2 * G * S * 2) && dalloc(s, &st.part_cnt, 2 * W * S) && dalloc(s, &st.part_ccnt, 2 * G * S)
-        && dalloc(s, &st.part_tot, 2 * G * 4) && dalloc(s, &st.part_mm, G * 2 * S * 2) && dalloc(s, &st.mq_pj, 2 * S) && dalloc(s, &st.mq_side, 2 * S) && dalloc(s, &st.mq_var, 2 * S) && dalloc(s, &st.part_ll, G * S * 2) && dalloc(s, &st.diag_blocks, G * 16) && dalloc(s, &st.part_old, G)
+        && dalloc(s, &st.part_tot, 2 * G * 4) && dalloc(s, &st.part_mm, G * 2 * S * 2) && dalloc(s, &st.mq_pj, 2 * S) && dalloc(s, &st.mq_side, 2 * S) && dalloc(s, &st.mq_var, 2 * S) && dalloc(s, &st.mq_u3, 2 * S) && dalloc(s, &st.es_thr, 2 * S) && dalloc(s, &st.part_ll, G * S * 2) && dalloc(s, &st.diag_blocks, G * 16) && dalloc(s, &st.part_old, G)
         && dalloc(s, &st.info_depths, M) && dalloc(s, &st.ctrl, 1);
     if (!ok) return bail();
     {
@@ -740,6 +742,7 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
     if (std::strcmp(key, "root_tile_groups") == 0) { s->st.root_tile_groups = std::atoi(value); return 0; }
     if (std::strcmp(key, "root_stages") == 0) { s->st.root_stages = std::atoi(value); return 0; }
     if (std::strcmp(key, "root_dbg") == 0) { s->st.root_dbg = std::atoi(value); return 0; }
+    if (std::strcmp(key, "early_stats") == 0) { s->st.early_stats = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "issue_ahead") == 0) { s->st.issue_ahead = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "prune_dead_proposals") == 0) { s->st.prune = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "prefetch_next") == 0) { s->st.prefetch_next = std::atoi(value) != 0; return 0; }

@@ -36,6 +36,8 @@
 // block and streams nothing (its SM keeps the control code in its instruction caches), so pass block = blockIdx - 1.
 #define PG_BID (sm.base->pass_bid)
 
+__device__ __forceinline__ void pg_spin_until(const unsigned* p, unsigned target, PgCtrl* c);   // defined with the other grid-level primitives below
+
 // Buffers a pass works on, selected by the command flags (PgCtrl.flags): which of the two A buffers it reads /
 // writes, and which parity of the job / partial-result buffers it uses.  The generic control code always
 // issues flags = 0 (in-place A, parity 0); the speculative root passes of pg_serial_fast.cuh use both parities.
@@ -116,12 +118,19 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     int pred_tried;                              // early commit: the predicted root pass of this update has been issued once
     // look-ahead caches of the update in progress (rounds 1 and 2), indexed [round-1][slot]
     int mm_valid[2][32]; unsigned mm_seg[2][32]; int mm_var[2][32]; float mm_lo[2][32], mm_hi[2][32];
-    int sc_valid[32]; unsigned sc_seg[32]; int sc_var[32]; float sc_thr[32]; unsigned sc_cnt[32], sc_cntL[32]; double sc_So[32], sc_Sr[32];
-    int sc_job[32], from_cache;                  // job index the prefetched statistics had in their pass (its per-block counts live there)
+    // statistics known ahead of their round, indexed [round-1][slot]: prefetched by the round-1 statistics pass (round 2) or
+    // computed by the early statistics pass queued behind the partition pass (rounds 1 and 2)
+    int sc_valid[2][32]; unsigned sc_seg[2][32]; int sc_var[2][32]; float sc_thr[2][32]; unsigned sc_cnt[2][32], sc_cntL[2][32]; double sc_So[2][32], sc_Sr[2][32];
+    int sc_job[2][32], from_cache;                  // job index the prefetched statistics had in their pass (its per-block counts live there)
     int rq_r[64], rq_s[64]; unsigned rq_seg[64];  // request -> (round, slot, child segment)
     int n_mq, pf_n, pf_slot[32];
     unsigned long long pre_upd;                  // update whose root jobs are already staged in the global job arrays
     int pre_J, pre_G, spec_now;
+    // early statistics pass: queued behind the partition pass (early_now), then the pass in progress whose
+    // results the round logic waits for (es_pending); es_resume = what to do when they arrive (SN_DRAW_ROUND: finish the
+    // round whose proposals are parked in wj_*; SN_FINALIZE: nothing needed them any more)
+    int early_now, es_pending, es_resume, es_n;
+    int wj_live[32], wj_node[32], wj_var[32]; unsigned wj_seg[32], wj_len[32]; float wj_lo[32], wj_hi[32], wj_thr[32]; double wj_split[32];
     int sl_valid, sl_lin; unsigned sl_cnt[2], sl_len[2], sl_seg[2]; double sl_So[2], sl_Sr[2], sl_g[2];   // single lineage after round 0: its two leaves (mirror of the slot tables)
     int pq_job[32], pq_ident[32]; unsigned pq_len[32];   // partition jobs of the round (mirrors of pj_job / pj_src_off / pj_len)
     int pred_valid, pred_sel, pred_lin, pred_ok;  // early commit: the tree this update will commit, predicted after round 0
@@ -138,6 +147,8 @@ struct PgSmem {
     int cstaged;           // split prior / column min-max are staged in the dynamic area
     int pass_bid;          // this block's index among the pass blocks (-1: serial-only block)
     int is_last;
+    unsigned pass_gen;     // generation of the command being executed (P <= 32 kernels)
+    int es_groups;         // early statistics pass: number of job groups (child segments) it found
     // ---- ring root pass (pg_pass_root_ring): bulk-copy ring in the staging area behind the dynamic arrays
     unsigned long long mbar_full[PGR_MAXST];   // per stage: the tile's bytes have landed
     unsigned r_done[PGR_MAXST];            // per stage: warps that have finished with the tile it holds (the last one refills it)
@@ -344,7 +355,7 @@ __device__ __forceinline__ void pg_acc_left(double& a, double& b, unsigned& c, f
 // BLOCKR: the block's rows are pg_block_range (the block-unit scheme of the P <= 32 persistent kernel), split among its
 // warps; otherwise every global warp owns one pg_warp_range (generic control code, stepwise driver).
 template <bool BERN, bool BLOCKR>
-__device__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+__device__ __forceinline__ void pg_pass_root(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     const PgCmd& cm = sm.base->cmd;
     const int J = cm.n_jobs * (cm.phase == PH_ROOT ? 1 : 0);
     const int t_add = cm.t_add, t_sub = cm.phase == PH_ROOT ? cm.t_sub : -1;
@@ -590,7 +601,7 @@ __device__ __forceinline__ double pg_tree_eval_staged(const PgState& st, int t, 
 // Returns false (block-uniformly, before touching anything) when the staging area cannot hold two tiles of one row group
 // for this pass's distinct columns: the caller then runs the direct pass.
 template <bool BERN, int JW>
-__device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+__device__ __forceinline__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgSmem* b = sm.base;
     const PgCmd& cm = sm.base->cmd;
     const bool is_root = cm.phase == PH_ROOT;
@@ -873,7 +884,7 @@ __device__ bool pg_pass_root_ring(const PgState& st, const PgBuf& bf, const PgSm
 // PH_MINMAX — splitting.rs:43-49 over index segments
 // =============================================================================
 template <bool ONEHOT>   // ONEHOT: the generic kernels, where OneHotSplit columns ask for a presence mask instead of min / max
-__device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+__device__ __forceinline__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     const int J = sm.base->cmd.n_jobs;
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -931,7 +942,7 @@ __device__ void pg_pass_minmax(const PgState& st, const PgBuf& bf, const PgSmemV
 // PH_STATS — over index segments (gather); jobs sharing a segment share idx/A/y loads
 // =============================================================================
 // LEFT count, sum A, sum y-A per job; identity segments allowed.
-__device__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+__device__ __forceinline__ void pg_pass_seg(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     const int J = sm.base->cmd.n_jobs, G = sm.base->cmd.n_groups;
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1087,7 +1098,7 @@ __device__ __forceinline__ void pg_bern_block(const PgState& st, const PgSmemVie
     }
 }
 
-__device__ void pg_pass_bern(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+__device__ __forceinline__ void pg_pass_bern(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     const int J = sm.base->cmd.n_jobs, G = sm.base->cmd.n_groups;
     const int S = st.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1164,14 +1175,70 @@ __device__ void pg_pass_bern(const PgState& st, const PgBuf& bf, const PgSmemVie
 // Same sums as pg_pass_seg<0>, but a block takes its contiguous entries of the segment (pg_seg_block_range) 8 per
 // thread at once: 8 index loads in flight, then the gathers of A, y and up to four jobs' columns for all 8 entries
 // together — three memory round trips per 4096 entries instead of three per 128 per warp.  Emits per-block results.
-__device__ void pg_pass_seg_block(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
-    const int J = sm.base->cmd.n_jobs, G = sm.base->cmd.n_groups;
+__device__ __forceinline__ void pg_pass_seg_block(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+    const int J = sm.base->cmd.n_jobs;
+    int G = sm.base->cmd.n_groups;
     const int S = st.S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (sm.base->cmd.flags & 8) {
+        // ---- early statistics pass (queued behind the partition pass; pg_serial_fast.cuh, fw_r0_finish): job q = look-ahead
+        // request q of that pass.  Nobody has digested its results yet, so (i) wait until every pass block has finished it (its
+        // completion counter: the index lists and the min / max partials come from all of them), (ii) reduce the requests'
+        // min / max here — one warp per request, lanes over the blocks — and (iii) derive the split value from the recorded
+        // draw with the arithmetic of fw_decide / pg_split_draw.  A request without a split (min >= max, or a draw that
+        // would have to be repeated) keeps no job: its threshold is reported as NaN and the control block falls back.
+        if (tid == 0) {
+            const unsigned gp = sm.base->pass_gen - 1u;
+            pg_spin_until(&st.ctrl->cnt[gp & 1u][0], ((gp + 1u) >> 1) * (gridDim.x - 1u), st.ctrl);
+        }
+        __syncthreads();
+        const unsigned dst0 = __ldcg(&st.pj_dst_off[0]), cntL0 = __ldcg(&st.pj_cntL[0]), len0 = __ldcg(&st.pj_len[0]);
+        int n_left = 0;
+        for (int q = warp; q < J; q += PG_WARPS) {
+            unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+            for (int b = lane; b < st.grid; b += 32) {
+                const uint2 v = __ldcg(reinterpret_cast<const uint2*>(st.part_mm + ((size_t)b * 2 * S + q) * 2));
+                kmin = min(kmin, v.x); kmax = max(kmax, v.y);
+            }
+            kmin = __reduce_min_sync(PG_FULL, kmin);
+            kmax = __reduce_max_sync(PG_FULL, kmax);
+            if (lane == 0) {
+                const float lo = pg_key2f(kmin), hi = pg_key2f(kmax);
+                const int side = __ldcg(&st.mq_side[q]);
+                float thr = -INFINITY;
+                bool ok = lo < hi;
+                if (ok) {
+                    const double split = __dadd_rn(__dmul_rn(__ldcg(&st.mq_u3[q]), (double)hi - (double)lo), (double)lo);
+                    ok = split < (double)hi;
+                    if (ok) thr = pg_thr32(split);
+                }
+                sm.jvar[q] = __ldcg(&st.mq_var[q]);
+                sm.jthr[q] = thr;                       // -inf: no row is LEFT, the job's sums stay zero
+                sm.jorder[q] = q;
+                sm.base->s_seg[q] = dst0 + (side ? cntL0 : 0u);
+                sm.base->s_len[q] = side ? len0 - cntL0 : cntL0;
+                if (PG_BID == 0) st.es_thr[q] = ok ? thr : __int_as_float(0x7fc00000);
+            }
+        }
+        __syncthreads();
+        // requests come ordered: the left child's (round 1) first, then the right child's (round 2): at most two groups
+        if (tid == 0) {
+            for (int q = 0; q < J; ++q) n_left += sm.base->s_seg[q] == dst0 ? 1 : 0;
+            int g = 0;
+            sm.grp[0] = 0;
+            if (n_left > 0) sm.grp[++g] = n_left;
+            if (J - n_left > 0) sm.grp[++g] = J;
+            sm.base->es_groups = g;
+        }
+        pg_zero_acc(sm, S);
+        __syncthreads();
+    } else {
     pg_stage_jobs(st, bf, sm, J, G, false);
     for (int j = tid; j < J && j < 32; j += blockDim.x) { sm.base->s_seg[j] = __ldcg(&bf.job_seg_off[j]); sm.base->s_len[j] = __ldcg(&bf.job_len[j]); }
     pg_zero_acc(sm, S);
     __syncthreads();
+    }
+    if (sm.base->cmd.flags & 8) G = sm.base->es_groups;
     const size_t ld = (size_t)st.ld;
     constexpr int E = 8;
     for (int g = 0; g < G; ++g) {
@@ -1249,7 +1316,7 @@ __device__ void pg_pass_seg_block(const PgState& st, const PgBuf& bf, const PgSm
 // kept by a warp scan + a 16-entry cross-warp prefix per chunk.  Look-ahead min/max requests stream the two columns
 // the same way (no gathers: the segment is the identity).
 #define PGP_CH (PG_THREADS * 4)      // rows per chunk
-__device__ void pg_part_ident(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int k, int Q,
+__device__ __forceinline__ void pg_part_ident(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int k, int Q,
                               const float* col, float thr, unsigned long long L) {
     PgCtrl* c = st.ctrl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
@@ -1386,7 +1453,7 @@ __device__ void pg_part_ident(const PgState& st, const PgBuf& bf, const PgSmemVi
 // Pool segment (a non-root node's rows), block-unit scheme: block b compacts its own contiguous entries
 // (pg_seg_block_range; the statistics pass's per-block LEFT counts give the offsets) — 4 entries per thread, 2 chunks in
 // flight, same scan as pg_part_ident; the split column is gathered through the index list.
-__device__ void pg_part_seg(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int k, unsigned src,
+__device__ __forceinline__ void pg_part_seg(const PgState& st, const PgBuf& bf, const PgSmemView& sm, int k, unsigned src,
                             const float* col, float thr, unsigned long long L) {
     PgCtrl* c = st.ctrl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
@@ -1456,7 +1523,7 @@ __device__ void pg_part_seg(const PgState& st, const PgBuf& bf, const PgSmemView
 }
 
 template <bool FASTP>
-__device__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
+__device__ __forceinline__ void pg_pass_part(const PgState& st, const PgBuf& bf, const PgSmemView& sm) {
     PgCtrl* c = st.ctrl;
     const int K = sm.base->cmd.n_pjobs;
     const int Q = sm.base->cmd.n_groups;     // look-ahead min/max requests riding on this pass (0 in the generic control code)

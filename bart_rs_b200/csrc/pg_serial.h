@@ -32,7 +32,8 @@ struct PgTeam {
 };
 
 enum PgSerialNext : int { SN_NONE = 0, SN_BEGIN_UPDATE, SN_DRAW_ROUND, SN_FINISH_ROUND, SN_PREP_PART, SN_FINALIZE,
-                          SN_PART_ISSUED /* pg_serial_fast.cuh: the partition pass is already in flight */ };
+                          SN_PART_ISSUED /* pg_serial_fast.cuh: the partition pass is already in flight */,
+                          SN_WAIT_EARLY /* pg_serial_fast.cuh: the round waits for the early statistics pass in flight */ };
 
 #define PG_FOR(i, N) for (int i = tm.rank; i < (N); i += tm.size)
 #define PG_SINGLE if (tm.rank == 0)

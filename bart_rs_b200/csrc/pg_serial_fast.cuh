@@ -49,7 +49,7 @@ __device__ __forceinline__ int fw_imax(int v) { return __reduce_max_sync(PG_FULL
 __device__ __forceinline__ int fw_ctrl_words() { return (int)(offsetof(PgCtrl, bar_count) / 8); }
 
 // ---- kernel-lifetime state of block 0 ----------------------------------------------------------
-__device__ void fw_load_state(const PgState& st, PgFastSm* f) {
+__device__ __forceinline__ void fw_load_state(const PgState& st, PgFastSm* f) {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st.ctrl);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(&f->lc);
     for (int i = threadIdx.x; i < fw_ctrl_words(); i += blockDim.x) dst[i] = __ldcg(&src[i]);
@@ -65,10 +65,11 @@ __device__ void fw_load_state(const PgState& st, PgFastSm* f) {
     if (threadIdx.x < 3) f->d_upd[threadIdx.x] = ~0ull;
     if (threadIdx.x < 3 * (FW_DR + 1)) f->d_flag[threadIdx.x / (FW_DR + 1)][threadIdx.x % (FW_DR + 1)] = 0ull;
     if (threadIdx.x == 0) { f->issued = 0u; f->cur_gen = 0u; f->out_phase[0] = f->out_phase[1] = PH_BEGIN; f->out_J[0] = f->out_J[1] = 0; f->out_pb[0] = f->out_pb[1] = 0;
-                            f->quit = 0; f->pre_upd = ~0ull; f->spec_now = 0; f->stat_spec = 0; f->pred_tried = 0; f->lazy_J = 0; }
+                            f->quit = 0; f->pre_upd = ~0ull; f->spec_now = 0; f->stat_spec = 0; f->pred_tried = 0; f->lazy_J = 0;
+                            f->early_now = 0; f->es_pending = 0; f->es_resume = SN_NONE; f->es_n = 0; }
 }
 
-__device__ void fw_store_state(const PgState& st, PgFastSm* f) {
+__device__ __forceinline__ void fw_store_state(const PgState& st, PgFastSm* f) {
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(st.ctrl);
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&f->lc);
     for (int i = threadIdx.x; i < fw_ctrl_words(); i += blockDim.x) dst[i] = src[i];
@@ -90,7 +91,7 @@ __device__ __forceinline__ void fw_publish(const PgState& st, PgFastSm* f, int l
 // lane = job, warp = subset of blocks {warp, warp + PG_WARPS, ...}; rows of the [block][job] partial
 // arrays are contiguous in job: coalesced, and all of a warp's loads are in flight at once.
 #define FW_RB 10   // blocks per warp per batch (grid 148 / 16 warps = 9.25)
-__device__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int pb) {
+__device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int pb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = st.grid, S = st.S;
     const double* p_sum = st.part_sum + pg_off_part_sum(st, pb);
@@ -190,7 +191,7 @@ __device__ __forceinline__ void fw_st_mail(unsigned long long* p, unsigned long 
 __device__ __forceinline__ void fw_ld_mail(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-__device__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, int lane) {
+__device__ __forceinline__ void fw_exchange(const PgState& st, PgFastSm* f, int phase, int J, int lane) {
     const int W = st.world, me = st.rank;
     const bool sums = phase == PH_ROOT || phase == PH_STATS || phase == PH_BERN;
     const bool mm = phase == PH_MINMAX || phase == PH_PART;
@@ -336,7 +337,7 @@ __device__ __forceinline__ bool fw_tape_ok(const PgState& st, unsigned long long
 
 // warp hw (1..FW_DR): round hw-1; warp FW_DR+1: resampling / selection uniforms.  `scr` is a scratch control
 // block: helpers must not raise errors for draws that may never be consumed.
-__device__ void fw_prefetch_draws(const PgState& st, const FwCx& x, unsigned long long upd, int hw, int lane, PgCtrl* scr) {
+__device__ __forceinline__ void fw_prefetch_draws(const PgState& st, const FwCx& x, unsigned long long upd, int hw, int lane, PgCtrl* scr) {
     PgFastSm* f = x.f;
     const int buf = (int)(upd % 3ull);
     const int S = st.S;
@@ -657,7 +658,7 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     bool passed;
     int status;
     const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
-    f->mm_valid[0][lane] = 0; f->mm_valid[1][lane] = 0; f->sc_valid[lane] = 0;
+    f->mm_valid[0][lane] = 0; f->mm_valid[1][lane] = 0; f->sc_valid[0][lane] = 0; f->sc_valid[1][lane] = 0;
     if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; f->pred_valid = 0; f->pred_ok = 0; f->pred_sel = 0; f->pred_tried = 0; f->sl_valid = 0; }
     if (lane < S) {
         const int s = lane;
@@ -693,6 +694,31 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
 
 __device__ __forceinline__ int fw_after_stats(const PgState& st, const FwCx& x, int lane, int phase);
 __device__ __forceinline__ void fw_issue_part(const PgState& st, const FwCx& x, int lane);
+__device__ __forceinline__ int fw_round_stats(const PgState& st, const FwCx& x, int lane, FwJob jb);
+// (defined here, ahead of its first use: a call the front end cannot inline passes `st` by reference and puts the whole
+// kernel parameter block on the stack)
+__device__ __forceinline__ void fw_issue(const PgState& st, const FwCx& x, int lane, int phase, int t_add, int t_sub,
+                                         int n_jobs, int n_groups, int n_pjobs, int flags) {
+    PgFastSm* f = x.f;
+    const unsigned g = f->issued + 1u;                       // this command's generation; its buffer: the one generation g - 2 used
+    if (lane < 16) {
+        int v = reinterpret_cast<const int*>(&f->lc)[lane];
+        if (lane == 0) v = phase; else if (lane == 4) v = t_add; else if (lane == 5) v = t_sub; else if (lane == 7) v = n_jobs;
+        else if (lane == 8) v = n_groups; else if (lane == 9) v = n_pjobs; else if (lane == 15) v = flags;
+        st.ctrl->cmd[g & 1u][lane] = v;
+    }
+#ifdef PG_DIAG
+    if (lane == 0) { st.ctrl->dbg[1] = 0ull; st.ctrl->dbg[2] = 0ull; st.ctrl->dbg[3] = 0ull; st.ctrl->dbg[0] = pg_globaltimer(); }
+#endif
+    __syncwarp();                                            // the lanes' stores are ordered before lane 0's release store
+    if (lane == 0) {
+        f->issued = g;
+        f->out_phase[g & 1u] = phase; f->out_J[g & 1u] = n_jobs; f->out_pb[g & 1u] = (flags >> 2) & 1;
+        pg_st_release(&st.ctrl->bar_gen, g);
+    }
+    __syncwarp();
+}
+
 
 // rounds >= 1: pop the next expandable node of every slot, depth-prior test, split variable (smc.rs:61-86 front half)
 __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, int lane) {
@@ -787,14 +813,38 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
         __syncwarp();
         return SN_FINISH_ROUND;
     }
-    const bool sc_hit = !jb.live || (f->sc_valid[lane] && f->sc_seg[lane] == jb.seg_off && f->sc_var[lane] == jb.var && f->sc_thr[lane] == jb.thr);
+    if (f->es_pending) {
+        // the early statistics pass (queued behind the partition pass) is computing exactly these proposals' statistics:
+        // park the round here until it completes (pg_control_fast resumes it through fw_round_stats)
+        f->wj_live[lane] = jb.live ? 1 : 0; f->wj_node[lane] = jb.node; f->wj_var[lane] = jb.var; f->wj_seg[lane] = jb.seg_off;
+        f->wj_len[lane] = jb.len; f->wj_lo[lane] = jb.lo; f->wj_hi[lane] = jb.hi; f->wj_thr[lane] = jb.thr; f->wj_split[lane] = jb.split;
+        if (lane == 0) f->es_resume = SN_DRAW_ROUND;
+        __syncwarp();
+        return SN_WAIT_EARLY;
+    }
+    return fw_round_stats(st, x, lane, jb);
+}
+
+// Second half of a round >= 1 (split values decided): statistics from the cache, or a statistics pass.
+__device__ __forceinline__ int fw_round_stats(const PgState& st, const FwCx& x, int lane, FwJob jb) {
+    PgCtrl* c = x.c;
+    PgFastSm* f = x.f;
+    const int cur = c->cur, r = c->round, S = st.S;
+    const unsigned long long upd = c->upd;
+    const int buf = (int)(upd % 3ull);
+    const int pb = (int)(upd & 1ull);
+    const int ri = r - 1;
+    int G;
+    const bool cacheable = r == 1 || r == 2;
+    const int rc = cacheable ? ri : 0;
+    const bool sc_hit = !jb.live || (cacheable && f->sc_valid[rc][lane] && f->sc_seg[rc][lane] == jb.seg_off && f->sc_var[rc][lane] == jb.var && f->sc_thr[rc][lane] == jb.thr);
     if (__all_sync(PG_FULL, sc_hit)) {
         // the statistics were prefetched too: no pass at all for this round
         const int J = fw_write_jobs(st, x, jb, lane, true, pb, false, true, &G);
         if (lane == 0) f->from_cache = 1;       // per-block counts of these jobs sit at the prefetch jobs' indices (sc_job)
         if (lane < J) {
             const int s = f->jslot[lane];
-            f->rCnt[lane] = f->sc_cnt[s]; f->rCntL[lane] = f->sc_cntL[s]; f->rSo[lane] = f->sc_So[s]; f->rSr[lane] = f->sc_Sr[s];
+            f->rCnt[lane] = f->sc_cnt[rc][s]; f->rCntL[lane] = f->sc_cntL[rc][s]; f->rSo[lane] = f->sc_So[rc][s]; f->rSr[lane] = f->sc_Sr[rc][s];
         }
         __syncwarp();
         if (lane == 0) { unsigned long long bc = 0; for (int j = 0; j < J; ++j) bc += 28ull * f->jlen[j]; c->bytes_contract += bc; }
@@ -830,7 +880,7 @@ __device__ __forceinline__ int fw_draw_round(const PgState& st, const FwCx& x, i
             st.job_slot[jo] = lane; st.job_node[jo] = 2; st.job_split[jo] = split2;
             f->jseg[J + q] = f->mm_seg[1][lane]; f->jlen[J + q] = len2v;
             f->pf_slot[q] = lane;
-            f->sc_seg[lane] = f->mm_seg[1][lane]; f->sc_var[lane] = f->mm_var[1][lane]; f->sc_thr[lane] = thr2;
+            f->sc_seg[1][lane] = f->mm_seg[1][lane]; f->sc_var[1][lane] = f->mm_var[1][lane]; f->sc_thr[1][lane] = thr2;
         }
         __threadfence_block();
         __syncwarp();
@@ -1105,7 +1155,7 @@ __device__ __forceinline__ int fw_plan_partitions(const PgState& st, const FwCx&
     __syncwarp();
     if (leader) {
         st.pj_of_anc[anc] = k;
-        const int cj = f->from_cache ? f->sc_job[f->jslot[j]] : j;   // where the pass left this job's per-block counts
+        const int cj = f->from_cache ? f->sc_job[(c->round == 2) ? 1 : 0][f->jslot[j]] : j;   // where the pass left this job's per-block counts
         st.pj_anc[k] = anc; st.pj_job[k] = cj;
         f->pq_job[k] = cj; f->pq_len[k] = len; f->pq_ident[k] = f->jseg[j] == PG_SEG_IDENTITY ? 1 : 0;
         st.pj_var[k] = f->jvar[j]; st.pj_thr32[k] = f->jthr[j];
@@ -1387,6 +1437,7 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
     // the resampling does in between.  Let the partition pass compute the min/max those proposals need.
     const int buf = (int)(c->upd % 3ull);
     const bool single = K == 1 && st.family != PG_BERNOULLI_LOGIT && __all_sync(PG_FULL, !act || need) && st.maxn > 6;
+    int es_n = 0;
     {
         int nq = 0;
         if (single && !st.tr_upd && c->k + 1 < c->batch && lane == 0) { f->pred_lin = anc; f->pred_sel = -1 - f->hsjob[anc]; }   // fw_predict, after PART is issued
@@ -1400,17 +1451,40 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
                 const int q = nq + __popc(m & ((1u << lane) - 1u));
                 if (want && q < 32) {
                     st.mq_pj[q] = 0; st.mq_side[q] = r - 1; st.mq_var[q] = f->d_var[buf][r][lane];
+                    st.mq_u3[q] = f->d_u3[buf][r][lane];
                     f->rq_r[q] = r; f->rq_s[q] = lane; f->rq_seg[q] = r == 1 ? off : off + cLl;
                 }
                 nq += __popc(m);
             }
+            // Early statistics pass: every proposal of rounds 1 and 2 is one of these requests, so the statistics pass can be
+            // queued right behind the partition pass — it reduces the look-ahead min / max itself, derives the split values
+            // from the recorded draws exactly as fw_decide will, and leaves its results for both rounds — instead of waiting
+            // for this block to digest the partition pass first (that section was ~20 us of idle pass blocks per update).
+            es_n = (st.early_stats && st.world == 1 && !st.prune && nq > 0 && nq <= 32 && nq <= S && f->d_ok[buf][1] && f->d_ok[buf][2]) ? nq : 0;
             if (nq > 32) nq = 32;
         }
-        if (lane == 0) f->n_mq = nq;
+        if (lane == 0) { f->n_mq = nq; f->es_n = es_n; }
     }
     __syncwarp();
     if (c->error != PG_OK) return SN_NONE;
     fw_issue_part(st, x, lane);          // K >= 1 here; after PH_PART the general rounds continue
+    if (es_n > 0) {
+        const int pb = (int)(c->upd & 1ull);
+        if (lane == 0) {
+            const unsigned cLl = f->jr_cLl[f->hsjob[anc]];
+            const unsigned long long Ll = cLl, Lr = (unsigned long long)st.n - cLl;
+            int n1 = 0;
+#pragma unroll 1
+            for (int q = 0; q < es_n; ++q) n1 += f->rq_r[q] == 1 ? 1 : 0;
+            c->bytes_model += (n1 > 0 ? 16ull * Ll + 4ull * Ll * (unsigned long long)n1 : 0ull)
+                            + (es_n - n1 > 0 ? 16ull * Lr + 4ull * Lr * (unsigned long long)(es_n - n1) : 0ull);
+            c->n_phases += 1;
+        }
+        __syncwarp();
+        fw_issue(st, x, lane, PH_STATS, c->t_add, -1, es_n, 0, 0, c->a_cur | (c->a_cur << 1) | (pb << 2) | 8);
+        if (lane == 0) f->early_now = 1;
+        __syncwarp();
+    }
     // ---- the slot tables, while the partition pass streams
     if (single) {
         const int j = f->hsjob[anc];
@@ -1460,28 +1534,6 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
 // ---- commands to the pass blocks ---------------------------------------------------------------------
 // The pass blocks read the first 16 ints of the global PgCtrl (phase, t_add, t_sub, n_jobs, n_groups, n_pjobs,
 // flags, ...) after observing bar_gen; issuing = publish those words, then release-store the new generation.
-__device__ __forceinline__ void fw_issue(const PgState& st, const FwCx& x, int lane, int phase, int t_add, int t_sub,
-                                         int n_jobs, int n_groups, int n_pjobs, int flags) {
-    PgFastSm* f = x.f;
-    const unsigned g = f->issued + 1u;                       // this command's generation; its buffer: the one generation g - 2 used
-    if (lane < 16) {
-        int v = reinterpret_cast<const int*>(&f->lc)[lane];
-        if (lane == 0) v = phase; else if (lane == 4) v = t_add; else if (lane == 5) v = t_sub; else if (lane == 7) v = n_jobs;
-        else if (lane == 8) v = n_groups; else if (lane == 9) v = n_pjobs; else if (lane == 15) v = flags;
-        st.ctrl->cmd[g & 1u][lane] = v;
-    }
-#ifdef PG_DIAG
-    if (lane == 0) { st.ctrl->dbg[1] = 0ull; st.ctrl->dbg[2] = 0ull; st.ctrl->dbg[3] = 0ull; st.ctrl->dbg[0] = pg_globaltimer(); }
-#endif
-    __syncwarp();                                            // the lanes' stores are ordered before lane 0's release store
-    if (lane == 0) {
-        f->issued = g;
-        f->out_phase[g & 1u] = phase; f->out_J[g & 1u] = n_jobs; f->out_pb[g & 1u] = (flags >> 2) & 1;
-        pg_st_release(&st.ctrl->bar_gen, g);
-    }
-    __syncwarp();
-}
-
 // passes of one generation parity completed when generation g has: 147 x (generations <= g of g's parity)
 __device__ __forceinline__ unsigned fw_cnt_target(unsigned g) { return ((g + 1u) >> 1) * (gridDim.x - 1u); }
 
@@ -1670,7 +1722,7 @@ __device__ __forceinline__ bool fw_issue_predicted(const PgState& st, const FwCx
 }
 
 // ---- the serial block's whole-kernel control loop ------------------------------------------------------
-__device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
+__device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
     __shared__ PgCtrl fw_scratch[FW_DR + 1];   // helpers must not raise errors for draws that may never be consumed
     PgFastSm* f = sm.fast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1701,7 +1753,7 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
         // ---- (A) the outstanding pass (if any) completes
         if (!first && threadIdx.x == 0) {
             const long long tw = clock64();
-            const unsigned g = f->issued - (f->spec_now ? 1u : 0u);   // the OLDEST outstanding pass: a root pass issued ahead queues behind it
+            const unsigned g = f->issued - ((f->spec_now || f->early_now) ? 1u : 0u);   // the OLDEST outstanding pass: a pass issued ahead queues behind it
             pg_spin_until(&st.ctrl->cnt[g & 1u][0], fw_cnt_target(g), st.ctrl);
             f->cur_gen = g;
             const int ph = f->out_phase[g & 1u];
@@ -1729,9 +1781,14 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
             // not be issued then (draws / staged jobs not ready), issue it now before anything else: after a root pass the
             // next update's root pass on a stump; after the last data pass of an update whose outcome was predicted after
             // round 0 (the statistics pass; with pruning the partition pass) the next root pass on the predicted tree.
+            if (phase == PH_PART && f->early_now) {          // the early statistics pass queued behind this partition pass is now the pass in progress
+                __syncwarp();
+                if (lane == 0) { f->early_now = 0; f->es_pending = 1; f->es_resume = SN_NONE; }
+                __syncwarp();
+            }
             bool sp = f->spec_now != 0;
             if (!sp) sp = (phase == PH_ROOT && fw_issue_prestaged(st, x, lane)) ||
-                          ((phase == PH_STATS || (phase == PH_PART && st.prune)) && fw_issue_predicted(st, x, lane));
+                          ((phase == PH_STATS || (phase == PH_PART && (st.prune || f->es_pending))) && fw_issue_predicted(st, x, lane));
             __syncwarp();
             if (lane == 0) { f->spec_now = sp ? 1 : 0; f->stat_spec = sp ? 1 : 0; }
         }
@@ -1769,11 +1826,37 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
                     FW_TICK(1);
                     break;
                 case PH_STATS:
+                    if (f->es_pending) {
+                        // the early statistics pass: job q = look-ahead request q of the partition pass; its results are the
+                        // statistics of rounds 1 and 2 (keyed by the threshold the pass derived: fw_round_stats compares)
+                        const int nq = f->es_n;
+                        if (lane < nq) {
+                            const int ri = f->rq_r[lane] - 1, s = f->rq_s[lane];
+                            f->sc_cnt[ri][s] = f->rCnt[lane]; f->sc_cntL[ri][s] = f->rCntL[lane]; f->sc_So[ri][s] = f->rSo[lane]; f->sc_Sr[ri][s] = f->rSr[lane];
+                            f->sc_job[ri][s] = lane; f->sc_seg[ri][s] = f->rq_seg[lane]; f->sc_var[ri][s] = st.mq_var[lane];
+                            const float th = __ldcg(&st.es_thr[lane]);
+                            f->sc_thr[ri][s] = th; f->sc_valid[ri][s] = th == th ? 1 : 0;
+                        }
+                        __syncwarp();
+                        const int resume = f->es_resume;
+                        if (lane == 0) { f->es_pending = 0; f->es_n = 0; }
+                        __syncwarp();
+                        spec = f->spec_now != 0;
+                        if (resume == SN_DRAW_ROUND) {
+                            FwJob jb;
+                            jb.live = f->wj_live[lane] != 0; jb.slot = lane; jb.node = f->wj_node[lane]; jb.var = f->wj_var[lane];
+                            jb.seg_off = f->wj_seg[lane]; jb.len = f->wj_len[lane]; jb.lo = f->wj_lo[lane]; jb.hi = f->wj_hi[lane];
+                            jb.thr = f->wj_thr[lane]; jb.split = f->wj_split[lane];
+                            sn = fw_round_stats(st, x, lane, jb);
+                        } else sn = resume == SN_FINALIZE ? SN_FINALIZE : SN_WAIT_EARLY;   // SN_NONE cannot happen: the round logic always parks first
+                        FW_TICK(1);
+                        break;
+                    }
                     if (f->pf_n > 0) {   // results of the prefetch jobs (round-2 proposals) go to the statistics cache
                         const int J0 = c->n_jobs;
                         if (lane >= J0 && lane < J0 + f->pf_n) {
                             const int s = f->pf_slot[lane - J0];
-                            f->sc_cnt[s] = f->rCnt[lane]; f->sc_cntL[s] = f->rCntL[lane]; f->sc_So[s] = f->rSo[lane]; f->sc_Sr[s] = f->rSr[lane]; f->sc_job[s] = lane; f->sc_valid[s] = 1;
+                            f->sc_cnt[1][s] = f->rCnt[lane]; f->sc_cntL[1][s] = f->rCntL[lane]; f->sc_So[1][s] = f->rSo[lane]; f->sc_Sr[1][s] = f->rSr[lane]; f->sc_job[1][s] = lane; f->sc_valid[1][s] = 1;
                         }
                         __syncwarp();
                         if (lane == 0) f->pf_n = 0;
@@ -1814,7 +1897,14 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
 #pragma unroll 1
             for (int it = 0; it < (1 << 20); ++it) {
                 if (c->error != PG_OK) { sn = SN_NONE; break; }
-                if (sn == SN_NONE || sn == SN_PART_ISSUED) break;
+                if (sn == SN_NONE || sn == SN_PART_ISSUED || sn == SN_WAIT_EARLY) break;
+                if (sn == SN_FINALIZE && f->es_pending) {      // nothing asked for the early statistics after all: let the pass finish first
+                    __syncwarp();
+                    if (lane == 0) f->es_resume = SN_FINALIZE;
+                    __syncwarp();
+                    sn = SN_WAIT_EARLY;
+                    break;
+                }
                 if (sn == SN_BEGIN_UPDATE) {
                     __syncwarp();
                     if (spec && f->spec_now && (phase == PH_ROOT || f->pred_ok)) {   // the guess held: the root pass in flight is the next update's
@@ -1836,8 +1926,16 @@ __device__ void pg_control_fast(const PgState& st, const PgSmemView& sm) {
             if (sn == SN_PART_ISSUED) {
                 FW_TICK(4);
                 fw_predict(st, x, lane);            // off the critical path: the partition pass is streaming
+            } else if (sn == SN_WAIT_EARLY) {
+                // nothing to issue: the early statistics pass is in flight (and, normally, the predicted root pass behind it)
+                __syncwarp();
             } else {
                 __syncwarp();
+                if (f->es_pending || f->early_now) {    // odd paths (an error, a pass nobody planned for): the early statistics are dropped
+                    fw_await(st, x, lane);
+                    if (lane == 0) { f->es_pending = 0; f->early_now = 0; f->es_n = 0; }
+                    __syncwarp();
+                }
                 if (f->spec_now && !spec_commit) {      // drain a wrong guess (odd paths, and before PH_DONE on an error)
                     fw_await(st, x, lane);
                     if (lane == 0) { c->n_drain += 1ull; f->spec_now = 0; }

@@ -99,6 +99,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
             if (phase == PH_DONE) break;
             const long long t0 = clock64();
             const int flags = sm.base->cmd.flags;
+            if (threadIdx.x == 0) sm.base->pass_gen = g;
             pg_run_pass<VAR>(st, sm, phase);
             __syncthreads();
             const long long t1 = clock64();

@@ -187,6 +187,7 @@ struct PgState {
     int pg_correct;              // SURVEY.md 8(f4) weight mode (NOT the reference's behaviour, off by default): slot log-weights are kept as
                                  // log-likelihoods and permuted with the ancestors, particle 0 is the tree being replaced (conditional SMC)
     int generic;                 // 1 = the generic control code (pg_serial.h) runs the step: P > 32, pg_correct, or a OneHotSplit column
+    int early_stats;             // P <= 32 control block: 1 (default) = the statistics pass of rounds 1-2 is queued behind the partition pass and derives its own thresholds
     int issue_ahead;             // P <= 32 control block: 1 (default) = the next update's root pass is issued right behind the pass in progress
     int root_dbg;                // ring root pass, timing experiments only (results are wrong): 1 no proxy fence in the loop, 2 no job loop, 4 no row work at all
     // data
@@ -244,6 +245,7 @@ struct PgState {
     unsigned int* part_ccnt;     // [grid][S]     left count per block
     double* part_tot;            // [grid][4]
     unsigned int* part_mm;       // [grid][2S][2] ordered-uint keys of min / max (2S: the partition pass may carry look-ahead requests)
+    double* mq_u3; float* es_thr;   // [2S] early statistics pass: the split draw of each request; the threshold the pass derived (NaN: none)
     int* mq_pj; int* mq_side; int* mq_var;   // [2S] look-ahead min/max requests of the partition pass: (partition job, child side, column)
     double* part_ll;             // [grid][S][2]  Bernoulli: log-likelihood of the left / right child
     double* part_old;            // [grid] per-block sum behind ll_old (root pass, pg_correct only)
