@@ -724,6 +724,19 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
         if (std::strcmp(value, "reference") == 0) { s->st.pg_correct = 0; s->st.generic = (s->st.P > 32 || s->any_onehot) ? 1 : 0; return 0; }
         if (std::strcmp(value, "pg_correct") == 0) {
             if (s->st.S > 512) { s->err = "weight_mode pg_correct supports at most 513 particles"; return 1; }
+            // In this mode distinct lineages do survive and grow level by level: every surviving lineage that grew appends the
+            // rows of its node, so a tree update can append up to S * (max_depth + 1) * n entries to the segment pool (the
+            // reference mode's default, 2 S n, covers one split per tree).  Size the pool for that now.
+            unsigned long long cap = (unsigned long long)s->st.S * (unsigned long long)(s->st.max_depth + 1) * (unsigned long long)s->st.n;
+            if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+            if (cap > s->st.pool_cap) {
+                unsigned* np = nullptr;
+                if (!ck(s, cudaStreamSynchronize(s->stream), "synchronize")) return 2;
+                if (!ck(s, cudaMalloc(&np, (size_t)cap * 4), "cudaMalloc pool (weight_mode pg_correct)")) return 2;
+                auto it = std::find(s->allocs.begin(), s->allocs.end(), (void*)s->st.pool);
+                if (it != s->allocs.end()) { cudaFree(*it); *it = np; } else s->allocs.push_back(np);
+                s->st.pool = np; s->st.pool_cap = cap;
+            }
             s->st.pg_correct = 1; s->st.generic = 1; return 0;
         }
         s->err = "weight_mode must be 'reference' or 'pg_correct'";

@@ -394,3 +394,15 @@ def test_gpu_onehot_rejects_wide_code_range():
     st = PyBartSettings(4, 4, 4, 0.95, 2.0, 0.1, [1.0, 1.0], ["OneHotSplit", "ContinuousSplit"], "constant", "systematic", 1.0, 1.0, 0)
     with pytest.raises(ValueError, match="at most 64 consecutive codes"):
         PySampler.init(np.asfortranarray(X), y, DeviceLikelihood("gaussian", 1.0), st)
+
+
+def test_gpu_pg_correct_many_lineages_need_a_larger_pool():
+    """weight_mode pg_correct with enough particles and tree updates that distinct lineages survive several rounds: the
+    segment pool sized for the reference mode (2 S n entries) would overflow; selecting the mode sizes it for S (depth + 1) n.
+    Free-running Philox, so the oracle generates the same draws independently."""
+    n, p, m, P = 30_000, 6, 6, 16
+    X, y = datagen.friedman(n, p, seed=11)
+    cfg = cfg_for(y, m, P, p, seed=4, beta=1.2, max_depth=12)
+    cfg["pg_correct"] = True
+    tr = parity.philox_parity(make_gpu(), X, y, cfg, 0, 1.0, [True, True], r_cap=64)
+    assert np.max(tr.upd[:2 * m, 0]) >= 11
