@@ -117,8 +117,10 @@ int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd,
  * place and meet next round's log-likelihoods, the reference particle is a fresh stump) | "pg_correct" (NOT the
  * reference's behaviour: every slot keeps the log-likelihood of the particle it holds, permuted with the ancestors, and
  * particle 0 is the tree being replaced — conditional SMC; runs on the generic control code; set before the first step);
- * "root_pass" = "direct" (default: register loads over warp sub-ranges of the block's rows) | "quarters" (row quarter x job
- * group, per-lane accumulators) | "staged" (async-copy ring in shared memory; only in -DPGBART_WITH_STAGED builds);
+ * "root_pass" = "auto" (default: the ring pass when a pass block holds at most 2048 rows, else the direct pass) | "direct"
+ * (register loads over warp sub-ranges of the block's rows) | "ring" (bulk-copy ring in shared memory, cp.async.bulk);
+ * "issue_ahead" = 1 | 0 (the next update's root pass is published while the current pass streams); "early_stats" = 1 | 0
+ * (the statistics pass of rounds 1-2 is queued behind the partition pass and derives its own thresholds);
  * "prefetch_next" = 0 | 1 (L2 prefetch of the next tree update's root columns after a root pass);
  * "prewarm_host" = 1: create now the page-locked staging buffer that pgbart_step uses for pageable out_pred (observation-
  * sharded samplers call it before their first step: nothing may be allocated while the peers' kernels wait for this rank). */
