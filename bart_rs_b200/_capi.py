@@ -22,7 +22,7 @@ EXPORTS = [
     "pgbart_step_device", "pgbart_sync", "pgbart_predictions_device", "pgbart_get_predictions", "pgbart_get_info",
     "pgbart_tree_size", "pgbart_get_tree", "pgbart_get_leaf_indices", "pgbart_get_state", "pgbart_set_rng_philox",
     "pgbart_set_rng_tape", "pgbart_trace_enable", "pgbart_trace_read", "pgbart_set_option", "pgbart_get_counters",
-    "pgbart_timer_start", "pgbart_timer_stop", "pgbart_get_profile", "pgbart_debug_block_cycles", "pgbart_debug_state",
+    "pgbart_timer_start", "pgbart_timer_stop", "pgbart_get_profile", "pgbart_debug_block_cycles", "pgbart_debug_state", "pgbart_get_early_stats_counters",
     "pgbart_shard_config", "pgbart_shard_mailbox", "pgbart_shard_connect", "pgbart_predict", "pgbart_variable_inclusion",
     "pgbart_get_spec_counters", "pgbart_host_alloc", "pgbart_host_free",
 ]
@@ -80,6 +80,7 @@ def lib():
     L.pgbart_timer_stop.argtypes = [vp, C.POINTER(dbl)]
     L.pgbart_debug_block_cycles.argtypes = [vp, vp, i32]
     L.pgbart_debug_state.argtypes = [vp, vp]
+    L.pgbart_get_early_stats_counters.argtypes = [vp, vp]
     L.pgbart_shard_config.argtypes = [vp, i32, i32, u64, dbl, vp, vp]
     L.pgbart_shard_mailbox.argtypes = [vp, vp]
     L.pgbart_shard_connect.argtypes = [vp, vp]

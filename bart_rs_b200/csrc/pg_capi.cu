@@ -801,6 +801,14 @@ int pgbart_get_spec_counters(pgbart_handle h, uint64_t* out4) {
     return 0;
 }
 
+int pgbart_get_early_stats_counters(pgbart_handle h, uint64_t* out2) {
+    if (!h || !out2) return 1;
+    Sampler* s = &h->s;
+    if (!fetch_ctrl(s)) return 2;
+    out2[0] = s->host_ctrl.n_es; out2[1] = s->host_ctrl.n_es_miss;
+    return 0;
+}
+
 int pgbart_get_profile(pgbart_handle h, double* out32) {
     if (!h) return 1;   // a null handle is a bad argument, not a crash
     Sampler* s = &h->s;

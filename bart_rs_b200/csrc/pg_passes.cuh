@@ -129,7 +129,7 @@ struct PgFastSm {          // state of the latency-organised serial section (pg_
     // early statistics pass: queued behind the partition pass (early_now), then the pass in progress whose
     // results the round logic waits for (es_pending); es_resume = what to do when they arrive (SN_DRAW_ROUND: finish the
     // round whose proposals are parked in wj_*; SN_FINALIZE: nothing needed them any more)
-    int early_now, es_pending, es_resume, es_n;
+    int early_now, es_pending, es_resume, es_n, es_mask;   // es_mask: rounds (bit round-1) of this update an early statistics pass covered
     int wj_live[32], wj_node[32], wj_var[32]; unsigned wj_seg[32], wj_len[32]; float wj_lo[32], wj_hi[32], wj_thr[32]; double wj_split[32];
     int sl_valid, sl_lin; unsigned sl_cnt[2], sl_len[2], sl_seg[2]; double sl_So[2], sl_Sr[2], sl_g[2];   // single lineage after round 0: its two leaves (mirror of the slot tables)
     int pq_job[32], pq_ident[32]; unsigned pq_len[32];   // partition jobs of the round (mirrors of pj_job / pj_src_off / pj_len)

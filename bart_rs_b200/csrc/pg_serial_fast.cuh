@@ -66,7 +66,7 @@ __device__ __forceinline__ void fw_load_state(const PgState& st, PgFastSm* f) {
     if (threadIdx.x < 3 * (FW_DR + 1)) f->d_flag[threadIdx.x / (FW_DR + 1)][threadIdx.x % (FW_DR + 1)] = 0ull;
     if (threadIdx.x == 0) { f->issued = 0u; f->cur_gen = 0u; f->out_phase[0] = f->out_phase[1] = PH_BEGIN; f->out_J[0] = f->out_J[1] = 0; f->out_pb[0] = f->out_pb[1] = 0;
                             f->quit = 0; f->pre_upd = ~0ull; f->spec_now = 0; f->stat_spec = 0; f->pred_tried = 0; f->lazy_J = 0;
-                            f->early_now = 0; f->es_pending = 0; f->es_resume = SN_NONE; f->es_n = 0; }
+                            f->early_now = 0; f->es_pending = 0; f->es_resume = SN_NONE; f->es_n = 0; f->es_mask = 0; }
 }
 
 __device__ __forceinline__ void fw_store_state(const PgState& st, PgFastSm* f) {
@@ -659,6 +659,7 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     int status;
     const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
     f->mm_valid[0][lane] = 0; f->mm_valid[1][lane] = 0; f->sc_valid[0][lane] = 0; f->sc_valid[1][lane] = 0;
+    if (lane == 0) f->es_mask = 0;
     if (lane == 0) { f->n_mq = 0; f->pf_n = 0; f->from_cache = 0; f->pred_valid = 0; f->pred_ok = 0; f->pred_sel = 0; f->pred_tried = 0; f->sl_valid = 0; }
     if (lane < S) {
         const int s = lane;
@@ -850,6 +851,7 @@ __device__ __forceinline__ int fw_round_stats(const PgState& st, const FwCx& x, 
         if (lane == 0) { unsigned long long bc = 0; for (int j = 0; j < J; ++j) bc += 28ull * f->jlen[j]; c->bytes_contract += bc; }
         return fw_after_stats(st, x, lane, PH_STATS);
     }
+    if (lane == 0 && cacheable && ((f->es_mask >> rc) & 1)) st.ctrl->n_es_miss += 1ull;   // an early statistics pass covered this round, and yet: a regular pass
     // statistics pass for this round's jobs ...
     const int J = fw_write_jobs(st, x, jb, lane, true, pb, true, true, &G);
     // ... carrying, for round 1, the round-2 proposals of every slot (node 2: the other child) as prefetch jobs
@@ -1482,7 +1484,7 @@ __device__ __forceinline__ int fw_r0_finish(const PgState& st, const FwCx& x, in
         }
         __syncwarp();
         fw_issue(st, x, lane, PH_STATS, c->t_add, -1, es_n, 0, 0, c->a_cur | (c->a_cur << 1) | (pb << 2) | 8);
-        if (lane == 0) f->early_now = 1;
+        if (lane == 0) { f->early_now = 1; st.ctrl->n_es += 1ull; }
         __syncwarp();
     }
     // ---- the slot tables, while the partition pass streams
@@ -1839,7 +1841,8 @@ __device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemV
                         }
                         __syncwarp();
                         const int resume = f->es_resume;
-                        if (lane == 0) { f->es_pending = 0; f->es_n = 0; }
+                        const unsigned m1 = __ballot_sync(PG_FULL, lane < nq && f->rq_r[lane] == 1), m2 = __ballot_sync(PG_FULL, lane < nq && f->rq_r[lane] == 2);
+                        if (lane == 0) { f->es_pending = 0; f->es_n = 0; f->es_mask = (m1 ? 1 : 0) | (m2 ? 2 : 0); }
                         __syncwarp();
                         spec = f->spec_now != 0;
                         if (resume == SN_DRAW_ROUND) {

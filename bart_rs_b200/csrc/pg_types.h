@@ -145,8 +145,9 @@ struct PgCtrl {
     // ---- set by pg_prepare_step when an earlier step left a device error behind: steps queued after it must not run on
     // the broken state (pgbart_step_device can be queued several times before pgbart_sync reports the error)
     int poisoned;
-    int pad_cmd[27];
+    int pad_cmd[23];
     double ll_old;                  // weight_mode pg_correct: log-likelihood of the current predictions (= of the tree being replaced)
+    unsigned long long n_es, n_es_miss;   // early statistics passes issued / rounds that had to run a regular statistics pass after one (written in place by the control block)
     // ---- P <= 32 persistent kernels: command buffers by generation parity, and completion counters by generation parity
     // (zeroed with bar_gen by pg_prepare_step); counter q holds 147 x (generations of parity q completed)
     int cmd[2][16];

@@ -320,6 +320,12 @@ class PySampler:
         self._check(self._L.pgbart_get_spec_counters(self._h, out.ctypes.data_as(C.c_void_p)))
         return dict(zip(["issued_ahead", "predictions", "mispredictions", "drained"], (int(v) for v in out)))
 
+    def early_stats_counters(self) -> dict:
+        """Early statistics passes issued / rounds that fell back to a regular statistics pass, since creation."""
+        out = np.zeros(2, dtype=np.uint64)
+        self._check(self._L.pgbart_get_early_stats_counters(self._h, out.ctypes.data_as(C.c_void_p)))
+        return {"issued": int(out[0]), "fallbacks": int(out[1])}
+
     def profile(self) -> dict:
         """In-kernel stopwatch (SM cycles since creation), by phase; see include/pgbart.h."""
         out = np.zeros(69)

@@ -136,6 +136,9 @@ int pgbart_get_counters(pgbart_handle h, double* out8);
  * they depend on, [1] tree updates whose outcome was predicted after round 0, [2] predictions the final selection
  * contradicted (the pass issued ahead was drained and re-issued), [3] passes issued ahead that were awaited and discarded. */
 int pgbart_get_spec_counters(pgbart_handle h, uint64_t* out4);
+/* Early statistics pass (statistics of rounds 1-2 queued behind the partition pass): out2 = passes issued since creation,
+ * rounds that nevertheless had to run a regular statistics pass (the cached threshold did not match). */
+int pgbart_get_early_stats_counters(pgbart_handle h, uint64_t* out2);
 
 /* In-kernel stopwatch, SM cycles since creation: out32[0..7] pass time by phase as seen by block 0,
  * [8..15] pass end -> barrier exit (wait for the slowest block + serial section), [16..23] serial section alone,

@@ -406,3 +406,34 @@ def test_gpu_pg_correct_many_lineages_need_a_larger_pool():
     cfg["pg_correct"] = True
     tr = parity.philox_parity(make_gpu(), X, y, cfg, 0, 1.0, [True, True], r_cap=64)
     assert np.max(tr.upd[:2 * m, 0]) >= 11
+
+
+def test_gpu_early_statistics_pass_changes_nothing():
+    """The statistics pass of rounds 1-2 queued behind the partition pass (option early_stats, on by default) computes the
+    same per-job sums over the same rows in the same order as the pass the control block would issue after digesting the
+    partition pass: forests and predictions are bit-identical with the option off, it is used in every all-grew update, and
+    its thresholds always match the ones the control block derives (no fallback)."""
+    from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
+    n, p, m, P = 200_000, 20, 40, 20
+    X, y = datagen.friedman(n, p, seed=5)
+    prm = datagen.pgbart_params(y, m, p)
+    preds, counters = [], []
+    for on in ("1", "0"):
+        st = PyBartSettings(m, P, prm["max_depth"], 0.95, 2.0, prm["sigma"], list(prm["split_prior"]), ["ContinuousSplit"] * p,
+                            "constant", "systematic", 1.0, 1.0, 3)
+        s = PySampler.init(np.asfortranarray(X.astype(np.float64)), y, DeviceLikelihood("gaussian", 1.0), st)
+        s.set_option("early_stats", on)
+        preds.append([s.step(t).copy() for t in (True, True, False)])
+        counters.append(s.early_stats_counters())
+        trees = [s.tree(t) for t in range(m)]
+        if on == "1":
+            trees_on = trees
+        else:
+            for a, b in zip(trees_on, trees):
+                for u, v in zip(a, b):
+                    np.testing.assert_array_equal(np.nan_to_num(u, nan=-7e300), np.nan_to_num(v, nan=-7e300))
+        s.close()
+    for a, b in zip(*preds):
+        np.testing.assert_array_equal(a, b)
+    assert counters[0]["issued"] >= 20 and counters[0]["fallbacks"] == 0, counters
+    assert counters[1]["issued"] == 0
