@@ -175,6 +175,9 @@ def run_reference(args):
     w = WORKLOADS[args.workload]
     X, y, prm = make_data(w)
     per_step = bounded_updates(w, max(1, int(args.ref_updates)))
+    # the whole --steps K --warmup W run should end within a few minutes: about two minutes of CPU work in total
+    per_update_s = w["n"] * max(w["P"] - 1, 1) * (3.5e-8 if w["family"] == "bernoulli_logit" else 1.8e-8)
+    per_step = max(min(per_step, int(120.0 / ((args.warmup + args.steps) * per_update_s))), min(per_step, 4))
     times, done_total = [], 0
     for i in range(args.warmup + args.steps):
         done, dt = oracle_sample(X, y, prm, w, per_step, seed=i, warm=1)
