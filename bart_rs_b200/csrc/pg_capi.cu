@@ -45,6 +45,7 @@ struct Sampler {
     std::vector<cudaEvent_t> chunk_ev;   // one event per staged chunk of that copy
     std::vector<void*> ipc_open;     // peer mailboxes opened through CUDA IPC (observation sharding)
     long long steps_done = 0;
+    unsigned long long* hostdiag = nullptr;   // host-mapped: filled by a block that traps on a watchdog
     bool any_onehot = false;         // some split_rules entry is OneHotSplit: the step runs on the generic control code
 };
 
@@ -201,6 +202,7 @@ void free_all(Sampler* s) {
     if (s->tm0) cudaEventDestroy(s->tm0);
     if (s->tm1) cudaEventDestroy(s->tm1);
     if (s->pin_pred) cudaFreeHost(s->pin_pred);
+    if (s->hostdiag) cudaFreeHost(s->hostdiag);
     for (cudaEvent_t e : s->chunk_ev) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
 }
@@ -211,7 +213,19 @@ bool fetch_ctrl(Sampler* s) {
 }
 
 int finish_step(Sampler* s) {
-    if (!fetch_ctrl(s)) return 2;
+    if (!fetch_ctrl(s)) {
+        if (s->hostdiag && s->hostdiag[0]) {      // a block recorded what it was waiting for before it trapped
+            char b[512];
+            snprintf(b, sizeof b, " [watchdog record: code %llx, offset/update %llu, wanted %llu, saw %llu, aux %llu %llu %llu %llx; control heartbeat %llx %llx %llx %llx]",
+                     s->hostdiag[0], s->hostdiag[1], s->hostdiag[2], s->hostdiag[3], s->hostdiag[4], s->hostdiag[5], s->hostdiag[6], s->hostdiag[7],
+                     s->hostdiag[8], s->hostdiag[9], s->hostdiag[10], s->hostdiag[11]);
+            s->err += b;
+            std::string w = " [control block warps, (commands issued << 32 | barrier) :";
+            for (int q = 16; q < 32; ++q) { snprintf(b, sizeof b, " %llx", s->hostdiag[q]); w += b; }
+            s->err += w + "]";
+        }
+        return 2;
+    }
     if (s->host_ctrl.error != PG_OK) {
         s->err = pg_error_text(s->host_ctrl.error);
         // the sampler state is no longer meaningful after a device-side failure
@@ -416,6 +430,8 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
     st.root_dbg = 0;
     st.issue_ahead = 1;
     st.early_stats = 1;
+    st.heartbeat = 0;
+    if (const char* e = std::getenv("PGBART_HEARTBEAT")) st.heartbeat = std::atoi(e) != 0;
     if (const char* e = std::getenv("PGBART_EARLY_STATS")) st.early_stats = std::atoi(e) != 0;
     st.pg_correct = 0;
     st.generic = (st.P > 32 || any_onehot) ? 1 : 0;
@@ -520,6 +536,11 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
 
     PgCtrl c0{};
     c0.phase = PH_DONE; c0.tune = 1; c0.t_add = -1; c0.t_sub = -1;
+    if (cudaHostAlloc((void**)&s->hostdiag, 256, cudaHostAllocMapped) == cudaSuccess) {
+        std::memset(s->hostdiag, 0, 256);
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, s->hostdiag, 0) == cudaSuccess) c0.hostdiag = (unsigned long long)dp;
+    } else { s->hostdiag = nullptr; cudaGetLastError(); }
     if (!ck(s, cudaMemcpyAsync(st.ctrl, &c0, sizeof c0, cudaMemcpyHostToDevice, s->stream), "init ctrl")) return bail();
     if (!ck(s, pg_launch_fill(st.A, st.n, st.y_mean, s->stream), "fill predictions")) return bail();   // kernel.rs:48
     if (!ck(s, pg_launch_init_forest(st, s->stream), "init forest")) return bail();
@@ -755,6 +776,7 @@ int pgbart_set_option(pgbart_handle h, const char* key, const char* value) {
     if (std::strcmp(key, "root_tile_groups") == 0) { s->st.root_tile_groups = std::atoi(value); return 0; }
     if (std::strcmp(key, "root_stages") == 0) { s->st.root_stages = std::atoi(value); return 0; }
     if (std::strcmp(key, "root_dbg") == 0) { s->st.root_dbg = std::atoi(value); return 0; }
+    if (std::strcmp(key, "heartbeat") == 0) { s->st.heartbeat = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "early_stats") == 0) { s->st.early_stats = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "issue_ahead") == 0) { s->st.issue_ahead = std::atoi(value) != 0; return 0; }
     if (std::strcmp(key, "prune_dead_proposals") == 0) { s->st.prune = std::atoi(value) != 0; return 0; }

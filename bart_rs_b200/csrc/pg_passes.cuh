@@ -1721,6 +1721,14 @@ __device__ __forceinline__ void pg_spin_until(const unsigned* p, unsigned target
         if (ns < 160) ns <<= 1;
         if (clock64() - t0 > 80000000000ll) {   // ~40 s at 2 GHz (twice the exchange time-out of a sharded run): a lost block becomes an error, not a hang
             c->error = PG_ERR_WATCHDOG;
+            unsigned long long* hd = reinterpret_cast<unsigned long long*>(c->hostdiag);
+            if (hd && atomicCAS(&hd[0], 0ull, 0xD1A60000ull + blockIdx.x) == 0ull) {     // who waited for what (read by the host after the trap)
+                hd[1] = (unsigned long long)(reinterpret_cast<const char*>(p) - reinterpret_cast<const char*>(c));
+                hd[2] = target; hd[3] = pg_ld_relaxed(p);
+                hd[4] = pg_ld_relaxed(&c->bar_gen); hd[5] = pg_ld_relaxed(&c->cnt[0][0]); hd[6] = pg_ld_relaxed(&c->cnt[1][0]);
+                hd[7] = ((unsigned long long)(unsigned)c->cmd[0][0] << 32) | (unsigned)c->cmd[1][0];
+                __threadfence_system();
+            }
             __threadfence();
             __trap();
         }

@@ -147,6 +147,7 @@ __device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int ph
         }
         if (lane == 0) { f->wsT[warp][0] = t0; f->wsT[warp][1] = t1; f->wsT[warp][2] = t2; f->wsT[warp][3] = t3; }
     }
+        if (st.heartbeat && (threadIdx.x & 31) == 0) { volatile unsigned long long* hw_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hw_) hw_[16 + (threadIdx.x >> 5)] = ((unsigned long long)f->issued << 32) | 2ull; }
     __syncthreads();
     if (warp == 0) {   // fixed-order combine over warps
         if (sums && lane < J) {
@@ -394,11 +395,24 @@ __device__ __forceinline__ void fw_prefetch_draws(const PgState& st, const FwCx&
     if (lane == 0) f->d_flag[buf][hw - 1] = upd + 1ull;
 }
 
-__device__ __forceinline__ void fw_wait_draws(PgFastSm* f, unsigned long long upd) {
+__device__ __forceinline__ void fw_wait_draws(const PgState& st, PgFastSm* f, unsigned long long upd) {
     const int buf = (int)(upd % 3ull);
 #pragma unroll 1
-    for (int q = 0; q <= FW_DR; ++q)
-        while (f->d_flag[buf][q] != upd + 1ull) __nanosleep(20);
+    for (int q = 0; q <= FW_DR; ++q) {
+        const long long t0 = clock64();
+        while (f->d_flag[buf][q] != upd + 1ull) {
+            __nanosleep(20);
+            if (clock64() - t0 > 40000000000ll) {       // the helper warps never produced these draws: report it instead of hanging
+                unsigned long long* hd = reinterpret_cast<unsigned long long*>(st.ctrl->hostdiag);
+                if (hd && atomicCAS(&hd[0], 0ull, 0xD2A30000ull + (unsigned)q) == 0ull) {
+                    hd[1] = upd; hd[2] = f->d_flag[buf][q]; hd[3] = f->d_upd[buf]; hd[4] = f->d_upd[0]; hd[5] = f->d_upd[1]; hd[6] = f->d_upd[2]; hd[7] = f->issued;
+                    __threadfence_system();
+                }
+                f->lc.error = PG_ERR_WATCHDOG;
+                break;
+            }
+        }
+    }
     __threadfence_block();
 }
 
@@ -654,7 +668,7 @@ __device__ __forceinline__ void fw_start_update(const PgState& st, const FwCx& x
     __syncwarp();
     const unsigned long long upd = c->upd;
     const int buf = (int)(upd % 3ull);
-    fw_wait_draws(f, upd);
+    fw_wait_draws(st, f, upd);
     bool passed;
     int status;
     const FwJob jb = fw_root_job(st, x, upd, lane, &passed, &status);
@@ -1607,6 +1621,10 @@ __device__ __forceinline__ bool fw_try_speculate(const PgState& st, const FwCx& 
               && f->d_upd[buf] == U1 && f->d_ok[buf][0];
 #pragma unroll 1
     for (int q = 0; q <= FW_DR && ok; ++q) ok = f->d_flag[buf][q] == U1 + 1ull;
+    // The helper warps write these flags while this warp reads them: lanes can see different values.  The decision must be
+    // the warp's, not the lane's — a lane that left here while the others went on into the warp-wide votes below hung the
+    // control block once in ~1500 sweeps.
+    ok = __all_sync(PG_FULL, ok);
     if (!ok) return false;
     __threadfence_block();
     bool passed;
@@ -1636,6 +1654,7 @@ __device__ __forceinline__ void fw_prestage(const PgState& st, const FwCx& x, in
               && f->d_upd[buf] == U1 && f->d_ok[buf][0];
 #pragma unroll 1
     for (int q = 0; q <= FW_DR && ok; ++q) ok = f->d_flag[buf][q] == U1 + 1ull;
+    ok = __all_sync(PG_FULL, ok);          // warp-uniform: the flags are being written by the helper warps (see fw_try_speculate)
     if (!ok) return;
     __threadfence_block();
     bool passed;
@@ -1748,6 +1767,7 @@ __device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemV
     __syncthreads();
     if (threadIdx.x == 0) c->a_cur = 0;        // `predictions` live in buffer 0 between steps
     bool first = true;
+#define FW_BEAT(slot, code) do { if (st.heartbeat && threadIdx.x == 0) { volatile unsigned long long* hb_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hb_) hb_[8 + (slot)] = ((unsigned long long)f->issued << 32) | ((unsigned long long)(c->round & 0xff) << 24) | ((unsigned long long)(c->k & 0xfff) << 8) | (unsigned long long)(code); } } while (0)
 #define FW_TICK(slot) do { if (lane == 0) { const long long now_ = clock64(); c->prof2[slot] += (unsigned long long)(now_ - tq); c->prof2[8 + slot] += 1ull; tq = now_; } } while (0)
 
 #pragma unroll 1
@@ -1770,6 +1790,8 @@ __device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemV
             }
 #endif
         }
+        FW_BEAT(0, 1);
+        if (st.heartbeat && (threadIdx.x & 31) == 0) { volatile unsigned long long* hw_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hw_) hw_[16 + (threadIdx.x >> 5)] = ((unsigned long long)f->issued << 32) | 1ull; }
         __syncthreads();
         const int phase = first ? PH_BEGIN : f->out_phase[f->cur_gen & 1u];
         const int J = first ? 0 : f->out_J[f->cur_gen & 1u];
@@ -1794,14 +1816,18 @@ __device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemV
             __syncwarp();
             if (lane == 0) { f->spec_now = sp ? 1 : 0; f->stat_spec = sp ? 1 : 0; }
         }
+        FW_BEAT(0, 2);
         fw_reduce(st, f, phase, J, pb);   // contains a __syncthreads before its combine step
+        FW_BEAT(0, 3);
         if (st.world > 1 && warp == 0) fw_exchange(st, f, phase, J, lane);
         if (threadIdx.x == 0 && gerr != PG_OK) c->error = gerr;
+        if (st.heartbeat && (threadIdx.x & 31) == 0) { volatile unsigned long long* hw_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hw_) hw_[16 + (threadIdx.x >> 5)] = ((unsigned long long)f->issued << 32) | 3ull; }
         __syncthreads();
         const unsigned long long upd0 = c->upd;   // the update in progress at entry
         bool need[3];
 #pragma unroll
         for (int q = 0; q < 3; ++q) need[q] = f->d_upd[(int)((upd0 + q) % 3ull)] != upd0 + q;
+        if (st.heartbeat && (threadIdx.x & 31) == 0) { volatile unsigned long long* hw_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hw_) hw_[16 + (threadIdx.x >> 5)] = ((unsigned long long)f->issued << 32) | 4ull; }
         __syncthreads();                           // ... all read by every warp before anything is advanced
         long long tq = clock64();
         if (threadIdx.x == 0) { c->prof2[0] += (unsigned long long)(tq - t_entry); c->prof2[8] += 1ull; }
@@ -1899,6 +1925,8 @@ __device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemV
             // warp-only sub-steps chain without block barriers until a grid pass or a block-wide step is needed
 #pragma unroll 1
             for (int it = 0; it < (1 << 20); ++it) {
+                FW_BEAT(1, 0x10 + sn);
+                if (lane == 0 && st.heartbeat) { volatile unsigned long long* hb_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hb_) hb_[10] = (unsigned long long)it; }
                 if (c->error != PG_OK) { sn = SN_NONE; break; }
                 if (sn == SN_NONE || sn == SN_PART_ISSUED || sn == SN_WAIT_EARLY) break;
                 if (sn == SN_FINALIZE && f->es_pending) {      // nothing asked for the early statistics after all: let the pass finish first
@@ -1959,7 +1987,10 @@ __device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemV
                 __syncwarp();
             }
             if (lane == 0) { f->sn = sn; f->quit = c->phase == PH_DONE ? 1 : 0; }
+            FW_BEAT(0, 8);
         }
+        if (warp == 1 && lane == 0 && st.heartbeat) { volatile unsigned long long* hb_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hb_) hb_[11] = ((unsigned long long)f->issued << 32) | 9ull; }
+        if (st.heartbeat && (threadIdx.x & 31) == 0) { volatile unsigned long long* hw_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hw_) hw_[16 + (threadIdx.x >> 5)] = ((unsigned long long)f->issued << 32) | 5ull; }
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned long long d = (unsigned long long)(clock64() - t_entry);

@@ -145,7 +145,9 @@ struct PgCtrl {
     // ---- set by pg_prepare_step when an earlier step left a device error behind: steps queued after it must not run on
     // the broken state (pgbart_step_device can be queued several times before pgbart_sync reports the error)
     int poisoned;
-    int pad_cmd[23];
+    int pad_cmd[21];
+    unsigned long long hostdiag;    // device address of a host-mapped buffer (8 x u64) that a block fills before it traps on a watchdog: the
+                                    // context is lost after the trap, the host memory is not (pgbart_last_error then says who waited for what)
     double ll_old;                  // weight_mode pg_correct: log-likelihood of the current predictions (= of the tree being replaced)
     unsigned long long n_es, n_es_miss;   // early statistics passes issued / rounds that had to run a regular statistics pass after one (written in place by the control block)
     // ---- P <= 32 persistent kernels: command buffers by generation parity, and completion counters by generation parity
@@ -188,6 +190,7 @@ struct PgState {
     int pg_correct;              // SURVEY.md 8(f4) weight mode (NOT the reference's behaviour, off by default): slot log-weights are kept as
                                  // log-likelihoods and permuted with the ancestors, particle 0 is the tree being replaced (conditional SMC)
     int generic;                 // 1 = the generic control code (pg_serial.h) runs the step: P > 32, pg_correct, or a OneHotSplit column
+    int heartbeat;               // diagnostics: the control block records where it is in the host-mapped watchdog buffer (PgCtrl.hostdiag)
     int early_stats;             // P <= 32 control block: 1 (default) = the statistics pass of rounds 1-2 is queued behind the partition pass and derives its own thresholds
     int issue_ahead;             // P <= 32 control block: 1 (default) = the next update's root pass is issued right behind the pass in progress
     int root_dbg;                // ring root pass, timing experiments only (results are wrong): 1 no proxy fence in the loop, 2 no job loop, 4 no row work at all
