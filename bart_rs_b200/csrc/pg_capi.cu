@@ -523,6 +523,16 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         // every surviving lineage appends at most n entries per tree level; 2S*n covers the reference's
         // behaviour (one split per tree, Q1), (max_depth+2)*n covers one lineage growing to full depth
         unsigned long long cap = std::max<unsigned long long>(s->pool_factor * (unsigned long long)S, (unsigned long long)st.max_depth + 2) * n;
+        // The bound that cannot be exceeded in any mode is S * (max_depth + 1) * n (every lineage distinct, each growing one
+        // level per round).  It is 0.7 GB at BASELINE C3 and 9 GB at C5, so take it whenever it costs less than a quarter of
+        // the free device memory: PG_ERR_POOL (which ends the chain; the reference has no such failure) is then unreachable.
+        {
+            const unsigned long long worst = (unsigned long long)S * (unsigned long long)(st.max_depth + 1) * n;
+            size_t free_b = 0, total_b = 0;
+            if (worst > cap && worst <= 0xFFFFFFF0ull && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess
+                && worst * 4ull <= (unsigned long long)free_b / 4ull)
+                cap = worst;
+        }
         if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;   // u32 offsets
         if (cap < n) cap = n;
         st.pool_cap = cap;

@@ -112,7 +112,9 @@ int pgbart_set_rng_tape(pgbart_handle h, const double* slot, const double* round
 int pgbart_trace_enable(pgbart_handle h, int64_t u_cap, int r_cap);
 int pgbart_trace_read(pgbart_handle h, double* slot, double* round, double* upd, int64_t* n_upd, int* overflow);
 
-/* Options: "driver" = "persistent" (default) | "stepwise"; "pool_factor" = integer >= 1;
+/* Options: "driver" = "persistent" (default) | "stepwise"; "pool_factor" = integer f >= 1 (segment pool of f * (P-1) * n
+ * entries; the default is the bound no tree update can exceed, (P-1) * (max_depth+1) * n, whenever that is under a quarter
+ * of the free device memory, so the pool cannot run out; a pool that does run out ends the step with status 2);
  * "weight_mode" = "reference" (default: the reference's arithmetic, smc.rs:53,89-102 — slot weights are normalised in
  * place and meet next round's log-likelihoods, the reference particle is a fresh stump) | "pg_correct" (NOT the
  * reference's behaviour: every slot keeps the log-likelihood of the particle it holds, permuted with the ancestors, and

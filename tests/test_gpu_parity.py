@@ -408,6 +408,65 @@ def test_gpu_pg_correct_many_lineages_need_a_larger_pool():
     assert np.max(tr.upd[:2 * m, 0]) >= 11
 
 
+@pytest.mark.parametrize("mode", ["reference", "pg_correct"])
+def test_gpu_segment_pool_default_cannot_overflow_and_a_small_pool_fails_cleanly(mode):
+    """The default segment pool is the bound no tree update can exceed, S (depth + 1) n entries, whenever that fits in a
+    quarter of the free memory, so the sampler has no failure the reference lacks.  A pool made too small on purpose
+    (option pool_factor) ends the step with an error message instead of a hang, and later steps are refused.  One growing
+    particle (it always survives the resampling) with a shallow prior: almost every tree splits the root and then a child,
+    n + n/2 entries, more than the S n = n entries of pool_factor 1.  Both control codes (fast and generic)."""
+    from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
+    n, p, m, P = 20_000, 6, 10, 2
+    X, y = datagen.friedman(n, p, seed=11)
+    prm = datagen.pgbart_params(y, m, p)
+
+    def sampler():
+        st = PyBartSettings(m, P, 12, 0.95, 1.0, prm["sigma"], list(prm["split_prior"]), ["ContinuousSplit"] * p,
+                            "constant", "systematic", 1.0, 1.0, 4)
+        s = PySampler.init(np.asfortranarray(X.astype(np.float64)), y, DeviceLikelihood("gaussian", 1.0), st)
+        s.set_option("weight_mode", mode)
+        return s
+
+    s = sampler()
+    for _ in range(10):
+        s.step(True)
+    s.close()
+    s = sampler()
+    s.set_option("pool_factor", "1")
+    with pytest.raises(RuntimeError, match="segment pool exhausted"):
+        for _ in range(10):
+            s.step(True)
+    with pytest.raises(RuntimeError):
+        s.step(True)
+    s.close()
+
+
+def test_gpu_default_path_soak():
+    """Regression guard for the hand-offs between the control warp, its helper warps and the pass blocks (a lane-divergent
+    read of a helper's flag once stalled one sweep in ~1500): 400 sweeps = 80 000 tree updates queued
+    back to back on the default path (issue-ahead, speculation, early statistics pass), which must end without the watchdog
+    firing, with finite predictions and with every mechanism used."""
+    from bart_rs_b200 import DeviceLikelihood, PyBartSettings, PySampler
+    n, p, m, P = 20_000, 10, 200, 20
+    X, y = datagen.friedman(n, p, seed=3)
+    prm = datagen.pgbart_params(y, m, p)
+    st = PyBartSettings(m, P, prm["max_depth"], 0.95, 2.0, prm["sigma"], list(prm["split_prior"]), ["ContinuousSplit"] * p,
+                        "constant", "systematic", 1.0, 1.0, 9)
+    s = PySampler.init(np.asfortranarray(X.astype(np.float64)), y, DeviceLikelihood("gaussian", 1.0), st)
+    for i in range(400):
+        s.step_device(i < 200)
+        if i % 50 == 49:
+            s.sync()
+    pred = s.step(False)
+    assert np.all(np.isfinite(pred))
+    assert abs(float(np.mean(pred)) - float(np.mean(y))) < 2.0      # one draw: the leaf noise alone moves the mean by ~0.5
+    assert np.corrcoef(pred, y)[0, 1] > 0.5
+    es = s.early_stats_counters()
+    assert es["issued"] > 1000 and es["fallbacks"] == 0, es
+    assert s.counters()["tree_updates"] == 401 * m
+    s.close()
+
+
 def test_gpu_early_statistics_pass_changes_nothing():
     """The statistics pass of rounds 1-2 queued behind the partition pass (option early_stats, on by default) computes the
     same per-job sums over the same rows in the same order as the pass the control block would issue after digesting the
