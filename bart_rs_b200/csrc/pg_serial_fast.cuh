@@ -98,12 +98,18 @@ __device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int ph
     const unsigned* p_ccnt = st.part_ccnt + pg_off_part_ccnt(st, pb);
     const double* p_tot = st.part_tot + pg_off_part_tot(st, pb);
     const bool sums = phase == PH_ROOT || phase == PH_STATS || phase == PH_BERN;
+    // Root pass: the block's four totals ride along as two more "jobs" (lanes J and J + 1 take them as two double2), so they
+    // cost no load stage, no shuffle tree and no combine loop of their own.  J = 31 leaves no room: the separate stage below.
+    const bool tot_lanes = phase == PH_ROOT && J + 2 <= 32;
     if (sums) {
         const double* src = phase == PH_BERN ? st.part_ll : p_sum;
-        const bool cnts = phase != PH_BERN;
+        const bool isjob = lane < J;
+        const bool cnts = phase != PH_BERN && isjob;
         double a = 0.0, bsum = 0.0;
         unsigned cc = 0u;
-        if (lane < J) {
+        if (isjob || (tot_lanes && lane < J + 2)) {
+            const double* base = isjob ? src + (size_t)lane * 2 : p_tot + (size_t)(lane - J) * 2;
+            const size_t stride = isjob ? (size_t)S * 2 : (size_t)4;
 #pragma unroll 1
             for (int b0 = warp; b0 < G; b0 += PG_WARPS * FW_RB) {
                 double2 v[FW_RB];
@@ -112,7 +118,7 @@ __device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int ph
                 for (int q = 0; q < FW_RB; ++q) {
                     const int b = b0 + q * PG_WARPS;
                     if (b < G) {
-                        v[q] = __ldcg(reinterpret_cast<const double2*>(src + ((size_t)b * S + lane) * 2));
+                        v[q] = __ldcg(reinterpret_cast<const double2*>(base + (size_t)b * stride));
                         k[q] = cnts ? __ldcg(&p_ccnt[(size_t)b * S + lane]) : 0u;
                     } else { v[q] = make_double2(0.0, 0.0); k[q] = 0u; }
                 }
@@ -133,7 +139,7 @@ __device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int ph
         f->wsC[warp][lane] = kmin;
         f->wsD[warp][lane] = kmax;
     }
-    if (phase == PH_ROOT) {   // root totals: thread = block
+    if (phase == PH_ROOT && !tot_lanes) {   // root totals: thread = block
         double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
         for (int b = threadIdx.x; b < G; b += blockDim.x) {
             const double2 u = __ldcg(reinterpret_cast<const double2*>(p_tot + (size_t)b * 4));
@@ -150,21 +156,22 @@ __device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int ph
         if (st.heartbeat && (threadIdx.x & 31) == 0) { volatile unsigned long long* hw_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hw_) hw_[16 + (threadIdx.x >> 5)] = ((unsigned long long)f->issued << 32) | 2ull; }
     __syncthreads();
     if (warp == 0) {   // fixed-order combine over warps
-        if (sums && lane < J) {
+        if (sums && (lane < J || (tot_lanes && lane < J + 2))) {
             double a = 0.0, b = 0.0;
             unsigned cc = 0u;
-#pragma unroll 1
+#pragma unroll 4
             for (int w = 0; w < PG_WARPS; ++w) { a += f->wsA[w][lane]; b += f->wsB[w][lane]; cc += f->wsC[w][lane]; }
-            if (phase == PH_BERN) { f->rllL[lane] = a; f->rllR[lane] = b; }
+            if (lane >= J) { f->tot[2 * (lane - J)] = a; f->tot[2 * (lane - J) + 1] = b; }
+            else if (phase == PH_BERN) { f->rllL[lane] = a; f->rllR[lane] = b; }
             else { f->rSo[lane] = a; f->rSr[lane] = b; f->rCnt[lane] = cc; f->rCntL[lane] = cc; }
         }
         if ((phase == PH_MINMAX || phase == PH_PART) && lane < J) {
             unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
-#pragma unroll 1
+#pragma unroll 4
             for (int w = 0; w < PG_WARPS; ++w) { kmin = min(kmin, f->wsC[w][lane]); kmax = max(kmax, f->wsD[w][lane]); }
             f->rMin[lane] = kmin; f->rMax[lane] = kmax;
         }
-        if (phase == PH_ROOT && lane < 4) {
+        if (phase == PH_ROOT && !tot_lanes && lane < 4) {
             double v = 0.0;
 #pragma unroll 1
             for (int w = 0; w < PG_WARPS; ++w) v += f->wsT[w][lane];
