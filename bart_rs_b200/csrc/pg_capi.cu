@@ -516,7 +516,7 @@ int pgbart_create(const void* x, int x_dtype, int x_order, uint64_t n, uint64_t 
         && dalloc(s, &st.pj_src_off, S) && dalloc(s, &st.pj_len, S) && dalloc(s, &st.pj_dst_off, S) && dalloc(s, &st.pj_cntL, S)
         && dalloc(s, &st.pj_warp_left, S * W) && dalloc(s, &st.pj_of_anc, S) && dalloc(s, &st.scan_tmp, PG_THREADS + 1)
         && dalloc(s, &st.part_sum, 2 * G * S * 2) && dalloc(s, &st.part_cnt, 2 * W * S) && dalloc(s, &st.part_ccnt, 2 * G * S)
-        && dalloc(s, &st.part_tot, 2 * G * 4) && dalloc(s, &st.part_mm, G * 2 * S * 2) && dalloc(s, &st.mq_pj, 2 * S) && dalloc(s, &st.mq_side, 2 * S) && dalloc(s, &st.mq_var, 2 * S) && dalloc(s, &st.mq_u3, 2 * S) && dalloc(s, &st.es_thr, 2 * S) && dalloc(s, &st.part_ll, G * S * 2) && dalloc(s, &st.diag_blocks, G * 16) && dalloc(s, &st.part_old, G)
+        && dalloc(s, &st.part_tot, 2 * G * 4) && dalloc(s, &st.part_mm, G * 2 * S * 2) && dalloc(s, &st.mq_pj, 2 * S) && dalloc(s, &st.mq_side, 2 * S) && dalloc(s, &st.mq_var, 2 * S) && dalloc(s, &st.mq_u3, 2 * S) && dalloc(s, &st.es_thr, 2 * S) && dalloc(s, &st.part_ll, G * S * 2) && dalloc(s, &st.diag_blocks, G * 16) && dalloc(s, &st.part_old, G) && dalloc(s, &st.blk_done, G + 32)
         && dalloc(s, &st.info_depths, M) && dalloc(s, &st.ctrl, 1);
     if (!ok) return bail();
     {

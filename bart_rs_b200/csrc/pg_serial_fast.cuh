@@ -90,8 +90,23 @@ __device__ __forceinline__ void fw_publish(const PgState& st, PgFastSm* f, int l
 // ---- stage A: reduce the pass's per-block partials --------------------------------------------
 // lane = job, warp = subset of blocks {warp, warp + PG_WARPS, ...}; rows of the [block][job] partial
 // arrays are contiguous in job: coalesced, and all of a warp's loads are in flight at once.
-#define FW_RB 10   // blocks per warp per batch (grid 148 / 16 warps = 9.25)
-__device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int pb) {
+#define FW_RW (PG_WARPS - 1)   // loading warps: 1 .. PG_WARPS - 1 (warp 0 waits for the completion count and issues ahead meanwhile)
+#define FW_RB 10               // blocks per loading warp per batch (147 pass blocks / 15 warps = 9.8)
+// A loading warp waits for ITS blocks only (per-block completion flags, PgState::blk_done) and fetches their partials at
+// once: the fetch of ~56 KB through one SM's L2 port (1.4 us when it started after the slowest block) overlaps the pass's
+// tail, and what remains after the last arrival is one warp's share.
+__device__ __forceinline__ void fw_wait_blocks(const PgState& st, int warp, int lane, unsigned g) {
+    bool seen;
+    do {
+        seen = true;
+        for (int b = warp - 1 + lane * FW_RW; b < st.grid; b += 32 * FW_RW)
+            seen = seen && (int)(pg_ld_acquire(&st.blk_done[b]) - g) >= 0;
+        seen = __all_sync(PG_FULL, seen);
+        if (!seen) __nanosleep(20);
+    } while (!seen);        // a block that never arrives: the watchdog of thread 0's wait on the count ends the kernel
+    __syncwarp();
+}
+__device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int phase, int J, int pb, unsigned g) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = st.grid, S = st.S;
     const double* p_sum = st.part_sum + pg_off_part_sum(st, pb);
@@ -107,16 +122,17 @@ __device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int ph
         const bool cnts = phase != PH_BERN && isjob;
         double a = 0.0, bsum = 0.0;
         unsigned cc = 0u;
-        if (isjob || (tot_lanes && lane < J + 2)) {
+        if (warp > 0) fw_wait_blocks(st, warp, lane, g);
+        if (warp > 0 && (isjob || (tot_lanes && lane < J + 2))) {
             const double* base = isjob ? src + (size_t)lane * 2 : p_tot + (size_t)(lane - J) * 2;
             const size_t stride = isjob ? (size_t)S * 2 : (size_t)4;
 #pragma unroll 1
-            for (int b0 = warp; b0 < G; b0 += PG_WARPS * FW_RB) {
+            for (int b0 = warp - 1; b0 < G; b0 += FW_RW * FW_RB) {
                 double2 v[FW_RB];
                 unsigned k[FW_RB];
 #pragma unroll
                 for (int q = 0; q < FW_RB; ++q) {
-                    const int b = b0 + q * PG_WARPS;
+                    const int b = b0 + q * FW_RW;
                     if (b < G) {
                         v[q] = __ldcg(reinterpret_cast<const double2*>(base + (size_t)b * stride));
                         k[q] = cnts ? __ldcg(&p_ccnt[(size_t)b * S + lane]) : 0u;
@@ -129,9 +145,10 @@ __device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int ph
         f->wsA[warp][lane] = a; f->wsB[warp][lane] = bsum; f->wsC[warp][lane] = cc;
     } else if (phase == PH_MINMAX || phase == PH_PART) {
         unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
-        if (lane < J) {
+        if (warp > 0) fw_wait_blocks(st, warp, lane, g);
+        if (warp > 0 && lane < J) {
 #pragma unroll 1
-            for (int b = warp; b < G; b += PG_WARPS) {
+            for (int b = warp - 1; b < G; b += FW_RW) {
                 const uint2 v = __ldcg(reinterpret_cast<const uint2*>(st.part_mm + ((size_t)b * 2 * S + lane) * 2));
                 kmin = min(kmin, v.x); kmax = max(kmax, v.y);
             }
@@ -142,6 +159,7 @@ __device__ __forceinline__ void fw_reduce(const PgState& st, PgFastSm* f, int ph
     if (phase == PH_ROOT && !tot_lanes) {   // root totals: thread = block
         double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
         for (int b = threadIdx.x; b < G; b += blockDim.x) {
+            while ((int)(pg_ld_acquire(&st.blk_done[b]) - g) < 0) __nanosleep(20);
             const double2 u = __ldcg(reinterpret_cast<const double2*>(p_tot + (size_t)b * 4));
             const double2 v = __ldcg(reinterpret_cast<const double2*>(p_tot + (size_t)b * 4 + 2));
             t0 += u.x; t1 += u.y; t2 += v.x; t3 += v.y;
@@ -1780,11 +1798,22 @@ __device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemV
 #pragma unroll 1
     for (long long guard = 0; guard < (1ll << 40); ++guard) {
         // ---- (A) the outstanding pass (if any) completes
+        if (!first && threadIdx.x == 0)
+            f->cur_gen = f->issued - ((f->spec_now || f->early_now) ? 1u : 0u);   // the OLDEST outstanding pass: a pass issued ahead queues behind it
+        FW_BEAT(0, 1);
+        if (st.heartbeat && (threadIdx.x & 31) == 0) { volatile unsigned long long* hw_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hw_) hw_[16 + (threadIdx.x >> 5)] = ((unsigned long long)f->issued << 32) | 1ull; }
+        __syncthreads();
+        const unsigned gcur = f->cur_gen;
+        const int phase = first ? PH_BEGIN : f->out_phase[gcur & 1u];
+        const int J = first ? 0 : f->out_J[gcur & 1u];
+        const int pb = first ? 0 : f->out_pb[gcur & 1u];
+        // Warp 0 waits for the completion COUNT (everything below that is not the reduce needs the whole pass done: the issue
+        // logic reuses the command buffer of the pass before it, the control code reads what the pass wrote); warps 1.. go
+        // straight into fw_reduce and fetch each block's partials as that block completes.
         if (!first && threadIdx.x == 0) {
             const long long tw = clock64();
-            const unsigned g = f->issued - ((f->spec_now || f->early_now) ? 1u : 0u);   // the OLDEST outstanding pass: a pass issued ahead queues behind it
+            const unsigned g = gcur;
             pg_spin_until(&st.ctrl->cnt[g & 1u][0], fw_cnt_target(g), st.ctrl);
-            f->cur_gen = g;
             const int ph = f->out_phase[g & 1u];
             c->prof3[ph == PH_ROOT ? 4 : ph == PH_STATS ? 5 : ph == PH_PART ? 6 : 7] += (unsigned long long)(clock64() - tw);
 #ifdef PG_DIAG
@@ -1797,12 +1826,7 @@ __device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemV
             }
 #endif
         }
-        FW_BEAT(0, 1);
-        if (st.heartbeat && (threadIdx.x & 31) == 0) { volatile unsigned long long* hw_ = reinterpret_cast<volatile unsigned long long*>(st.ctrl->hostdiag); if (hw_) hw_[16 + (threadIdx.x >> 5)] = ((unsigned long long)f->issued << 32) | 1ull; }
-        __syncthreads();
-        const int phase = first ? PH_BEGIN : f->out_phase[f->cur_gen & 1u];
-        const int J = first ? 0 : f->out_J[f->cur_gen & 1u];
-        const int pb = first ? 0 : f->out_pb[f->cur_gen & 1u];
+        if (warp == 0) __syncwarp();
         first = false;
         const long long t_entry = clock64();
         const int gerr = threadIdx.x == 0 ? __ldcg(&st.ctrl->error) : PG_OK;   // a pass may have flagged an error
@@ -1824,7 +1848,7 @@ __device__ __forceinline__ void pg_control_fast(const PgState& st, const PgSmemV
             if (lane == 0) { f->spec_now = sp ? 1 : 0; f->stat_spec = sp ? 1 : 0; }
         }
         FW_BEAT(0, 2);
-        fw_reduce(st, f, phase, J, pb);   // contains a __syncthreads before its combine step
+        fw_reduce(st, f, phase, J, pb, gcur);   // contains a __syncthreads before its combine step
         FW_BEAT(0, 3);
         if (st.world > 1 && warp == 0) fw_exchange(st, f, phase, J, lane);
         if (threadIdx.x == 0 && gerr != PG_OK) c->error = gerr;

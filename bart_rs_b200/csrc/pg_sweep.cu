@@ -109,7 +109,9 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
                 st.diag_blocks[(size_t)(blockIdx.x - 1) * 8 + (phase & 7)] += (unsigned long long)(t1 - t0);
                 atomicMax(&c->dbg[2], pg_globaltimer());
 #endif
-                pg_red_release_add(&c->cnt[g & 1u][0], 1u);
+                __threadfence();                                      // one release fence for both signals
+                pg_st_relaxed(&st.blk_done[blockIdx.x - 1], g);       // per block: the control block's reduce polls these
+                pg_red_relaxed_add(&c->cnt[g & 1u][0], 1u);           // count: pass-side barriers, the control block's issue logic
             }
             if (phase == PH_ROOT && st.prefetch_next) pg_prefetch_next_root(st, flags);
             if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // stopwatch kept by the last pass block
@@ -176,6 +178,7 @@ extern "C" __global__ void pg_prepare_step(const PgState st, int tune) {
     c->bar_gen = 0u;
     c->cnt[0][0] = 0u;
     c->cnt[1][0] = 0u;
+    for (int b = 0; b < st.grid + 32; ++b) st.blk_done[b] = 0u;
 }
 
 extern "C" __global__ void pg_fill_f64(double* p, long long n, double v) {

@@ -253,6 +253,8 @@ struct PgState {
     int* mq_pj; int* mq_side; int* mq_var;   // [2S] look-ahead min/max requests of the partition pass: (partition job, child side, column)
     double* part_ll;             // [grid][S][2]  Bernoulli: log-likelihood of the left / right child
     double* part_old;            // [grid] per-block sum behind ll_old (root pass, pg_correct only)
+    unsigned* blk_done;          // [grid] generation of the last command each pass block completed (fast kernels): the control
+                                 // block's reduce loads a block's partials as soon as that block is done, not after the slowest one
     unsigned long long* diag_blocks;   // [grid][8] per pass block, by phase: cycles spent in pass bodies (-DPG_DIAG only)
     // segment pool
     unsigned int* pool; unsigned long long pool_cap;
