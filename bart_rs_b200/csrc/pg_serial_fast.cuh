@@ -34,12 +34,12 @@ struct FwCx {               // passed by value: stays in registers
 
 __device__ __forceinline__ double fw_sum_seq(double v, int n) {   // lanes 0..n-1 in order; uniform result
     double acc = 0.0;
-#pragma unroll 1
+#pragma unroll 8            // the shuffles of a batch are in flight together; the chain of additions keeps its order
     for (int k = 0; k < n; ++k) acc += __shfl_sync(PG_FULL, v, k);
     return acc;
 }
 __device__ __forceinline__ double fw_max(double v) {
-#pragma unroll 1
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(PG_FULL, v, o));
     return v;
 }
@@ -1143,7 +1143,7 @@ __device__ __forceinline__ int fw_normalize_resample(const PgState& st, const Fw
     const double target = ((double)lane + u6) / (double)S;
     int cidx = 0;
     double cum = 0.0;
-#pragma unroll 1
+#pragma unroll 8
     for (int k = 0; k < S; ++k) {          // cum == sum of the first k weights, in order, on every lane
         if (cum < target) cidx = k + 1;     // the reference's pointer passes k
         cum += __shfl_sync(PG_FULL, wn, k);
@@ -1321,7 +1321,7 @@ __device__ __forceinline__ int fw_select(const PgState& st, const FwCx& x, int l
     {
         double cum = 0.0;
         bool open = true;
-#pragma unroll 1
+#pragma unroll 8
         for (int i = 0; i + 1 < P; ++i) {
             cum += __shfl_sync(PG_FULL, Wn, i);
             if (open && cum <= chosen) sel = i + 1; else open = false;
@@ -1732,7 +1732,7 @@ __device__ __forceinline__ void fw_predict(const PgState& st, const FwCx& x, int
     {
         double cum = 0.0;
         bool open = true;
-#pragma unroll 1
+#pragma unroll 8
         for (int i = 0; i + 1 < P; ++i) {
             cum += __shfl_sync(PG_FULL, Wn, i);
             if (open && cum <= chosen) sel = i + 1; else open = false;
