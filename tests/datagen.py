@@ -50,3 +50,26 @@ def pgbart_params(y: np.ndarray, m: int, p: int, alpha: float = 0.95, beta: floa
     split_prior = np.cumsum(np.ones(p))
     max_depth = int(math.pow((1 / (1 - 0.99)) * alpha, 1.0 / beta) - 1)
     return dict(sigma=float(leaf_sd), split_prior=split_prior, max_depth=max_depth, alpha=alpha, beta=beta)
+
+
+def random_cases(count: int, seed: int, n_lo: int, n_hi: int):
+    """Deterministic random sampler configurations for the randomized replay-parity tests (host simulation and GPU):
+    (n, p, m, P, family, lik_sigma, kwargs for cfg_for, tunes, pg_correct, grid)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        n = int(rng.integers(n_lo, n_hi + 1))
+        p = int(rng.integers(2, 7))
+        m = int(rng.integers(2, 7))
+        P = int(rng.choice([2, 3, 4, 6, 9, 16, 20, 31, 32, 33, 48]))
+        family = int(rng.choice([0, 0, 1, 2]))
+        lik_sigma = float(rng.choice([1.0, 0.5, 0.05])) if family == 0 else 1.0
+        alpha = float(rng.choice([0.95, 0.95, 0.9999]))
+        beta = float(rng.choice([1.0, 1.5, 2.0]))
+        prior = bool(rng.integers(0, 2))
+        batch = (float(rng.choice([1.0, 0.5])), float(rng.choice([1.0, 0.34])))
+        tunes = [bool(b) for b in rng.integers(0, 2, size=int(rng.integers(1, 4)))]
+        pg_correct = bool(rng.integers(0, 4) == 0)
+        grid = int(rng.integers(1, 6))
+        out.append((n, p, m, P, family, lik_sigma, dict(alpha=alpha, beta=beta, max_depth=12, prior=prior, batch=batch), tunes, pg_correct, grid))
+    return out

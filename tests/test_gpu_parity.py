@@ -77,6 +77,18 @@ def test_gpu_replay_parity(n, p, m, P, family, lik_sigma, kw, tunes):
     parity.replay_parity(make_gpu(), X, y, cfg, family, lik_sigma, tunes, r_cap=64)
 
 
+@pytest.mark.parametrize("case", range(12))
+def test_gpu_replay_parity_randomized(case):
+    """Seeded random configurations (particle counts on both sides of 32, families, priors, batch fractions, weight modes)
+    at n = 500 .. 30 000: fast and generic control code against the oracle."""
+    n, p, m, P, family, lik_sigma, kw, tunes, pg_correct, _ = datagen.random_cases(12, 777, 500, 30_000)[case]
+    X, y = datagen.small(n, p, seed=2000 + case, bernoulli=(family == 1))
+    cfg = cfg_for(y, m, P, p, seed=case, **kw)
+    if pg_correct:
+        cfg["pg_correct"] = True
+    parity.replay_parity(make_gpu(), X, y, cfg, family, lik_sigma, tunes, r_cap=128)
+
+
 @pytest.mark.parametrize("case", [0, 2, 4])
 def test_gpu_stepwise_driver_matches(case):
     n, p, m, P, family, lik_sigma, kw, tunes = CASES[case]

@@ -48,6 +48,18 @@ def test_sim_replay_parity(n, p, m, P, family, lik_sigma, kw, tunes, grid):
     parity.replay_parity(make_sim(grid), X, y, cfg, family, lik_sigma, tunes, r_cap=64)
 
 
+@pytest.mark.parametrize("case", range(10))
+def test_sim_replay_parity_randomized(case):
+    """Seeded random configurations (sizes, particle counts on both sides of 32, families, priors, batch fractions, weight
+    modes, grid sizes): the same generator feeds the GPU suite with larger n (tests/test_gpu_parity.py)."""
+    n, p, m, P, family, lik_sigma, kw, tunes, pg_correct, grid = datagen.random_cases(10, 2024, 20, 300)[case]
+    X, y = datagen.small(n, p, seed=1000 + case, bernoulli=(family == 1))
+    cfg = cfg_for(y, m, P, p, seed=case, **kw)
+    if pg_correct:
+        cfg["pg_correct"] = True
+    parity.replay_parity(make_sim(grid), X, y, cfg, family, lik_sigma, tunes, r_cap=128)
+
+
 def test_sim_philox_parity():
     X, y = datagen.friedman(300, 5, seed=2)
     cfg = cfg_for(y, 12, 10, 5, seed=5)
