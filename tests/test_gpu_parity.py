@@ -213,6 +213,38 @@ def test_gpu_large_n_properties():
     np.testing.assert_allclose(outs[0], outs[2], rtol=1e-9)       # stepwise driver: generic serial code, other reduction order
 
 
+@pytest.mark.timeout(900)
+def test_gpu_C3_full_sweeps_properties():
+    """BASELINE C3 at full size (n = 1M, p = 50, m = 200, P = 20), two full sweeps on the default path (no trace): the
+    predictions are the sum over the 200 trees of leaf_val[leaf_indices] recomputed on the host (linearity), every tree's
+    leaf_indices are leaves of that tree, the out-of-sample path on the training rows gives the same numbers, and two runs
+    are bit-identical."""
+    n, p, m, P = 1_000_000, 50, 200, 20
+    X, y = datagen.friedman(n, p, seed=0)
+    cfg = cfg_for(y, m, P, p, seed=0)
+    outs = []
+    for run in range(2):
+        dev = make_gpu()(X, y, cfg)
+        dev.set_rng_philox(5)
+        for _ in range(2):
+            pred = dev.step(True)
+        if run == 0:
+            total = np.zeros(n)
+            grown = 0
+            for t in range(m):
+                sv, sp, lv = dev.tree(t)
+                li = dev.leaf_indices(t)
+                assert np.all(sv[li] < 0)                       # every row sits in a leaf
+                total += lv[li]
+                grown += int(len(sv) > 1)
+            assert grown > 20
+            np.testing.assert_allclose(pred, total, rtol=1e-9)
+            np.testing.assert_allclose(dev.predict(X[:200_000]), total[:200_000], rtol=1e-9)
+        outs.append(pred)
+        dev.close()
+    np.testing.assert_array_equal(outs[0], outs[1])
+
+
 @pytest.mark.gpu
 def test_gpu_pruned_dead_proposals_same_forest():
     """Option prune_dead_proposals: proposals of particles whose weight is provably 0 are not evaluated.
