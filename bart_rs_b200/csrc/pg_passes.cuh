@@ -1703,6 +1703,9 @@ __device__ __forceinline__ unsigned pg_ld_relaxed(const unsigned* p) {
 __device__ __forceinline__ void pg_red_release_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// acquire / release fence at gpu scope (MEMBAR.ALL.GPU + L1 invalidate).  __threadfence() is the sequentially consistent
+// one (MEMBAR.SC.GPU), which none of the hand-offs here needs: they are all message passing (data, then flag).
+__device__ __forceinline__ void pg_fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void pg_red_relaxed_add(unsigned* p, unsigned v) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -1744,6 +1747,6 @@ __device__ __forceinline__ void pg_spin_until(const unsigned* p, unsigned target
             __trap();
         }
     }
-    __threadfence();   // acquire side of the fence/atomic/fence pattern
+    pg_fence_acq_rel();   // acquire side of the fence/atomic/fence pattern
 }
 

@@ -109,7 +109,7 @@ __device__ __forceinline__ void pg_sweep_body(const PgState& st) {
                 st.diag_blocks[(size_t)(blockIdx.x - 1) * 8 + (phase & 7)] += (unsigned long long)(t1 - t0);
                 atomicMax(&c->dbg[2], pg_globaltimer());
 #endif
-                __threadfence();                                      // one release fence for both signals
+                pg_fence_acq_rel();                                   // one release fence for both signals
                 pg_st_relaxed(&st.blk_done[blockIdx.x - 1], g);       // per block: the control block's reduce polls these
                 pg_red_relaxed_add(&c->cnt[g & 1u][0], 1u);           // count: pass-side barriers, the control block's issue logic
             }
